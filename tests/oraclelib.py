@@ -1,0 +1,238 @@
+"""ctypes bindings for the TEST-ONLY checkers under oracle/ (see oracle/gpc_oracle.h).
+
+`Oracle`    -> oracle/_build/libgpc_oracle.so  (plain-C restatement, always buildable)
+`Reference` -> oracle/_ref/libgpc_ref.so       (unmodified reference headers; built only where
+                                                /root/reference exists, travels prebuilt)
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "libgpc_oracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libgpc_ref.so")
+FOREST_TAU = os.path.join(ROOT, "forests", "defaultTauForest.txt")
+FOREST_ZERO = os.path.join(ROOT, "forests", "defaultZeroForest.txt")
+
+SUPPORT_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("d", "<f4")])
+
+
+class GpcoForest(C.Structure):
+    _fields_ = [("n_tests", C.c_int32), ("type", C.c_int32), ("n_discarded", C.c_int32),
+                ("ix", C.c_int32 * 32), ("iy", C.c_int32 * 32), ("jx", C.c_int32 * 32),
+                ("jy", C.c_int32 * 32), ("tau", C.c_int32 * 32)]
+
+
+class GpcoSettings(C.Structure):
+    _fields_ = [("gradient_threshold", C.c_int32), ("disp_high", C.c_int32),
+                ("vertical_tolerance", C.c_int32), ("epipolar_mode", C.c_int32)]
+
+
+def build_oracle(force=False):
+    """Compile the checkers (gcc; the reference build only where /root/reference exists)."""
+    if force or not os.path.exists(ORACLE_SO) or \
+            os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(ORACLE_DIR, "gpc_oracle.c")):
+        subprocess.run(["make", "-C", ORACLE_DIR, "oracle"], check=True, capture_output=True)
+    if os.path.isdir("/root/reference/lib/gpc"):
+        subprocess.run(["make", "-C", ORACLE_DIR, "ref"], check=True, capture_output=True)
+
+
+def _p(a, t=C.c_void_p):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def settings(thr=5, disp_high=128, vt=0, epipolar=True):
+    return GpcoSettings(int(thr), int(disp_high), int(vt), int(bool(epipolar)))
+
+
+def digest(supp):
+    """FNV-1a-64 variant over the ordered support list."""
+    h = 1469598103934665603
+    vals = np.stack([supp["x"].astype(np.int64), supp["y"].astype(np.int64),
+                     supp["d"].astype(np.int64)], axis=1).reshape(-1) & 0xFFFFFFFF
+    for v in vals.tolist():
+        h ^= v
+        h = (h * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+class Oracle:
+    def __init__(self):
+        build_oracle()
+        self.lib = C.CDLL(ORACLE_SO)
+        L = self.lib
+        L.gpco_digest.restype = C.c_uint64
+        L.gpco_candidates.restype = C.c_int
+        L.gpco_find_correspondences.restype = C.c_int
+        L.gpco_match.restype = C.c_int
+        L.gpco_read_forest.restype = C.c_int
+        L.gpco_pair.restype = C.c_int
+
+    def synth(self, w, h, seed):
+        Lm = np.empty((h, w), np.uint8)
+        Rm = np.empty((h, w), np.uint8)
+        self.lib.gpco_synth(_p(Lm), _p(Rm), C.c_int(w), C.c_int(h), C.c_uint32(seed))
+        return Lm, Rm
+
+    def digest(self, supp):
+        supp = np.ascontiguousarray(supp)
+        return int(self.lib.gpco_digest(_p(supp), C.c_int(len(supp))))
+
+    def read_forest(self, path):
+        f = GpcoForest()
+        rc = self.lib.gpco_read_forest(path.encode(), C.byref(f))
+        if rc != 0:
+            raise FileNotFoundError(path)
+        return f
+
+    @staticmethod
+    def make_forest(tests, taus, type_=None, n_discarded=0):
+        """tests: iterable of (ix, iy, jx, jy); taus: iterable of int."""
+        f = GpcoForest()
+        tests = list(tests)[:32]
+        taus = list(taus)[:32]
+        f.n_tests = len(tests)
+        for t, (ix, iy, jx, jy) in enumerate(tests):
+            f.ix[t], f.iy[t], f.jx[t], f.jy[t] = ix, iy, jx, jy
+            f.tau[t] = taus[t]
+        f.type = int(any(taus)) if type_ is None else type_
+        f.n_discarded = n_discarded
+        return f
+
+    def box(self, img):
+        h, w = img.shape
+        out = np.empty((h, w), np.uint8)
+        self.lib.gpco_box(_p(np.ascontiguousarray(img)), _p(out), C.c_int(w), C.c_int(h))
+        return out
+
+    def sobel(self, img, thr):
+        h, w = img.shape
+        out = np.empty((h, w), np.uint8)
+        self.lib.gpco_sobel(_p(np.ascontiguousarray(img)), _p(out), C.c_int(w), C.c_int(h), C.c_int(thr))
+        return out
+
+    def candidates(self, grad):
+        h, w = grad.shape
+        mask = np.empty(h * w + 1, np.int32)
+        n = self.lib.gpco_candidates(_p(np.ascontiguousarray(grad)), C.c_int(w), C.c_int(h), _p(mask))
+        return mask[:n].copy()
+
+    def hash(self, smooth, forest, mask):
+        h, w = smooth.shape
+        mask = np.ascontiguousarray(mask, np.int32)
+        st = np.empty(max(len(mask), 1), np.uint32)
+        self.lib.gpco_hash(_p(np.ascontiguousarray(smooth)), C.c_int(w), C.c_int(h), C.byref(forest),
+                           _p(mask), C.c_int(len(mask)), _p(st))
+        return st[:len(mask)].copy()
+
+    def find_correspondences(self, src, tar):
+        src = np.ascontiguousarray(src, np.uint64)
+        tar = np.ascontiguousarray(tar, np.uint64)
+        out = np.empty(2 * max(min(len(src), len(tar)), 1), np.int32)
+        m = self.lib.gpco_find_correspondences(_p(src), C.c_int(len(src)), _p(tar), C.c_int(len(tar)), _p(out))
+        return out[:2 * m].reshape(-1, 2).copy()
+
+    def match(self, mask_l, st_l, mask_r, st_r, w, s):
+        mask_l = np.ascontiguousarray(mask_l, np.int32)
+        mask_r = np.ascontiguousarray(mask_r, np.int32)
+        st_l = np.ascontiguousarray(st_l, np.uint32)
+        st_r = np.ascontiguousarray(st_r, np.uint32)
+        cap = max(min(len(mask_l), len(mask_r)), 1)
+        supp = np.empty(cap, SUPPORT_DTYPE)
+        n = self.lib.gpco_match(_p(mask_l), _p(st_l), C.c_int(len(mask_l)), _p(mask_r), _p(st_r),
+                                C.c_int(len(mask_r)), C.c_int(w), C.byref(s), None, None, _p(supp))
+        return supp[:n].copy()
+
+    def pair(self, Lm, Rm, forest, s):
+        h, w = Lm.shape
+        supp = np.empty(max((w - 26) * (h - 26), 1), SUPPORT_DTYPE)
+        ncl, ncr = C.c_int(0), C.c_int(0)
+        n = self.lib.gpco_pair(_p(np.ascontiguousarray(Lm)), _p(np.ascontiguousarray(Rm)), C.c_int(w),
+                               C.c_int(h), C.byref(forest), C.byref(s), _p(supp), C.byref(ncl), C.byref(ncr))
+        return supp[:n].copy(), ncl.value, ncr.value
+
+    def stages(self, img, forest, thr):
+        """All per-image intermediates: smooth, grad, mask, states."""
+        sm = self.box(img)
+        gr = self.sobel(img, thr)
+        mk = self.candidates(gr)
+        st = self.hash(sm, forest, mk)
+        return sm, gr, mk, st
+
+
+class Reference:
+    """The compiled, unmodified reference (None-like if the prebuilt library is absent)."""
+
+    @staticmethod
+    def available():
+        if not os.path.exists(REF_SO) and os.path.isdir("/root/reference/lib/gpc"):
+            build_oracle()
+        return os.path.exists(REF_SO)
+
+    def __init__(self):
+        if not self.available():
+            raise RuntimeError("oracle/_ref/libgpc_ref.so not built (needs /root/reference)")
+        self.lib = C.CDLL(REF_SO)
+        L = self.lib
+        for name in ("ref_read_forest", "ref_preprocess", "ref_hash", "ref_find_correspondences", "ref_pair",
+                     "ref_sizeof_descriptor", "ref_sizeof_support", "ref_sizeof_correspondence"):
+            getattr(L, name).restype = C.c_int
+        L.ref_time_pairs.restype = C.c_double
+
+    def read_forest(self, path, w, h):
+        off = np.zeros(64, np.int32)
+        tau = np.zeros(32, np.int32)
+        typ, ntau = C.c_int(0), C.c_int(0)
+        T = self.lib.ref_read_forest(path.encode(), C.c_int(w), C.c_int(h), _p(off), _p(tau),
+                                     C.byref(typ), C.byref(ntau))
+        return off[:2 * T].copy(), tau[:ntau.value].copy(), typ.value
+
+    def preprocess(self, img, thr):
+        h, w = img.shape
+        sm = np.empty((h, w), np.uint8)
+        gr = np.empty((h, w), np.uint8)
+        mk = np.empty(h * w, np.int32)
+        n = self.lib.ref_preprocess(_p(np.ascontiguousarray(img)), C.c_int(w), C.c_int(h), C.c_int(thr),
+                                    _p(sm), _p(gr), _p(mk))
+        return sm, gr, mk[:n].copy()
+
+    def hash(self, img, thr, forest_path, num_threads=1):
+        h, w = img.shape
+        st = np.empty(h * w, np.uint32)
+        n = self.lib.ref_hash(_p(np.ascontiguousarray(img)), C.c_int(w), C.c_int(h), C.c_int(thr),
+                              forest_path.encode(), C.c_int(num_threads), _p(st))
+        return st[:n].copy()
+
+    def find_correspondences(self, src, tar):
+        src = np.ascontiguousarray(src, np.uint64)
+        tar = np.ascontiguousarray(tar, np.uint64)
+        out = np.empty(2 * max(min(len(src), len(tar)), 1), np.int32)
+        m = self.lib.ref_find_correspondences(_p(src), C.c_int(len(src)), _p(tar), C.c_int(len(tar)), _p(out))
+        return out[:2 * m].reshape(-1, 2).copy()
+
+    def pair(self, Lm, Rm, forest_path, thr=5, disp_high=128, vt=0, epipolar=True, num_threads=1):
+        h, w = Lm.shape
+        cap = max((w - 26) * (h - 26), 1)
+        supp = np.empty(cap, SUPPORT_DTYPE)
+        ncl, ncr = C.c_int(0), C.c_int(0)
+        t_pre, t_match = C.c_double(0), C.c_double(0)
+        n = self.lib.ref_pair(_p(np.ascontiguousarray(Lm)), _p(np.ascontiguousarray(Rm)), C.c_int(w), C.c_int(h),
+                              forest_path.encode(), C.c_int(thr), C.c_int(disp_high), C.c_int(vt),
+                              C.c_int(int(epipolar)), C.c_int(num_threads), _p(supp), C.c_int(cap),
+                              C.byref(ncl), C.byref(ncr), C.byref(t_pre), C.byref(t_match))
+        assert n >= 0
+        return supp[:n].copy(), ncl.value, ncr.value, (t_pre.value, t_match.value)
+
+    def time_pairs(self, images, forest_path, threads, iters, thr=5, disp_high=128, vt=0, epipolar=True):
+        """images: uint8 [n_pairs, 2, h, w].  Returns (wall seconds, total supports)."""
+        images = np.ascontiguousarray(images, np.uint8)
+        n_pairs, _, h, w = images.shape
+        tot = C.c_longlong(0)
+        sec = self.lib.ref_time_pairs(_p(images), C.c_int(n_pairs), C.c_int(w), C.c_int(h), forest_path.encode(),
+                                      C.c_int(thr), C.c_int(disp_high), C.c_int(vt), C.c_int(int(epipolar)),
+                                      C.c_int(threads), C.c_int(iters), C.byref(tot))
+        return sec, tot.value
