@@ -1,0 +1,125 @@
+/*
+ * gpc_b200.h -- C ABI of libgpc_b200.so: the B200 (sm_100a) implementation of openGPC's
+ * Global Patch Collider inference path (the window timed by samples/sparsematch.cpp:45-52).
+ *
+ * The reference has no FFI of its own (header-only C++); this ABI is the seam a binding would
+ * sit on.  Each entry point names the reference interface it replaces (paths relative to the
+ * openGPC tree).  The drop-in C++ headers include/gpc/{inference,buffer}.hpp forward to it.
+ *
+ * Conventions
+ *  - plain pointers and sizes only, POD structs, no exceptions or aborts across the ABI;
+ *  - every function returns a gpc_status (0 = ok); gpc_last_error() gives the text;
+ *  - images are uint8 row-major with width % 16 == 0 (reference: filter.hpp:294,405,549,621);
+ *  - a gpc_ctx owns one CUDA device's resident buffers + one stream; it is not thread-safe,
+ *    distinct contexts are independent (one per GPU / host thread);
+ *  - outputs are caller-owned with an explicit capacity; GPC_E_CAPACITY reports the need;
+ *  - there is no CPU fallback: without a CUDA device gpc_create fails with GPC_E_CUDA.
+ */
+#ifndef GPC_B200_H
+#define GPC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPC_MAX_TESTS 32   /* inference.hpp:426 */
+#define GPC_PATCH_RADIUS 13 /* inference.hpp:322 border; shipped forests stay within +-13 */
+
+typedef enum {
+  GPC_OK = 0,
+  GPC_E_ARG = 1,          /* null pointer / negative size */
+  GPC_E_WIDTH16 = 2,      /* width not a multiple of 16 (assert at filter.hpp:294) */
+  GPC_E_DIMS = 3,         /* exceeds the context's max_w / max_h / max_batch */
+  GPC_E_CUDA = 4,         /* CUDA runtime error or no device */
+  GPC_E_CAPACITY = 5,     /* output buffer too small; counts still report the need */
+  GPC_E_UNSUPPORTED = 6,  /* useHashtable(true) (inference.hpp:204-225), out of scope */
+  GPC_E_FOREST = 7,       /* no forest set / more than 32 tests / offset outside +-13 */
+  GPC_E_IO = 8            /* forest file cannot be opened (inference.hpp:409-412) */
+} gpc_status;
+
+/* == ndb::Support (buffer.hpp:86-92): 12 bytes */
+typedef struct { int32_t x, y; float d; } gpc_support;
+
+/* mirrors gpc::inference::InferenceSettings (inference.hpp:71-131) */
+typedef struct {
+  int32_t gradient_threshold;   /* gradientThreshold_, uint8 range */
+  int32_t disp_high;            /* dispHigh_ */
+  int32_t vertical_tolerance;   /* verticalTolerance_ */
+  int32_t epipolar_mode;        /* epipolarMode_ */
+  int32_t use_hashtable;        /* useHashtable_: must be 0 */
+  int32_t num_threads;          /* numThreads_: accepted, ignored */
+} gpc_settings;
+
+/* result of Forest::readForest (inference.hpp:404-446) before the per-width offset baking */
+typedef struct {
+  int32_t n_tests;              /* min(#tests in file, 32) */
+  int32_t type;                 /* 0 zero forest, 1 tau forest */
+  int32_t n_discarded;          /* tests dropped by the 32-test cap (one "Note:" line each) */
+  int32_t ix[GPC_MAX_TESTS], iy[GPC_MAX_TESTS], jx[GPC_MAX_TESTS], jy[GPC_MAX_TESTS];
+  int32_t tau[GPC_MAX_TESTS];
+} gpc_forest;
+
+typedef struct gpc_ctx gpc_ctx;
+
+/* ---- lifetime --------------------------------------------------------------------------- */
+/* One resident context per GPU.  Buffers are sized for max_batch pairs of max_w x max_h. */
+int gpc_create(gpc_ctx** out, int device, int max_w, int max_h, int max_batch);
+void gpc_destroy(gpc_ctx* ctx);
+const char* gpc_last_error(const gpc_ctx* ctx);   /* ctx may be NULL: last create error */
+const char* gpc_status_string(int status);
+/* Run all work of this context on an existing CUDA stream (cudaStream_t); NULL restores the
+ * context's own stream. */
+int gpc_set_stream(gpc_ctx* ctx, void* cuda_stream);
+int gpc_synchronize(gpc_ctx* ctx);
+
+/* ---- forest (replaces Forest::readForest, inference.hpp:404-446) ------------------------ */
+/* Host-side parser of the reference's text format; no device work. */
+int gpc_read_forest(const char* path, gpc_forest* out);
+int gpc_set_forest(gpc_ctx* ctx, const gpc_forest* forest);
+
+/* ---- whole path, host buffers (replaces preprocessImage x2 + rectifiedMatch,
+ *      inference.hpp:302, :375; the sparsematch.cpp:46-51 window) ------------------------- */
+int gpc_match_pair(gpc_ctx* ctx, const uint8_t* left, const uint8_t* right, int w, int h, int stride,
+                   const gpc_settings* s, gpc_support* out, int cap, int* n_out,
+                   int* n_cand_l, int* n_cand_r);
+
+/* Batch of independent pairs, host buffers.  images = [n_pairs][2][h][w] (left, right).
+ * out receives the pairs' support lists back to back; offsets[i]..offsets[i+1] delimit pair i
+ * (offsets has n_pairs+1 entries).  n_cand (optional) = [n_pairs][2]. */
+int gpc_match_batch(gpc_ctx* ctx, const uint8_t* images, int n_pairs, int w, int h,
+                    const gpc_settings* s, gpc_support* out, int64_t cap, int64_t* offsets,
+                    int32_t* n_cand);
+
+/* ---- whole path, device-resident, stream-ordered (no host synchronisation) ---------------
+ * d_images = [n_pairs][2][h][w] uint8 in device memory; d_out = [n_pairs][cap_per_pair]
+ * gpc_support in device memory; d_n_out = [n_pairs] int32 (true counts, may exceed the
+ * capacity, in which case that pair's list is truncated); d_n_cand = [n_pairs][2] or NULL. */
+int gpc_match_batch_device(gpc_ctx* ctx, const uint8_t* d_images, int n_pairs, int w, int h,
+                           const gpc_settings* s, gpc_support* d_out, int cap_per_pair,
+                           int32_t* d_n_out, int32_t* d_n_cand);
+
+/* ---- stage-level seams for parity tests -------------------------------------------------- */
+/* ndb::box + clearBoundary, ndb::sobel, ndb::arr2ind + border filter (filter.hpp:293, :404,
+ * :60; inference.hpp:302-333).  smooth / grad = [h][w] uint8 or NULL; mask = candidate indices
+ * y*w+x in raster order (capacity mask_cap) or NULL. */
+int gpc_preprocess(gpc_ctx* ctx, const uint8_t* img, int w, int h, int gradient_threshold,
+                   uint8_t* smooth, uint8_t* grad, int32_t* mask, int mask_cap, int* n_mask);
+/* Forest::evalFastMaskOnSubsetSSE (inference.hpp:266-292): one state per candidate, in mask
+ * order.  hash_image (optional) = the raw [h][w] uint32 image the kernel writes: bit 31 marks
+ * a candidate, bits 0..30 are its state, non-candidates are 0. */
+int gpc_hash(gpc_ctx* ctx, const uint8_t* img, int w, int h, int gradient_threshold,
+             uint32_t* states, int32_t* mask, int cap, int* n, uint32_t* hash_image);
+/* Forest::findCorrespondences + rectifiedMatch filter (inference.hpp:227-254, :384-391) on
+ * caller-provided hash images (same encoding as gpc_hash's hash_image). */
+int gpc_match_hash_images(gpc_ctx* ctx, const uint32_t* hash_l, const uint32_t* hash_r, int w, int h,
+                          const gpc_settings* s, gpc_support* out, int cap, int* n_out);
+
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t gpc_launch_count(const gpc_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

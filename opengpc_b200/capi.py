@@ -1,0 +1,224 @@
+"""ctypes binding of the C ABI in include/gpc_b200.h (libgpc_b200.so).
+
+This is the thin host layer tests and bench.py drive; the drop-in C++ API lives in
+include/gpc/*.hpp.  There is no CPU fallback: if the CUDA library is missing or no device is
+present, construction fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libgpc_b200.so")
+
+GPC_OK, GPC_E_ARG, GPC_E_WIDTH16, GPC_E_DIMS, GPC_E_CUDA, GPC_E_CAPACITY, GPC_E_UNSUPPORTED, GPC_E_FOREST, GPC_E_IO = range(9)
+
+SUPPORT_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("d", "<f4")])   # == ndb::Support, 12 bytes
+
+# every symbol include/gpc_b200.h declares (checked by tests/test_capi_cpu.py)
+SYMBOLS = ["gpc_create", "gpc_destroy", "gpc_last_error", "gpc_status_string", "gpc_set_stream", "gpc_synchronize",
+           "gpc_read_forest", "gpc_set_forest", "gpc_match_pair", "gpc_match_batch", "gpc_match_batch_device",
+           "gpc_preprocess", "gpc_hash", "gpc_match_hash_images", "gpc_launch_count"]
+
+
+class GpcSettings(C.Structure):
+    """gpc_settings == gpc::inference::InferenceSettings (inference.hpp:71-131)."""
+    _fields_ = [("gradient_threshold", C.c_int32), ("disp_high", C.c_int32), ("vertical_tolerance", C.c_int32),
+                ("epipolar_mode", C.c_int32), ("use_hashtable", C.c_int32), ("num_threads", C.c_int32)]
+
+
+class GpcForest(C.Structure):
+    _fields_ = [("n_tests", C.c_int32), ("type", C.c_int32), ("n_discarded", C.c_int32),
+                ("ix", C.c_int32 * 32), ("iy", C.c_int32 * 32), ("jx", C.c_int32 * 32), ("jy", C.c_int32 * 32),
+                ("tau", C.c_int32 * 32)]
+
+
+class GpcError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"gpc status {status}: {message}")
+        self.status = status
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libgpc_b200.so; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(opengpc_b200 has no CPU or PyTorch fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.gpc_last_error.restype = C.c_char_p
+    lib.gpc_last_error.argtypes = [C.c_void_p]
+    lib.gpc_status_string.restype = C.c_char_p
+    lib.gpc_launch_count.restype = C.c_int64
+    lib.gpc_launch_count.argtypes = [C.c_void_p]
+    lib.gpc_destroy.restype = None
+    lib.gpc_destroy.argtypes = [C.c_void_p]
+    for name in SYMBOLS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int:
+            fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def make_settings(thr=10, disp_high=128, vt=1, epipolar=False, use_hashtable=False, num_threads=1):
+    """Defaults are the reference's (inference.hpp:74-89)."""
+    return GpcSettings(int(thr), int(disp_high), int(vt), int(bool(epipolar)), int(bool(use_hashtable)), int(num_threads))
+
+
+def sparsematch_settings():
+    """The settings samples/sparsematch.cpp:29-34 fixes."""
+    return make_settings(thr=5, disp_high=128, vt=0, epipolar=True, use_hashtable=False)
+
+
+def read_forest(path):
+    """Forest::readForest's parser (inference.hpp:404-446); GpcError(GPC_E_IO) if unreadable."""
+    lib = load_library()
+    f = GpcForest()
+    rc = lib.gpc_read_forest(os.fsencode(path), C.byref(f))
+    if rc != GPC_OK:
+        raise GpcError(rc, lib.gpc_status_string(rc).decode())
+    return f
+
+
+def make_forest(tests, taus, type_=None):
+    f = GpcForest()
+    tests, taus = list(tests), list(taus)
+    f.n_discarded = max(len(tests) - 32, 0)
+    nz = any(t != 0 for t in taus)
+    tests, taus = tests[:32], taus[:32]
+    f.n_tests = len(tests)
+    for t, (ix, iy, jx, jy) in enumerate(tests):
+        f.ix[t], f.iy[t], f.jx[t], f.jy[t], f.tau[t] = ix, iy, jx, jy, taus[t]
+    f.type = int(nz) if type_ is None else int(type_)
+    return f
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+class Context:
+    """One resident context per GPU (gpc_create / gpc_destroy)."""
+
+    def __init__(self, device=0, max_w=1024, max_h=436, max_batch=1):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        rc = self.lib.gpc_create(C.byref(self._h), int(device), int(max_w), int(max_h), int(max_batch))
+        if rc != GPC_OK:
+            raise GpcError(rc, self.lib.gpc_last_error(None).decode())
+        self.device, self.max_w, self.max_h, self.max_batch = device, max_w, max_h, max_batch
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.gpc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != GPC_OK:
+            raise GpcError(rc, self.lib.gpc_last_error(self._h).decode())
+
+    @property
+    def launches(self):
+        return int(self.lib.gpc_launch_count(self._h))
+
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.gpc_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        self._check(self.lib.gpc_synchronize(self._h))
+
+    def set_forest(self, forest):
+        if isinstance(forest, (str, bytes, os.PathLike)):
+            forest = read_forest(forest)
+        self._check(self.lib.gpc_set_forest(self._h, C.byref(forest)))
+        return forest
+
+    # ---- whole path -------------------------------------------------------------------------
+    def match_pair(self, left, right, settings, cap=None):
+        left = np.ascontiguousarray(left, np.uint8)
+        right = np.ascontiguousarray(right, np.uint8)
+        h, w = left.shape
+        cap = max((w - 26) * (h - 26), 1) if cap is None else cap
+        out = np.empty(max(cap, 1), SUPPORT_DTYPE)
+        n, ncl, ncr = C.c_int(0), C.c_int(0), C.c_int(0)
+        rc = self.lib.gpc_match_pair(self._h, _ptr(left), _ptr(right), w, h, w, C.byref(settings), _ptr(out),
+                                     C.c_int(cap), C.byref(n), C.byref(ncl), C.byref(ncr))
+        self._check(rc)
+        return out[:n.value].copy(), ncl.value, ncr.value
+
+    def match_batch(self, images, settings, out=None):
+        """images: uint8 [n_pairs, 2, h, w] (host).  Returns (supports, offsets[n+1], n_cand[n,2])."""
+        images = np.ascontiguousarray(images, np.uint8)
+        n_pairs, two, h, w = images.shape
+        assert two == 2
+        if out is None:
+            out = np.empty(max(n_pairs * max(w - 26, 0) * max(h - 26, 0), 1), SUPPORT_DTYPE)
+        offsets = np.zeros(n_pairs + 1, np.int64)
+        n_cand = np.zeros((n_pairs, 2), np.int32)
+        rc = self.lib.gpc_match_batch(self._h, _ptr(images), n_pairs, w, h, C.byref(settings), _ptr(out),
+                                      C.c_int64(len(out)), _ptr(offsets), _ptr(n_cand))
+        self._check(rc)
+        return out[:offsets[-1]], offsets, n_cand
+
+    def match_batch_raw(self, images_ptr, n_pairs, w, h, settings, out_ptr, cap, offsets_ptr, n_cand_ptr=None):
+        """Pointer-level gpc_match_batch (pinned host buffers owned by the caller)."""
+        self._check(self.lib.gpc_match_batch(self._h, C.c_void_p(images_ptr), n_pairs, w, h, C.byref(settings),
+                                             C.c_void_p(out_ptr), C.c_int64(cap), C.c_void_p(offsets_ptr),
+                                             C.c_void_p(n_cand_ptr or 0)))
+
+    def match_batch_device(self, d_images, n_pairs, w, h, settings, d_out, cap_per_pair, d_n_out, d_n_cand=0):
+        """Device pointers (ints); stream-ordered, no host synchronisation."""
+        self._check(self.lib.gpc_match_batch_device(self._h, C.c_void_p(d_images), n_pairs, w, h, C.byref(settings),
+                                                    C.c_void_p(d_out), C.c_int(cap_per_pair), C.c_void_p(d_n_out),
+                                                    C.c_void_p(d_n_cand or 0)))
+
+    # ---- stage seams ------------------------------------------------------------------------
+    def preprocess(self, img, thr):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        smooth = np.empty((h, w), np.uint8)
+        grad = np.empty((h, w), np.uint8)
+        mask = np.empty(h * w, np.int32)
+        n = C.c_int(0)
+        self._check(self.lib.gpc_preprocess(self._h, _ptr(img), w, h, int(thr), _ptr(smooth), _ptr(grad), _ptr(mask),
+                                            C.c_int(h * w), C.byref(n)))
+        return smooth, grad, mask[:n.value].copy()
+
+    def hash(self, img, thr, want_image=False):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        states = np.empty(h * w, np.uint32)
+        mask = np.empty(h * w, np.int32)
+        himg = np.empty((h, w), np.uint32) if want_image else None
+        n = C.c_int(0)
+        self._check(self.lib.gpc_hash(self._h, _ptr(img), w, h, int(thr), _ptr(states), _ptr(mask), C.c_int(h * w),
+                                      C.byref(n), _ptr(himg)))
+        if want_image:
+            return states[:n.value].copy(), mask[:n.value].copy(), himg
+        return states[:n.value].copy(), mask[:n.value].copy()
+
+    def match_hash_images(self, hash_l, hash_r, settings):
+        hash_l = np.ascontiguousarray(hash_l, np.uint32)
+        hash_r = np.ascontiguousarray(hash_r, np.uint32)
+        h, w = hash_l.shape
+        cap = max(h * w, 1)
+        out = np.empty(cap, SUPPORT_DTYPE)
+        n = C.c_int(0)
+        self._check(self.lib.gpc_match_hash_images(self._h, _ptr(hash_l), _ptr(hash_r), w, h, C.byref(settings),
+                                                   _ptr(out), C.c_int(cap), C.byref(n)))
+        return out[:n.value].copy()

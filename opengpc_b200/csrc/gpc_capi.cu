@@ -1,0 +1,471 @@
+// gpc_capi.cu -- the C ABI of include/gpc_b200.h: resident per-GPU context, forest upload,
+// batched launch sequence, host<->device staging.  No CPU fallback: every compute entry point
+// runs the CUDA kernels of preprocess_hash.cu / match_rows.cu or fails with GPC_E_CUDA.
+#include "../../include/gpc_b200.h"
+#include "gpc_device.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+namespace gpc {
+size_t preprocess_smem_bytes();
+cudaError_t configure_preprocess_hash();
+cudaError_t launch_preprocess_hash(const PreprocessArgs&, const ForestDev&, int n_img, bool debug_out, cudaStream_t);
+size_t match_smem_bytes(int wcap, int table_log2);
+cudaError_t configure_match_rows(int max_smem);
+cudaError_t launch_match_rows(const MatchArgs&, int n_pairs, cudaStream_t);
+cudaError_t launch_row_scan(const int32_t* rowmatch, const int32_t* rowcnt, int H, int n_pairs, int32_t* rowoff,
+                            int32_t* totals, int32_t* n_cand, cudaStream_t);
+cudaError_t launch_pair_scan(const int32_t* totals, int n_pairs, long long* pair_base, cudaStream_t);
+cudaError_t launch_emit_supports(const uint32_t* stage, const int32_t* rowmatch, const int32_t* rowoff,
+                                 const long long* pair_base, void* out, long long cap, int W, int H, int n_pairs,
+                                 cudaStream_t);
+cudaError_t launch_mask_list(const uint32_t* hash, const int32_t* rowcnt, int32_t* rowoff, int W, int H, int32_t* mask,
+                             int cap, cudaStream_t);
+}  // namespace gpc
+
+static thread_local std::string g_create_error;
+
+struct gpc_ctx {
+  int device = 0;
+  int max_w = 0, max_h = 0, max_batch = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  bool has_forest = false;
+  gpc_forest forest_host{};
+  gpc::ForestDev forest_dev{};
+  // resident device buffers
+  uint8_t* d_raw = nullptr;        // [2B][H][W]
+  uint32_t* d_hash = nullptr;      // [2B][H][W]
+  uint32_t* d_stage = nullptr;     // [B][H][W]
+  int32_t* d_rows = nullptr;       // rowcnt [2B][H] | lastrow [2B]   (cleared per launch)
+  int32_t* d_rowmatch = nullptr;   // [B][H]
+  int32_t* d_rowoff = nullptr;     // [B][H+1]
+  int32_t* d_totals = nullptr;     // [B]
+  int32_t* d_ncand = nullptr;      // [B][2]
+  long long* d_pair_base = nullptr;  // [B+1]
+  gpc_support* d_out = nullptr;    // [out_cap]
+  uint8_t* d_dbg8 = nullptr;       // smooth | grad, debug entry points (lazily allocated)
+  int32_t* d_mask = nullptr;       // candidate list, debug entry points (lazily allocated)
+  long long out_cap = 0;
+  // pinned host scratch for counts
+  int32_t* h_counts = nullptr;     // totals [B] | ncand [2B]
+  long long* h_pair_base = nullptr;  // [B+1]
+  int64_t launches = 0;
+  int match_smem_max = 0;
+  std::string err;
+};
+
+namespace {
+
+int fail(gpc_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+
+#define GPC_CUDA(ctx, call)                                                                       \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return fail((ctx), GPC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));        \
+  } while (0)
+
+int floordiv4(int v) { return (v >= 0) ? v / 4 : -((-v + 3) / 4); }
+
+// Bake the forest for the kernel's shared-memory tile pitch (the reference bakes it for the
+// image width instead, inference.hpp:427-428).
+void bake_forest(const gpc_forest& f, gpc::ForestDev* d) {
+  std::memset(d, 0, sizeof(*d));
+  d->n_tests = f.n_tests;
+  d->type = f.type;
+  for (int t = 0; t < f.n_tests; t++) {
+    int oa = f.iy[t] * gpc::kPitch + f.ix[t], ob = f.jy[t] * gpc::kPitch + f.jx[t];
+    d->woff_a[t] = (int16_t)floordiv4(oa);
+    d->woff_b[t] = (int16_t)floordiv4(ob);
+    d->sh_a[t] = (uint8_t)(8 * (oa - 4 * floordiv4(oa)));
+    d->sh_b[t] = (uint8_t)(8 * (ob - 4 * floordiv4(ob)));
+    uint32_t t8 = (uint32_t)(uint8_t)(int8_t)f.tau[t];      // _mm_set1_epi8(tau): low 8 bits
+    d->tau4[t] = t8 * 0x01010101u;
+  }
+}
+
+int check_dims(gpc_ctx* c, int w, int h, int n_pairs) {
+  if (w <= 0 || h <= 0 || n_pairs <= 0) return fail(c, GPC_E_ARG, "non-positive dimension");
+  if (w % 16 != 0) return fail(c, GPC_E_WIDTH16, "width must be multiple of 16!");   // filter.hpp:294
+  if (w > c->max_w || h > c->max_h || (long long)w * h > (long long)c->max_w * c->max_h || n_pairs > c->max_batch)
+    return fail(c, GPC_E_DIMS, "image or batch exceeds the context's capacity");
+  return GPC_OK;
+}
+
+int check_settings(gpc_ctx* c, const gpc_settings* s) {
+  if (!s) return fail(c, GPC_E_ARG, "settings is NULL");
+  if (s->use_hashtable) return fail(c, GPC_E_UNSUPPORTED, "useHashtable(true) is not supported (sort-path semantics only)");
+  if (!s->epipolar_mode) return fail(c, GPC_E_UNSUPPORTED, "epipolarMode(false) (global matching) is not implemented yet");
+  if (s->gradient_threshold < 0 || s->gradient_threshold > 255)
+    return fail(c, GPC_E_ARG, "gradientThreshold needs to be within 0...255");     // inference.hpp:303
+  return GPC_OK;
+}
+
+int table_log2_for(int wcap) {
+  int l = 4;
+  while ((1 << l) < 2 * wcap) l++;
+  return l;
+}
+
+// Kernel A over n_img resident images; clears and fills rowcnt / lastrow.
+int run_preprocess(gpc_ctx* c, const uint8_t* d_images, int n_img, int w, int h, int thr, const gpc::ForestDev& forest,
+                   uint8_t* d_smooth, uint8_t* d_grad) {
+  int32_t* rowcnt = c->d_rows;
+  int32_t* lastrow = c->d_rows + (size_t)n_img * h;
+  GPC_CUDA(c, cudaMemsetAsync(rowcnt, 0, (size_t)n_img * h * sizeof(int32_t), c->stream));
+  GPC_CUDA(c, cudaMemsetAsync(lastrow, 0xff, (size_t)n_img * sizeof(int32_t), c->stream));   // -1
+  gpc::PreprocessArgs a{};
+  a.raw = d_images; a.hash = c->d_hash; a.rowcnt = rowcnt; a.lastrow = lastrow;
+  a.smooth_out = d_smooth; a.grad_out = d_grad; a.W = w; a.H = h;
+  a.thr2 = (int32_t)(int16_t)(thr * thr);                                          // filter.hpp:418
+  GPC_CUDA(c, gpc::launch_preprocess_hash(a, forest, n_img, d_smooth || d_grad, c->stream));
+  c->launches += 1;
+  return GPC_OK;
+}
+
+// Kernels B, scan, C over hash images already in c->d_hash (or `hash`).
+int run_match(gpc_ctx* c, const uint32_t* hash, int n_pairs, int w, int h, const gpc_settings* s, gpc_support* d_out,
+              long long cap, bool packed, int32_t* d_n_out, int32_t* d_n_cand) {
+  const int32_t* rowcnt = c->d_rows;
+  const int32_t* lastrow = c->d_rows + (size_t)(2 * n_pairs) * h;
+  gpc::MatchArgs m{};
+  m.hash = hash; m.lastrow = lastrow; m.stage = c->d_stage; m.rowmatch = c->d_rowmatch;
+  m.W = w; m.H = h; m.disp_high = s->disp_high; m.vertical_tolerance = s->vertical_tolerance;
+  m.wcap = std::max(w - 2 * gpc::kRadius, 16);
+  m.table_log2 = table_log2_for(m.wcap);
+  if ((int)gpc::match_smem_bytes(m.wcap, m.table_log2) > c->match_smem_max)
+    return fail(c, GPC_E_DIMS, "image too wide for the row matcher's shared memory");
+  if (h - 2 * gpc::kRadius <= 0) GPC_CUDA(c, cudaMemsetAsync(c->d_rowmatch, 0, (size_t)n_pairs * h * sizeof(int32_t), c->stream));
+  GPC_CUDA(c, gpc::launch_match_rows(m, n_pairs, c->stream));
+  GPC_CUDA(c, gpc::launch_row_scan(c->d_rowmatch, rowcnt, h, n_pairs, c->d_rowoff, d_n_out, d_n_cand, c->stream));
+  c->launches += 2;
+  const long long* pair_base = nullptr;
+  if (packed) {
+    GPC_CUDA(c, gpc::launch_pair_scan(d_n_out, n_pairs, c->d_pair_base, c->stream));
+    c->launches += 1;
+    pair_base = c->d_pair_base;
+  }
+  GPC_CUDA(c, gpc::launch_emit_supports(c->d_stage, c->d_rowmatch, c->d_rowoff, pair_base, d_out, cap, w, h, n_pairs, c->stream));
+  if (h - 2 * gpc::kRadius > 0) c->launches += 1;
+  return GPC_OK;
+}
+
+int ensure_debug_buffers(gpc_ctx* c) {
+  size_t P = (size_t)c->max_w * c->max_h;
+  if (!c->d_dbg8) GPC_CUDA(c, cudaMalloc(&c->d_dbg8, 2 * P));
+  if (!c->d_mask) GPC_CUDA(c, cudaMalloc(&c->d_mask, P * sizeof(int32_t)));
+  return GPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gpc_status_string(int status) {
+  switch (status) {
+    case GPC_OK: return "ok";
+    case GPC_E_ARG: return "invalid argument";
+    case GPC_E_WIDTH16: return "width must be multiple of 16";
+    case GPC_E_DIMS: return "dimensions exceed context capacity";
+    case GPC_E_CUDA: return "CUDA error";
+    case GPC_E_CAPACITY: return "output capacity too small";
+    case GPC_E_UNSUPPORTED: return "unsupported mode";
+    case GPC_E_FOREST: return "invalid or missing forest";
+    case GPC_E_IO: return "cannot open file";
+    default: return "unknown status";
+  }
+}
+
+const char* gpc_last_error(const gpc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int gpc_create(gpc_ctx** out, int device, int max_w, int max_h, int max_batch) {
+  if (!out) return fail(nullptr, GPC_E_ARG, "out is NULL");
+  *out = nullptr;
+  if (max_w <= 0 || max_h <= 0 || max_batch <= 0) return fail(nullptr, GPC_E_ARG, "non-positive capacity");
+  if (max_w % 16 != 0) return fail(nullptr, GPC_E_WIDTH16, "max_w must be a multiple of 16");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(nullptr, GPC_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                         " (libgpc_b200 has no CPU fallback)");
+  if (device < 0 || device >= n_dev) return fail(nullptr, GPC_E_ARG, "device index out of range");
+  gpc_ctx* c = new gpc_ctx();
+  c->device = device; c->max_w = max_w; c->max_h = max_h; c->max_batch = max_batch;
+  auto bail = [&](const char* what, cudaError_t err) {
+    std::string msg = std::string(what) + ": " + cudaGetErrorString(err);
+    gpc_destroy(c);
+    return fail(nullptr, GPC_E_CUDA, msg);
+  };
+#define TRY(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) return bail(#call, e2); } while (0)
+  TRY(cudaSetDevice(device));
+  TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  TRY(gpc::configure_preprocess_hash());
+  int smem_optin = 0;
+  TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  c->match_smem_max = smem_optin - 1024;
+  TRY(gpc::configure_match_rows(c->match_smem_max));
+  const size_t P = (size_t)max_w * max_h, B = (size_t)max_batch;
+  TRY(cudaMalloc(&c->d_raw, 2 * B * P));
+  TRY(cudaMalloc(&c->d_hash, 2 * B * P * sizeof(uint32_t)));
+  TRY(cudaMalloc(&c->d_stage, B * P * sizeof(uint32_t)));
+  TRY(cudaMalloc(&c->d_rows, (2 * B * max_h + 2 * B) * sizeof(int32_t)));
+  TRY(cudaMalloc(&c->d_rowmatch, B * max_h * sizeof(int32_t)));
+  TRY(cudaMalloc(&c->d_rowoff, B * (max_h + 1) * sizeof(int32_t)));
+  TRY(cudaMalloc(&c->d_totals, B * sizeof(int32_t)));
+  TRY(cudaMalloc(&c->d_ncand, 2 * B * sizeof(int32_t)));
+  TRY(cudaMalloc(&c->d_pair_base, (B + 1) * sizeof(long long)));
+  long long per_pair = (long long)std::max(max_w - 26, 0) * std::max(max_h - 26, 0);
+  c->out_cap = std::max<long long>(per_pair * (long long)B, 1);
+  TRY(cudaMalloc(&c->d_out, (size_t)c->out_cap * sizeof(gpc_support)));
+  TRY(cudaMallocHost(&c->h_counts, 3 * B * sizeof(int32_t)));
+  TRY(cudaMallocHost(&c->h_pair_base, (B + 1) * sizeof(long long)));
+  TRY(cudaMemsetAsync(c->d_rowmatch, 0, B * max_h * sizeof(int32_t), c->stream));
+  TRY(cudaStreamSynchronize(c->stream));
+#undef TRY
+  *out = c;
+  return GPC_OK;
+}
+
+void gpc_destroy(gpc_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_raw); cudaFree(c->d_hash); cudaFree(c->d_stage); cudaFree(c->d_rows); cudaFree(c->d_rowmatch);
+  cudaFree(c->d_rowoff); cudaFree(c->d_totals); cudaFree(c->d_ncand); cudaFree(c->d_pair_base); cudaFree(c->d_out);
+  cudaFree(c->d_dbg8); cudaFree(c->d_mask);
+  if (c->h_counts) cudaFreeHost(c->h_counts);
+  if (c->h_pair_base) cudaFreeHost(c->h_pair_base);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+int gpc_set_stream(gpc_ctx* c, void* cuda_stream) {
+  if (!c) return GPC_E_ARG;
+  c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+  return GPC_OK;
+}
+
+int gpc_synchronize(gpc_ctx* c) {
+  if (!c) return GPC_E_ARG;
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GPC_OK;
+}
+
+int64_t gpc_launch_count(const gpc_ctx* c) { return c ? c->launches : 0; }
+
+// Forest::readForest (inference.hpp:404-446): whitespace-separated text; scale tag ignored;
+// at most 32 tests kept; type 1 iff ANY test of the file (kept or not) has tau != 0.
+int gpc_read_forest(const char* path, gpc_forest* out) {
+  if (!path || !out) return GPC_E_ARG;
+  std::memset(out, 0, sizeof(*out));
+  std::ifstream ff(path);
+  if (ff.fail()) return GPC_E_IO;
+  int num_ferns = 0, nonzero = 0;
+  ff >> num_ferns;
+  for (int i = 0; i < num_ferns && ff.good(); i++) {
+    int id = 0, nt = 0;
+    std::string scale;
+    ff >> id >> scale >> nt;
+    for (int j = 0; j < nt; j++) {
+      int lvl = 0, ix = 0, iy = 0, jx = 0, jy = 0, tau = 0;
+      ff >> lvl >> ix >> iy >> jx >> jy >> tau;
+      if (ff.fail()) break;
+      if (out->n_tests < GPC_MAX_TESTS) {
+        int t = out->n_tests++;
+        out->ix[t] = ix; out->iy[t] = iy; out->jx[t] = jx; out->jy[t] = jy; out->tau[t] = tau;
+      } else {
+        out->n_discarded++;
+      }
+      if (tau != 0) nonzero++;
+    }
+  }
+  out->type = nonzero ? 1 : 0;
+  return GPC_OK;
+}
+
+int gpc_set_forest(gpc_ctx* c, const gpc_forest* f) {
+  if (!c || !f) return GPC_E_ARG;
+  if (f->n_tests < 0 || f->n_tests > GPC_MAX_TESTS) return fail(c, GPC_E_FOREST, "a forest has at most 32 tests");
+  for (int t = 0; t < f->n_tests; t++) {
+    const int v[4] = {f->ix[t], f->iy[t], f->jx[t], f->jy[t]};
+    for (int k = 0; k < 4; k++)
+      if (v[k] < -GPC_PATCH_RADIUS || v[k] > GPC_PATCH_RADIUS)
+        return fail(c, GPC_E_FOREST, "test offset outside the 27x27 patch (|offset| <= 13)");
+  }
+  c->forest_host = *f;
+  bake_forest(*f, &c->forest_dev);
+  c->has_forest = true;
+  return GPC_OK;
+}
+
+int gpc_match_batch_device(gpc_ctx* c, const uint8_t* d_images, int n_pairs, int w, int h, const gpc_settings* s,
+                           gpc_support* d_out, int cap_per_pair, int32_t* d_n_out, int32_t* d_n_cand) {
+  if (!c || !d_images || !d_out || !d_n_out || cap_per_pair < 0) return fail(c, GPC_E_ARG, "null argument");
+  int rc = check_dims(c, w, h, n_pairs); if (rc) return rc;
+  rc = check_settings(c, s); if (rc) return rc;
+  if (!c->has_forest) return fail(c, GPC_E_FOREST, "no forest set");
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  rc = run_preprocess(c, d_images, 2 * n_pairs, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
+  if (rc) return rc;
+  return run_match(c, c->d_hash, n_pairs, w, h, s, d_out, cap_per_pair, false, d_n_out, d_n_cand);
+}
+
+int gpc_match_batch(gpc_ctx* c, const uint8_t* images, int n_pairs, int w, int h, const gpc_settings* s,
+                    gpc_support* out, int64_t cap, int64_t* offsets, int32_t* n_cand) {
+  if (!c || !images || !offsets || cap < 0 || (cap > 0 && !out)) return fail(c, GPC_E_ARG, "null argument");
+  int rc = check_dims(c, w, h, n_pairs); if (rc) return rc;
+  rc = check_settings(c, s); if (rc) return rc;
+  if (!c->has_forest) return fail(c, GPC_E_FOREST, "no forest set");
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  const size_t P = (size_t)w * h;
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, images, 2 * (size_t)n_pairs * P, cudaMemcpyHostToDevice, c->stream));
+  rc = run_preprocess(c, c->d_raw, 2 * n_pairs, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
+  if (rc) return rc;
+  rc = run_match(c, c->d_hash, n_pairs, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
+  if (rc) return rc;
+  GPC_CUDA(c, cudaMemcpyAsync(c->h_pair_base, c->d_pair_base, (size_t)(n_pairs + 1) * sizeof(long long),
+                              cudaMemcpyDeviceToHost, c->stream));
+  if (n_cand)
+    GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_ncand, 2 * (size_t)n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int p = 0; p <= n_pairs; p++) offsets[p] = c->h_pair_base[p];
+  if (n_cand) std::memcpy(n_cand, c->h_counts, 2 * (size_t)n_pairs * sizeof(int32_t));
+  const long long total = c->h_pair_base[n_pairs];
+  if (total > cap) return fail(c, GPC_E_CAPACITY, "support buffer too small: need " + std::to_string(total));
+  if (total > 0) {
+    GPC_CUDA(c, cudaMemcpyAsync(out, c->d_out, (size_t)total * sizeof(gpc_support), cudaMemcpyDeviceToHost, c->stream));
+    GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return GPC_OK;
+}
+
+int gpc_match_pair(gpc_ctx* c, const uint8_t* left, const uint8_t* right, int w, int h, int stride, const gpc_settings* s,
+                   gpc_support* out, int cap, int* n_out, int* n_cand_l, int* n_cand_r) {
+  if (!c || !left || !right || !n_out || cap < 0 || (cap > 0 && !out)) return fail(c, GPC_E_ARG, "null argument");
+  if (stride < w) return fail(c, GPC_E_ARG, "stride smaller than width");
+  int rc = check_dims(c, w, h, 1); if (rc) return rc;
+  rc = check_settings(c, s); if (rc) return rc;
+  if (!c->has_forest) return fail(c, GPC_E_FOREST, "no forest set");
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  const size_t P = (size_t)w * h;
+  GPC_CUDA(c, cudaMemcpy2DAsync(c->d_raw, w, left, stride, w, h, cudaMemcpyHostToDevice, c->stream));
+  GPC_CUDA(c, cudaMemcpy2DAsync(c->d_raw + P, w, right, stride, w, h, cudaMemcpyHostToDevice, c->stream));
+  rc = run_preprocess(c, c->d_raw, 2, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
+  if (rc) return rc;
+  rc = run_match(c, c->d_hash, 1, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
+  if (rc) return rc;
+  GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_totals, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA(c, cudaMemcpyAsync(c->h_counts + 1, c->d_ncand, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  *n_out = c->h_counts[0];
+  if (n_cand_l) *n_cand_l = c->h_counts[1];
+  if (n_cand_r) *n_cand_r = c->h_counts[2];
+  if (*n_out > cap) return fail(c, GPC_E_CAPACITY, "support buffer too small: need " + std::to_string(*n_out));
+  if (*n_out > 0) {
+    GPC_CUDA(c, cudaMemcpyAsync(out, c->d_out, (size_t)*n_out * sizeof(gpc_support), cudaMemcpyDeviceToHost, c->stream));
+    GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return GPC_OK;
+}
+
+int gpc_preprocess(gpc_ctx* c, const uint8_t* img, int w, int h, int thr, uint8_t* smooth, uint8_t* grad,
+                   int32_t* mask, int mask_cap, int* n_mask) {
+  if (!c || !img) return fail(c, GPC_E_ARG, "null argument");
+  int rc = check_dims(c, w, h, 1); if (rc) return rc;
+  if (thr < 0 || thr > 255) return fail(c, GPC_E_ARG, "gradientThreshold needs to be within 0...255");
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  rc = ensure_debug_buffers(c); if (rc) return rc;
+  const size_t P = (size_t)w * h;
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, img, P, cudaMemcpyHostToDevice, c->stream));
+  gpc::ForestDev none{};                           // no tests: hash image carries the candidate flag only
+  uint8_t* d_smooth = c->d_dbg8;
+  uint8_t* d_grad = c->d_dbg8 + (size_t)c->max_w * c->max_h;
+  rc = run_preprocess(c, c->d_raw, 1, w, h, thr, none, d_smooth, d_grad);
+  if (rc) return rc;
+  GPC_CUDA(c, gpc::launch_mask_list(c->d_hash, c->d_rows, c->d_rowoff, w, h, c->d_mask, (int)std::min<size_t>(P, 0x7fffffff), c->stream));
+  c->launches += 2;
+  GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_rowoff + h, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (smooth) GPC_CUDA(c, cudaMemcpyAsync(smooth, d_smooth, P, cudaMemcpyDeviceToHost, c->stream));
+  if (grad) GPC_CUDA(c, cudaMemcpyAsync(grad, d_grad, P, cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int n = c->h_counts[0];
+  if (n_mask) *n_mask = n;
+  if (mask) {
+    if (n > mask_cap) return fail(c, GPC_E_CAPACITY, "mask buffer too small: need " + std::to_string(n));
+    GPC_CUDA(c, cudaMemcpy(mask, c->d_mask, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  }
+  return GPC_OK;
+}
+
+int gpc_hash(gpc_ctx* c, const uint8_t* img, int w, int h, int thr, uint32_t* states, int32_t* mask, int cap, int* n,
+             uint32_t* hash_image) {
+  if (!c || !img || !n) return fail(c, GPC_E_ARG, "null argument");
+  int rc = check_dims(c, w, h, 1); if (rc) return rc;
+  if (!c->has_forest) return fail(c, GPC_E_FOREST, "no forest set");
+  if (thr < 0 || thr > 255) return fail(c, GPC_E_ARG, "gradientThreshold needs to be within 0...255");
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  rc = ensure_debug_buffers(c); if (rc) return rc;
+  const size_t P = (size_t)w * h;
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, img, P, cudaMemcpyHostToDevice, c->stream));
+  rc = run_preprocess(c, c->d_raw, 1, w, h, thr, c->forest_dev, nullptr, nullptr);
+  if (rc) return rc;
+  GPC_CUDA(c, gpc::launch_mask_list(c->d_hash, c->d_rows, c->d_rowoff, w, h, c->d_mask, (int)std::min<size_t>(P, 0x7fffffff), c->stream));
+  c->launches += 2;
+  GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_rowoff + h, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  std::vector<uint32_t> himg(P);
+  GPC_CUDA(c, cudaMemcpyAsync(himg.data(), c->d_hash, P * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  *n = c->h_counts[0];
+  if (hash_image) std::memcpy(hash_image, himg.data(), P * sizeof(uint32_t));
+  if (*n > cap && (states || mask)) return fail(c, GPC_E_CAPACITY, "state buffer too small: need " + std::to_string(*n));
+  std::vector<int32_t> hmask((size_t)std::max(*n, 1));
+  GPC_CUDA(c, cudaMemcpy(hmask.data(), c->d_mask, (size_t)*n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < *n; i++) {                   // gather in mask order (inference.hpp:282-290)
+    if (mask) mask[i] = hmask[i];
+    if (states) states[i] = himg[(size_t)hmask[i]] & 0x7fffffffu;
+  }
+  return GPC_OK;
+}
+
+int gpc_match_hash_images(gpc_ctx* c, const uint32_t* hash_l, const uint32_t* hash_r, int w, int h, const gpc_settings* s,
+                          gpc_support* out, int cap, int* n_out) {
+  if (!c || !hash_l || !hash_r || !n_out || cap < 0 || (cap > 0 && !out)) return fail(c, GPC_E_ARG, "null argument");
+  int rc = check_dims(c, w, h, 1); if (rc) return rc;
+  rc = check_settings(c, s); if (rc) return rc;
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  const size_t P = (size_t)w * h;
+  // rowcnt / lastrow are derived on the host here (kernel A normally provides them)
+  std::vector<int32_t> rows((size_t)2 * h + 2, 0);
+  rows[(size_t)2 * h] = rows[(size_t)2 * h + 1] = -1;
+  const uint32_t* src[2] = {hash_l, hash_r};
+  for (int k = 0; k < 2; k++)
+    for (int y = 0; y < h; y++) {
+      int cnt = 0;
+      for (int x = 0; x < w; x++) cnt += (int)(src[k][(size_t)y * w + x] >> 31);
+      rows[(size_t)k * h + y] = cnt;
+      if (cnt) rows[(size_t)2 * h + k] = y;
+    }
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_hash, hash_l, P * 4, cudaMemcpyHostToDevice, c->stream));
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_hash + P, hash_r, P * 4, cudaMemcpyHostToDevice, c->stream));
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_rows, rows.data(), rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  GPC_CUDA(c, cudaStreamSynchronize(c->stream));   // `rows` is pageable and about to go out of scope
+  rc = run_match(c, c->d_hash, 1, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
+  if (rc) return rc;
+  GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_totals, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  *n_out = c->h_counts[0];
+  if (*n_out > cap) return fail(c, GPC_E_CAPACITY, "support buffer too small: need " + std::to_string(*n_out));
+  if (*n_out > 0) GPC_CUDA(c, cudaMemcpy(out, c->d_out, (size_t)*n_out * sizeof(gpc_support), cudaMemcpyDeviceToHost));
+  return GPC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+// gpc_device.cuh -- shared device-side definitions of the B200 Global Patch Collider path.
+//
+// Data layout in HBM (all resident in the context, see gpc_capi.cu):
+//   raw    uint8  [n_img][H][W]        input images, image 2p = left, 2p+1 = right of pair p
+//   hash   uint32 [n_img][H][W]        bit 31 = "candidate", bits 0..30 = fern state
+//   rowcnt int32  [n_img][H]           candidates per image row
+//   lastrow int32 [n_img]              largest row with a candidate (-1 if none)
+//   stage  uint32 [n_pair][H][W]       per-row match lists, xL<<16 | xR, sorted by state
+//   rowmatch int32 [n_pair][H]         matches per row
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gpc {
+
+constexpr int kRadius = 13;            // patch radius / candidate border (inference.hpp:322)
+constexpr int kMaxTests = 32;          // inference.hpp:426
+constexpr uint32_t kCandFlag = 0x80000000u;
+
+// ---- kernel A tile geometry -------------------------------------------------------------
+constexpr int kTileW = 256;                    // output pixels per tile row
+constexpr int kTileH = 32;                     // output rows per tile
+constexpr int kPitch = kTileW + 32;            // smem row pitch in bytes: image cols x0-16 .. x0+kTileW+15
+constexpr int kPitchW = kPitch / 4;            // ... in 32-bit words
+constexpr int kRawRows = kTileH + 2 * kRadius + 2;   // image rows y0-14 .. y0+kTileH+13
+constexpr int kSmRows = kTileH + 2 * kRadius;        // image rows y0-13 .. y0+kTileH+12
+constexpr int kThreadsA = 256;
+
+// Forest baked for the smem tile pitch (replaces the per-width baking of inference.hpp:427-428).
+struct ForestDev {
+  int32_t n_tests;
+  int32_t type;                  // 0: a > b ; 1: a > sat_int8(b - tau)
+  int16_t woff_a[kMaxTests];     // word offset of operand a relative to the quad's word
+  int16_t woff_b[kMaxTests];
+  uint8_t sh_a[kMaxTests];       // funnel-shift amount in bits (0, 8, 16, 24)
+  uint8_t sh_b[kMaxTests];
+  uint32_t tau4[kMaxTests];      // int8 tau replicated into 4 byte lanes
+};
+
+struct PreprocessArgs {
+  const uint8_t* raw;      // [n_img][H][W]
+  uint32_t* hash;          // [n_img][H][W]
+  int32_t* rowcnt;         // [n_img][H]
+  int32_t* lastrow;        // [n_img]
+  uint8_t* smooth_out;     // optional [n_img][H][W]
+  uint8_t* grad_out;       // optional [n_img][H][W]
+  int32_t W, H;
+  int32_t thr2;            // (int16)(thr*thr), filter.hpp:418
+};
+
+struct MatchArgs {
+  const uint32_t* hash;    // [2*n_pair][H][W]
+  const int32_t* lastrow;  // [2*n_pair]
+  uint32_t* stage;         // [n_pair][H][W]
+  int32_t* rowmatch;       // [n_pair][H]
+  int32_t W, H;
+  int32_t disp_high, vertical_tolerance;
+  int32_t table_log2;      // log2 of the per-row hash table size (>= 2 * candidates)
+  int32_t wcap;            // per-side candidate capacity used to carve shared memory
+};
+
+}  // namespace gpc
