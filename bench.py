@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the Global Patch Collider inference path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--forest tau|zero]
+                  [--shape 1024x436] [--batch 256]
+
+A "step" is one pass of the whole hot path (kernel A: box + Sobel + fern hashing, kernel B: per-row
+matching, scans, kernel C: ordered support emission) over one batch of synthetic stereo pairs.
+
+  value      stereo pairs/s, inputs resident in HBM, timed with CUDA events on the launching
+             stream (max over ranks); `mpix_per_s` = value * 2*W*H / 1e6 (BASELINE.json's second unit)
+  e2e        same metric through the C ABI with HOST (pinned) buffers: H2D of the images and D2H
+             of the support lists inside the timed region (gpc_match_batch)
+  roofline   dominant kernel's algorithmic bytes / its CUDA-event duration vs the measured HBM peak
+  cpu_baseline  the unmodified reference (oracle/_ref) on the box's host cores, bounded sample
+
+Multi-GPU (torchrun, one rank per GPU): pairs shard across ranks, no data-path collective;
+weak scaling (every rank processes its own batch).  `--impl reference` times the reference's CPU
+path only (rank 0), none of this repo's kernels.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FORESTS = {"tau": os.path.join(ROOT, "forests", "defaultTauForest.txt"),
+           "zero": os.path.join(ROOT, "forests", "defaultZeroForest.txt"),
+           "deep": os.path.join(ROOT, "forests", "deepRandomForest16x12.txt")}
+METRIC = "stereo pairs/s (sparsematch: preprocessImage x2 + rectifiedMatch)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--forest", default="tau", choices=list(FORESTS))
+    ap.add_argument("--shape", default="1024x436")
+    ap.add_argument("--batch", type=int, default=256, help="pairs per step per GPU")
+    ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic pairs (seeds 1234+i), tiled to the batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def workload_name(args, w, h):
+    cfg = {"tau": "configs[0]", "zero": "configs[1]"}.get(args.forest, "configs[4] stand-in")
+    return f"{cfg}: sparsematch, forests/{os.path.basename(FORESTS[args.forest])}, synthetic {w}x{h} stereo pairs"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_images(w, h, batch, distinct):
+    from opengpc_b200.synth import synth_batch
+    base = synth_batch(w, h, min(distinct, batch), seed0=1234)
+    reps = (batch + len(base) - 1) // len(base)
+    return np.ascontiguousarray(np.tile(base, (reps, 1, 1, 1))[:batch])
+
+
+def cpu_reference_run(images, forest_path, threads, iters):
+    """Times the compiled, unmodified reference (oracle/_ref) or, if absent, the C port."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oraclelib import Oracle, Reference, settings
+    n_pairs, _, h, w = images.shape
+    if Reference.available():
+        ref = Reference()
+        sec, tot = ref.time_pairs(images, forest_path, threads=threads, iters=iters)
+        return threads * iters / sec, "reference", tot
+    o = Oracle()   # scalar port, single thread
+    f = o.read_forest(forest_path)
+    t0 = time.perf_counter()
+    tot = 0
+    n = max(1, iters)
+    for i in range(n):
+        s, _, _ = o.pair(images[i % n_pairs, 0], images[i % n_pairs, 1], f, settings())
+        tot += len(s)
+    return n / (time.perf_counter() - t0), "port", tot
+
+
+def run_reference_arm(args, w, h):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    images = make_images(w, h, min(args.distinct, 8), args.distinct)
+    # one step = every host thread runs the sparsematch window on one pair (bounded sample)
+    rates = []
+    for _ in range(args.warmup):
+        cpu_reference_run(images, FORESTS[args.forest], cores, 1)
+    t0 = time.perf_counter()
+    kind = "reference"
+    for _ in range(args.steps):
+        r, kind, _ = cpu_reference_run(images, FORESTS[args.forest], cores, 1)
+        rates.append(r)
+    wall = time.perf_counter() - t0
+    threads = cores if kind == "reference" else 1
+    value = threads * args.steps / wall
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "mpix_per_s": value * 2 * w * h / 1e6,
+            "config": {"workload": workload_name(args, w, h), "pairs_per_step": threads},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": kind,
+                             "sample": f"{threads} pairs per step ({threads} host threads x 1 pair), "
+                                       f"t0..t2 window of sparsematch.cpp:45-52"},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    w, h = (int(v) for v in args.shape.lower().split("x"))
+    if args.impl == "reference":
+        run_reference_arm(args, w, h)
+        return
+
+    import torch
+    import opengpc_b200 as g
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    B = args.batch
+    P = w * h
+    images = make_images(w, h, B, args.distinct)                  # [B, 2, h, w] uint8
+    if world > 1:   # each rank gets its own pairs (seeds shifted) -- independent units, no collective
+        images = np.roll(images, rank, axis=0)
+    settings = g.sparsematch_settings()
+    ctx = g.Context(device=local_rank, max_w=w, max_h=h, max_batch=B)
+    ctx.set_forest(FORESTS[args.forest])
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    cap = (w - 26) * (h - 26) // 4                                # device-resident capacity per pair
+    with torch.cuda.stream(stream):
+        d_img = torch.from_numpy(images).cuda(non_blocking=False)
+        d_out = torch.empty((B, cap, 3), dtype=torch.int32, device="cuda")
+        d_n = torch.zeros(B, dtype=torch.int32, device="cuda")
+        d_nc = torch.zeros((B, 2), dtype=torch.int32, device="cuda")
+
+    def step():
+        ctx.match_batch_device(d_img.data_ptr(), B, w, h, settings, d_out.data_ptr(), cap, d_n.data_ptr(), d_nc.data_ptr())
+
+    def barrier():
+        stream.synchronize()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            step()
+    barrier()
+    n_sup = d_n.cpu().numpy().astype(np.int64)
+    assert (n_sup <= cap).all(), "device capacity per pair too small for this workload"
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launches
+    ctx.enable_kernel_timing(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    kms, kruns = ctx.kernel_times()
+    ctx.enable_kernel_timing(False)
+    launches = ctx.launches - launches0
+    clocks = sampler.stop()
+    if dist is not None:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    ms_per_step = ms_total / args.steps
+    value = world * B / (ms_per_step / 1e3)
+
+    # ---- end to end through the C ABI with host buffers -----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_img = torch.from_numpy(images).pin_memory()
+        tot_sup = int(n_sup.sum())
+        h_out = torch.empty((max(tot_sup, 1) + 1024, 3), dtype=torch.int32).pin_memory()
+        h_off = torch.zeros(B + 1, dtype=torch.int64).pin_memory()
+
+        def e2e_step():
+            ctx.match_batch_raw(h_img.data_ptr(), B, w, h, settings, h_out.data_ptr(), h_out.shape[0], h_off.data_ptr())
+
+        for _ in range(max(args.warmup, 3)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()                                            # synchronous: returns with results on the host
+        barrier()
+        sec = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        assert int(h_off[B]) == tot_sup
+        e2e = {"value": world * B * args.steps / sec, "unit": "pairs/s",
+               "h2d_bytes_per_step": int(2 * B * P), "d2h_bytes_per_step": int(tot_sup * 12 + (B + 1) * 8),
+               "api": "gpc_match_batch (pinned host buffers, synchronous)"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    peak, peak_src = peaks()
+    per_kernel_ms = {k: v / max(kruns, 1) for k, v in kms.items()}
+    dominant = max(per_kernel_ms, key=per_kernel_ms.get)
+    mean_sup = float(n_sup.mean())
+    alg_bytes = {"preprocess_hash": 10.0 * P * B,                 # read 2 u8 images, write 2 u32 hash images
+                 "match_rows": (8.0 * P + 4.0 * mean_sup) * B,    # read 2 hash images, write staged matches
+                 "scans": 0.0, "emit_supports": 16.0 * mean_sup * B}
+    dom_ms = per_kernel_ms[dominant]
+    achieved = alg_bytes[dominant] / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    path_bytes = (10.0 * P + 12.0 * mean_sup)                     # B_alg per pair
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms_per_step": per_kernel_ms,
+                "path_bytes_per_pair": path_bytes,
+                "path_frac": path_bytes * value / world / 1e9 / peak}
+
+    line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "mpix_per_s": value * 2 * P / 1e6,
+            "config": {"workload": workload_name(args, w, h), "pairs_per_step_per_gpu": B,
+                       "distinct_pairs": min(args.distinct, B), "sharding": f"pairs round-robin over {world} GPU(s), no collective",
+                       "supports_per_pair": mean_sup,
+                       "l2": f"inputs larger than L2: {2 * B * P / 1e6:.0f} MB raw + {8 * B * P / 1e6:.0f} MB hash per step vs 126 MB L2"},
+            "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
+    if e2e:
+        line["e2e"] = e2e
+
+    # ---- CPU baseline: the unmodified reference on this box's host cores -------------------------
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        iters = max(1, min(8, int(round(20.0 / (0.09 * (P / 446464.0) * cores))) or 1))
+        rate, kind, _ = cpu_reference_run(images[:min(8, B)], FORESTS[args.forest], cores if True else 1, iters)
+        threads = cores if kind == "reference" else 1
+        line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": kind,
+                                "sample": f"{threads * iters} pairs ({threads} host threads x {iters}), same synthetic "
+                                          f"workload, t0..t2 window of sparsematch.cpp:45-52"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

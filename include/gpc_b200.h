@@ -119,6 +119,16 @@ int gpc_match_hash_images(gpc_ctx* ctx, const uint32_t* hash_l, const uint32_t* 
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t gpc_launch_count(const gpc_ctx* ctx);
 
+/* Per-kernel device times, measured with CUDA events on the launching stream around each
+ * kernel of the whole-path entry points (bench.py's roofline figures).  Slots:
+ *   0 preprocess_hash (kernel A)   1 match_rows (kernel B)
+ *   2 row/pair scans               3 emit_supports (kernel C)
+ * gpc_kernel_times synchronises the stream and returns accumulated milliseconds per slot and
+ * the number of batch runs they cover. */
+#define GPC_N_KERNELS 4
+int gpc_enable_kernel_timing(gpc_ctx* ctx, int on);
+int gpc_kernel_times(gpc_ctx* ctx, double* ms, int64_t* runs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,9 @@ SUPPORT_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("d", "<f4")])   # == ndb:
 # every symbol include/gpc_b200.h declares (checked by tests/test_capi_cpu.py)
 SYMBOLS = ["gpc_create", "gpc_destroy", "gpc_last_error", "gpc_status_string", "gpc_set_stream", "gpc_synchronize",
            "gpc_read_forest", "gpc_set_forest", "gpc_match_pair", "gpc_match_batch", "gpc_match_batch_device",
-           "gpc_preprocess", "gpc_hash", "gpc_match_hash_images", "gpc_launch_count"]
+           "gpc_preprocess", "gpc_hash", "gpc_match_hash_images", "gpc_launch_count", "gpc_enable_kernel_timing",
+           "gpc_kernel_times"]
+KERNEL_NAMES = ["preprocess_hash", "match_rows", "scans", "emit_supports"]
 
 
 class GpcSettings(C.Structure):
@@ -135,6 +137,16 @@ class Context:
     @property
     def launches(self):
         return int(self.lib.gpc_launch_count(self._h))
+
+    def enable_kernel_timing(self, on=True):
+        self._check(self.lib.gpc_enable_kernel_timing(self._h, int(bool(on))))
+
+    def kernel_times(self):
+        """(dict kernel -> accumulated ms, number of batch runs); synchronises the stream."""
+        ms = (C.c_double * 4)()
+        runs = C.c_int64(0)
+        self._check(self.lib.gpc_kernel_times(self._h, ms, C.byref(runs)))
+        return dict(zip(KERNEL_NAMES, list(ms))), runs.value
 
     def set_stream(self, cuda_stream):
         self._check(self.lib.gpc_set_stream(self._h, C.c_void_p(cuda_stream or 0)))

@@ -56,6 +56,12 @@ struct gpc_ctx {
   long long* h_pair_base = nullptr;  // [B+1]
   int64_t launches = 0;
   int match_smem_max = 0;
+  // optional per-kernel timing (CUDA events on the launching stream), see gpc_kernel_times
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  double k_ms[GPC_N_KERNELS] = {0, 0, 0, 0};
+  int64_t k_runs = 0;
   std::string err;
 };
 
@@ -73,6 +79,18 @@ int fail(gpc_ctx* c, int code, const std::string& msg) {
       return fail((ctx), GPC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));        \
   } while (0)
 
+// Record a timing event on the context's stream (no-op unless gpc_enable_kernel_timing).
+int mark(gpc_ctx* c) {
+  if (!c->timing) return GPC_OK;
+  if (c->ev_used == c->ev_pool.size()) {
+    cudaEvent_t e;
+    GPC_CUDA(c, cudaEventCreate(&e));
+    c->ev_pool.push_back(e);
+  }
+  GPC_CUDA(c, cudaEventRecord(c->ev_pool[c->ev_used++], c->stream));
+  return GPC_OK;
+}
+
 int floordiv4(int v) { return (v >= 0) ? v / 4 : -((-v + 3) / 4); }
 
 // Bake the forest for the kernel's shared-memory tile pitch (the reference bakes it for the
@@ -83,18 +101,20 @@ void bake_forest(const gpc_forest& f, gpc::ForestDev* d) {
   d->type = f.type;
   for (int t = 0; t < f.n_tests; t++) {
     int oa = f.iy[t] * gpc::kPitch + f.ix[t], ob = f.jy[t] * gpc::kPitch + f.jx[t];
-    d->woff_a[t] = (int16_t)floordiv4(oa);
-    d->woff_b[t] = (int16_t)floordiv4(ob);
-    d->sh_a[t] = (uint8_t)(8 * (oa - 4 * floordiv4(oa)));
-    d->sh_b[t] = (uint8_t)(8 * (ob - 4 * floordiv4(ob)));
-    uint32_t t8 = (uint32_t)(uint8_t)(int8_t)f.tau[t];      // _mm_set1_epi8(tau): low 8 bits
-    d->tau4[t] = t8 * 0x01010101u;
+    d->off_a[t] = 4 * floordiv4(oa);
+    d->off_b[t] = 4 * floordiv4(ob);
+    d->sh_a[t] = (uint32_t)(8 * (oa - 4 * floordiv4(oa)));
+    d->sh_b[t] = (uint32_t)(8 * (ob - 4 * floordiv4(ob)));
+    int tau8 = (int)(int8_t)f.tau[t];                        // _mm_set1_epi8(tau): low 8 bits, signed
+    uint32_t m = (uint32_t)(uint16_t)(int16_t)(-tau8);
+    d->mtau2[t] = (f.type == 1) ? (m | (m << 16)) : 0u;
   }
 }
 
 int check_dims(gpc_ctx* c, int w, int h, int n_pairs) {
   if (w <= 0 || h <= 0 || n_pairs <= 0) return fail(c, GPC_E_ARG, "non-positive dimension");
   if (w % 16 != 0) return fail(c, GPC_E_WIDTH16, "width must be multiple of 16!");   // filter.hpp:294
+  if (w > 8192) return fail(c, GPC_E_DIMS, "width above 8192 is not supported by the row matcher");
   if (w > c->max_w || h > c->max_h || (long long)w * h > (long long)c->max_w * c->max_h || n_pairs > c->max_batch)
     return fail(c, GPC_E_DIMS, "image or batch exceeds the context's capacity");
   return GPC_OK;
@@ -126,9 +146,10 @@ int run_preprocess(gpc_ctx* c, const uint8_t* d_images, int n_img, int w, int h,
   a.raw = d_images; a.hash = c->d_hash; a.rowcnt = rowcnt; a.lastrow = lastrow;
   a.smooth_out = d_smooth; a.grad_out = d_grad; a.W = w; a.H = h;
   a.thr2 = (int32_t)(int16_t)(thr * thr);                                          // filter.hpp:418
+  int rc = mark(c); if (rc) return rc;                                             // event 0
   GPC_CUDA(c, gpc::launch_preprocess_hash(a, forest, n_img, d_smooth || d_grad, c->stream));
   c->launches += 1;
-  return GPC_OK;
+  return mark(c);                                                                  // event 1
 }
 
 // Kernels B, scan, C over hash images already in c->d_hash (or `hash`).
@@ -141,10 +162,12 @@ int run_match(gpc_ctx* c, const uint32_t* hash, int n_pairs, int w, int h, const
   m.W = w; m.H = h; m.disp_high = s->disp_high; m.vertical_tolerance = s->vertical_tolerance;
   m.wcap = std::max(w - 2 * gpc::kRadius, 16);
   m.table_log2 = table_log2_for(m.wcap);
+  m.key_bits = 31;   // hash images may come from the caller (gpc_match_hash_images): assume full 31-bit states
   if ((int)gpc::match_smem_bytes(m.wcap, m.table_log2) > c->match_smem_max)
     return fail(c, GPC_E_DIMS, "image too wide for the row matcher's shared memory");
   if (h - 2 * gpc::kRadius <= 0) GPC_CUDA(c, cudaMemsetAsync(c->d_rowmatch, 0, (size_t)n_pairs * h * sizeof(int32_t), c->stream));
   GPC_CUDA(c, gpc::launch_match_rows(m, n_pairs, c->stream));
+  int rc = mark(c); if (rc) return rc;                                             // event 2
   GPC_CUDA(c, gpc::launch_row_scan(c->d_rowmatch, rowcnt, h, n_pairs, c->d_rowoff, d_n_out, d_n_cand, c->stream));
   c->launches += 2;
   const long long* pair_base = nullptr;
@@ -153,9 +176,10 @@ int run_match(gpc_ctx* c, const uint32_t* hash, int n_pairs, int w, int h, const
     c->launches += 1;
     pair_base = c->d_pair_base;
   }
+  rc = mark(c); if (rc) return rc;                                                 // event 3
   GPC_CUDA(c, gpc::launch_emit_supports(c->d_stage, c->d_rowmatch, c->d_rowoff, pair_base, d_out, cap, w, h, n_pairs, c->stream));
   if (h - 2 * gpc::kRadius > 0) c->launches += 1;
-  return GPC_OK;
+  return mark(c);                                                                  // event 4
 }
 
 int ensure_debug_buffers(gpc_ctx* c) {
@@ -243,6 +267,7 @@ void gpc_destroy(gpc_ctx* c) {
   cudaFree(c->d_dbg8); cudaFree(c->d_mask);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->h_pair_base) cudaFreeHost(c->h_pair_base);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -261,6 +286,35 @@ int gpc_synchronize(gpc_ctx* c) {
 }
 
 int64_t gpc_launch_count(const gpc_ctx* c) { return c ? c->launches : 0; }
+
+int gpc_enable_kernel_timing(gpc_ctx* c, int on) {
+  if (!c) return GPC_E_ARG;
+  c->timing = (on != 0);
+  c->ev_used = 0;
+  for (int k = 0; k < GPC_N_KERNELS; k++) c->k_ms[k] = 0.0;
+  c->k_runs = 0;
+  return GPC_OK;
+}
+
+// Synchronises the stream, folds the recorded event quintuples into per-kernel sums and returns
+// the accumulated milliseconds per kernel and the number of batch runs they cover.
+int gpc_kernel_times(gpc_ctx* c, double* ms, int64_t* runs) {
+  if (!c || !ms || !runs) return GPC_E_ARG;
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i + 5 <= c->ev_used; i += 5) {
+    for (int k = 0; k < GPC_N_KERNELS; k++) {
+      float t = 0.f;
+      GPC_CUDA(c, cudaEventElapsedTime(&t, c->ev_pool[i + k], c->ev_pool[i + k + 1]));
+      c->k_ms[k] += t;
+    }
+    c->k_runs++;
+  }
+  c->ev_used = 0;
+  for (int k = 0; k < GPC_N_KERNELS; k++) ms[k] = c->k_ms[k];
+  *runs = c->k_runs;
+  return GPC_OK;
+}
 
 // Forest::readForest (inference.hpp:404-446): whitespace-separated text; scale tag ignored;
 // at most 32 tests kept; type 1 iff ANY test of the file (kept or not) has tau != 0.

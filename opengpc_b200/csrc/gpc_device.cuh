@@ -27,14 +27,16 @@ constexpr int kSmRows = kTileH + 2 * kRadius;        // image rows y0-13 .. y0+k
 constexpr int kThreadsA = 256;
 
 // Forest baked for the smem tile pitch (replaces the per-width baking of inference.hpp:427-428).
+// Passed by value as a kernel parameter: with the test loop fully unrolled every field is read
+// from a fixed constant-bank address (uniform datapath), never through an indexed load.
 struct ForestDev {
   int32_t n_tests;
   int32_t type;                  // 0: a > b ; 1: a > sat_int8(b - tau)
-  int16_t woff_a[kMaxTests];     // word offset of operand a relative to the quad's word
-  int16_t woff_b[kMaxTests];
-  uint8_t sh_a[kMaxTests];       // funnel-shift amount in bits (0, 8, 16, 24)
-  uint8_t sh_b[kMaxTests];
-  uint32_t tau4[kMaxTests];      // int8 tau replicated into 4 byte lanes
+  int32_t off_a[kMaxTests];      // byte offset (multiple of 4) of operand a's first word relative to the quad
+  int32_t off_b[kMaxTests];
+  uint32_t sh_a[kMaxTests];      // funnel-shift amount in bits (0, 8, 16, 24)
+  uint32_t sh_b[kMaxTests];
+  uint32_t mtau2[kMaxTests];     // -tau (int8 tau) as int16 replicated into both 16-bit lanes; 0 = no tau
 };
 
 struct PreprocessArgs {
@@ -57,6 +59,7 @@ struct MatchArgs {
   int32_t disp_high, vertical_tolerance;
   int32_t table_log2;      // log2 of the per-row hash table size (>= 2 * candidates)
   int32_t wcap;            // per-side candidate capacity used to carve shared memory
+  int32_t key_bits;        // number of significant state bits (forest dependent)
 };
 
 }  // namespace gpc

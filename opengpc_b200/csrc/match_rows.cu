@@ -17,229 +17,267 @@
 namespace gpc {
 
 constexpr int kThreadsB = 256;
-constexpr uint32_t kEmpty16 = 0xffffu;
+constexpr uint32_t kEmptyKey = 0xffffffffu;   // states never have bit 31 set
+constexpr uint32_t kNoX = 0xffffffffu;
+constexpr int kBuckets = 256;
+constexpr int kBucketLimit = 64;              // above this the bucket rank pass falls back to a bitonic network
 
-__device__ __forceinline__ uint32_t slot_of(uint32_t key, int log2) {
-  return (key * 0x9E3779B1u) >> (32 - log2);
+__device__ __forceinline__ uint32_t slot_of(uint32_t key, int log2ts) {
+  return (key * 0x9E3779B1u) >> (32 - log2ts);
 }
 
-struct RowSmem {
-  uint32_t* key_l; uint32_t* key_r;        // [wcap]
-  uint16_t* x_l; uint16_t* x_r;            // [wcap]
-  uint16_t* cur_l; uint16_t* cur_r;        // [wcap] current / final slot per candidate
-  uint16_t* tab_l; uint16_t* tab_r;        // [table] owner candidate per slot
-  uint8_t* dup_l; uint8_t* dup_r;          // [table]
-  unsigned long long* out;                 // [wcap]  state<<32 | xL<<16 | xR
-};
+// Shared-memory atomics in this kernel always consume their return value.  Fire-and-forget
+// shared atomics (ATOMS with an RZ destination, addressed through a uniform register into the
+// dynamic shared window) were observed on B200 / nvcc 12.9 to land late or at a wrong address
+// (lost flag bits, corrupted neighbours, occasional illegal-address faults; reproduced with
+// scripts/micro/match_harness.cu) -- the value-returning form does not show it.
+__device__ __forceinline__ uint32_t atomic_inc_ret(uint32_t* p) { return atomicAdd(p, 1u); }
 
 size_t match_smem_bytes(int wcap, int table_log2) {
   size_t ts = (size_t)1 << table_log2;
   size_t pow2 = 1; while ((int)pow2 < wcap) pow2 <<= 1;
-  return pow2 * 8 + (size_t)wcap * (4 + 4 + 2 + 2 + 2 + 2) + ts * (2 + 2 + 1 + 1) + 64;
+  return pow2 * 8 + ts * (4 + 4 + 2 + 1) + 3 * kBuckets * 4 + 16;
 }
 
-// Compact the candidates (bit 31) of one hash row into key[] / x[]; order is irrelevant.
-__device__ __forceinline__ void compact_row(const uint32_t* __restrict__ row, int W, uint32_t* key, uint16_t* xs,
-                                            int* counter) {
-  const int lane = threadIdx.x & 31;
-  const int nquads = W / 4;                                           // W % 16 == 0
-  for (int q0 = threadIdx.x & ~31; q0 < nquads; q0 += kThreadsB) {    // warp-uniform trip count (ballots below)
-    const int q = q0 + lane;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (q < nquads) v = __ldg(reinterpret_cast<const uint4*>(row) + q);
-    uint32_t vv[4] = {v.x, v.y, v.z, v.w};
-    uint32_t b[4];
-    int total = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) { b[k] = __ballot_sync(0xffffffffu, vv[k] >> 31); total += __popc(b[k]); }
-    if (total == 0) continue;   // warp-uniform
-    int base = 0;
-    if (lane == 0) base = atomicAdd(counter, total);
-    base = __shfl_sync(0xffffffffu, base, 0);
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      if (vv[k] >> 31) {
-        int p = base + __popc(b[k] & ((1u << lane) - 1u));
-        key[p] = vv[k] & 0x7fffffffu;
-        xs[p] = (uint16_t)(4 * q + k);
-      }
-      base += __popc(b[k]);
-    }
-  }
-}
-
+// One CTA per (row, pair).  Every thread keeps its 4*KQ left and right pixels of the row in
+// registers (no compaction pass).  Shared-memory atomics are cheap on sm_100 (measured 2.8 SM
+// cycles per warp-wide atomicAdd/Exch, 5.3 per atomicCAS, scripts/micro/atoms_bench.cu):
+//   left  : one atomicCAS per probe inserts the state into an open-addressing table; the owner
+//           of a slot stores its x, a later equal state marks the slot dead (not unique)
+//   right : probes the table; the first hit records its x with an atomicExch, a second hit
+//           marks the slot dead
+//   emit  : slot owners whose slot is alive and was hit exactly once are matches
+// and only the matches (about a tenth of the candidates) are then ordered by state.
+template <int KQ>
 __global__ void __launch_bounds__(kThreadsB)
 match_rows_kernel(const MatchArgs args) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int W = args.W, H = args.H, wcap = args.wcap, log2 = args.table_log2;
-  const int ts = 1 << log2;
-  const int tid = threadIdx.x;
+  const int W = args.W, H = args.H, log2ts = args.table_log2;
+  const int ts = 1 << log2ts;
+  const uint32_t tmask = (uint32_t)ts - 1u;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int y = kRadius + blockIdx.x, pair = blockIdx.y;
 
-  int pow2cap = 1; while (pow2cap < wcap) pow2cap <<= 1;
-  RowSmem s;
-  s.out = reinterpret_cast<unsigned long long*>(smem);
-  s.key_l = reinterpret_cast<uint32_t*>(s.out + pow2cap);
-  s.key_r = s.key_l + wcap;
-  s.x_l = reinterpret_cast<uint16_t*>(s.key_r + wcap);
-  s.x_r = s.x_l + wcap;
-  s.cur_l = s.x_r + wcap;
-  s.cur_r = s.cur_l + wcap;
-  s.tab_l = s.cur_r + wcap;
-  s.tab_r = s.tab_l + ts;
-  s.dup_l = reinterpret_cast<uint8_t*>(s.tab_r + ts);
-  s.dup_r = s.dup_l + ts;
-  __shared__ int n_l, n_r, n_out, pending;
-  __shared__ uint32_t kmax_s;
-  __shared__ int cmax_s, xmin_s;
+  int pow2cap = 1; while (pow2cap < args.wcap) pow2cap <<= 1;
+  unsigned long long* out = reinterpret_cast<unsigned long long*>(smem);           // [pow2cap] emitted matches
+  uint32_t* tab = reinterpret_cast<uint32_t*>(out + pow2cap);                       // [ts] left states
+  uint32_t* xr_tab = tab + ts;                                                      // [ts] x of the first right hit
+  unsigned long long* out2 = reinterpret_cast<unsigned long long*>(tab);            // reuses tab+xr_tab after the emit
+  uint32_t* bcnt = xr_tab + ts;                                                     // [kBuckets] x3
+  uint32_t* bstart = bcnt + kBuckets;
+  uint32_t* bfill = bstart + kBuckets;
+  uint16_t* xl_tab = reinterpret_cast<uint16_t*>(bfill + kBuckets);                 // [ts] x of the slot owner
+  uint8_t* dead = reinterpret_cast<uint8_t*>(xl_tab + ts);                          // [ts] state not unique (either side)
+  __shared__ int n_out, have_s[2];
+  __shared__ uint32_t kmax_s, big_bucket;
+  __shared__ int cmax_r, cmax_l, xmin_s;
 
-  if (tid == 0) { n_l = 0; n_r = 0; n_out = 0; kmax_s = 0; cmax_s = 0; xmin_s = 0x7fffffff; }
-  for (int i = tid; i < ts; i += kThreadsB) { s.tab_l[i] = kEmpty16; s.tab_r[i] = kEmpty16; s.dup_l[i] = 0; s.dup_r[i] = 0; }
+  if (tid == 0) { n_out = 0; have_s[0] = 0; have_s[1] = 0; kmax_s = 0; cmax_r = 0; cmax_l = 0; xmin_s = 0x7fffffff; big_bucket = 0; }
+  for (int i = tid; i < ts; i += kThreadsB) { tab[i] = kEmptyKey; xr_tab[i] = kNoX; dead[i] = 0; }
+  for (int i = tid; i < 3 * kBuckets; i += kThreadsB) bcnt[i] = 0u;
   __syncthreads();
 
-  const uint32_t* row_l = args.hash + ((size_t)(2 * pair) * H + y) * W;
-  const uint32_t* row_r = args.hash + ((size_t)(2 * pair + 1) * H + y) * W;
-  compact_row(row_l, W, s.key_l, s.x_l, &n_l);
-  compact_row(row_r, W, s.key_r, s.x_r, &n_r);
+  // ---- this thread's pixels of the left and right hash rows ---------------------------------------
+  const uint4* row_l = reinterpret_cast<const uint4*>(args.hash + ((size_t)(2 * pair) * H + y) * W);
+  const uint4* row_r = reinterpret_cast<const uint4*>(args.hash + ((size_t)(2 * pair + 1) * H + y) * W);
+  const int nquads = W / 4;
+  uint32_t vl[4 * KQ], vr[4 * KQ];
+  uint32_t any_l = 0, any_r = 0;
+#pragma unroll
+  for (int k = 0; k < KQ; k++) {
+    const int q = tid + k * kThreadsB;
+    uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+    if (q < nquads) { a = __ldg(row_l + q); b = __ldg(row_r + q); }
+    vl[4 * k] = a.x; vl[4 * k + 1] = a.y; vl[4 * k + 2] = a.z; vl[4 * k + 3] = a.w;
+    vr[4 * k] = b.x; vr[4 * k + 1] = b.y; vr[4 * k + 2] = b.z; vr[4 * k + 3] = b.w;
+    any_l |= a.x | a.y | a.z | a.w;
+    any_r |= b.x | b.y | b.z | b.w;
+  }
+  if (any_l >> 31) have_s[0] = 1;                                              // benign same-value race
+  if (any_r >> 31) have_s[1] = 1;
   __syncthreads();
-  const int nl = n_l, nr = n_r;
   int m = 0;
 
-  if (nl > 0 && nr > 0) {
-    // ---- left table: store, barrier, verify; losers of a slot probe on ---------------------
-    for (int i = tid; i < nl; i += kThreadsB) s.cur_l[i] = (uint16_t)slot_of(s.key_l[i], log2);
-    for (;;) {
-      for (int i = tid; i < nl; i += kThreadsB) {
-        uint32_t c = s.cur_l[i];
-        if (!(c & 0x8000u)) s.tab_l[c] = (uint16_t)i;           // bit 15 = settled
-      }
-      if (tid == 0) pending = 0;
-      __syncthreads();
-      bool mine = false;
-      for (int i = tid; i < nl; i += kThreadsB) {
-        uint32_t c = s.cur_l[i];
-        if (c & 0x8000u) continue;
-        const uint32_t key = s.key_l[i];
-        uint32_t w = s.tab_l[c];
-        if (w == (uint32_t)i) { s.cur_l[i] = (uint16_t)(c | 0x8000u); continue; }   // owns slot c
-        for (;;) {                                              // table is read-only in this phase
-          if (s.key_l[w] == key) { s.dup_l[c] = 1; c = 0xffffu; break; }            // duplicate of the owner
-          c = (c + 1) & (ts - 1);
-          w = s.tab_l[c];
-          if (w == kEmpty16) break;
+  if (have_s[0] && have_s[1]) {
+    // ---- left states: one atomicCAS per probe ------------------------------------------------------
+    uint32_t myslot[4 * KQ];
+#pragma unroll
+    for (int e = 0; e < 4 * KQ; e++) {
+      myslot[e] = 0xffffffffu;
+      if (vl[e] >> 31) {
+        const uint32_t key = vl[e] & 0x7fffffffu;
+        uint32_t c = slot_of(key, log2ts);
+        for (int probe = 0; probe < ts; probe++) {            // bounded: the table is at most half full
+          const uint32_t old = atomicCAS(&tab[c], kEmptyKey, key);
+          if (old == kEmptyKey) {                                                     // owner records xL
+            xl_tab[c] = (uint16_t)(4 * (tid + (e >> 2) * kThreadsB) + (e & 3));
+            myslot[e] = c;
+            break;
+          }
+          if (old == key) { dead[c] = 1; break; }                                     // state not unique on the left
+          c = (c + 1) & tmask;
         }
-        s.cur_l[i] = (uint16_t)c;                               // 0xffff = settled as a duplicate
-        if (c != 0xffffu) mine = true;
       }
-      if (mine) pending = 1;
-      __syncthreads();
-      if (!pending) break;
-      __syncthreads();
-    }
-    // ---- right probes -------------------------------------------------------------------------
-    for (int j = tid; j < nr; j += kThreadsB) {
-      const uint32_t key = s.key_r[j];
-      uint32_t c = slot_of(key, log2);
-      for (;;) {
-        uint32_t w = s.tab_l[c];
-        if (w == kEmpty16) { c = 0xffffu; break; }
-        if (s.key_l[w] == key) { s.tab_r[c] = (uint16_t)j; break; }
-        c = (c + 1) & (ts - 1);
-      }
-      s.cur_r[j] = (uint16_t)c;
     }
     __syncthreads();
-    for (int j = tid; j < nr; j += kThreadsB) {
-      uint32_t c = s.cur_r[j];
-      if (c != 0xffffu && s.tab_r[c] != (uint16_t)j) s.dup_r[c] = 1;   // another right pixel has this state
+    // ---- right states probe the table --------------------------------------------------------------
+#pragma unroll
+    for (int e = 0; e < 4 * KQ; e++) {
+      if (vr[e] >> 31) {
+        const uint32_t key = vr[e] & 0x7fffffffu;
+        uint32_t c = slot_of(key, log2ts);
+        for (int probe = 0; probe < ts; probe++) {
+          const uint32_t t = tab[c];
+          if (t == kEmptyKey) break;
+          if (t == key) {
+            const uint32_t x = 4u * (uint32_t)(tid + (e >> 2) * kThreadsB) + (uint32_t)(e & 3);
+            if (atomicExch(&xr_tab[c], x) != kNoX) dead[c] = 2;                       // a second right pixel with this state
+            break;
+          }
+          c = (c + 1) & tmask;
+        }
+      }
     }
-    // ---- tail rules: only the globally last right key (largest row with right candidates) ---
+    // ---- tail rules: only the globally last right key (largest row with right candidates) -----------
     const bool last_row = (args.lastrow[2 * pair + 1] == y);
     if (last_row) {
       uint32_t km = 0;
-      for (int j = tid; j < nr; j += kThreadsB) km = max(km, s.key_r[j]);
+#pragma unroll
+      for (int e = 0; e < 4 * KQ; e++) if (vr[e] >> 31) km = max(km, vr[e] & 0x7fffffffu);
       km = __reduce_max_sync(0xffffffffu, km);
-      if ((tid & 31) == 0) atomicMax(&kmax_s, km);
+      if (lane == 0 && atomicMax(&kmax_s, km) == 0xffffffffu) __trap();
       __syncthreads();
       km = kmax_s;
-      int c = 0, xm = 0x7fffffff;
-      for (int j = tid; j < nr; j += kThreadsB)
-        if (s.key_r[j] == km) { c++; xm = min(xm, (int)s.x_r[j]); }
-      c = __reduce_add_sync(0xffffffffu, c);
+      int cr = 0, cl = 0, xm = 0x7fffffff;
+#pragma unroll
+      for (int e = 0; e < 4 * KQ; e++) {
+        if ((vr[e] >> 31) && (vr[e] & 0x7fffffffu) == km) { cr++; xm = min(xm, 4 * (tid + (e >> 2) * kThreadsB) + (e & 3)); }
+        if ((vl[e] >> 31) && (vl[e] & 0x7fffffffu) == km) cl++;
+      }
+      cr = __reduce_add_sync(0xffffffffu, cr);
+      cl = __reduce_add_sync(0xffffffffu, cl);
       xm = __reduce_min_sync(0xffffffffu, xm);
-      if ((tid & 31) == 0) { atomicAdd(&cmax_s, c); atomicMin(&xmin_s, xm); }
+      if (lane == 0) {
+        if (atomicAdd(&cmax_r, cr) < 0 || atomicAdd(&cmax_l, cl) < 0 || atomicMin(&xmin_s, xm) < 0) __trap();
+      }
     }
     __syncthreads();
-    // ---- emit: left states that own a slot, unique on both sides -------------------------------
+    // ---- emit: left states that own a live slot hit exactly once ----------------------------------------
     const uint32_t kmax = kmax_s;
-    const int cmax = cmax_s, xmin = xmin_s;
-    for (int i0 = 0; i0 < nl; i0 += kThreadsB) {
-      const int i = i0 + tid;
+    const int cmr = cmax_r, cml = cmax_l, xmin = xmin_s;
+#pragma unroll
+    for (int e = 0; e < 4 * KQ; e++) {
       bool ok = false;
       unsigned long long rec = 0;
-      if (i < nl) {
-        uint32_t c = s.cur_l[i];
-        if (c != 0xffffu) {
-          c &= 0x7fffu;
-          const uint32_t j = s.tab_r[c];
-          if (!s.dup_l[c] && j != kEmpty16) {
-            const uint32_t key = s.key_l[i];
-            int xl = s.x_l[i], xr = s.x_r[j];
-            ok = !s.dup_r[c];
-            if (last_row && key == kmax) {       // inference.hpp:243-249 on the tail of sorted tar
-              ok = (cmax == 2);                  // 1: the last element never matches; >=3: duplicates
-              xr = xmin;                         // 2: "first of the two" := smaller x (stable order)
-            }
-            int dx = xl - xr;
-            ok = ok && (dx <= args.disp_high && -dx <= args.disp_high) && (0 <= args.vertical_tolerance);
-            rec = ((unsigned long long)key << 32) | ((unsigned long long)xl << 16) | (unsigned long long)xr;
-          }
+      if (myslot[e] != 0xffffffffu) {
+        const uint32_t c = myslot[e];
+        const uint32_t key = vl[e] & 0x7fffffffu;
+        const int xl = 4 * (tid + (e >> 2) * kThreadsB) + (e & 3);
+        uint32_t xr = xr_tab[c];
+        ok = (xr != kNoX) && (dead[c] == 0);
+        if (last_row && key == kmax) {         // inference.hpp:243-249 on the tail of the sorted right keys
+          ok = (cml == 1) && (cmr == 2);       // 1 right: the last element never matches; >=3: duplicates
+          xr = (uint32_t)xmin;                 // 2: "first of the two" := smaller x (stable order)
+        }
+        if (ok) {
+          const int dx = xl - (int)xr;
+          ok = (dx <= args.disp_high && -dx <= args.disp_high) && (0 <= args.vertical_tolerance);
+          rec = ((unsigned long long)key << 32) | ((unsigned long long)xl << 16) | (unsigned long long)xr;
         }
       }
-      const uint32_t b = __ballot_sync(0xffffffffu, ok);
-      if (b) {
+      const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+      if (bal) {
         int base = 0;
-        if ((tid & 31) == 0) base = atomicAdd(&n_out, __popc(b));
+        if (lane == 0) base = atomicAdd(&n_out, __popc(bal));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (ok) s.out[base + __popc(b & ((1u << (tid & 31)) - 1u))] = rec;
+        if (ok) out[base + __popc(bal & ((1u << lane) - 1u))] = rec;
       }
     }
     __syncthreads();
     m = n_out;
-    // ---- order by state (keys are unique): bitonic network over the matches only --------------
-    if (m > 1) {
+  }
+
+  // ---- order the matches by state (unique keys) and stage them ------------------------------------------
+  uint32_t* stage = args.stage + ((size_t)pair * H + y) * W;
+  if (m > 1) {
+    // counting pass on the top 8 state bits, then an exact rank inside each (tiny) bucket
+    const int shift = args.key_bits > 8 ? args.key_bits - 8 : 0;
+    uint32_t seen = 0;
+    for (int i = tid; i < m; i += kThreadsB) seen |= atomic_inc_ret(&bcnt[(uint32_t)(out[i] >> 32) >> shift]);
+    if (seen == 0xffffffffu) __trap();
+    __syncthreads();
+    if (tid < 32) {                                   // exclusive scan of 256 counters: 8 per lane
+      uint32_t c[8], sum = 0, mx = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) { c[k] = bcnt[8 * tid + k]; sum += c[k]; mx = max(mx, c[k]); }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+      uint32_t run = incl - sum;
+#pragma unroll
+      for (int k = 0; k < 8; k++) { bstart[8 * tid + k] = run; run += c[k]; }
+      mx = __reduce_max_sync(0xffffffffu, mx);
+      if (tid == 0) big_bucket = (mx > (uint32_t)kBucketLimit) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!big_bucket) {
+      for (int i = tid; i < m; i += kThreadsB) {      // scatter into bucket segments (arbitrary order inside)
+        const unsigned long long rec = out[i];
+        const uint32_t b = (uint32_t)(rec >> 32) >> shift;
+        out2[bstart[b] + atomic_inc_ret(&bfill[b])] = rec;
+      }
+      __syncthreads();
+      for (int i = tid; i < m; i += kThreadsB) {      // rank inside the bucket, write to the final position
+        const unsigned long long rec = out2[i];
+        const uint32_t b = (uint32_t)(rec >> 32) >> shift;
+        const uint32_t s0 = bstart[b], n = bcnt[b];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < n; j++) rank += (out2[s0 + j] < rec) ? 1u : 0u;
+        stage[s0 + rank] = (uint32_t)(rec & 0xffffffffull);
+      }
+    } else {                                          // skewed states: bitonic network over all matches
       int p2 = 1; while (p2 < m) p2 <<= 1;
-      for (int i = m + tid; i < p2; i += kThreadsB) s.out[i] = ~0ull;
+      for (int i = m + tid; i < p2; i += kThreadsB) out[i] = ~0ull;
       __syncthreads();
       for (int k = 2; k <= p2; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
           for (int i = tid; i < p2; i += kThreadsB) {
-            int l = i ^ j;
+            const int l = i ^ j;
             if (l > i) {
-              unsigned long long a = s.out[i], b2 = s.out[l];
-              bool up = ((i & k) == 0);
-              if ((a > b2) == up) { s.out[i] = b2; s.out[l] = a; }
+              const unsigned long long a = out[i], b2 = out[l];
+              const bool up = ((i & k) == 0);
+              if ((a > b2) == up) { out[i] = b2; out[l] = a; }
             }
           }
           __syncthreads();
         }
+      for (int i = tid; i < m; i += kThreadsB) stage[i] = (uint32_t)(out[i] & 0xffffffffull);
     }
+  } else if (m == 1 && tid == 0) {
+    stage[0] = (uint32_t)(out[0] & 0xffffffffull);
   }
-  // ---- stage the row's ordered matches ------------------------------------------------------------
-  uint32_t* stage = args.stage + ((size_t)pair * H + y) * W;
-  for (int i = tid; i < m; i += kThreadsB) stage[i] = (uint32_t)(s.out[i] & 0xffffffffull);
   if (tid == 0) args.rowmatch[(size_t)pair * H + y] = m;
 }
 
 cudaError_t configure_match_rows(int max_smem) {
-  return cudaFuncSetAttribute(match_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaError_t e = cudaFuncSetAttribute(match_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(match_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(match_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(match_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  return e;
 }
 
 cudaError_t launch_match_rows(const MatchArgs& args, int n_pairs, cudaStream_t stream) {
   int rows = args.H - 2 * kRadius;
   if (rows <= 0 || n_pairs <= 0) return cudaSuccess;
   size_t smem = match_smem_bytes(args.wcap, args.table_log2);
-  match_rows_kernel<<<dim3(rows, n_pairs), kThreadsB, smem, stream>>>(args);
+  const int kq = (args.W / 4 + kThreadsB - 1) / kThreadsB;
+  dim3 grid(rows, n_pairs);
+  if (kq <= 1) match_rows_kernel<1><<<grid, kThreadsB, smem, stream>>>(args);
+  else if (kq <= 2) match_rows_kernel<2><<<grid, kThreadsB, smem, stream>>>(args);
+  else if (kq <= 4) match_rows_kernel<4><<<grid, kThreadsB, smem, stream>>>(args);
+  else if (kq <= 8) match_rows_kernel<8><<<grid, kThreadsB, smem, stream>>>(args);
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 

@@ -31,6 +31,28 @@ __device__ __forceinline__ void hthirds(uint32_t wm1, uint32_t w, uint32_t wp1, 
   h[3] = third(__dp4a(__funnelshift_r(w, wp1, 16), 0x00010101u, 0u));
 }
 
+// One fern test on 4 horizontally adjacent pixels: msb of byte j = test result of pixel j.
+//   zero forest (filter.hpp:575):  a > b                      (unsigned bytes)
+//   tau forest  (filter.hpp:647-652): a > sat_int8(b - tau)   (signed saturating subtract of the byte
+//   reinterpreted as int8, then an unsigned compare).  In the biased domain x = b ^ 0x80 the
+//   saturating subtract is clamp(x - tau, 0, 255), done on two 16-bit lanes per register with the
+//   native VIADDMNMX (DPX) instruction; the result is compared without un-biasing it.
+__device__ __forceinline__ uint32_t eval_test(const uint8_t* base, const ForestDev& forest, const int t) {
+  const uint32_t* pa = reinterpret_cast<const uint32_t*>(base + forest.off_a[t]);
+  const uint32_t* pb = reinterpret_cast<const uint32_t*>(base + forest.off_b[t]);
+  uint32_t a = pa[0], b = pb[0];
+  if (forest.sh_a[t]) a = __funnelshift_r(a, pa[1], forest.sh_a[t]);       // uniform branches
+  if (forest.sh_b[t]) b = __funnelshift_r(b, pb[1], forest.sh_b[t]);
+  const uint32_t mt = forest.mtau2[t];
+  if (mt == 0u) return gtu4_msb(a, b);
+  const uint32_t x = b ^ 0x80808080u;
+  const uint32_t lo = __viaddmin_s16x2_relu(__byte_perm(x, 0u, 0x4140), mt, 0x00ff00ffu);
+  const uint32_t hi = __viaddmin_s16x2_relu(__byte_perm(x, 0u, 0x4342), mt, 0x00ff00ffu);
+  const uint32_t c = __byte_perm(lo, hi, 0x6420);                          // clamp(x - tau, 0, 255); b' = c ^ 0x80
+  const uint32_t s = (a & 0x7f7f7f7fu) + (~c & 0x7f7f7f7fu);               // low-7-bit compare (bit 7 unaffected by ^0x80)
+  return (a & c) | ((a ^ c) & s);                                          // msb: a7 > b'7, or equal and low7(a) > low7(b')
+}
+
 template <bool kDebugOut>
 __global__ void __launch_bounds__(kThreadsA)
 preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
@@ -84,6 +106,7 @@ preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
       };
       load_h(j0, ha);       // raw-tile row j = image row y0-14+j; smooth row j needs raw rows j..j+2
       load_h(j0 + 1, hb);
+#pragma unroll 3
       for (int j = j0; j < j1; j++) {
         load_h(j + 2, hc);
         uint32_t v = third(ha[0] + hb[0] + hc[0]) | (third(ha[1] + hb[1] + hc[1]) << 8) |
@@ -153,30 +176,25 @@ preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
     uint32_t* __restrict__ hash = args.hash + img_off;
     const uint32_t m8 = (gx & 4) ? 0x01010101u : 0x01010100u;   // test #8: byte lanes x%8==0 dropped (filter.hpp:582)
     const int T = forest.n_tests;
+#pragma unroll 1
     for (int ry = tid >> 6; ry < kTileH; ry += kThreadsA / 64) {
       const int gy = y0 + ry;
       const bool inside = gx < W && gy < H;                      // cand is 0 outside the image
       const uint32_t cm = (cand[ry * (kTileW / 16) + (qx >> 2)] >> ((qx & 3) * 4)) & 15u;
       uint32_t st[4] = {0u, 0u, 0u, 0u};
       if (cm != 0u && gy >= kRadius && gy < H - 15) {            // hashed rows (filter.hpp:601-604)
-        const uint32_t* base = sm32 + (ry + kRadius) * kPitchW + 4 + qx;
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(sm32 + (ry + kRadius) * kPitchW + 4 + qx);
         uint32_t acc[4] = {0u, 0u, 0u, 0u};
-        auto eval = [&](int t) -> uint32_t {
-          const uint32_t* pa = base + forest.woff_a[t];
-          const uint32_t* pb = base + forest.woff_b[t];
-          uint32_t sa = forest.sh_a[t], sb = forest.sh_b[t];
-          uint32_t a = pa[0], b = pb[0];
-          if (sa) a = __funnelshift_r(a, pa[1], sa);
-          if (sb) b = __funnelshift_r(b, pb[1], sb);
-          if (forest.type == 1 && forest.tau4[t] != 0u) b = __vsubss4(b, forest.tau4[t]);   // _mm_subs_epi8, :649
-          return gtu4_msb(a, b);
-        };
-        // bit placement of filter.hpp:574-584: t<8 -> bit t; t==8 -> bit 0 (masked); t>=9 -> bit t-1
-        for (int t = 0; t < min(T, 8); t++) acc[0] |= (eval(t) >> (7 - t)) & (0x01010101u << t);
-        if (T > 8) acc[0] |= (eval(8) >> 7) & m8;
-        for (int t = 9; t < min(T, 17); t++) acc[1] |= (eval(t) >> (16 - t)) & (0x01010101u << (t - 9));
-        for (int t = 17; t < min(T, 25); t++) acc[2] |= (eval(t) >> (24 - t)) & (0x01010101u << (t - 17));
-        for (int t = 25; t < min(T, 32); t++) acc[3] |= (eval(t) >> (32 - t)) & (0x01010101u << (t - 25));
+#pragma unroll
+        for (int t = 0; t < kMaxTests; t++) {
+          if (t < T) {                                           // uniform
+            const uint32_t r = eval_test(base, forest, t);
+            // bit placement of filter.hpp:574-584: t<8 -> bit t; t==8 -> bit 0 (masked); t>=9 -> bit t-1
+            if (t < 8) acc[0] |= (r >> (7 - t)) & (0x01010101u << t);
+            else if (t == 8) acc[0] |= (r >> 7) & m8;
+            else { const int p = t - 1; acc[p >> 3] |= (r >> (7 - (p & 7))) & (0x01010101u << (p & 7)); }
+          }
+        }
         // 4x4 byte transpose: state of pixel j = byte j of acc[0..3]
         uint32_t lo01 = __byte_perm(acc[0], acc[1], 0x5140), hi01 = __byte_perm(acc[0], acc[1], 0x7362);
         uint32_t lo23 = __byte_perm(acc[2], acc[3], 0x5140), hi23 = __byte_perm(acc[2], acc[3], 0x7362);

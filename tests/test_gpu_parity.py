@@ -210,3 +210,18 @@ def test_error_codes(g, ctx_small):
     with pytest.raises(g.GpcError) as e:
         ctx_small.match_pair(img, img, s, cap=0) if False else ctx_small.set_forest(g.make_forest([(14, 0, 0, 0)], [0]))
     assert e.value.status == capi.GPC_E_FOREST
+
+
+def test_repeatability_stress(g, ctx_small, oracle):
+    """The row matcher uses shared-memory atomics: the same batch, run many times, must give the
+    same ordered result every time (guards against timing-dependent races)."""
+    from opengpc_b200.synth import synth_batch
+    imgs = synth_batch(1024, 436, 4, seed0=1234)
+    ctx_small.set_forest(FORESTS["tau"])
+    s = g.sparsematch_settings()
+    of = oracle.read_forest(FORESTS["tau"])
+    refs = [oracle.pair(imgs[p, 0], imgs[p, 1], of, osettings())[0] for p in range(4)]
+    for rep in range(25):
+        supp, offsets, _ = ctx_small.match_batch(imgs, s)
+        for p in range(4):
+            assert np.array_equal(supp[offsets[p]:offsets[p + 1]], refs[p]), (rep, p)
