@@ -59,6 +59,7 @@ typedef struct {
   int32_t n_discarded;          /* tests dropped by the 32-test cap (one "Note:" line each) */
   int32_t ix[GPC_MAX_TESTS], iy[GPC_MAX_TESTS], jx[GPC_MAX_TESTS], jy[GPC_MAX_TESTS];
   int32_t tau[GPC_MAX_TESTS];
+  int32_t n_ferns;              /* first number of the file ("number of ferns:" line, inference.hpp:417) */
 } gpc_forest;
 
 typedef struct gpc_ctx gpc_ctx;
@@ -115,6 +116,45 @@ int gpc_hash(gpc_ctx* ctx, const uint8_t* img, int w, int h, int gradient_thresh
  * caller-provided hash images (same encoding as gpc_hash's hash_image). */
 int gpc_match_hash_images(gpc_ctx* ctx, const uint32_t* hash_l, const uint32_t* hash_r, int w, int h,
                           const gpc_settings* s, gpc_support* out, int cap, int* n_out);
+
+/* Forest::evalFastMaskOnSubsetSSE (inference.hpp:266-292) / ndb::gpcFilter[Tau] (filter.hpp:547,
+ * :619) on a caller-provided SMOOTHED image: states[i] = state of pixel idx[i] (= y*w + x).
+ * Entries outside the 13-pixel border (where the reference reads across row ends) and in the
+ * never-hashed rows >= h-15 (filter.hpp:601-604) give 0. */
+int gpc_hash_smooth(gpc_ctx* ctx, const uint8_t* smooth, int w, int h, const int32_t* idx, int n,
+                    uint32_t* states);
+
+/* ---- resident images: the device side of Forest::PreprocessedImage (inference.hpp:157-166) --
+ * gpc_image_upload copies a raw image to the context's device once; gpc_image_preprocess is
+ * preprocessImage (inference.hpp:302-333) on it, gpc_match_images is rectifiedMatch
+ * (inference.hpp:375-393) on two resident images without another host->device copy. */
+typedef struct gpc_image gpc_image;
+int gpc_image_upload(gpc_ctx* ctx, const uint8_t* img, int w, int h, int stride, gpc_image** out);
+void gpc_image_release(gpc_image* image);
+int gpc_image_preprocess(gpc_ctx* ctx, const gpc_image* image, int gradient_threshold, uint8_t* smooth,
+                         uint8_t* grad, int32_t* mask, int mask_cap, int* n_mask);
+int gpc_match_images(gpc_ctx* ctx, const gpc_image* left, const gpc_image* right, const gpc_settings* s,
+                     gpc_support* out, int cap, int* n_out, int* n_cand_l, int* n_cand_r);
+
+/* == ndb::Correspondence (buffer.hpp:94-97): source point, target point */
+typedef struct { int32_t xs, ys, xt, yt; } gpc_correspondence;
+/* Forest::stereoMatch / depthPriorFast (inference.hpp:344-361, :184-226): every unique-unique
+ * correspondence before rectifiedMatch's filter, ascending key order (both matching modes). */
+int gpc_correspond_images(gpc_ctx* ctx, const gpc_image* left, const gpc_image* right, const gpc_settings* s,
+                          gpc_correspondence* out, int cap, int* n_out);
+/* Forest::findCorrespondences (inference.hpp:227-254) on explicit 64-bit keys (Descriptor::state):
+ * out_pairs[2i], out_pairs[2i+1] = indices into src_keys / tar_keys of match i, ascending src key;
+ * among equal keys the input order is kept (stable).  n_tar == 0 (undefined behaviour in the
+ * reference) yields no matches. */
+int gpc_find_correspondences(gpc_ctx* ctx, const uint64_t* src_keys, int n_src, const uint64_t* tar_keys,
+                             int n_tar, int32_t* out_pairs, int cap, int* n_out);
+
+/* Matcher selection.  AUTO: epipolar mode uses the per-row shared-memory matcher, global mode the
+ * device-wide radix sort + segmented scan.  SORT forces the radix-sort matcher for both (same
+ * results; used to cross-check the two implementations). */
+#define GPC_MATCHER_AUTO 0
+#define GPC_MATCHER_SORT 1
+int gpc_set_matcher(gpc_ctx* ctx, int matcher);
 
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t gpc_launch_count(const gpc_ctx* ctx);

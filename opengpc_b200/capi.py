@@ -15,12 +15,15 @@ LIB_PATH = os.path.join(PKG, "libgpc_b200.so")
 GPC_OK, GPC_E_ARG, GPC_E_WIDTH16, GPC_E_DIMS, GPC_E_CUDA, GPC_E_CAPACITY, GPC_E_UNSUPPORTED, GPC_E_FOREST, GPC_E_IO = range(9)
 
 SUPPORT_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("d", "<f4")])   # == ndb::Support, 12 bytes
+CORR_DTYPE = np.dtype([("xs", "<i4"), ("ys", "<i4"), ("xt", "<i4"), ("yt", "<i4")])   # == ndb::Correspondence
+MATCHER_AUTO, MATCHER_SORT = 0, 1
 
 # every symbol include/gpc_b200.h declares (checked by tests/test_capi_cpu.py)
 SYMBOLS = ["gpc_create", "gpc_destroy", "gpc_last_error", "gpc_status_string", "gpc_set_stream", "gpc_synchronize",
            "gpc_read_forest", "gpc_set_forest", "gpc_match_pair", "gpc_match_batch", "gpc_match_batch_device",
            "gpc_preprocess", "gpc_hash", "gpc_match_hash_images", "gpc_launch_count", "gpc_enable_kernel_timing",
-           "gpc_kernel_times"]
+           "gpc_kernel_times", "gpc_hash_smooth", "gpc_image_upload", "gpc_image_release", "gpc_image_preprocess",
+           "gpc_match_images", "gpc_correspond_images", "gpc_find_correspondences", "gpc_set_matcher"]
 KERNEL_NAMES = ["preprocess_hash", "match_rows", "scans", "emit_supports"]
 
 
@@ -33,7 +36,7 @@ class GpcSettings(C.Structure):
 class GpcForest(C.Structure):
     _fields_ = [("n_tests", C.c_int32), ("type", C.c_int32), ("n_discarded", C.c_int32),
                 ("ix", C.c_int32 * 32), ("iy", C.c_int32 * 32), ("jx", C.c_int32 * 32), ("jy", C.c_int32 * 32),
-                ("tau", C.c_int32 * 32)]
+                ("tau", C.c_int32 * 32), ("n_ferns", C.c_int32)]
 
 
 class GpcError(RuntimeError):
@@ -61,6 +64,8 @@ def load_library():
     lib.gpc_launch_count.argtypes = [C.c_void_p]
     lib.gpc_destroy.restype = None
     lib.gpc_destroy.argtypes = [C.c_void_p]
+    lib.gpc_image_release.restype = None
+    lib.gpc_image_release.argtypes = [C.c_void_p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int:
@@ -234,3 +239,73 @@ class Context:
         self._check(self.lib.gpc_match_hash_images(self._h, _ptr(hash_l), _ptr(hash_r), w, h, C.byref(settings),
                                                    _ptr(out), C.c_int(cap), C.byref(n)))
         return out[:n.value].copy()
+
+    def hash_smooth(self, smooth, idx):
+        """evalFastMaskOnSubsetSSE on a caller-provided smoothed image: one state per idx entry."""
+        smooth = np.ascontiguousarray(smooth, np.uint8)
+        idx = np.ascontiguousarray(idx, np.int32)
+        h, w = smooth.shape
+        states = np.zeros(max(len(idx), 1), np.uint32)
+        self._check(self.lib.gpc_hash_smooth(self._h, _ptr(smooth), w, h, _ptr(idx), C.c_int(len(idx)), _ptr(states)))
+        return states[:len(idx)].copy()
+
+    def set_matcher(self, matcher):
+        self._check(self.lib.gpc_set_matcher(self._h, int(matcher)))
+
+    def find_correspondences(self, src_keys, tar_keys):
+        """findCorrespondences on explicit 64-bit keys -> int32 [n, 2] (src index, tar index)."""
+        src_keys = np.ascontiguousarray(src_keys, np.uint64)
+        tar_keys = np.ascontiguousarray(tar_keys, np.uint64)
+        cap = max(min(len(src_keys), len(tar_keys)), 1)
+        out = np.zeros((cap, 2), np.int32)
+        n = C.c_int(0)
+        self._check(self.lib.gpc_find_correspondences(self._h, _ptr(src_keys), C.c_int(len(src_keys)), _ptr(tar_keys),
+                                                      C.c_int(len(tar_keys)), _ptr(out), C.c_int(cap), C.byref(n)))
+        return out[:n.value].copy()
+
+    # ---- resident images ----------------------------------------------------------------------
+    def upload(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        handle = C.c_void_p()
+        self._check(self.lib.gpc_image_upload(self._h, _ptr(img), w, h, w, C.byref(handle)))
+        return ResidentImage(self, handle, w, h)
+
+    def match_images(self, left, right, settings, cap=None):
+        cap = max((left.w - 26) * (left.h - 26), 1) if cap is None else cap
+        out = np.empty(max(cap, 1), SUPPORT_DTYPE)
+        n, ncl, ncr = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._check(self.lib.gpc_match_images(self._h, left.handle, right.handle, C.byref(settings), _ptr(out), C.c_int(cap),
+                                              C.byref(n), C.byref(ncl), C.byref(ncr)))
+        return out[:n.value].copy(), ncl.value, ncr.value
+
+    def correspond_images(self, left, right, settings, cap=None):
+        cap = max((left.w - 26) * (left.h - 26), 1) if cap is None else cap
+        out = np.empty(max(cap, 1), CORR_DTYPE)
+        n = C.c_int(0)
+        self._check(self.lib.gpc_correspond_images(self._h, left.handle, right.handle, C.byref(settings), _ptr(out),
+                                                   C.c_int(cap), C.byref(n)))
+        return out[:n.value].copy()
+
+
+class ResidentImage:
+    """A raw image kept on the context's device (gpc_image_upload / gpc_image_release)."""
+
+    def __init__(self, ctx, handle, w, h):
+        self.ctx, self.handle, self.w, self.h = ctx, handle, w, h
+
+    def preprocess(self, thr):
+        smooth = np.empty((self.h, self.w), np.uint8)
+        grad = np.empty((self.h, self.w), np.uint8)
+        mask = np.empty(self.h * self.w, np.int32)
+        n = C.c_int(0)
+        self.ctx._check(self.ctx.lib.gpc_image_preprocess(self.ctx._h, self.handle, int(thr), _ptr(smooth), _ptr(grad),
+                                                          _ptr(mask), C.c_int(self.h * self.w), C.byref(n)))
+        return smooth, grad, mask[:n.value].copy()
+
+    def release(self):
+        if self.handle is not None and self.handle.value:
+            self.ctx.lib.gpc_image_release(self.handle)
+            self.handle = None
+
+    __del__ = release

@@ -14,7 +14,7 @@
 namespace gpc {
 size_t preprocess_smem_bytes();
 cudaError_t configure_preprocess_hash();
-cudaError_t launch_preprocess_hash(const PreprocessArgs&, const ForestDev&, int n_img, bool debug_out, cudaStream_t);
+cudaError_t launch_preprocess_hash(const PreprocessArgs&, const ForestDev&, int n_img, int mode, cudaStream_t);
 size_t match_smem_bytes(int wcap, int table_log2);
 cudaError_t configure_match_rows(int max_smem);
 cudaError_t launch_match_rows(const MatchArgs&, int n_pairs, cudaStream_t);
@@ -26,11 +26,21 @@ cudaError_t launch_emit_supports(const uint32_t* stage, const int32_t* rowmatch,
                                  cudaStream_t);
 cudaError_t launch_mask_list(const uint32_t* hash, const int32_t* rowcnt, int32_t* rowoff, int W, int H, int32_t* mask,
                              int cap, cudaStream_t);
+size_t global_workspace_bytes_padded(long long max_records, int key_bytes);
+cudaError_t launch_match_global(const uint32_t* hash_l, const uint32_t* hash_r, const int32_t* rowcnt, int32_t* rowoff2,
+                                int W, int H, int epipolar, int key_bits, int disp_high, int vertical_tolerance, int mode,
+                                void* ws, long long max_records, void* out, long long cap, int32_t* n_out,
+                                cudaStream_t stream, int* launches);
+cudaError_t launch_match_keys(void* ws, long long max_records, int ns, int nt, int key_bits, int32_t* out_pairs, long long cap,
+                              int32_t* n_out, cudaStream_t stream, int* launches);
+void* global_key_buffer(void* ws, long long max_records);
+int32_t* global_nside_ptr(void* ws);
 }  // namespace gpc
 
 static thread_local std::string g_create_error;
 
 struct gpc_ctx {
+  long long id = 0;
   int device = 0;
   int max_w = 0, max_h = 0, max_batch = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -54,6 +64,10 @@ struct gpc_ctx {
   // pinned host scratch for counts
   int32_t* h_counts = nullptr;     // totals [B] | ncand [2B]
   long long* h_pair_base = nullptr;  // [B+1]
+  void* d_gws = nullptr;           // radix-sort matcher workspace (lazily allocated)
+  long long gws_records = 0;
+  int32_t* d_rowoff2 = nullptr;    // [2][H] candidate offsets of the sort matcher (lazily allocated)
+  int matcher = GPC_MATCHER_AUTO;
   int64_t launches = 0;
   int match_smem_max = 0;
   // optional per-kernel timing (CUDA events on the launching stream), see gpc_kernel_times
@@ -63,6 +77,14 @@ struct gpc_ctx {
   double k_ms[GPC_N_KERNELS] = {0, 0, 0, 0};
   int64_t k_runs = 0;
   std::string err;
+};
+
+// A raw image resident on a context's device (Forest::PreprocessedImage's device side).
+struct gpc_image {
+  long long ctx_id = 0;       // serial of the owning context (a context pointer may be reused)
+  int device = 0;
+  uint8_t* d_raw = nullptr;   // [h][w], tightly packed
+  int w = 0, h = 0;
 };
 
 namespace {
@@ -123,7 +145,6 @@ int check_dims(gpc_ctx* c, int w, int h, int n_pairs) {
 int check_settings(gpc_ctx* c, const gpc_settings* s) {
   if (!s) return fail(c, GPC_E_ARG, "settings is NULL");
   if (s->use_hashtable) return fail(c, GPC_E_UNSUPPORTED, "useHashtable(true) is not supported (sort-path semantics only)");
-  if (!s->epipolar_mode) return fail(c, GPC_E_UNSUPPORTED, "epipolarMode(false) (global matching) is not implemented yet");
   if (s->gradient_threshold < 0 || s->gradient_threshold > 255)
     return fail(c, GPC_E_ARG, "gradientThreshold needs to be within 0...255");     // inference.hpp:303
   return GPC_OK;
@@ -137,24 +158,71 @@ int table_log2_for(int wcap) {
 
 // Kernel A over n_img resident images; clears and fills rowcnt / lastrow.
 int run_preprocess(gpc_ctx* c, const uint8_t* d_images, int n_img, int w, int h, int thr, const gpc::ForestDev& forest,
-                   uint8_t* d_smooth, uint8_t* d_grad) {
+                   uint8_t* d_smooth, uint8_t* d_grad, const uint8_t* d_flags = nullptr) {
   int32_t* rowcnt = c->d_rows;
   int32_t* lastrow = c->d_rows + (size_t)n_img * h;
   GPC_CUDA(c, cudaMemsetAsync(rowcnt, 0, (size_t)n_img * h * sizeof(int32_t), c->stream));
   GPC_CUDA(c, cudaMemsetAsync(lastrow, 0xff, (size_t)n_img * sizeof(int32_t), c->stream));   // -1
   gpc::PreprocessArgs a{};
   a.raw = d_images; a.hash = c->d_hash; a.rowcnt = rowcnt; a.lastrow = lastrow;
-  a.smooth_out = d_smooth; a.grad_out = d_grad; a.W = w; a.H = h;
+  a.smooth_out = d_smooth; a.grad_out = d_grad; a.flags = d_flags; a.W = w; a.H = h;
   a.thr2 = (int32_t)(int16_t)(thr * thr);                                          // filter.hpp:418
   int rc = mark(c); if (rc) return rc;                                             // event 0
-  GPC_CUDA(c, gpc::launch_preprocess_hash(a, forest, n_img, d_smooth || d_grad, c->stream));
+  const int mode = d_flags ? 2 : ((d_smooth || d_grad) ? 1 : 0);
+  GPC_CUDA(c, gpc::launch_preprocess_hash(a, forest, n_img, mode, c->stream));
   c->launches += 1;
   return mark(c);                                                                  // event 1
 }
 
+int ensure_global_ws(gpc_ctx* c, long long records) {
+  if (records > c->gws_records) {
+    if (c->d_gws) { GPC_CUDA(c, cudaStreamSynchronize(c->stream)); cudaFree(c->d_gws); c->d_gws = nullptr; c->gws_records = 0; }
+    GPC_CUDA(c, cudaMalloc(&c->d_gws, gpc::global_workspace_bytes_padded(records, 8)));
+    c->gws_records = records;
+  }
+  if (!c->d_rowoff2) GPC_CUDA(c, cudaMalloc(&c->d_rowoff2, 2 * (size_t)c->max_h * sizeof(int32_t)));
+  return GPC_OK;
+}
+
+// Radix-sort matcher (match_global.cu) for ONE pair whose hash images / rowcnt sit at index `p`.
+// mode 0: filtered supports, 1: unfiltered correspondences.  Output goes to d_out[0..cap), the
+// count to d_n_out[0].
+int run_match_sort_pair(gpc_ctx* c, const uint32_t* hash, int p, int w, int h, const gpc_settings* s, int mode, void* d_out,
+                        long long cap, int32_t* d_n_out, int32_t* d_n_cand) {
+  const size_t P = (size_t)w * h;
+  const long long records = 2ll * std::max(w - 2 * gpc::kRadius, 0) * std::max(h - 2 * gpc::kRadius, 0) + 2;
+  int rc = ensure_global_ws(c, records); if (rc) return rc;
+  int launches = 0;
+  GPC_CUDA(c, gpc::launch_match_global(hash + (size_t)(2 * p) * P, hash + (size_t)(2 * p + 1) * P, c->d_rows + (size_t)(2 * p) * h,
+                                       c->d_rowoff2, w, h, s->epipolar_mode ? 1 : 0, 31, s->disp_high, s->vertical_tolerance,
+                                       mode, c->d_gws, c->gws_records, d_out, cap, d_n_out, c->stream, &launches));
+  c->launches += launches;
+  if (d_n_cand)
+    GPC_CUDA(c, cudaMemcpyAsync(d_n_cand, gpc::global_nside_ptr(c->d_gws), 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+  return GPC_OK;
+}
+
+bool use_sort_matcher(const gpc_ctx* c, const gpc_settings* s) { return !s->epipolar_mode || c->matcher == GPC_MATCHER_SORT; }
+
 // Kernels B, scan, C over hash images already in c->d_hash (or `hash`).
 int run_match(gpc_ctx* c, const uint32_t* hash, int n_pairs, int w, int h, const gpc_settings* s, gpc_support* d_out,
               long long cap, bool packed, int32_t* d_n_out, int32_t* d_n_cand) {
+  if (use_sort_matcher(c, s)) {
+    // radix sort + segmented scan, pair by pair (strided output only; the packed host entry
+    // points run one pair at a time)
+    if (packed && n_pairs != 1) return fail(c, GPC_E_ARG, "internal: packed sort matcher handles one pair per call");
+    for (int k = 0; k < 2; k++) { int rc = mark(c); if (rc) return rc; }   // events 2, 3 (no row kernels here)
+    for (int p = 0; p < n_pairs; p++) {
+      int rc = run_match_sort_pair(c, hash, p, w, h, s, 0, d_out + (packed ? 0 : (size_t)p * cap), cap, d_n_out + p,
+                                   d_n_cand ? d_n_cand + 2 * p : nullptr);
+      if (rc) return rc;
+    }
+    if (packed) {
+      GPC_CUDA(c, gpc::launch_pair_scan(d_n_out, 1, c->d_pair_base, c->stream));
+      c->launches += 1;
+    }
+    return mark(c);                                                                // event 4
+  }
   const int32_t* rowcnt = c->d_rows;
   const int32_t* lastrow = c->d_rows + (size_t)(2 * n_pairs) * h;
   gpc::MatchArgs m{};
@@ -221,7 +289,9 @@ int gpc_create(gpc_ctx** out, int device, int max_w, int max_h, int max_batch) {
     return fail(nullptr, GPC_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
                                          " (libgpc_b200 has no CPU fallback)");
   if (device < 0 || device >= n_dev) return fail(nullptr, GPC_E_ARG, "device index out of range");
+  static long long next_id = 1;
   gpc_ctx* c = new gpc_ctx();
+  c->id = next_id++;
   c->device = device; c->max_w = max_w; c->max_h = max_h; c->max_batch = max_batch;
   auto bail = [&](const char* what, cudaError_t err) {
     std::string msg = std::string(what) + ": " + cudaGetErrorString(err);
@@ -264,7 +334,7 @@ void gpc_destroy(gpc_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->d_raw); cudaFree(c->d_hash); cudaFree(c->d_stage); cudaFree(c->d_rows); cudaFree(c->d_rowmatch);
   cudaFree(c->d_rowoff); cudaFree(c->d_totals); cudaFree(c->d_ncand); cudaFree(c->d_pair_base); cudaFree(c->d_out);
-  cudaFree(c->d_dbg8); cudaFree(c->d_mask);
+  cudaFree(c->d_dbg8); cudaFree(c->d_mask); cudaFree(c->d_gws); cudaFree(c->d_rowoff2);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->h_pair_base) cudaFreeHost(c->h_pair_base);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -325,6 +395,7 @@ int gpc_read_forest(const char* path, gpc_forest* out) {
   if (ff.fail()) return GPC_E_IO;
   int num_ferns = 0, nonzero = 0;
   ff >> num_ferns;
+  out->n_ferns = num_ferns;
   for (int i = 0; i < num_ferns && ff.good(); i++) {
     int id = 0, nt = 0;
     std::string scale;
@@ -384,6 +455,27 @@ int gpc_match_batch(gpc_ctx* c, const uint8_t* images, int n_pairs, int w, int h
   GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, images, 2 * (size_t)n_pairs * P, cudaMemcpyHostToDevice, c->stream));
   rc = run_preprocess(c, c->d_raw, 2 * n_pairs, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
   if (rc) return rc;
+  if (use_sort_matcher(c, s) && n_pairs > 1) {
+    // radix-sort matcher: one pair at a time, results appended on the host
+    long long total = 0;
+    offsets[0] = 0;
+    bool overflow = false;
+    for (int p = 0; p < n_pairs; p++) {
+      rc = run_match_sort_pair(c, c->d_hash, p, w, h, s, 0, c->d_out, c->out_cap, c->d_totals, c->d_ncand);
+      if (rc) return rc;
+      GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_totals, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+      GPC_CUDA(c, cudaMemcpyAsync(c->h_counts + 1, c->d_ncand, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+      GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+      const int n = c->h_counts[0];
+      if (n_cand) { n_cand[2 * p] = c->h_counts[1]; n_cand[2 * p + 1] = c->h_counts[2]; }
+      if (total + n > cap) overflow = true;
+      else if (n > 0) GPC_CUDA(c, cudaMemcpy(out + total, c->d_out, (size_t)n * sizeof(gpc_support), cudaMemcpyDeviceToHost));
+      total += n;
+      offsets[p + 1] = total;
+    }
+    if (overflow) return fail(c, GPC_E_CAPACITY, "support buffer too small: need " + std::to_string(total));
+    return GPC_OK;
+  }
   rc = run_match(c, c->d_hash, n_pairs, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
   if (rc) return rc;
   GPC_CUDA(c, cudaMemcpyAsync(c->h_pair_base, c->d_pair_base, (size_t)(n_pairs + 1) * sizeof(long long),
@@ -431,33 +523,17 @@ int gpc_match_pair(gpc_ctx* c, const uint8_t* left, const uint8_t* right, int w,
   return GPC_OK;
 }
 
+static int preprocess_device(gpc_ctx* c, const uint8_t* d_img, int w, int h, int thr, uint8_t* smooth, uint8_t* grad,
+                             int32_t* mask, int mask_cap, int* n_mask);
+
 int gpc_preprocess(gpc_ctx* c, const uint8_t* img, int w, int h, int thr, uint8_t* smooth, uint8_t* grad,
                    int32_t* mask, int mask_cap, int* n_mask) {
   if (!c || !img) return fail(c, GPC_E_ARG, "null argument");
   int rc = check_dims(c, w, h, 1); if (rc) return rc;
   if (thr < 0 || thr > 255) return fail(c, GPC_E_ARG, "gradientThreshold needs to be within 0...255");
   GPC_CUDA(c, cudaSetDevice(c->device));
-  rc = ensure_debug_buffers(c); if (rc) return rc;
-  const size_t P = (size_t)w * h;
-  GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, img, P, cudaMemcpyHostToDevice, c->stream));
-  gpc::ForestDev none{};                           // no tests: hash image carries the candidate flag only
-  uint8_t* d_smooth = c->d_dbg8;
-  uint8_t* d_grad = c->d_dbg8 + (size_t)c->max_w * c->max_h;
-  rc = run_preprocess(c, c->d_raw, 1, w, h, thr, none, d_smooth, d_grad);
-  if (rc) return rc;
-  GPC_CUDA(c, gpc::launch_mask_list(c->d_hash, c->d_rows, c->d_rowoff, w, h, c->d_mask, (int)std::min<size_t>(P, 0x7fffffff), c->stream));
-  c->launches += 2;
-  GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_rowoff + h, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-  if (smooth) GPC_CUDA(c, cudaMemcpyAsync(smooth, d_smooth, P, cudaMemcpyDeviceToHost, c->stream));
-  if (grad) GPC_CUDA(c, cudaMemcpyAsync(grad, d_grad, P, cudaMemcpyDeviceToHost, c->stream));
-  GPC_CUDA(c, cudaStreamSynchronize(c->stream));
-  const int n = c->h_counts[0];
-  if (n_mask) *n_mask = n;
-  if (mask) {
-    if (n > mask_cap) return fail(c, GPC_E_CAPACITY, "mask buffer too small: need " + std::to_string(n));
-    GPC_CUDA(c, cudaMemcpy(mask, c->d_mask, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  }
-  return GPC_OK;
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, img, (size_t)w * h, cudaMemcpyHostToDevice, c->stream));
+  return preprocess_device(c, c->d_raw, w, h, thr, smooth, grad, mask, mask_cap, n_mask);
 }
 
 int gpc_hash(gpc_ctx* c, const uint8_t* img, int w, int h, int thr, uint32_t* states, int32_t* mask, int cap, int* n,
@@ -519,6 +595,198 @@ int gpc_match_hash_images(gpc_ctx* c, const uint32_t* hash_l, const uint32_t* ha
   *n_out = c->h_counts[0];
   if (*n_out > cap) return fail(c, GPC_E_CAPACITY, "support buffer too small: need " + std::to_string(*n_out));
   if (*n_out > 0) GPC_CUDA(c, cudaMemcpy(out, c->d_out, (size_t)*n_out * sizeof(gpc_support), cudaMemcpyDeviceToHost));
+  return GPC_OK;
+}
+
+// ---- resident images (the device side of Forest::PreprocessedImage) ---------------------------
+int gpc_image_upload(gpc_ctx* c, const uint8_t* img, int w, int h, int stride, gpc_image** out) {
+  if (!c || !img || !out) return fail(c, GPC_E_ARG, "null argument");
+  *out = nullptr;
+  if (stride < w) return fail(c, GPC_E_ARG, "stride smaller than width");
+  int rc = check_dims(c, w, h, 1); if (rc) return rc;
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  gpc_image* im = new gpc_image();
+  im->ctx_id = c->id; im->device = c->device; im->w = w; im->h = h;
+  cudaError_t e = cudaMalloc(&im->d_raw, (size_t)w * h);
+  if (e == cudaSuccess) e = cudaMemcpy2DAsync(im->d_raw, w, img, stride, w, h, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // the caller's buffer may be pageable / short-lived
+  if (e != cudaSuccess) {
+    cudaFree(im->d_raw);
+    delete im;
+    return fail(c, GPC_E_CUDA, std::string("gpc_image_upload: ") + cudaGetErrorString(e));
+  }
+  *out = im;
+  return GPC_OK;
+}
+
+void gpc_image_release(gpc_image* im) {
+  if (!im) return;
+  cudaSetDevice(im->device);
+  cudaFree(im->d_raw);
+  delete im;
+}
+
+static int preprocess_device(gpc_ctx* c, const uint8_t* d_img, int w, int h, int thr, uint8_t* smooth, uint8_t* grad,
+                             int32_t* mask, int mask_cap, int* n_mask) {
+  int rc = ensure_debug_buffers(c); if (rc) return rc;
+  const size_t P = (size_t)w * h;
+  gpc::ForestDev none{};                           // no tests: hash image carries the candidate flag only
+  uint8_t* d_smooth = c->d_dbg8;
+  uint8_t* d_grad = c->d_dbg8 + (size_t)c->max_w * c->max_h;
+  rc = run_preprocess(c, d_img, 1, w, h, thr, none, d_smooth, d_grad);
+  if (rc) return rc;
+  GPC_CUDA(c, gpc::launch_mask_list(c->d_hash, c->d_rows, c->d_rowoff, w, h, c->d_mask, (int)std::min<size_t>(P, 0x7fffffff), c->stream));
+  c->launches += 2;
+  GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_rowoff + h, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (smooth) GPC_CUDA(c, cudaMemcpyAsync(smooth, d_smooth, P, cudaMemcpyDeviceToHost, c->stream));
+  if (grad) GPC_CUDA(c, cudaMemcpyAsync(grad, d_grad, P, cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int n = c->h_counts[0];
+  if (n_mask) *n_mask = n;
+  if (mask) {
+    if (n > mask_cap) return fail(c, GPC_E_CAPACITY, "mask buffer too small: need " + std::to_string(n));
+    GPC_CUDA(c, cudaMemcpy(mask, c->d_mask, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  }
+  return GPC_OK;
+}
+
+int gpc_image_preprocess(gpc_ctx* c, const gpc_image* im, int thr, uint8_t* smooth, uint8_t* grad, int32_t* mask,
+                         int mask_cap, int* n_mask) {
+  if (!c || !im || im->ctx_id != c->id) return fail(c, GPC_E_ARG, "image does not belong to this context");
+  int rc = check_dims(c, im->w, im->h, 1); if (rc) return rc;
+  if (thr < 0 || thr > 255) return fail(c, GPC_E_ARG, "gradientThreshold needs to be within 0...255");
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  return preprocess_device(c, im->d_raw, im->w, im->h, thr, smooth, grad, mask, mask_cap, n_mask);
+}
+
+int gpc_match_images(gpc_ctx* c, const gpc_image* l, const gpc_image* r, const gpc_settings* s, gpc_support* out, int cap,
+                     int* n_out, int* n_cand_l, int* n_cand_r) {
+  if (!c || !l || !r || !n_out || cap < 0 || (cap > 0 && !out)) return fail(c, GPC_E_ARG, "null argument");
+  if (l->ctx_id != c->id || r->ctx_id != c->id) return fail(c, GPC_E_ARG, "image does not belong to this context");
+  if (l->w != r->w || l->h != r->h) return fail(c, GPC_E_DIMS, "left and right image dimensions differ");   // inference.hpp:350-353
+  const int w = l->w, h = l->h;
+  int rc = check_dims(c, w, h, 1); if (rc) return rc;
+  rc = check_settings(c, s); if (rc) return rc;
+  if (!c->has_forest) return fail(c, GPC_E_FOREST, "no forest set");
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  const size_t P = (size_t)w * h;
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, l->d_raw, P, cudaMemcpyDeviceToDevice, c->stream));
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_raw + P, r->d_raw, P, cudaMemcpyDeviceToDevice, c->stream));
+  rc = run_preprocess(c, c->d_raw, 2, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
+  if (rc) return rc;
+  rc = run_match(c, c->d_hash, 1, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
+  if (rc) return rc;
+  GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_totals, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA(c, cudaMemcpyAsync(c->h_counts + 1, c->d_ncand, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  *n_out = c->h_counts[0];
+  if (n_cand_l) *n_cand_l = c->h_counts[1];
+  if (n_cand_r) *n_cand_r = c->h_counts[2];
+  if (*n_out > cap) return fail(c, GPC_E_CAPACITY, "support buffer too small: need " + std::to_string(*n_out));
+  if (*n_out > 0) {
+    GPC_CUDA(c, cudaMemcpyAsync(out, c->d_out, (size_t)*n_out * sizeof(gpc_support), cudaMemcpyDeviceToHost, c->stream));
+    GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return GPC_OK;
+}
+
+// Forest::evalFastMaskOnSubsetSSE (inference.hpp:266-292) on a caller-provided smoothed image:
+// states[i] = state of pixel idx[i] (= y*w + x).  Entries outside the 13-pixel border, where
+// the reference reads across row ends, and rows H-15.. (never hashed, filter.hpp:601-604) give 0.
+int gpc_hash_smooth(gpc_ctx* c, const uint8_t* smooth, int w, int h, const int32_t* idx, int n, uint32_t* states) {
+  if (!c || !smooth || n < 0 || (n > 0 && (!idx || !states))) return fail(c, GPC_E_ARG, "null argument");
+  int rc = check_dims(c, w, h, 1); if (rc) return rc;
+  if (!c->has_forest) return fail(c, GPC_E_FOREST, "no forest set");
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  rc = ensure_debug_buffers(c); if (rc) return rc;
+  const size_t P = (size_t)w * h;
+  std::vector<uint8_t> flags(P, 0);
+  for (int i = 0; i < n; i++) {
+    if (idx[i] < 0 || (size_t)idx[i] >= P) return fail(c, GPC_E_ARG, "candidate index outside the image");
+    flags[(size_t)idx[i]] = 255;
+  }
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, smooth, P, cudaMemcpyHostToDevice, c->stream));
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_dbg8, flags.data(), P, cudaMemcpyHostToDevice, c->stream));
+  rc = run_preprocess(c, c->d_raw, 1, w, h, 0, c->forest_dev, nullptr, nullptr, c->d_dbg8);
+  if (rc) return rc;
+  std::vector<uint32_t> himg(P);
+  GPC_CUDA(c, cudaMemcpyAsync(himg.data(), c->d_hash, P * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < n; i++) states[i] = himg[(size_t)idx[i]] & 0x7fffffffu;
+  return GPC_OK;
+}
+
+int gpc_set_matcher(gpc_ctx* c, int matcher) {
+  if (!c) return GPC_E_ARG;
+  if (matcher != GPC_MATCHER_AUTO && matcher != GPC_MATCHER_SORT) return fail(c, GPC_E_ARG, "unknown matcher");
+  c->matcher = matcher;
+  return GPC_OK;
+}
+
+// Forest::stereoMatch (inference.hpp:344-361): every unique-unique correspondence, before the
+// rectifiedMatch filter, in ascending key order.  Always runs the radix-sort matcher.
+int gpc_correspond_images(gpc_ctx* c, const gpc_image* l, const gpc_image* r, const gpc_settings* s,
+                          gpc_correspondence* out, int cap, int* n_out) {
+  if (!c || !l || !r || !n_out || cap < 0 || (cap > 0 && !out)) return fail(c, GPC_E_ARG, "null argument");
+  if (l->ctx_id != c->id || r->ctx_id != c->id) return fail(c, GPC_E_ARG, "image does not belong to this context");
+  if (l->w != r->w || l->h != r->h) return fail(c, GPC_E_DIMS, "left and right image dimensions differ");
+  const int w = l->w, h = l->h;
+  int rc = check_dims(c, w, h, 1); if (rc) return rc;
+  rc = check_settings(c, s); if (rc) return rc;
+  if (!c->has_forest) return fail(c, GPC_E_FOREST, "no forest set");
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  const size_t P = (size_t)w * h;
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, l->d_raw, P, cudaMemcpyDeviceToDevice, c->stream));
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_raw + P, r->d_raw, P, cudaMemcpyDeviceToDevice, c->stream));
+  rc = run_preprocess(c, c->d_raw, 2, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
+  if (rc) return rc;
+  // a correspondence is 16 bytes, a support 12: d_out holds out_cap * 12 / 16 correspondences
+  const long long dcap = c->out_cap * 12 / 16;
+  rc = run_match_sort_pair(c, c->d_hash, 0, w, h, s, 1, c->d_out, dcap, c->d_totals, nullptr);
+  if (rc) return rc;
+  GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_totals, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  *n_out = c->h_counts[0];
+  if (*n_out > cap || *n_out > dcap) return fail(c, GPC_E_CAPACITY, "correspondence buffer too small: need " + std::to_string(*n_out));
+  if (*n_out > 0) GPC_CUDA(c, cudaMemcpy(out, c->d_out, (size_t)*n_out * sizeof(gpc_correspondence), cudaMemcpyDeviceToHost));
+  return GPC_OK;
+}
+
+// Forest::findCorrespondences (inference.hpp:227-254) on explicit 64-bit keys.  out_pairs[2i],
+// out_pairs[2i+1] = indices into src / tar (original order) of match i, ascending src key.
+int gpc_find_correspondences(gpc_ctx* c, const uint64_t* src_keys, int n_src, const uint64_t* tar_keys, int n_tar,
+                             int32_t* out_pairs, int cap, int* n_out) {
+  if (!c || !n_out || n_src < 0 || n_tar < 0 || cap < 0 || (cap > 0 && !out_pairs)) return fail(c, GPC_E_ARG, "null argument");
+  *n_out = 0;
+  if (n_src == 0 || n_tar == 0) return GPC_OK;                 // len(tar) == 0 is UB in the reference; defined as no matches
+  if (!src_keys || !tar_keys) return fail(c, GPC_E_ARG, "null argument");
+  if ((long long)n_src + n_tar >= 0x7fffffffll) return fail(c, GPC_E_DIMS, "too many descriptors");
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  const long long n = (long long)n_src + n_tar;
+  int rc = ensure_global_ws(c, n + 2); if (rc) return rc;
+  uint64_t kmax = 0;
+  for (int i = 0; i < n_src; i++) kmax = std::max(kmax, src_keys[i]);
+  for (int i = 0; i < n_tar; i++) kmax = std::max(kmax, tar_keys[i]);
+  int key_bits = 8;
+  while (key_bits < 64 && (kmax >> key_bits) != 0) key_bits += 8;
+  uint64_t* d_keys = reinterpret_cast<uint64_t*>(gpc::global_key_buffer(c->d_gws, c->gws_records));
+  GPC_CUDA(c, cudaMemcpyAsync(d_keys, src_keys, (size_t)n_src * 8, cudaMemcpyHostToDevice, c->stream));
+  GPC_CUDA(c, cudaMemcpyAsync(d_keys + n_src, tar_keys, (size_t)n_tar * 8, cudaMemcpyHostToDevice, c->stream));
+  const long long need = std::min<long long>(n_src, n_tar);
+  int32_t* d_pairs = nullptr;
+  GPC_CUDA(c, cudaMalloc(&d_pairs, (size_t)std::max<long long>(need, 1) * 2 * sizeof(int32_t)));
+  int launches = 0;
+  cudaError_t e = gpc::launch_match_keys(c->d_gws, c->gws_records, n_src, n_tar, key_bits, d_pairs, need, c->d_totals, c->stream, &launches);
+  c->launches += launches;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_counts, c->d_totals, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess) {
+    *n_out = c->h_counts[0];
+    if (*n_out <= cap && *n_out > 0) e = cudaMemcpy(out_pairs, d_pairs, (size_t)*n_out * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d_pairs);
+  if (e != cudaSuccess) return fail(c, GPC_E_CUDA, std::string("gpc_find_correspondences: ") + cudaGetErrorString(e));
+  if (*n_out > cap) return fail(c, GPC_E_CAPACITY, "pair buffer too small: need " + std::to_string(*n_out));
   return GPC_OK;
 }
 

@@ -46,6 +46,7 @@ struct PreprocessArgs {
   int32_t* lastrow;        // [n_img]
   uint8_t* smooth_out;     // optional [n_img][H][W]
   uint8_t* grad_out;       // optional [n_img][H][W]
+  const uint8_t* flags;    // mode 2 only: [n_img][H][W], non-zero = hash this pixel
   int32_t W, H;
   int32_t thr2;            // (int16)(thr*thr), filter.hpp:418
 };

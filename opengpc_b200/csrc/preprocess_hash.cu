@@ -53,9 +53,13 @@ __device__ __forceinline__ uint32_t eval_test(const uint8_t* base, const ForestD
   return (a & c) | ((a ^ c) & s);                                          // msb: a7 > b'7, or equal and low7(a) > low7(b')
 }
 
-template <bool kDebugOut>
+// kMode 0: product path.  1: also writes smooth / grad (stage-parity seam gpc_preprocess).
+// 2: evalFastMaskOnSubsetSSE seam (gpc_hash_smooth): args.raw is an already smoothed image and
+//    args.flags a u8 image whose non-zero bytes mark the pixels to hash; phases 1-2 are skipped.
+template <int kMode>
 __global__ void __launch_bounds__(kThreadsA)
 preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
+  constexpr bool kDebugOut = (kMode == 1);
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* raw32 = reinterpret_cast<uint32_t*>(smem);                          // [kRawRows][kPitchW]
   uint32_t* sm32 = raw32 + kRawRows * kPitchW;                                  // [kSmRows][kPitchW]
@@ -69,7 +73,38 @@ preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
   const uint8_t* __restrict__ raw = args.raw + img_off;
 
   // ---- phase 0: stage the raw tile (zero outside the image) --------------------------------
-  {
+  if (kMode == 2) {
+    constexpr int kChunks = kPitch / 16;
+    uint4* dst = reinterpret_cast<uint4*>(sm32);
+    for (int c = tid; c < kSmRows * kChunks; c += kThreadsA) {
+      int r = c / kChunks, k = c - r * kChunks;
+      int gy = y0 - kRadius + r, gx = x0 - 16 + 16 * k;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+        v = __ldg(reinterpret_cast<const uint4*>(raw + (size_t)gy * W + gx));
+      dst[c] = v;
+    }
+    const uint8_t* __restrict__ flags = args.flags + img_off;
+    for (int sr = tid; sr < kTileH * (kTileW / 16); sr += kThreadsA) {
+      const int ry = sr / (kTileW / 16), sg = sr - ry * (kTileW / 16);
+      const int gy = y0 + ry, gxs = x0 + 16 * sg;
+      uint32_t m = 0;
+      if (gy >= kRadius && gy < H - kRadius && gxs < W) {
+        const uint4 f = __ldg(reinterpret_cast<const uint4*>(flags + (size_t)gy * W + gxs));
+        const uint32_t wv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+          for (int b = 0; b < 4; b++)
+            if ((wv[k] >> (8 * b)) & 0xffu) m |= 1u << (4 * k + b);
+        const int lowcut = kRadius - gxs;
+        if (lowcut >= 16) m = 0; else if (lowcut > 0) m &= ~((1u << lowcut) - 1u);
+        const int keep = W - kRadius - gxs;
+        if (keep <= 0) m = 0; else if (keep < 16) m &= (1u << keep) - 1u;
+      }
+      cand[sr] = (uint16_t)m;
+    }
+  } else {
     constexpr int kChunks = kPitch / 16;
     uint4* dst = reinterpret_cast<uint4*>(smem);
     for (int c = tid; c < kRawRows * kChunks; c += kThreadsA) {
@@ -81,12 +116,12 @@ preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
       dst[c] = v;
     }
   }
-  __syncthreads();
+  if (kMode != 2) __syncthreads();
 
   // ---- phase 1: smoothed tile -----------------------------------------------------------------
   // thread = (quad column, one of 3 row segments); walks down its rows with a 3-row window of
   // horizontal thirds held in registers.
-  {
+  if (kMode != 2) {
     constexpr int kSegs = 3;
     constexpr int kSegRows = (kSmRows + kSegs - 1) / kSegs;
     const int q = tid % kPitchW, seg = tid / kPitchW;
@@ -124,7 +159,7 @@ preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
   }
 
   // ---- phase 2: Sobel predicate per 16-pixel segment -> candidate bit masks -----------------
-  {
+  if (kMode != 2) {
     const uint8_t* raw8 = smem;
     for (int sr = tid; sr < kTileH * (kTileW / 16); sr += kThreadsA) {
       const int ry = sr / (kTileW / 16), sg = sr - ry * (kTileW / 16);
@@ -225,19 +260,22 @@ size_t preprocess_smem_bytes() {
 
 cudaError_t configure_preprocess_hash() {   // per device: opt in to > 48 KB dynamic shared memory
   int smem = (int)preprocess_smem_bytes();
-  cudaError_t e = cudaFuncSetAttribute(preprocess_hash_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(preprocess_hash_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(preprocess_hash_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(preprocess_hash_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(preprocess_hash_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  return e;
 }
 
 cudaError_t launch_preprocess_hash(const PreprocessArgs& args, const ForestDev& forest, int n_img,
-                                   bool debug_out, cudaStream_t stream) {
+                                   int mode, cudaStream_t stream) {
   size_t smem = preprocess_smem_bytes();
   dim3 grid((args.W + kTileW - 1) / kTileW, (args.H + kTileH - 1) / kTileH, n_img);
-  if (debug_out)
-    preprocess_hash_kernel<true><<<grid, kThreadsA, smem, stream>>>(args, forest);
+  if (mode == 2)
+    preprocess_hash_kernel<2><<<grid, kThreadsA, smem, stream>>>(args, forest);
+  else if (mode == 1)
+    preprocess_hash_kernel<1><<<grid, kThreadsA, smem, stream>>>(args, forest);
   else
-    preprocess_hash_kernel<false><<<grid, kThreadsA, smem, stream>>>(args, forest);
+    preprocess_hash_kernel<0><<<grid, kThreadsA, smem, stream>>>(args, forest);
   return cudaGetLastError();
 }
 

@@ -147,6 +147,20 @@ class Oracle:
                                 C.c_int(len(mask_r)), C.c_int(w), C.byref(s), None, None, _p(supp))
         return supp[:n].copy()
 
+    def correspondences(self, Lm, Rm, forest, s):
+        """stereoMatch: every unique-unique correspondence (xs, ys, xt, yt) before the filter."""
+        h, w = Lm.shape
+        thr = s.gradient_threshold
+        _, _, mkl, stl = self.stages(Lm, forest, thr)
+        _, _, mkr, str_ = self.stages(Rm, forest, thr)
+        cap = max(min(len(mkl), len(mkr)), 1)
+        corr = np.empty((cap, 4), np.int32)
+        supp = np.empty(cap, SUPPORT_DTYPE)
+        nc = C.c_int(0)
+        self.lib.gpco_match(_p(mkl), _p(stl), C.c_int(len(mkl)), _p(mkr), _p(str_), C.c_int(len(mkr)), C.c_int(w),
+                            C.byref(s), _p(corr), C.byref(nc), _p(supp))
+        return corr[:nc.value].copy()
+
     def pair(self, Lm, Rm, forest, s):
         h, w = Lm.shape
         supp = np.empty(max((w - 26) * (h - 26), 1), SUPPORT_DTYPE)

@@ -1,0 +1,131 @@
+"""The drop-in C++ API (include/gpc/{inference,buffer}.hpp): builds on CPU, results on the GPU."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from helpers import FORESTS
+from oraclelib import ROOT, settings as osettings
+
+API_TEST = os.path.join(ROOT, "tests", "cpp", "api_test")
+SPARSEMATCH = os.path.join(ROOT, "samples", "sparsematch")
+
+
+def _build():
+    from opengpc_b200.build import build_native
+    build_native()
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "samples")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def _write_png(path, arr):
+    from PIL import Image
+    Image.fromarray(arr).save(path)
+
+
+def test_cpp_host_builds():
+    """sparsematch, api_test and the PNG codec compile against the drop-in headers; the reference's
+    own samples/sparsematch.cpp compiles UNCHANGED against them where the tree is present."""
+    _build()
+    assert os.path.exists(API_TEST) and os.path.exists(SPARSEMATCH)
+    ref_src = "/root/reference/samples/sparsematch.cpp"
+    if os.path.exists(ref_src):
+        with tempfile.TemporaryDirectory() as d:
+            r = subprocess.run(["g++", "-std=c++11", "-w", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "sm"), ref_src,
+                                "-L" + os.path.join(ROOT, "opengpc_b200"), "-lgpc_b200", "-lz", "-lpthread"],
+                               capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+
+
+def test_png_codec_roundtrip():
+    """readPNG: gray8 as is, RGB -> (r+g+b)/3, gray16 truncated to the low byte (buffer.hpp:280-299),
+    width padded to a multiple of 16; writePNG output is readable by an independent decoder."""
+    from PIL import Image
+    rng = np.random.default_rng(1)
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "png_test")
+        r = subprocess.run(["g++", "-std=c++11", "-O1", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                            os.path.join(ROOT, "tests", "cpp", "png_test.cpp"), "-lz"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        gray = rng.integers(0, 256, (37, 50), dtype=np.uint8)
+        rgb = rng.integers(0, 256, (20, 33, 3), dtype=np.uint8)
+        g16 = rng.integers(0, 65536, (9, 16), dtype=np.uint16)
+        cases = {"gray": (gray, gray), "rgb": (rgb, (rgb.astype(np.int32).sum(2) // 3).astype(np.uint8)),
+                 "g16": (g16, (g16 & 0xff).astype(np.uint8))}
+        for name, (src, want) in cases.items():
+            pin, pout, praw = (os.path.join(d, f"{name}{e}") for e in (".png", "_out.png", ".raw"))
+            if name == "g16":
+                Image.fromarray(src).save(pin)        # mode I;16
+            else:
+                Image.fromarray(src).save(pin)
+            r = subprocess.run([exe, pin, pout, praw], capture_output=True, text=True)
+            assert r.returncode == 0, (name, r.returncode, r.stdout)
+            raw = np.fromfile(praw, np.uint8)
+            w, h, cols = np.frombuffer(raw[:12].tobytes(), np.int32)
+            assert (w, h) == (want.shape[1], want.shape[0]) and cols % 16 == 0
+            buf = raw[12:].reshape(h, cols)
+            assert np.array_equal(buf[:, :w], want), name
+            assert not buf[:, w:].any()
+            back = np.array(Image.open(pout))
+            assert np.array_equal(back, want), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("forest,epipolar,vt,dh,thr,w,h", [("tau", 1, 0, 128, 5, 1024, 436), ("zero", 1, 0, 128, 5, 640, 200),
+                                                          ("tau", 0, 1, 128, 10, 512, 160), ("deep", 1, 0, 64, 5, 500, 130)])
+def test_cpp_api_vs_oracle(oracle, forest, epipolar, vt, dh, thr, w, h):
+    """preprocessImage / rectifiedMatch / stereoMatch / evalFastMaskOnSubsetSSE / findCorrespondences through
+    the C++ headers, on PNG inputs (width 500 exercises the 16-pixel padding), against the oracle."""
+    from opengpc_b200.synth import synth_pair
+    _build()
+    wa = (w + 15) // 16 * 16
+    L, R = synth_pair(wa, h, 4321)
+    L, R = np.ascontiguousarray(L[:, :w]), np.ascontiguousarray(R[:, :w])
+    Lp, Rp = np.zeros((h, wa), np.uint8), np.zeros((h, wa), np.uint8)      # what readPNG hands the library
+    Lp[:, :w], Rp[:, :w] = L, R
+    of = oracle.read_forest(FORESTS[forest])
+    s = osettings(thr, dh, vt, bool(epipolar))
+    with tempfile.TemporaryDirectory() as d:
+        pl, pr, pout = (os.path.join(d, n) for n in ("l.png", "r.png", "out.bin"))
+        _write_png(pl, L); _write_png(pr, R)
+        r = subprocess.run([API_TEST, FORESTS[forest], pl, pr, pout, str(epipolar), str(vt), str(dh), str(thr)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
+        if forest == "deep":
+            assert r.stdout.count("Note: A maximum of 32 fern features") == 160
+        assert "number of ferns:" in r.stdout
+        v = np.fromfile(pout, np.int32)
+    nL, nR, nS, nC, nS2, nD = v[:6]
+    p = 6
+    maskL = v[p:p + nL]; p += nL
+    maskR = v[p:p + nR]; p += nR
+    supp = v[p:p + 3 * nS].reshape(-1, 3); p += 3 * nS
+    corr = v[p:p + 4 * nC].reshape(-1, 4); p += 4 * nC
+    supp2 = v[p:p + 3 * nS2].reshape(-1, 3); p += 3 * nS2
+    states = v[p:p + nD].view(np.uint32)
+    _, _, omkL, ostL = oracle.stages(Lp, of, thr)
+    _, _, omkR, _ = oracle.stages(Rp, of, thr)
+    assert np.array_equal(maskL, omkL) and np.array_equal(maskR, omkR)
+    assert np.array_equal(states, ostL)
+    ref, _, _ = oracle.pair(Lp, Rp, of, s)
+    want = np.stack([ref["x"], ref["y"], ref["d"].astype(np.int32)], 1)
+    assert np.array_equal(supp, want)
+    assert np.array_equal(supp2, want), "hand-built PreprocessedImage path differs"
+    assert np.array_equal(corr, oracle.correspondences(Lp, Rp, of, s))
+
+
+@pytest.mark.gpu
+def test_sparsematch_cli(oracle):
+    from opengpc_b200.synth import synth_pair
+    _build()
+    L, R = synth_pair(1024, 436, 1234)
+    with tempfile.TemporaryDirectory() as d:
+        pl, pr, po = (os.path.join(d, n) for n in ("l.png", "r.png", "disp.png"))
+        _write_png(pl, L); _write_png(pr, R)
+        r = subprocess.run([SPARSEMATCH, FORESTS["tau"], pl, pr, po, "3"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "#candidatesL:377030, #candidatesR:378097" in r.stdout and "num matches:40839" in r.stdout, r.stdout
+        from PIL import Image
+        assert np.array(Image.open(po)).shape == (436, 1024, 3)

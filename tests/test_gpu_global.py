@@ -1,0 +1,160 @@
+"""GPU parity tests of the rows added after the first slice: global matching mode (radix sort +
+segmented scan), the sort matcher cross-checked against the per-row matcher, explicit-key
+findCorrespondences, evalFastMaskOnSubsetSSE on a caller's smoothed image, resident images."""
+import numpy as np
+import pytest
+
+from helpers import FORESTS, make_pair, supp_to_i32
+from oraclelib import settings as osettings
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def g():
+    import opengpc_b200
+    return opengpc_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(g):
+    with g.Context(device=0, max_w=1024, max_h=436, max_batch=3) as c:
+        yield c
+
+
+def test_global_mode_small_cases(g, ctx, small_cases):
+    """Fixtures generated from the compiled reference with epipolarMode(false)."""
+    from helpers import write_forest
+    n = 0
+    for name, c in small_cases.items():
+        thr, epi, vt, dh = (int(v) for v in c["cfg"])
+        if epi:
+            continue
+        ctx.set_forest(write_forest(c["forest"]))
+        supp, ncl, ncr = ctx.match_pair(c["L"], c["R"], g.make_settings(thr=thr, disp_high=dh, vt=vt, epipolar=False))
+        assert (ncl, ncr) == (len(c["maskL"]), len(c["maskR"]))
+        assert np.array_equal(supp_to_i32(supp), c["supp"].reshape(-1, 3)), name
+        n += 1
+    assert n >= 1
+
+
+@pytest.mark.parametrize("forest", ["tau", "zero", "deep"])
+def test_global_mode_vs_oracle(g, ctx, oracle, forest):
+    """Library default settings (inference.hpp:74-89: global mode, vt=1, thr=10) and variations."""
+    from opengpc_b200.synth import sparsify, synth_pair
+    of = oracle.read_forest(FORESTS[forest])
+    ctx.set_forest(FORESTS[forest])
+    for (w, h, seed, thr, dh, vt, sparse) in [(1024, 436, 1234, 10, 128, 1, False), (512, 200, 7, 5, 64, 0, False),
+                                              (640, 120, 9, 5, 128, 3, True), (256, 64, 3, 0, 1000, 100, False)]:
+        L, R = synth_pair(w, h, seed)
+        if sparse:
+            L, R = sparsify(L), sparsify(R)
+        ref, ocl, ocr = oracle.pair(L, R, of, osettings(thr, dh, vt, False))
+        supp, ncl, ncr = ctx.match_pair(L, R, g.make_settings(thr=thr, disp_high=dh, vt=vt, epipolar=False))
+        assert (ncl, ncr) == (ocl, ocr)
+        assert np.array_equal(supp, ref), (forest, w, h, len(supp), len(ref))
+
+
+def test_golden_global(g, golden, oracle):
+    recs = [r for r in golden["pairs"] if not r["epipolar"]]
+    if not recs:
+        pytest.skip("no global-mode golden records")
+    for rec in recs:
+        L, R = make_pair(rec)
+        with g.Context(device=0, max_w=rec["w"], max_h=rec["h"], max_batch=1) as c:
+            c.set_forest(FORESTS[rec["forest"]])
+            supp, ncl, ncr = c.match_pair(L, R, g.make_settings(thr=5, disp_high=rec["disp_high"], vt=rec["vt"], epipolar=False))
+        assert (ncl, ncr, len(supp)) == (rec["n_cand_l"], rec["n_cand_r"], rec["n_supports"]), rec
+        assert "%016x" % oracle.digest(supp) == rec["digest"], rec
+
+
+def test_sort_matcher_equals_row_matcher(g, ctx, oracle):
+    """Epipolar mode through the radix-sort matcher (64-bit keys y<<32|state) must give exactly the
+    per-row matcher's result -- two independent implementations of inference.hpp:227-254."""
+    from opengpc_b200.synth import sparsify, synth_batch
+    imgs = synth_batch(1024, 436, 3, seed0=1234)
+    imgs[1, 0], imgs[1, 1] = sparsify(imgs[1, 0]), sparsify(imgs[1, 1])
+    s = g.sparsematch_settings()
+    for forest in ("tau", "zero"):
+        ctx.set_forest(FORESTS[forest])
+        ctx.set_matcher(g.MATCHER_AUTO)
+        a, oa, na = ctx.match_batch(imgs, s)
+        ctx.set_matcher(g.MATCHER_SORT)
+        try:
+            b, ob, nb = ctx.match_batch(imgs, s)
+        finally:
+            ctx.set_matcher(g.MATCHER_AUTO)
+        assert np.array_equal(oa, ob) and np.array_equal(na, nb)
+        assert np.array_equal(a, b), forest
+    of = oracle.read_forest(FORESTS["zero"])
+    ref, _, _ = oracle.pair(imgs[2, 0], imgs[2, 1], of, osettings())
+    assert np.array_equal(b[ob[2]:ob[3]], ref)
+
+
+def test_find_correspondences_kats_and_random(g, ctx, golden, oracle):
+    for kat in golden["kats"]:
+        got = ctx.find_correspondences(kat["src"], kat["tar"])
+        assert got.tolist() == [list(p) for p in kat["pairs"]], kat
+    rng = np.random.default_rng(5)
+    for it in range(8):
+        ns, nt = int(rng.integers(1, 4000)), int(rng.integers(1, 4000))
+        hi = int(rng.choice([8, 200, 5000, 1 << 20]))
+        src = rng.integers(0, hi, ns).astype(np.uint64)
+        tar = rng.integers(0, hi, nt).astype(np.uint64)
+        if it % 2:
+            src |= rng.integers(0, 300, ns).astype(np.uint64) << np.uint64(32)      # epipolar-style 64-bit keys
+            tar |= rng.integers(0, 300, nt).astype(np.uint64) << np.uint64(32)
+        if it == 3:
+            tar[-1] = tar.max() + np.uint64(1)                                        # unique last key: never matches
+            src[0] = tar[-1]
+        if it == 5:
+            tar[:2] = tar.max() + np.uint64(1)                                        # tail-dup-2
+            src[0] = tar[0]
+        want = oracle.find_correspondences(src, tar)
+        got = ctx.find_correspondences(src, tar)
+        assert np.array_equal(got, want), (it, len(got), len(want))
+    assert len(ctx.find_correspondences([1, 2], [])) == 0
+    assert len(ctx.find_correspondences([1], [1])) == 0
+
+
+def test_hash_smooth_seam(g, ctx, oracle):
+    """gpc_hash_smooth == gpcFilter / gpcFilterTau on a caller-provided smoothed image and index list."""
+    rng = np.random.default_rng(3)
+    for forest in ("tau", "zero", "deep"):
+        of = oracle.read_forest(FORESTS[forest])
+        ctx.set_forest(FORESTS[forest])
+        smooth = rng.integers(0, 256, (90, 272), dtype=np.uint8)     # any image, not necessarily a box-filter output
+        ys, xs = np.meshgrid(np.arange(13, 90 - 13), np.arange(13, 272 - 13), indexing="ij")
+        idx = (ys * 272 + xs).reshape(-1)
+        idx = idx[rng.random(len(idx)) < 0.4].astype(np.int32)
+        want = oracle.hash(smooth, of, idx)
+        got = ctx.hash_smooth(smooth, idx)
+        assert np.array_equal(got, want), forest
+        perm = rng.permutation(len(idx))                              # order of idx is the caller's
+        assert np.array_equal(ctx.hash_smooth(smooth, idx[perm]), want[perm])
+
+
+def test_resident_images(g, ctx, oracle):
+    from opengpc_b200.synth import synth_pair
+    L, R = synth_pair(768, 200, 77)
+    of = oracle.read_forest(FORESTS["tau"])
+    ctx.set_forest(FORESTS["tau"])
+    il, ir = ctx.upload(L), ctx.upload(R)
+    sm, gr, mk = il.preprocess(5)
+    osm, ogr, omk, _ = oracle.stages(L, of, 5)
+    assert np.array_equal(sm, osm) and np.array_equal(gr, ogr) and np.array_equal(mk, omk)
+    for epi, vt in ((True, 0), (False, 1)):
+        s = g.make_settings(thr=5, disp_high=128, vt=vt, epipolar=epi)
+        ref, ocl, ocr = oracle.pair(L, R, of, osettings(5, 128, vt, epi))
+        supp, ncl, ncr = ctx.match_images(il, ir, s)
+        assert (ncl, ncr) == (ocl, ocr) and np.array_equal(supp, ref)
+        corr = ctx.correspond_images(il, ir, s)
+        want = oracle.correspondences(L, R, of, osettings(5, 128, vt, epi))
+        got = np.stack([corr["xs"], corr["ys"], corr["xt"], corr["yt"]], 1)
+        assert np.array_equal(got, want), (epi, len(got), len(want))
+    il.release(); ir.release()
+    with g.Context(device=0, max_w=768, max_h=200, max_batch=1) as other:
+        io = other.upload(L)
+        with pytest.raises(g.GpcError):
+            ctx.match_images(io, io, g.sparsematch_settings())        # image of another context
+        io.release()
