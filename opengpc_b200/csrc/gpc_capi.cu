@@ -113,23 +113,29 @@ int mark(gpc_ctx* c) {
   return GPC_OK;
 }
 
-int floordiv4(int v) { return (v >= 0) ? v / 4 : -((-v + 3) / 4); }
-
-// Bake the forest for the kernel's shared-memory tile pitch (the reference bakes it for the
-// image width instead, inference.hpp:427-428).
+// Bake the forest for the kernel's shared-memory layout (the reference bakes it for the image
+// width instead, inference.hpp:427-428): see ForestDev.
 void bake_forest(const gpc_forest& f, gpc::ForestDev* d) {
   std::memset(d, 0, sizeof(*d));
   d->n_tests = f.n_tests;
   d->type = f.type;
+  auto imm = [](int dx, int dy) {
+    const int o = dy * gpc::kPitch + dx;
+    const int k = ((o % 4) + 4) % 4;
+    return k * gpc::kCopyBytes + (o - k);
+  };
   for (int t = 0; t < f.n_tests; t++) {
-    int oa = f.iy[t] * gpc::kPitch + f.ix[t], ob = f.jy[t] * gpc::kPitch + f.jx[t];
-    d->off_a[t] = 4 * floordiv4(oa);
-    d->off_b[t] = 4 * floordiv4(ob);
-    d->sh_a[t] = (uint32_t)(8 * (oa - 4 * floordiv4(oa)));
-    d->sh_b[t] = (uint32_t)(8 * (ob - 4 * floordiv4(ob)));
+    d->imm_a[t] = imm(f.ix[t], f.iy[t]);
+    d->imm_b[t] = imm(f.jx[t], f.jy[t]);
     int tau8 = (int)(int8_t)f.tau[t];                        // _mm_set1_epi8(tau): low 8 bits, signed
     uint32_t m = (uint32_t)(uint16_t)(int16_t)(-tau8);
     d->mtau2[t] = (f.type == 1) ? (m | (m << 16)) : 0u;
+  }
+  // tests beyond n_tests compare a pixel with itself: never true, state bit 0 (kernel A evaluates
+  // whole groups of tests without per-test guards); imm 0 = the quad's own word in copy 0
+  for (int t = 0; t < gpc::kMaxTests; t++) {                 // filter.hpp:574-584: t < 8 -> bit t, t >= 9 -> bit t - 1
+    const int p = (t < 8) ? t : t - 1;
+    d->pmul[t] = (t == 8) ? 1u : (1u << (p & 7));
   }
 }
 
@@ -150,9 +156,13 @@ int check_settings(gpc_ctx* c, const gpc_settings* s) {
   return GPC_OK;
 }
 
-int table_log2_for(int wcap) {
-  int l = 4;
-  while ((1 << l) < 2 * wcap) l++;
+int ceil_log2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+
+// log2 of the row matcher's bucket count: about half a candidate (left + right) per bucket, at
+// least 256 (scan layout) and at least 2 * W (so that remainder + side + x fit one 32-bit entry)
+int table_log2_for(int w, int wcap) {
+  int l = std::max(8, ceil_log2(w) + 1);
+  while ((1 << l) < 4 * wcap) l++;
   return l;
 }
 
@@ -229,7 +239,11 @@ int run_match(gpc_ctx* c, const uint32_t* hash, int n_pairs, int w, int h, const
   m.hash = hash; m.lastrow = lastrow; m.stage = c->d_stage; m.rowmatch = c->d_rowmatch;
   m.W = w; m.H = h; m.disp_high = s->disp_high; m.vertical_tolerance = s->vertical_tolerance;
   m.wcap = std::max(w - 2 * gpc::kRadius, 16);
-  m.table_log2 = table_log2_for(m.wcap);
+  m.table_log2 = table_log2_for(w, m.wcap);
+  m.x_bits = ceil_log2(w);
+  m.pow2cap = 1 << ceil_log2(m.wcap);
+  while ((int)gpc::match_smem_bytes(m.wcap, m.table_log2) > 72 * 1024 && m.table_log2 > std::max(8, m.x_bits + 1))
+    m.table_log2--;                                  // wide rows: fewer, longer buckets keep >= 3 CTAs per SM
   m.key_bits = 31;   // hash images may come from the caller (gpc_match_hash_images): assume full 31-bit states
   if ((int)gpc::match_smem_bytes(m.wcap, m.table_log2) > c->match_smem_max)
     return fail(c, GPC_E_DIMS, "image too wide for the row matcher's shared memory");

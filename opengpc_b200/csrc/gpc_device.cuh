@@ -24,19 +24,24 @@ constexpr int kPitch = kTileW + 32;            // smem row pitch in bytes: image
 constexpr int kPitchW = kPitch / 4;            // ... in 32-bit words
 constexpr int kRawRows = kTileH + 2 * kRadius + 2;   // image rows y0-14 .. y0+kTileH+13
 constexpr int kSmRows = kTileH + 2 * kRadius;        // image rows y0-13 .. y0+kTileH+12
+constexpr int kCopyBytes = kSmRows * kPitch;   // one copy of the smoothed tile
 constexpr int kThreadsA = 256;
 
-// Forest baked for the smem tile pitch (replaces the per-width baking of inference.hpp:427-428).
-// Passed by value as a kernel parameter: with the test loop fully unrolled every field is read
-// from a fixed constant-bank address (uniform datapath), never through an indexed load.
+// Forest baked for the kernel's shared-memory layout (replaces the per-width baking of
+// inference.hpp:427-428).  The smoothed tile is kept four times, copy k shifted left by k bytes,
+// so that the 4-pixel operand of every test is ONE aligned 32-bit load: imm = k * kCopyBytes +
+// (dy * kPitch + dx - k) with k = (dy * kPitch + dx) mod 4.  Passed by value as a kernel
+// parameter: with the test loop fully unrolled every field is read from a fixed constant-bank
+// address (uniform datapath), never through an indexed load.
 struct ForestDev {
   int32_t n_tests;
   int32_t type;                  // 0: a > b ; 1: a > sat_int8(b - tau)
-  int32_t off_a[kMaxTests];      // byte offset (multiple of 4) of operand a's first word relative to the quad
-  int32_t off_b[kMaxTests];
-  uint32_t sh_a[kMaxTests];      // funnel-shift amount in bits (0, 8, 16, 24)
-  uint32_t sh_b[kMaxTests];
+  int32_t imm_a[kMaxTests];      // byte offset of operand a's word relative to the quad's word in copy 0
+  int32_t imm_b[kMaxTests];
   uint32_t mtau2[kMaxTests];     // -tau (int8 tau) as int16 replicated into both 16-bit lanes; 0 = no tau
+  uint32_t pmul[kMaxTests];      // 1 << (bit position of the test inside its state byte); kept in the constant
+                                 // bank so that the accumulate stays one IMAD.WIDE (an immediate power of two
+                                 // is strength-reduced to five ALU-pipe instructions)
 };
 
 struct PreprocessArgs {
@@ -58,8 +63,10 @@ struct MatchArgs {
   int32_t* rowmatch;       // [n_pair][H]
   int32_t W, H;
   int32_t disp_high, vertical_tolerance;
-  int32_t table_log2;      // log2 of the per-row hash table size (>= 2 * candidates)
+  int32_t table_log2;      // log2 of the per-row bucket count (>= 256, >= 2 * W, ~ 4 * candidates per side)
+  int32_t x_bits;          // bits needed for a column index (ceil(log2 W))
   int32_t wcap;            // per-side candidate capacity used to carve shared memory
+  int32_t pow2cap;         // wcap rounded up to a power of two
   int32_t key_bits;        // number of significant state bits (forest dependent)
 };
 

@@ -8,23 +8,20 @@
 // global sort decomposes into H-26 independent row problems of <= 2(W-26) 31-bit states.  The
 // reference's result is "states that occur exactly once in the left row and exactly once in
 // the right row", ordered by (y, state), with two tail rules on the globally largest right key
-// (SURVEY.md 8a row M).  A row CTA therefore never sorts its candidates: it builds an
-// open-addressing table of the left states in shared memory with a store-then-verify protocol
-// (no atomics on the table), probes it with the right states, and sorts only the surviving
-// matches (about a tenth of the candidates) with a bitonic network before writing them out.
+// (SURVEY.md 8a row M).  A row CTA never sorts its candidates.  It partitions them by a
+// multiplicative hash of the state into ~one-element buckets in shared memory (one counting
+// atomic per candidate, one scan, one scatter), lets every left candidate scan its own bucket
+// for equal states (a handful of entries, early exit on the second duplicate), and sorts only
+// the surviving matches (about a tenth of the candidates) before writing them out.
 #include "gpc_device.cuh"
 
 namespace gpc {
 
 constexpr int kThreadsB = 256;
-constexpr uint32_t kEmptyKey = 0xffffffffu;   // states never have bit 31 set
-constexpr uint32_t kNoX = 0xffffffffu;
-constexpr int kBuckets = 256;
-constexpr int kBucketLimit = 64;              // above this the bucket rank pass falls back to a bitonic network
+constexpr int kBuckets = 256;                 // ordering pass: counting sort on the top 8 state bits
+constexpr int kBucketLimit = 64;              // above this the in-bucket rank pass falls back to a bitonic network
 
-__device__ __forceinline__ uint32_t slot_of(uint32_t key, int log2ts) {
-  return (key * 0x9E3779B1u) >> (32 - log2ts);
-}
+constexpr uint32_t kHashMul = 0x9E3779B1u;    // odd: state -> state * kHashMul is a bijection mod 2^32
 
 // Shared-memory atomics in this kernel always consume their return value.  Fire-and-forget
 // shared atomics (ATOMS with an RZ destination, addressed through a uniform register into the
@@ -33,117 +30,129 @@ __device__ __forceinline__ uint32_t slot_of(uint32_t key, int log2ts) {
 // scripts/micro/match_harness.cu) -- the value-returning form does not show it.
 __device__ __forceinline__ uint32_t atomic_inc_ret(uint32_t* p) { return atomicAdd(p, 1u); }
 
+// shared memory: out[pow2cap] u64 | cnt[nb] u32 | entry[2*wcap] u32 | bcnt/bstart/bfill
 size_t match_smem_bytes(int wcap, int table_log2) {
-  size_t ts = (size_t)1 << table_log2;
+  size_t nb = (size_t)1 << table_log2;
   size_t pow2 = 1; while ((int)pow2 < wcap) pow2 <<= 1;
-  return pow2 * 8 + ts * (4 + 4 + 2 + 1) + 3 * kBuckets * 4 + 16;
+  size_t body = ((size_t)2 * wcap * 4 + 15) / 16 * 16;
+  if (body < pow2 * 8) body = pow2 * 8;                       // out2 (ordering pass) reuses the entry array
+  return pow2 * 8 + nb * 4 + body + 3 * kBuckets * 4 + 64;
 }
 
 // One CTA per (row, pair).  Every thread keeps its 4*KQ left and right pixels of the row in
-// registers (no compaction pass).  Shared-memory atomics are cheap on sm_100 (measured 2.8 SM
-// cycles per warp-wide atomicAdd/Exch, 5.3 per atomicCAS, scripts/micro/atoms_bench.cu):
-//   left  : one atomicCAS per probe inserts the state into an open-addressing table; the owner
-//           of a slot stores its x, a later equal state marks the slot dead (not unique)
-//   right : probes the table; the first hit records its x with an atomicExch, a second hit
-//           marks the slot dead
-//   emit  : slot owners whose slot is alive and was hit exactly once are matches
-// and only the matches (about a tenth of the candidates) are then ordered by state.
+// registers.  h = state * odd constant (a bijection on 32-bit words): the top log2(nb) bits pick
+// the bucket, so inside a bucket two states are equal iff the remaining low bits of h are.  An
+// entry therefore fits one word: remainder | side | x  (needs nb >= 2 * W, see launch).
+//   count   : one atomicAdd per candidate on its bucket counter; the returned rank is kept
+//   scan    : exclusive prefix of the counters -> word = start | count << 16 (bank-conflict free:
+//             thread t owns buckets t, t+256, ...; the order of buckets in the entry array is free)
+//   scatter : entry stored at start[bucket] + rank
+//   resolve : every left candidate reads its bucket (<= 4 entries in one unrolled step, longer
+//             buckets in a loop) counting equal states per side; unique on both sides = match
 template <int KQ>
 __global__ void __launch_bounds__(kThreadsB)
 match_rows_kernel(const MatchArgs args) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int W = args.W, H = args.H, log2ts = args.table_log2;
-  const int ts = 1 << log2ts;
-  const uint32_t tmask = (uint32_t)ts - 1u;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int W = args.W, H = args.H, log2nb = args.table_log2, xb = args.x_bits;
+  const int nb = 1 << log2nb;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int y = kRadius + blockIdx.x, pair = blockIdx.y;
+  const int pow2cap = args.pow2cap;
 
-  int pow2cap = 1; while (pow2cap < args.wcap) pow2cap <<= 1;
   unsigned long long* out = reinterpret_cast<unsigned long long*>(smem);           // [pow2cap] emitted matches
-  uint32_t* tab = reinterpret_cast<uint32_t*>(out + pow2cap);                       // [ts] left states
-  uint32_t* xr_tab = tab + ts;                                                      // [ts] x of the first right hit
-  unsigned long long* out2 = reinterpret_cast<unsigned long long*>(tab);            // reuses tab+xr_tab after the emit
-  uint32_t* bcnt = xr_tab + ts;                                                     // [kBuckets] x3
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(out + pow2cap);                      // [nb] counters -> start | count << 16
+  uint32_t* entry = cnt + nb;                                                       // [2*wcap] remainder | side | x
+  unsigned long long* out2 = reinterpret_cast<unsigned long long*>(entry);          // ordering pass, reuses entry
+  size_t body = ((size_t)2 * args.wcap * 4 + 15) / 16 * 16;
+  if (body < (size_t)pow2cap * 8) body = (size_t)pow2cap * 8;
+  uint32_t* bcnt = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(entry) + body);   // [kBuckets] x3
   uint32_t* bstart = bcnt + kBuckets;
   uint32_t* bfill = bstart + kBuckets;
-  uint16_t* xl_tab = reinterpret_cast<uint16_t*>(bfill + kBuckets);                 // [ts] x of the slot owner
-  uint8_t* dead = reinterpret_cast<uint8_t*>(xl_tab + ts);                          // [ts] state not unique (either side)
   __shared__ int n_out, have_s[2];
-  __shared__ uint32_t kmax_s, big_bucket;
+  __shared__ uint32_t kmax_s, big_bucket, warp_tot[kThreadsB / 32];
   __shared__ int cmax_r, cmax_l, xmin_s;
 
   if (tid == 0) { n_out = 0; have_s[0] = 0; have_s[1] = 0; kmax_s = 0; cmax_r = 0; cmax_l = 0; xmin_s = 0x7fffffff; big_bucket = 0; }
-  for (int i = tid; i < ts; i += kThreadsB) { tab[i] = kEmptyKey; xr_tab[i] = kNoX; dead[i] = 0; }
-  for (int i = tid; i < 3 * kBuckets; i += kThreadsB) bcnt[i] = 0u;
-  __syncthreads();
+  {
+    uint4* z = reinterpret_cast<uint4*>(cnt);
+    for (int i = tid; i < nb / 4; i += kThreadsB) z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 3 * kBuckets; i += kThreadsB) bcnt[i] = 0u;
+  }
 
   // ---- this thread's pixels of the left and right hash rows ---------------------------------------
   const uint4* row_l = reinterpret_cast<const uint4*>(args.hash + ((size_t)(2 * pair) * H + y) * W);
   const uint4* row_r = reinterpret_cast<const uint4*>(args.hash + ((size_t)(2 * pair + 1) * H + y) * W);
   const int nquads = W / 4;
-  uint32_t vl[4 * KQ], vr[4 * KQ];
+  uint32_t v[2][4 * KQ];                       // [side][element]
   uint32_t any_l = 0, any_r = 0;
 #pragma unroll
   for (int k = 0; k < KQ; k++) {
     const int q = tid + k * kThreadsB;
     uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
     if (q < nquads) { a = __ldg(row_l + q); b = __ldg(row_r + q); }
-    vl[4 * k] = a.x; vl[4 * k + 1] = a.y; vl[4 * k + 2] = a.z; vl[4 * k + 3] = a.w;
-    vr[4 * k] = b.x; vr[4 * k + 1] = b.y; vr[4 * k + 2] = b.z; vr[4 * k + 3] = b.w;
+    v[0][4 * k] = a.x; v[0][4 * k + 1] = a.y; v[0][4 * k + 2] = a.z; v[0][4 * k + 3] = a.w;
+    v[1][4 * k] = b.x; v[1][4 * k + 1] = b.y; v[1][4 * k + 2] = b.z; v[1][4 * k + 3] = b.w;
     any_l |= a.x | a.y | a.z | a.w;
     any_r |= b.x | b.y | b.z | b.w;
   }
+  __syncthreads();
   if (any_l >> 31) have_s[0] = 1;                                              // benign same-value race
   if (any_r >> 31) have_s[1] = 1;
   __syncthreads();
   int m = 0;
 
   if (have_s[0] && have_s[1]) {
-    // ---- left states: one atomicCAS per probe ------------------------------------------------------
-    uint32_t myslot[4 * KQ];
+    const int rs = 32 - log2nb;                  // bucket = h >> rs
+    const int es = log2nb - xb - 1;              // entry  = (h << log2nb) >> es | side << xb | x
+    // ---- count: bucket counters; ranks packed two per register ------------------------------------
+    uint32_t rank[2][2 * KQ];
 #pragma unroll
-    for (int e = 0; e < 4 * KQ; e++) {
-      myslot[e] = 0xffffffffu;
-      if (vl[e] >> 31) {
-        const uint32_t key = vl[e] & 0x7fffffffu;
-        uint32_t c = slot_of(key, log2ts);
-        for (int probe = 0; probe < ts; probe++) {            // bounded: the table is at most half full
-          const uint32_t old = atomicCAS(&tab[c], kEmptyKey, key);
-          if (old == kEmptyKey) {                                                     // owner records xL
-            xl_tab[c] = (uint16_t)(4 * (tid + (e >> 2) * kThreadsB) + (e & 3));
-            myslot[e] = c;
-            break;
-          }
-          if (old == key) { dead[c] = 1; break; }                                     // state not unique on the left
-          c = (c + 1) & tmask;
-        }
+    for (int sd = 0; sd < 2; sd++)
+#pragma unroll
+      for (int e = 0; e < 4 * KQ; e++) {
+        uint32_t r = 0;
+        if (v[sd][e] >> 31) r = atomic_inc_ret(&cnt[((v[sd][e] & 0x7fffffffu) * kHashMul) >> rs]);
+        if (e & 1) rank[sd][e >> 1] |= r << 16; else rank[sd][e >> 1] = r;
+      }
+    __syncthreads();
+    // ---- exclusive scan: thread t owns buckets t, t + 256, ... (consecutive in the entry array) ------
+    {
+      const int per = nb / kThreadsB;              // nb >= 256 by construction
+      uint32_t sum = 0;
+      for (int k = 0; k < per; k++) sum += cnt[k * kThreadsB + tid];
+      uint32_t incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+      if (lane == 31) warp_tot[wid] = incl;
+      __syncthreads();
+      uint32_t base = incl - sum;
+#pragma unroll
+      for (int w = 0; w < kThreadsB / 32; w++) if (w < wid) base += warp_tot[w];
+      for (int k = 0; k < per; k++) {
+        const uint32_t c = cnt[k * kThreadsB + tid];
+        cnt[k * kThreadsB + tid] = base | (c << 16);
+        base += c;
       }
     }
     __syncthreads();
-    // ---- right states probe the table --------------------------------------------------------------
+    // ---- scatter ---------------------------------------------------------------------------------------
 #pragma unroll
-    for (int e = 0; e < 4 * KQ; e++) {
-      if (vr[e] >> 31) {
-        const uint32_t key = vr[e] & 0x7fffffffu;
-        uint32_t c = slot_of(key, log2ts);
-        for (int probe = 0; probe < ts; probe++) {
-          const uint32_t t = tab[c];
-          if (t == kEmptyKey) break;
-          if (t == key) {
-            const uint32_t x = 4u * (uint32_t)(tid + (e >> 2) * kThreadsB) + (uint32_t)(e & 3);
-            if (atomicExch(&xr_tab[c], x) != kNoX) dead[c] = 2;                       // a second right pixel with this state
-            break;
-          }
-          c = (c + 1) & tmask;
+    for (int sd = 0; sd < 2; sd++)
+#pragma unroll
+      for (int e = 0; e < 4 * KQ; e++) {
+        if (v[sd][e] >> 31) {
+          const uint32_t h = (v[sd][e] & 0x7fffffffu) * kHashMul;
+          const uint32_t r = (e & 1) ? (rank[sd][e >> 1] >> 16) : (rank[sd][e >> 1] & 0xffffu);
+          const uint32_t x = 4u * (uint32_t)(tid + (e >> 2) * kThreadsB) + (uint32_t)(e & 3);
+          entry[(cnt[h >> rs] & 0xffffu) + r] = ((h << log2nb) >> es) | ((uint32_t)sd << xb) | x;
         }
       }
-    }
     // ---- tail rules: only the globally last right key (largest row with right candidates) -----------
     const bool last_row = (args.lastrow[2 * pair + 1] == y);
     if (last_row) {
       uint32_t km = 0;
 #pragma unroll
-      for (int e = 0; e < 4 * KQ; e++) if (vr[e] >> 31) km = max(km, vr[e] & 0x7fffffffu);
+      for (int e = 0; e < 4 * KQ; e++) if (v[1][e] >> 31) km = max(km, v[1][e] & 0x7fffffffu);
       km = __reduce_max_sync(0xffffffffu, km);
       if (lane == 0 && atomicMax(&kmax_s, km) == 0xffffffffu) __trap();
       __syncthreads();
@@ -151,8 +160,8 @@ match_rows_kernel(const MatchArgs args) {
       int cr = 0, cl = 0, xm = 0x7fffffff;
 #pragma unroll
       for (int e = 0; e < 4 * KQ; e++) {
-        if ((vr[e] >> 31) && (vr[e] & 0x7fffffffu) == km) { cr++; xm = min(xm, 4 * (tid + (e >> 2) * kThreadsB) + (e & 3)); }
-        if ((vl[e] >> 31) && (vl[e] & 0x7fffffffu) == km) cl++;
+        if ((v[1][e] >> 31) && (v[1][e] & 0x7fffffffu) == km) { cr++; xm = min(xm, 4 * (tid + (e >> 2) * kThreadsB) + (e & 3)); }
+        if ((v[0][e] >> 31) && (v[0][e] & 0x7fffffffu) == km) cl++;
       }
       cr = __reduce_add_sync(0xffffffffu, cr);
       cl = __reduce_add_sync(0xffffffffu, cl);
@@ -162,19 +171,38 @@ match_rows_kernel(const MatchArgs args) {
       }
     }
     __syncthreads();
-    // ---- emit: left states that own a live slot hit exactly once ----------------------------------------
+    // ---- resolve + emit: a left state that is unique in its bucket on both sides is a match ---------
     const uint32_t kmax = kmax_s;
     const int cmr = cmax_r, cml = cmax_l, xmin = xmin_s;
+    const uint32_t xmask = (1u << xb) - 1u;
 #pragma unroll
     for (int e = 0; e < 4 * KQ; e++) {
       bool ok = false;
       unsigned long long rec = 0;
-      if (myslot[e] != 0xffffffffu) {
-        const uint32_t c = myslot[e];
-        const uint32_t key = vl[e] & 0x7fffffffu;
+      if (v[0][e] >> 31) {
+        const uint32_t key = v[0][e] & 0x7fffffffu;
+        const uint32_t h = key * kHashMul;
+        const uint32_t word = cnt[h >> rs];
+        const uint32_t s0 = word & 0xffffu, n = word >> 16;
+        const uint32_t mine = (h << log2nb) >> es;             // remainder field, side = 0, x = 0
+        uint32_t nl = 0, nr = 0, xr = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (j < (int)n) {
+            const uint32_t k = entry[s0 + j];
+            if (((k ^ mine) >> (xb + 1)) == 0u) {                // same state
+              if ((k >> xb) & 1u) { nr++; xr = k & xmask; } else nl++;
+            }
+          }
+        }
+        for (uint32_t j = 4; j < n && nl < 2u && nr < 2u; j++) { // rare: bucket longer than four entries
+          const uint32_t k = entry[s0 + j];
+          if (((k ^ mine) >> (xb + 1)) == 0u) {
+            if ((k >> xb) & 1u) { nr++; xr = k & xmask; } else nl++;
+          }
+        }
+        ok = (nl == 1u) && (nr == 1u);
         const int xl = 4 * (tid + (e >> 2) * kThreadsB) + (e & 3);
-        uint32_t xr = xr_tab[c];
-        ok = (xr != kNoX) && (dead[c] == 0);
         if (last_row && key == kmax) {         // inference.hpp:243-249 on the tail of the sorted right keys
           ok = (cml == 1) && (cmr == 2);       // 1 right: the last element never matches; >=3: duplicates
           xr = (uint32_t)xmin;                 // 2: "first of the two" := smaller x (stable order)

@@ -5,11 +5,19 @@
 //   ndb::sobel                         (filter.hpp:404-519, incl. the lane duplication at :504-507)
 //   ndb::arr2ind + border lambda       (filter.hpp:60-87, inference.hpp:318-330)
 //   ndb::gpcFilter / gpcFilterTau      (filter.hpp:547-606, :619-683)
-// Nothing here is a translation of the SSE code: a CTA stages a (32+28) x (256+32) raw tile in
-// shared memory, derives the smoothed tile with dp4a row sums, evaluates the Sobel predicate
-// per 16-pixel segment, and then evaluates all fern tests 4 pixels at a time with byte-SIMD
-// integer arithmetic (funnel-shifted unaligned loads from the smoothed tile).  Each pixel's
-// state is written once to the hash image (bit 31 = candidate).
+// Nothing here is a translation of the SSE code.  A CTA stages a (32+28) x (256+32) raw tile in
+// shared memory, derives the smoothed tile with dp4a row sums, evaluates the Sobel predicate per
+// 16-pixel segment, and then evaluates all fern tests 4 pixels at a time with byte-SIMD integer
+// arithmetic.  The kernel is bound by the SM's ALU pipe (LOP3/SHF/PRMT, one warp instruction per
+// two cycles per scheduler), not by HBM, so the test loop is written to minimise ALU-pipe work:
+//   * the smoothed tile is stored BIASED (s ^ 0x80) and four times, copy k shifted left by k
+//     bytes: every 4-pixel operand is one aligned LDS with a uniform offset (no funnel shifts);
+//   * in the biased domain the reference's "signed-saturating b - tau, then unsigned compare"
+//     (filter.hpp:647-652) is clamp(x - tau, 0, 255) -- two DPX VIADDMNMX on 16-bit lanes --
+//     followed by a SIGNED byte compare, which costs the same carry trick as the unsigned one;
+//   * result bits are accumulated with IMAD.WIDE on the otherwise idle FMA pipe:
+//     acc64 += (r & 0x80808080) * 2^p puts test p of pixel j at bit 8j+7+p without carries.
+// Each pixel's state is written once to the hash image (bit 31 = candidate).
 #include "gpc_device.cuh"
 
 namespace gpc {
@@ -17,11 +25,8 @@ namespace gpc {
 __device__ __forceinline__ uint32_t third(uint32_t s) { return __umulhi(s, 21846u << 16); }   // (s*21846)>>16
 __device__ __forceinline__ uint32_t ninth(uint32_t s) { return __umulhi(s, 7282u << 16); }    // (s*7282)>>16
 
-// msb of each byte = (a > b) unsigned; other bits are garbage.
-__device__ __forceinline__ uint32_t gtu4_msb(uint32_t a, uint32_t b) {
-  uint32_t t = (a & 0x7f7f7f7fu) + (~b & 0x7f7f7f7fu);
-  return (a & ~b) | (~(a ^ b) & t);
-}
+constexpr uint32_t kMsb = 0x80808080u;
+constexpr uint32_t kLow7 = 0x7f7f7f7fu;
 
 // Horizontal floor-thirds of 4 consecutive pixels: h[k] = (p[x+k-1] + p[x+k] + p[x+k+1]) / 3.
 __device__ __forceinline__ void hthirds(uint32_t wm1, uint32_t w, uint32_t wp1, uint32_t h[4]) {
@@ -31,39 +36,64 @@ __device__ __forceinline__ void hthirds(uint32_t wm1, uint32_t w, uint32_t wp1, 
   h[3] = third(__dp4a(__funnelshift_r(w, wp1, 16), 0x00010101u, 0u));
 }
 
-// One fern test on 4 horizontally adjacent pixels: msb of byte j = test result of pixel j.
-//   zero forest (filter.hpp:575):  a > b                      (unsigned bytes)
-//   tau forest  (filter.hpp:647-652): a > sat_int8(b - tau)   (signed saturating subtract of the byte
-//   reinterpreted as int8, then an unsigned compare).  In the biased domain x = b ^ 0x80 the
-//   saturating subtract is clamp(x - tau, 0, 255), done on two 16-bit lanes per register with the
-//   native VIADDMNMX (DPX) instruction; the result is compared without un-biasing it.
+// One fern test on 4 horizontally adjacent pixels; operands are BIASED bytes (pixel ^ 0x80).
+// Returns a word whose byte msbs are the test results (other bits are garbage).
+//   zero forest (filter.hpp:575):      a > b  unsigned           ==  xa > xb        signed
+//   tau forest  (filter.hpp:647-652):  a > (uint8)sat_int8((int8)b - tau)  unsigned
+//                                      ==  xa > clamp(xb - tau, 0, 255)    signed
+// Signed byte compare: msb = (~a7 & c7) | (~(a7 ^ c7) & carry7), carry from the low 7 bits.
+// The returned word is masked to the msbs.  No branches: a tau forest sends every test through
+// the clamp (tau == 0 leaves x unchanged), so that the tests of one state byte form a single
+// basic block the compiler can interleave.
+template <bool kTau>
 __device__ __forceinline__ uint32_t eval_test(const uint8_t* base, const ForestDev& forest, const int t) {
-  const uint32_t* pa = reinterpret_cast<const uint32_t*>(base + forest.off_a[t]);
-  const uint32_t* pb = reinterpret_cast<const uint32_t*>(base + forest.off_b[t]);
-  uint32_t a = pa[0], b = pb[0];
-  if (forest.sh_a[t]) a = __funnelshift_r(a, pa[1], forest.sh_a[t]);       // uniform branches
-  if (forest.sh_b[t]) b = __funnelshift_r(b, pb[1], forest.sh_b[t]);
-  const uint32_t mt = forest.mtau2[t];
-  if (mt == 0u) return gtu4_msb(a, b);
-  const uint32_t x = b ^ 0x80808080u;
-  const uint32_t lo = __viaddmin_s16x2_relu(__byte_perm(x, 0u, 0x4140), mt, 0x00ff00ffu);
-  const uint32_t hi = __viaddmin_s16x2_relu(__byte_perm(x, 0u, 0x4342), mt, 0x00ff00ffu);
-  const uint32_t c = __byte_perm(lo, hi, 0x6420);                          // clamp(x - tau, 0, 255); b' = c ^ 0x80
-  const uint32_t s = (a & 0x7f7f7f7fu) + (~c & 0x7f7f7f7fu);               // low-7-bit compare (bit 7 unaffected by ^0x80)
-  return (a & c) | ((a ^ c) & s);                                          // msb: a7 > b'7, or equal and low7(a) > low7(b')
+  const uint32_t a = *reinterpret_cast<const uint32_t*>(base + forest.imm_a[t]);
+  uint32_t c = *reinterpret_cast<const uint32_t*>(base + forest.imm_b[t]);
+  if (kTau) {
+    const uint32_t mt = forest.mtau2[t];
+    const uint32_t lo = __viaddmin_s16x2_relu(__byte_perm(c, 0u, 0x4140), mt, 0x00ff00ffu);
+    const uint32_t hi = __viaddmin_s16x2_relu(__byte_perm(c, 0u, 0x4342), mt, 0x00ff00ffu);
+    c = __byte_perm(lo, hi, 0x6420);                                         // clamp(x - tau, 0, 255)
+  }
+  const uint32_t s = (a & kLow7) + (~c & kLow7);                             // bit 7: low7(a) > low7(c)
+  return ((~a & c) | (~(a ^ c) & s)) & kMsb;
+}
+
+// All tests of state byte G (filter.hpp:574-584: tests 0..8 -> byte 0 with test 8 OR-ed into bit 0
+// under m8, 9..16 -> byte 1, 17..24 -> byte 2, 25..31 -> byte 3).  The forest is padded with
+// never-true dummy tests up to the end of its last group (bake_forest), so there is no per-test
+// guard.  acc += msb word * 2^p lands pixel j's bit at 8j + 7 + p without carries.
+template <bool kTau, int G>
+__device__ __forceinline__ unsigned long long eval_group(const uint8_t* base, const ForestDev& forest, uint32_t m8) {
+  constexpr int t0 = (G == 0) ? 0 : 8 * G + 1;
+  constexpr int t1 = (G == 3) ? kMaxTests : 8 * G + 9;           // exclusive
+  unsigned long long acc = 0ull;
+  if (G == 0) {
+    const uint32_t r0 = eval_test<kTau>(base, forest, 0), r8 = eval_test<kTau>(base, forest, 8);
+    acc = (unsigned long long)(r0 | (r8 & m8));
+  }
+#pragma unroll
+  for (int t = (G == 0) ? 1 : t0; t < ((G == 0) ? 8 : t1); t++)
+    acc += (unsigned long long)eval_test<kTau>(base, forest, t) * (unsigned long long)forest.pmul[t];
+  return acc;
 }
 
 // kMode 0: product path.  1: also writes smooth / grad (stage-parity seam gpc_preprocess).
 // 2: evalFastMaskOnSubsetSSE seam (gpc_hash_smooth): args.raw is an already smoothed image and
 //    args.flags a u8 image whose non-zero bytes mark the pixels to hash; phases 1-2 are skipped.
-template <int kMode>
+//
+// Shared memory: copies 0..3 of the biased smoothed tile, [kSmRows][kPitch] bytes each; the raw
+// tile [kRawRows][kPitch] is staged over copies 1..3 and is dead by the time they are built;
+// then the candidate masks [kTileH][kTileW/16] u16.
+template <int kMode, bool kTau>
 __global__ void __launch_bounds__(kThreadsA)
 preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
   constexpr bool kDebugOut = (kMode == 1);
   extern __shared__ __align__(16) uint8_t smem[];
-  uint32_t* raw32 = reinterpret_cast<uint32_t*>(smem);                          // [kRawRows][kPitchW]
-  uint32_t* sm32 = raw32 + kRawRows * kPitchW;                                  // [kSmRows][kPitchW]
-  uint16_t* cand = reinterpret_cast<uint16_t*>(sm32 + kSmRows * kPitchW);       // [kTileH][kTileW/16]
+  uint32_t* x32 = reinterpret_cast<uint32_t*>(smem);                            // copy 0: [kSmRows][kPitchW]
+  uint32_t* raw32 = reinterpret_cast<uint32_t*>(smem + kCopyBytes);             // [kRawRows][kPitchW], aliases copies 1..3
+  uint16_t* cand = reinterpret_cast<uint16_t*>(smem + 4 * kCopyBytes);          // [kTileH][kTileW/16]
+  static_assert(kRawRows * kPitch <= 3 * kCopyBytes, "raw staging must fit over copies 1..3");
 
   const int W = args.W, H = args.H;
   const int img = blockIdx.z;
@@ -75,13 +105,14 @@ preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
   // ---- phase 0: stage the raw tile (zero outside the image) --------------------------------
   if (kMode == 2) {
     constexpr int kChunks = kPitch / 16;
-    uint4* dst = reinterpret_cast<uint4*>(sm32);
+    uint4* dst = reinterpret_cast<uint4*>(x32);
     for (int c = tid; c < kSmRows * kChunks; c += kThreadsA) {
       int r = c / kChunks, k = c - r * kChunks;
       int gy = y0 - kRadius + r, gx = x0 - 16 + 16 * k;
       uint4 v = make_uint4(0, 0, 0, 0);
       if (gy >= 0 && gy < H && gx >= 0 && gx < W)
         v = __ldg(reinterpret_cast<const uint4*>(raw + (size_t)gy * W + gx));
+      v.x ^= kMsb; v.y ^= kMsb; v.z ^= kMsb; v.w ^= kMsb;
       dst[c] = v;
     }
     const uint8_t* __restrict__ flags = args.flags + img_off;
@@ -106,7 +137,7 @@ preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
     }
   } else {
     constexpr int kChunks = kPitch / 16;
-    uint4* dst = reinterpret_cast<uint4*>(smem);
+    uint4* dst = reinterpret_cast<uint4*>(raw32);
     for (int c = tid; c < kRawRows * kChunks; c += kThreadsA) {
       int r = c / kChunks, k = c - r * kChunks;
       int gy = y0 - (kRadius + 1) + r, gx = x0 - 16 + 16 * k;
@@ -118,7 +149,7 @@ preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
   }
   if (kMode != 2) __syncthreads();
 
-  // ---- phase 1: smoothed tile -----------------------------------------------------------------
+  // ---- phase 1: smoothed tile (biased) -> copy 0 ---------------------------------------------
   // thread = (quad column, one of 3 row segments); walks down its rows with a 3-row window of
   // horizontal thirds held in registers.
   if (kMode != 2) {
@@ -148,7 +179,7 @@ preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
                      (third(ha[2] + hb[2] + hc[2]) << 16) | (third(ha[3] + hb[3] + hc[3]) << 24);
         const int gy = y0 - kRadius + j;
         if (gy < 1 || gy > last_written) v = 0u; else v &= colmask;
-        sm32[j * kPitchW + q] = v;
+        x32[j * kPitchW + q] = v ^ kMsb;
         if (kDebugOut && args.smooth_out && j >= kRadius && j < kRadius + kTileH && q >= 4 && q < 4 + kTileW / 4 &&
             gy < H && gxq < W)
           *reinterpret_cast<uint32_t*>(args.smooth_out + img_off + (size_t)gy * W + gxq) = v;
@@ -160,7 +191,7 @@ preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
 
   // ---- phase 2: Sobel predicate per 16-pixel segment -> candidate bit masks -----------------
   if (kMode != 2) {
-    const uint8_t* raw8 = smem;
+    const uint8_t* raw8 = reinterpret_cast<const uint8_t*>(raw32);
     for (int sr = tid; sr < kTileH * (kTileW / 16); sr += kThreadsA) {
       const int ry = sr / (kTileW / 16), sg = sr - ry * (kTileW / 16);
       const int gy = y0 + ry, gxs = x0 + 16 * sg;
@@ -202,6 +233,16 @@ preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
       cand[sr] = (uint16_t)m;
     }
   }
+  __syncthreads();                                         // copy 0 and cand complete, raw tile dead
+
+  // ---- phase 2b: copies 1..3 = copy 0 shifted left by 1..3 bytes -----------------------------
+  for (int i = tid; i < kSmRows * kPitchW; i += kThreadsA) {
+    const int q = i % kPitchW;
+    const uint32_t lo = x32[i], hi = (q + 1 < kPitchW) ? x32[i + 1] : 0u;
+    x32[i + 1 * (kCopyBytes / 4)] = __funnelshift_r(lo, hi, 8);
+    x32[i + 2 * (kCopyBytes / 4)] = __funnelshift_r(lo, hi, 16);
+    x32[i + 3 * (kCopyBytes / 4)] = __funnelshift_r(lo, hi, 24);
+  }
   __syncthreads();
 
   // ---- phase 3: fern tests, 4 pixels per step ------------------------------------------------
@@ -209,8 +250,9 @@ preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
     const int qx = tid & 63;
     const int gx = x0 + 4 * qx;
     uint32_t* __restrict__ hash = args.hash + img_off;
-    const uint32_t m8 = (gx & 4) ? 0x01010101u : 0x01010100u;   // test #8: byte lanes x%8==0 dropped (filter.hpp:582)
+    const uint32_t m8 = (gx & 4) ? kMsb : 0x80808000u;          // test #8: byte lanes x%8==0 dropped (filter.hpp:582)
     const int T = forest.n_tests;
+    const int n_groups = (T <= 9) ? 1 : (T <= 17) ? 2 : (T <= 25) ? 3 : 4;
 #pragma unroll 1
     for (int ry = tid >> 6; ry < kTileH; ry += kThreadsA / 64) {
       const int gy = y0 + ry;
@@ -218,21 +260,18 @@ preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
       const uint32_t cm = (cand[ry * (kTileW / 16) + (qx >> 2)] >> ((qx & 3) * 4)) & 15u;
       uint32_t st[4] = {0u, 0u, 0u, 0u};
       if (cm != 0u && gy >= kRadius && gy < H - 15) {            // hashed rows (filter.hpp:601-604)
-        const uint8_t* base = reinterpret_cast<const uint8_t*>(sm32 + (ry + kRadius) * kPitchW + 4 + qx);
-        uint32_t acc[4] = {0u, 0u, 0u, 0u};
+        const uint8_t* base = smem + (ry + kRadius) * kPitch + 16 + 4 * qx;
+        unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+        acc[0] = eval_group<kTau, 0>(base, forest, m8);
+        if (n_groups > 1) acc[1] = eval_group<kTau, 1>(base, forest, m8);      // uniform branches
+        if (n_groups > 2) acc[2] = eval_group<kTau, 2>(base, forest, m8);
+        if (n_groups > 3) acc[3] = eval_group<kTau, 3>(base, forest, m8);
+        // byte j of (acc[g] >> 7) = state byte g of pixel j; 4x4 byte transpose -> one state per pixel
+        uint32_t w[4];
 #pragma unroll
-        for (int t = 0; t < kMaxTests; t++) {
-          if (t < T) {                                           // uniform
-            const uint32_t r = eval_test(base, forest, t);
-            // bit placement of filter.hpp:574-584: t<8 -> bit t; t==8 -> bit 0 (masked); t>=9 -> bit t-1
-            if (t < 8) acc[0] |= (r >> (7 - t)) & (0x01010101u << t);
-            else if (t == 8) acc[0] |= (r >> 7) & m8;
-            else { const int p = t - 1; acc[p >> 3] |= (r >> (7 - (p & 7))) & (0x01010101u << (p & 7)); }
-          }
-        }
-        // 4x4 byte transpose: state of pixel j = byte j of acc[0..3]
-        uint32_t lo01 = __byte_perm(acc[0], acc[1], 0x5140), hi01 = __byte_perm(acc[0], acc[1], 0x7362);
-        uint32_t lo23 = __byte_perm(acc[2], acc[3], 0x5140), hi23 = __byte_perm(acc[2], acc[3], 0x7362);
+        for (int g = 0; g < 4; g++) w[g] = (uint32_t)(acc[g] >> 7);
+        uint32_t lo01 = __byte_perm(w[0], w[1], 0x5140), hi01 = __byte_perm(w[0], w[1], 0x7362);
+        uint32_t lo23 = __byte_perm(w[2], w[3], 0x5140), hi23 = __byte_perm(w[2], w[3], 0x7362);
         st[0] = __byte_perm(lo01, lo23, 0x5410);
         st[1] = __byte_perm(lo01, lo23, 0x7632);
         st[2] = __byte_perm(hi01, hi23, 0x5410);
@@ -255,27 +294,40 @@ preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
 }
 
 size_t preprocess_smem_bytes() {
-  return (size_t)(kRawRows + kSmRows) * kPitch + (size_t)kTileH * (kTileW / 16) * sizeof(uint16_t);
+  return (size_t)4 * kCopyBytes + (size_t)kTileH * (kTileW / 16) * sizeof(uint16_t);
+}
+
+template <int kMode, bool kTau>
+static cudaError_t configure_one(int smem) {
+  return cudaFuncSetAttribute(preprocess_hash_kernel<kMode, kTau>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 cudaError_t configure_preprocess_hash() {   // per device: opt in to > 48 KB dynamic shared memory
   int smem = (int)preprocess_smem_bytes();
-  cudaError_t e = cudaFuncSetAttribute(preprocess_hash_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(preprocess_hash_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(preprocess_hash_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = configure_one<0, false>(smem);
+  if (e == cudaSuccess) e = configure_one<0, true>(smem);
+  if (e == cudaSuccess) e = configure_one<1, false>(smem);
+  if (e == cudaSuccess) e = configure_one<1, true>(smem);
+  if (e == cudaSuccess) e = configure_one<2, false>(smem);
+  if (e == cudaSuccess) e = configure_one<2, true>(smem);
   return e;
+}
+
+template <int kMode>
+static void launch_mode(const PreprocessArgs& args, const ForestDev& forest, dim3 grid, size_t smem, cudaStream_t stream) {
+  if (forest.type != 0)
+    preprocess_hash_kernel<kMode, true><<<grid, kThreadsA, smem, stream>>>(args, forest);
+  else
+    preprocess_hash_kernel<kMode, false><<<grid, kThreadsA, smem, stream>>>(args, forest);
 }
 
 cudaError_t launch_preprocess_hash(const PreprocessArgs& args, const ForestDev& forest, int n_img,
                                    int mode, cudaStream_t stream) {
   size_t smem = preprocess_smem_bytes();
   dim3 grid((args.W + kTileW - 1) / kTileW, (args.H + kTileH - 1) / kTileH, n_img);
-  if (mode == 2)
-    preprocess_hash_kernel<2><<<grid, kThreadsA, smem, stream>>>(args, forest);
-  else if (mode == 1)
-    preprocess_hash_kernel<1><<<grid, kThreadsA, smem, stream>>>(args, forest);
-  else
-    preprocess_hash_kernel<0><<<grid, kThreadsA, smem, stream>>>(args, forest);
+  if (mode == 2) launch_mode<2>(args, forest, grid, smem, stream);
+  else if (mode == 1) launch_mode<1>(args, forest, grid, smem, stream);
+  else launch_mode<0>(args, forest, grid, smem, stream);
   return cudaGetLastError();
 }
 

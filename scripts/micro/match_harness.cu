@@ -30,7 +30,7 @@ int main(int argc, char** argv) {
     cudaMemcpy(d_hash, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
     int last[2] = {Y, Y + 1}; cudaMemcpy(d_last, last, 8, cudaMemcpyHostToDevice);
     MatchArgs a{}; a.hash = d_hash; a.lastrow = d_last; a.stage = d_stage; a.rowmatch = d_rowmatch; a.W = W; a.H = H;
-    a.disp_high = 5000; a.vertical_tolerance = 0; a.wcap = W - 26; a.table_log2 = 11; a.key_bits = 31;
+    a.disp_high = 5000; a.vertical_tolerance = 0; a.wcap = W - 26; a.table_log2 = 12; a.x_bits = 10; a.pow2cap = 1024; a.key_bits = 31;
     int nbad = 0;
     for (int rep = 0; rep < 200; rep++) {
       cudaMemset(d_stage, 0xee, (size_t)H * W * 4);
