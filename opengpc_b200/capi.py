@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libgpc_b200.so")
+LIB_PATH = os.environ.get("GPC_B200_LIB") or os.path.join(PKG, "libgpc_b200.so")   # override: kernel tuning builds
 
 GPC_OK, GPC_E_ARG, GPC_E_WIDTH16, GPC_E_DIMS, GPC_E_CUDA, GPC_E_CAPACITY, GPC_E_UNSUPPORTED, GPC_E_FOREST, GPC_E_IO = range(9)
 

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <string>
@@ -51,7 +52,15 @@ struct gpc_ctx {
   uint8_t* d_raw = nullptr;        // [2B][H][W]
   uint32_t* d_hash = nullptr;      // [2B][H][W]
   uint32_t* d_stage = nullptr;     // [B][H][W]
-  int32_t* d_rows = nullptr;       // rowcnt [2B][H] | lastrow [2B]   (cleared per launch)
+  int32_t* d_rows = nullptr;       // rowcnt [2B][H]   (cleared per launch)
+  int32_t* d_lastrow = nullptr;    // [2B]             (cleared per launch)
+  // gpc_match_batch pipelines chunks of pairs over these lanes: H2D of chunk k+2, kernels of chunk
+  // k+1 and D2H of chunk k overlap (every chunk works on its own slice of the resident buffers)
+  static constexpr int kLanes = 3;
+  cudaStream_t lane_stream[kLanes] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr;
+  std::vector<cudaEvent_t> ev_chunk;
+  int chunk_pairs = 16;
   int32_t* d_rowmatch = nullptr;   // [B][H]
   int32_t* d_rowoff = nullptr;     // [B][H+1]
   int32_t* d_totals = nullptr;     // [B]
@@ -166,22 +175,31 @@ int table_log2_for(int w, int wcap) {
   return l;
 }
 
-// Kernel A over n_img resident images; clears and fills rowcnt / lastrow.
-int run_preprocess(gpc_ctx* c, const uint8_t* d_images, int n_img, int w, int h, int thr, const gpc::ForestDev& forest,
-                   uint8_t* d_smooth, uint8_t* d_grad, const uint8_t* d_flags = nullptr) {
-  int32_t* rowcnt = c->d_rows;
-  int32_t* lastrow = c->d_rows + (size_t)n_img * h;
-  GPC_CUDA(c, cudaMemsetAsync(rowcnt, 0, (size_t)n_img * h * sizeof(int32_t), c->stream));
-  GPC_CUDA(c, cudaMemsetAsync(lastrow, 0xff, (size_t)n_img * sizeof(int32_t), c->stream));   // -1
+// A slice of the context's resident buffers (pairs p0 .. p0 + n) and the stream that works on it.
+struct Slot {
+  int p0;
+  cudaStream_t stream;
+};
+
+int mark_on(gpc_ctx* c, const Slot& sl) { return (sl.stream == c->stream) ? mark(c) : GPC_OK; }
+
+// Kernel A over n_img resident images of the slot; clears and fills rowcnt / lastrow.
+int run_preprocess(gpc_ctx* c, const Slot& sl, const uint8_t* d_images, int n_img, int w, int h, int thr,
+                   const gpc::ForestDev& forest, uint8_t* d_smooth, uint8_t* d_grad, const uint8_t* d_flags = nullptr) {
+  const size_t P = (size_t)w * h;
+  int32_t* rowcnt = c->d_rows + (size_t)(2 * sl.p0) * h;
+  int32_t* lastrow = c->d_lastrow + 2 * sl.p0;
+  GPC_CUDA(c, cudaMemsetAsync(rowcnt, 0, (size_t)n_img * h * sizeof(int32_t), sl.stream));
+  GPC_CUDA(c, cudaMemsetAsync(lastrow, 0xff, (size_t)n_img * sizeof(int32_t), sl.stream));   // -1
   gpc::PreprocessArgs a{};
-  a.raw = d_images; a.hash = c->d_hash; a.rowcnt = rowcnt; a.lastrow = lastrow;
+  a.raw = d_images; a.hash = c->d_hash + (size_t)(2 * sl.p0) * P; a.rowcnt = rowcnt; a.lastrow = lastrow;
   a.smooth_out = d_smooth; a.grad_out = d_grad; a.flags = d_flags; a.W = w; a.H = h;
   a.thr2 = (int32_t)(int16_t)(thr * thr);                                          // filter.hpp:418
-  int rc = mark(c); if (rc) return rc;                                             // event 0
+  int rc = mark_on(c, sl); if (rc) return rc;                                      // event 0
   const int mode = d_flags ? 2 : ((d_smooth || d_grad) ? 1 : 0);
-  GPC_CUDA(c, gpc::launch_preprocess_hash(a, forest, n_img, mode, c->stream));
+  GPC_CUDA(c, gpc::launch_preprocess_hash(a, forest, n_img, mode, sl.stream));
   c->launches += 1;
-  return mark(c);                                                                  // event 1
+  return mark_on(c, sl);                                                           // event 1
 }
 
 int ensure_global_ws(gpc_ctx* c, long long records) {
@@ -214,12 +232,16 @@ int run_match_sort_pair(gpc_ctx* c, const uint32_t* hash, int p, int w, int h, c
 
 bool use_sort_matcher(const gpc_ctx* c, const gpc_settings* s) { return !s->epipolar_mode || c->matcher == GPC_MATCHER_SORT; }
 
-// Kernels B, scan, C over hash images already in c->d_hash (or `hash`).
-int run_match(gpc_ctx* c, const uint32_t* hash, int n_pairs, int w, int h, const gpc_settings* s, gpc_support* d_out,
+// Kernels B, scan, C over the slot's hash images.  packed: supports of the slot's pairs back to back
+// from d_out[0], prefix in d_pair_base + 2 * p0; else pair i at d_out + i * cap.
+int run_match(gpc_ctx* c, const Slot& sl, int n_pairs, int w, int h, const gpc_settings* s, gpc_support* d_out,
               long long cap, bool packed, int32_t* d_n_out, int32_t* d_n_cand) {
+  const size_t P = (size_t)w * h;
+  const uint32_t* hash = c->d_hash + (size_t)(2 * sl.p0) * P;
   if (use_sort_matcher(c, s)) {
-    // radix sort + segmented scan, pair by pair (strided output only; the packed host entry
-    // points run one pair at a time)
+    // radix sort + segmented scan, pair by pair on the context's stream (strided output only; the
+    // packed host entry points run one pair at a time)
+    if (sl.stream != c->stream || sl.p0 != 0) return fail(c, GPC_E_ARG, "internal: sort matcher runs on the context stream");
     if (packed && n_pairs != 1) return fail(c, GPC_E_ARG, "internal: packed sort matcher handles one pair per call");
     for (int k = 0; k < 2; k++) { int rc = mark(c); if (rc) return rc; }   // events 2, 3 (no row kernels here)
     for (int p = 0; p < n_pairs; p++) {
@@ -233,10 +255,12 @@ int run_match(gpc_ctx* c, const uint32_t* hash, int n_pairs, int w, int h, const
     }
     return mark(c);                                                                // event 4
   }
-  const int32_t* rowcnt = c->d_rows;
-  const int32_t* lastrow = c->d_rows + (size_t)(2 * n_pairs) * h;
+  const int32_t* rowcnt = c->d_rows + (size_t)(2 * sl.p0) * h;
+  int32_t* rowmatch = c->d_rowmatch + (size_t)sl.p0 * h;
+  int32_t* rowoff = c->d_rowoff + (size_t)sl.p0 * h;
+  uint32_t* stage = c->d_stage + (size_t)sl.p0 * P;
   gpc::MatchArgs m{};
-  m.hash = hash; m.lastrow = lastrow; m.stage = c->d_stage; m.rowmatch = c->d_rowmatch;
+  m.hash = hash; m.lastrow = c->d_lastrow + 2 * sl.p0; m.stage = stage; m.rowmatch = rowmatch;
   m.W = w; m.H = h; m.disp_high = s->disp_high; m.vertical_tolerance = s->vertical_tolerance;
   m.wcap = std::max(w - 2 * gpc::kRadius, 16);
   m.table_log2 = table_log2_for(w, m.wcap);
@@ -247,21 +271,21 @@ int run_match(gpc_ctx* c, const uint32_t* hash, int n_pairs, int w, int h, const
   m.key_bits = 31;   // hash images may come from the caller (gpc_match_hash_images): assume full 31-bit states
   if ((int)gpc::match_smem_bytes(m.wcap, m.table_log2) > c->match_smem_max)
     return fail(c, GPC_E_DIMS, "image too wide for the row matcher's shared memory");
-  if (h - 2 * gpc::kRadius <= 0) GPC_CUDA(c, cudaMemsetAsync(c->d_rowmatch, 0, (size_t)n_pairs * h * sizeof(int32_t), c->stream));
-  GPC_CUDA(c, gpc::launch_match_rows(m, n_pairs, c->stream));
-  int rc = mark(c); if (rc) return rc;                                             // event 2
-  GPC_CUDA(c, gpc::launch_row_scan(c->d_rowmatch, rowcnt, h, n_pairs, c->d_rowoff, d_n_out, d_n_cand, c->stream));
+  if (h - 2 * gpc::kRadius <= 0) GPC_CUDA(c, cudaMemsetAsync(rowmatch, 0, (size_t)n_pairs * h * sizeof(int32_t), sl.stream));
+  GPC_CUDA(c, gpc::launch_match_rows(m, n_pairs, sl.stream));
+  int rc = mark_on(c, sl); if (rc) return rc;                                      // event 2
+  GPC_CUDA(c, gpc::launch_row_scan(rowmatch, rowcnt, h, n_pairs, rowoff, d_n_out, d_n_cand, sl.stream));
   c->launches += 2;
   const long long* pair_base = nullptr;
   if (packed) {
-    GPC_CUDA(c, gpc::launch_pair_scan(d_n_out, n_pairs, c->d_pair_base, c->stream));
+    GPC_CUDA(c, gpc::launch_pair_scan(d_n_out, n_pairs, c->d_pair_base + 2 * sl.p0, sl.stream));
     c->launches += 1;
-    pair_base = c->d_pair_base;
+    pair_base = c->d_pair_base + 2 * sl.p0;
   }
-  rc = mark(c); if (rc) return rc;                                                 // event 3
-  GPC_CUDA(c, gpc::launch_emit_supports(c->d_stage, c->d_rowmatch, c->d_rowoff, pair_base, d_out, cap, w, h, n_pairs, c->stream));
+  rc = mark_on(c, sl); if (rc) return rc;                                          // event 3
+  GPC_CUDA(c, gpc::launch_emit_supports(stage, rowmatch, rowoff, pair_base, d_out, cap, w, h, n_pairs, sl.stream));
   if (h - 2 * gpc::kRadius > 0) c->launches += 1;
-  return mark(c);                                                                  // event 4
+  return mark_on(c, sl);                                                           // event 4
 }
 
 int ensure_debug_buffers(gpc_ctx* c) {
@@ -325,17 +349,21 @@ int gpc_create(gpc_ctx** out, int device, int max_w, int max_h, int max_batch) {
   TRY(cudaMalloc(&c->d_raw, 2 * B * P));
   TRY(cudaMalloc(&c->d_hash, 2 * B * P * sizeof(uint32_t)));
   TRY(cudaMalloc(&c->d_stage, B * P * sizeof(uint32_t)));
-  TRY(cudaMalloc(&c->d_rows, (2 * B * max_h + 2 * B) * sizeof(int32_t)));
+  TRY(cudaMalloc(&c->d_rows, 2 * B * max_h * sizeof(int32_t)));
+  TRY(cudaMalloc(&c->d_lastrow, 2 * B * sizeof(int32_t)));
+  for (int l = 0; l < gpc_ctx::kLanes; l++) TRY(cudaStreamCreateWithFlags(&c->lane_stream[l], cudaStreamNonBlocking));
+  TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  if (const char* e = std::getenv("GPC_CHUNK_PAIRS")) c->chunk_pairs = std::max(1, std::atoi(e));
   TRY(cudaMalloc(&c->d_rowmatch, B * max_h * sizeof(int32_t)));
   TRY(cudaMalloc(&c->d_rowoff, B * (max_h + 1) * sizeof(int32_t)));
   TRY(cudaMalloc(&c->d_totals, B * sizeof(int32_t)));
   TRY(cudaMalloc(&c->d_ncand, 2 * B * sizeof(int32_t)));
-  TRY(cudaMalloc(&c->d_pair_base, (B + 1) * sizeof(long long)));
+  TRY(cudaMalloc(&c->d_pair_base, (2 * B + 2) * sizeof(long long)));
   long long per_pair = (long long)std::max(max_w - 26, 0) * std::max(max_h - 26, 0);
   c->out_cap = std::max<long long>(per_pair * (long long)B, 1);
   TRY(cudaMalloc(&c->d_out, (size_t)c->out_cap * sizeof(gpc_support)));
   TRY(cudaMallocHost(&c->h_counts, 3 * B * sizeof(int32_t)));
-  TRY(cudaMallocHost(&c->h_pair_base, (B + 1) * sizeof(long long)));
+  TRY(cudaMallocHost(&c->h_pair_base, (2 * B + 2) * sizeof(long long)));
   TRY(cudaMemsetAsync(c->d_rowmatch, 0, B * max_h * sizeof(int32_t), c->stream));
   TRY(cudaStreamSynchronize(c->stream));
 #undef TRY
@@ -346,7 +374,10 @@ int gpc_create(gpc_ctx** out, int device, int max_w, int max_h, int max_batch) {
 void gpc_destroy(gpc_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaFree(c->d_raw); cudaFree(c->d_hash); cudaFree(c->d_stage); cudaFree(c->d_rows); cudaFree(c->d_rowmatch);
+  cudaFree(c->d_raw); cudaFree(c->d_hash); cudaFree(c->d_stage); cudaFree(c->d_rows); cudaFree(c->d_lastrow); cudaFree(c->d_rowmatch);
+  for (int l = 0; l < gpc_ctx::kLanes; l++) if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  for (cudaEvent_t e : c->ev_chunk) cudaEventDestroy(e);
   cudaFree(c->d_rowoff); cudaFree(c->d_totals); cudaFree(c->d_ncand); cudaFree(c->d_pair_base); cudaFree(c->d_out);
   cudaFree(c->d_dbg8); cudaFree(c->d_mask); cudaFree(c->d_gws); cudaFree(c->d_rowoff2);
   if (c->h_counts) cudaFreeHost(c->h_counts);
@@ -453,9 +484,67 @@ int gpc_match_batch_device(gpc_ctx* c, const uint8_t* d_images, int n_pairs, int
   rc = check_settings(c, s); if (rc) return rc;
   if (!c->has_forest) return fail(c, GPC_E_FOREST, "no forest set");
   GPC_CUDA(c, cudaSetDevice(c->device));
-  rc = run_preprocess(c, d_images, 2 * n_pairs, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
+  rc = run_preprocess(c, Slot{0, c->stream}, d_images, 2 * n_pairs, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
   if (rc) return rc;
-  return run_match(c, c->d_hash, n_pairs, w, h, s, d_out, cap_per_pair, false, d_n_out, d_n_cand);
+  return run_match(c, Slot{0, c->stream}, n_pairs, w, h, s, d_out, cap_per_pair, false, d_n_out, d_n_cand);
+}
+
+// Pipelined body of gpc_match_batch (row matcher): chunks of pairs rotate over kLanes streams, each
+// chunk on its own slice of the resident buffers, so that the upload of chunk k+2, the kernels of
+// chunk k+1 and the download of chunk k's supports overlap (PCIe is full duplex).
+static int match_batch_pipelined(gpc_ctx* c, const uint8_t* images, int n_pairs, int w, int h, const gpc_settings* s,
+                                 gpc_support* out, int64_t cap, int64_t* offsets, int32_t* n_cand) {
+  const size_t P = (size_t)w * h;
+  const int CH = c->chunk_pairs;
+  const int nch = (n_pairs + CH - 1) / CH;
+  const long long per_pair = c->out_cap / c->max_batch;
+  while ((int)c->ev_chunk.size() < nch) {
+    cudaEvent_t e;
+    GPC_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ev_chunk.push_back(e);
+  }
+  GPC_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));               // order after earlier work of the context
+  for (int l = 0; l < gpc_ctx::kLanes; l++) GPC_CUDA(c, cudaStreamWaitEvent(c->lane_stream[l], c->ev_fork, 0));
+  long long total = 0;
+  bool overflow = false;
+  offsets[0] = 0;
+  auto drain = [&](int k) -> int {                                     // download the supports of chunk k
+    const int p0 = k * CH, n = std::min(CH, n_pairs - p0);
+    cudaStream_t st = c->lane_stream[k % gpc_ctx::kLanes];
+    GPC_CUDA(c, cudaEventSynchronize(c->ev_chunk[k]));
+    const long long* pb = c->h_pair_base + 2 * p0;
+    for (int i = 0; i < n; i++) offsets[p0 + i + 1] = total + pb[i + 1];
+    if (n_cand) std::memcpy(n_cand + 2 * p0, c->h_counts + 2 * p0, 2 * (size_t)n * sizeof(int32_t));
+    const long long m = pb[n];
+    if (total + m > cap) overflow = true;
+    else if (m > 0)
+      GPC_CUDA(c, cudaMemcpyAsync(out + total, c->d_out + (size_t)p0 * per_pair, (size_t)m * sizeof(gpc_support),
+                                  cudaMemcpyDeviceToHost, st));
+    total += m;
+    return GPC_OK;
+  };
+  for (int k = 0; k < nch; k++) {
+    const int p0 = k * CH, n = std::min(CH, n_pairs - p0);
+    const Slot sl{p0, c->lane_stream[k % gpc_ctx::kLanes]};
+    uint8_t* d_img = c->d_raw + (size_t)(2 * p0) * P;
+    GPC_CUDA(c, cudaMemcpyAsync(d_img, images + (size_t)(2 * p0) * P, 2 * (size_t)n * P, cudaMemcpyHostToDevice, sl.stream));
+    int rc = run_preprocess(c, sl, d_img, 2 * n, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
+    if (rc) return rc;
+    rc = run_match(c, sl, n, w, h, s, c->d_out + (size_t)p0 * per_pair, (long long)n * per_pair, true, c->d_totals + p0,
+                   c->d_ncand + 2 * p0);
+    if (rc) return rc;
+    GPC_CUDA(c, cudaMemcpyAsync(c->h_pair_base + 2 * p0, c->d_pair_base + 2 * p0, (size_t)(n + 1) * sizeof(long long),
+                                cudaMemcpyDeviceToHost, sl.stream));
+    if (n_cand)
+      GPC_CUDA(c, cudaMemcpyAsync(c->h_counts + 2 * p0, c->d_ncand + 2 * p0, 2 * (size_t)n * sizeof(int32_t),
+                                  cudaMemcpyDeviceToHost, sl.stream));
+    GPC_CUDA(c, cudaEventRecord(c->ev_chunk[k], sl.stream));
+    if (k >= gpc_ctx::kLanes - 1) { rc = drain(k - (gpc_ctx::kLanes - 1)); if (rc) return rc; }
+  }
+  for (int k = std::max(0, nch - (gpc_ctx::kLanes - 1)); k < nch; k++) { int rc = drain(k); if (rc) return rc; }
+  for (int l = 0; l < gpc_ctx::kLanes; l++) GPC_CUDA(c, cudaStreamSynchronize(c->lane_stream[l]));
+  if (overflow) return fail(c, GPC_E_CAPACITY, "support buffer too small: need " + std::to_string(total));
+  return GPC_OK;
 }
 
 int gpc_match_batch(gpc_ctx* c, const uint8_t* images, int n_pairs, int w, int h, const gpc_settings* s,
@@ -466,8 +555,10 @@ int gpc_match_batch(gpc_ctx* c, const uint8_t* images, int n_pairs, int w, int h
   if (!c->has_forest) return fail(c, GPC_E_FOREST, "no forest set");
   GPC_CUDA(c, cudaSetDevice(c->device));
   const size_t P = (size_t)w * h;
+  if (!use_sort_matcher(c, s) && !c->timing && n_pairs >= 2 * c->chunk_pairs && h > 2 * gpc::kRadius)
+    return match_batch_pipelined(c, images, n_pairs, w, h, s, out, cap, offsets, n_cand);
   GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, images, 2 * (size_t)n_pairs * P, cudaMemcpyHostToDevice, c->stream));
-  rc = run_preprocess(c, c->d_raw, 2 * n_pairs, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
+  rc = run_preprocess(c, Slot{0, c->stream}, c->d_raw, 2 * n_pairs, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
   if (rc) return rc;
   if (use_sort_matcher(c, s) && n_pairs > 1) {
     // radix-sort matcher: one pair at a time, results appended on the host
@@ -490,7 +581,7 @@ int gpc_match_batch(gpc_ctx* c, const uint8_t* images, int n_pairs, int w, int h
     if (overflow) return fail(c, GPC_E_CAPACITY, "support buffer too small: need " + std::to_string(total));
     return GPC_OK;
   }
-  rc = run_match(c, c->d_hash, n_pairs, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
+  rc = run_match(c, Slot{0, c->stream}, n_pairs, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
   if (rc) return rc;
   GPC_CUDA(c, cudaMemcpyAsync(c->h_pair_base, c->d_pair_base, (size_t)(n_pairs + 1) * sizeof(long long),
                               cudaMemcpyDeviceToHost, c->stream));
@@ -519,9 +610,9 @@ int gpc_match_pair(gpc_ctx* c, const uint8_t* left, const uint8_t* right, int w,
   const size_t P = (size_t)w * h;
   GPC_CUDA(c, cudaMemcpy2DAsync(c->d_raw, w, left, stride, w, h, cudaMemcpyHostToDevice, c->stream));
   GPC_CUDA(c, cudaMemcpy2DAsync(c->d_raw + P, w, right, stride, w, h, cudaMemcpyHostToDevice, c->stream));
-  rc = run_preprocess(c, c->d_raw, 2, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
+  rc = run_preprocess(c, Slot{0, c->stream}, c->d_raw, 2, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
   if (rc) return rc;
-  rc = run_match(c, c->d_hash, 1, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
+  rc = run_match(c, Slot{0, c->stream}, 1, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
   if (rc) return rc;
   GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_totals, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   GPC_CUDA(c, cudaMemcpyAsync(c->h_counts + 1, c->d_ncand, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -560,7 +651,7 @@ int gpc_hash(gpc_ctx* c, const uint8_t* img, int w, int h, int thr, uint32_t* st
   rc = ensure_debug_buffers(c); if (rc) return rc;
   const size_t P = (size_t)w * h;
   GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, img, P, cudaMemcpyHostToDevice, c->stream));
-  rc = run_preprocess(c, c->d_raw, 1, w, h, thr, c->forest_dev, nullptr, nullptr);
+  rc = run_preprocess(c, Slot{0, c->stream}, c->d_raw, 1, w, h, thr, c->forest_dev, nullptr, nullptr);
   if (rc) return rc;
   GPC_CUDA(c, gpc::launch_mask_list(c->d_hash, c->d_rows, c->d_rowoff, w, h, c->d_mask, (int)std::min<size_t>(P, 0x7fffffff), c->stream));
   c->launches += 2;
@@ -600,9 +691,10 @@ int gpc_match_hash_images(gpc_ctx* c, const uint32_t* hash_l, const uint32_t* ha
     }
   GPC_CUDA(c, cudaMemcpyAsync(c->d_hash, hash_l, P * 4, cudaMemcpyHostToDevice, c->stream));
   GPC_CUDA(c, cudaMemcpyAsync(c->d_hash + P, hash_r, P * 4, cudaMemcpyHostToDevice, c->stream));
-  GPC_CUDA(c, cudaMemcpyAsync(c->d_rows, rows.data(), rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_rows, rows.data(), (size_t)2 * h * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_lastrow, rows.data() + (size_t)2 * h, 2 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   GPC_CUDA(c, cudaStreamSynchronize(c->stream));   // `rows` is pageable and about to go out of scope
-  rc = run_match(c, c->d_hash, 1, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
+  rc = run_match(c, Slot{0, c->stream}, 1, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
   if (rc) return rc;
   GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_totals, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   GPC_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -647,7 +739,7 @@ static int preprocess_device(gpc_ctx* c, const uint8_t* d_img, int w, int h, int
   gpc::ForestDev none{};                           // no tests: hash image carries the candidate flag only
   uint8_t* d_smooth = c->d_dbg8;
   uint8_t* d_grad = c->d_dbg8 + (size_t)c->max_w * c->max_h;
-  rc = run_preprocess(c, d_img, 1, w, h, thr, none, d_smooth, d_grad);
+  rc = run_preprocess(c, Slot{0, c->stream}, d_img, 1, w, h, thr, none, d_smooth, d_grad);
   if (rc) return rc;
   GPC_CUDA(c, gpc::launch_mask_list(c->d_hash, c->d_rows, c->d_rowoff, w, h, c->d_mask, (int)std::min<size_t>(P, 0x7fffffff), c->stream));
   c->launches += 2;
@@ -686,9 +778,9 @@ int gpc_match_images(gpc_ctx* c, const gpc_image* l, const gpc_image* r, const g
   const size_t P = (size_t)w * h;
   GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, l->d_raw, P, cudaMemcpyDeviceToDevice, c->stream));
   GPC_CUDA(c, cudaMemcpyAsync(c->d_raw + P, r->d_raw, P, cudaMemcpyDeviceToDevice, c->stream));
-  rc = run_preprocess(c, c->d_raw, 2, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
+  rc = run_preprocess(c, Slot{0, c->stream}, c->d_raw, 2, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
   if (rc) return rc;
-  rc = run_match(c, c->d_hash, 1, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
+  rc = run_match(c, Slot{0, c->stream}, 1, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
   if (rc) return rc;
   GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_totals, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   GPC_CUDA(c, cudaMemcpyAsync(c->h_counts + 1, c->d_ncand, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -721,7 +813,7 @@ int gpc_hash_smooth(gpc_ctx* c, const uint8_t* smooth, int w, int h, const int32
   }
   GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, smooth, P, cudaMemcpyHostToDevice, c->stream));
   GPC_CUDA(c, cudaMemcpyAsync(c->d_dbg8, flags.data(), P, cudaMemcpyHostToDevice, c->stream));
-  rc = run_preprocess(c, c->d_raw, 1, w, h, 0, c->forest_dev, nullptr, nullptr, c->d_dbg8);
+  rc = run_preprocess(c, Slot{0, c->stream}, c->d_raw, 1, w, h, 0, c->forest_dev, nullptr, nullptr, c->d_dbg8);
   if (rc) return rc;
   std::vector<uint32_t> himg(P);
   GPC_CUDA(c, cudaMemcpyAsync(himg.data(), c->d_hash, P * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -752,7 +844,7 @@ int gpc_correspond_images(gpc_ctx* c, const gpc_image* l, const gpc_image* r, co
   const size_t P = (size_t)w * h;
   GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, l->d_raw, P, cudaMemcpyDeviceToDevice, c->stream));
   GPC_CUDA(c, cudaMemcpyAsync(c->d_raw + P, r->d_raw, P, cudaMemcpyDeviceToDevice, c->stream));
-  rc = run_preprocess(c, c->d_raw, 2, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
+  rc = run_preprocess(c, Slot{0, c->stream}, c->d_raw, 2, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
   if (rc) return rc;
   // a correspondence is 16 bytes, a support 12: d_out holds out_cap * 12 / 16 correspondences
   const long long dcap = c->out_cap * 12 / 16;

@@ -18,14 +18,25 @@ constexpr int kMaxTests = 32;          // inference.hpp:426
 constexpr uint32_t kCandFlag = 0x80000000u;
 
 // ---- kernel A tile geometry -------------------------------------------------------------
-constexpr int kTileW = 256;                    // output pixels per tile row
-constexpr int kTileH = 32;                     // output rows per tile
+#ifndef GPC_TILE_W
+#define GPC_TILE_W 256
+#endif
+#ifndef GPC_TILE_H
+#define GPC_TILE_H 32
+#endif
+#ifndef GPC_THREADS_A
+#define GPC_THREADS_A 256
+#endif
+constexpr int kTileW = GPC_TILE_W;             // output pixels per tile row (multiple of 128)
+constexpr int kTileH = GPC_TILE_H;             // output rows per tile
 constexpr int kPitch = kTileW + 32;            // smem row pitch in bytes: image cols x0-16 .. x0+kTileW+15
 constexpr int kPitchW = kPitch / 4;            // ... in 32-bit words
 constexpr int kRawRows = kTileH + 2 * kRadius + 2;   // image rows y0-14 .. y0+kTileH+13
 constexpr int kSmRows = kTileH + 2 * kRadius;        // image rows y0-13 .. y0+kTileH+12
 constexpr int kCopyBytes = kSmRows * kPitch;   // one copy of the smoothed tile
-constexpr int kThreadsA = 256;
+constexpr int kThreadsA = GPC_THREADS_A;
+constexpr int kQuadsX = kTileW / 4;            // quads (4 pixels) per tile row
+static_assert(kThreadsA % kQuadsX == 0 && kThreadsA >= kPitchW, "thread block must cover whole quad rows");
 
 // Forest baked for the kernel's shared-memory layout (replaces the per-width baking of
 // inference.hpp:427-428).  The smoothed tile is kept four times, copy k shifted left by k bytes,

@@ -153,7 +153,7 @@ preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
   // thread = (quad column, one of 3 row segments); walks down its rows with a 3-row window of
   // horizontal thirds held in registers.
   if (kMode != 2) {
-    constexpr int kSegs = 3;
+    constexpr int kSegs = kThreadsA / kPitchW;
     constexpr int kSegRows = (kSmRows + kSegs - 1) / kSegs;
     const int q = tid % kPitchW, seg = tid / kPitchW;
     if (seg < kSegs) {
@@ -247,14 +247,14 @@ preprocess_hash_kernel(const PreprocessArgs args, const ForestDev forest) {
 
   // ---- phase 3: fern tests, 4 pixels per step ------------------------------------------------
   {
-    const int qx = tid & 63;
+    const int qx = tid % kQuadsX;
     const int gx = x0 + 4 * qx;
     uint32_t* __restrict__ hash = args.hash + img_off;
     const uint32_t m8 = (gx & 4) ? kMsb : 0x80808000u;          // test #8: byte lanes x%8==0 dropped (filter.hpp:582)
     const int T = forest.n_tests;
     const int n_groups = (T <= 9) ? 1 : (T <= 17) ? 2 : (T <= 25) ? 3 : 4;
 #pragma unroll 1
-    for (int ry = tid >> 6; ry < kTileH; ry += kThreadsA / 64) {
+    for (int ry = tid / kQuadsX; ry < kTileH; ry += kThreadsA / kQuadsX) {
       const int gy = y0 + ry;
       const bool inside = gx < W && gy < H;                      // cand is 0 outside the image
       const uint32_t cm = (cand[ry * (kTileW / 16) + (qx >> 2)] >> ((qx & 3) * 4)) & 15u;

@@ -158,3 +158,31 @@ def test_resident_images(g, ctx, oracle):
         with pytest.raises(g.GpcError):
             ctx.match_images(io, io, g.sparsematch_settings())        # image of another context
         io.release()
+
+
+def test_pipelined_batch(g, oracle, monkeypatch):
+    """gpc_match_batch splits large batches into chunks that rotate over three streams (upload,
+    kernels and download overlap).  Chunk size 2 forces that path on a 7-pair batch, including a
+    pair without candidates and a too-small output buffer."""
+    from opengpc_b200 import capi
+    from opengpc_b200.synth import synth_batch
+    monkeypatch.setenv("GPC_CHUNK_PAIRS", "2")
+    imgs = synth_batch(320, 90, 7, seed0=300)
+    imgs[3] = 50
+    of = oracle.read_forest(FORESTS["tau"])
+    with g.Context(device=0, max_w=320, max_h=90, max_batch=7) as c:
+        c.set_forest(FORESTS["tau"])
+        s = g.sparsematch_settings()
+        for rep in range(3):
+            supp, offsets, ncand = c.match_batch(imgs, s)
+            for p in range(7):
+                ref, ocl, ocr = oracle.pair(imgs[p, 0], imgs[p, 1], of, osettings())
+                assert (ncand[p, 0], ncand[p, 1]) == (ocl, ocr)
+                assert np.array_equal(supp[offsets[p]:offsets[p + 1]], ref), (rep, p)
+        assert offsets[4] == offsets[3]
+        small = np.empty(10, g.SUPPORT_DTYPE)
+        with pytest.raises(g.GpcError) as e:
+            c.match_batch(imgs, s, out=small)
+        assert e.value.status == capi.GPC_E_CAPACITY
+        supp2, offsets2, _ = c.match_batch(imgs, s)          # the context stays usable afterwards
+        assert np.array_equal(supp2, supp) and np.array_equal(offsets2, offsets)
