@@ -1,8 +1,14 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the Global Patch Collider inference path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--forest tau|zero]
-                  [--shape 1024x436] [--batch 256]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 0..4]
+                  [--forest tau|zero|deep] [--shape 1024x436] [--batch 256]
+
+--config picks a BASELINE.json configuration (default 1, the one the headline metric is quoted on):
+  0  sparsematch, defaultTauForest, 1024x436           1  sparsematch, defaultZeroForest, 1024x436
+  2  batch of 1920x1080 pairs (32 per GPU), tau forest  3  3840x2160 pair through a 4-level pyramid
+  4  deep random forest (16 x 12) on 1080p frames (32 per GPU)
+--forest / --shape / --batch override the configuration's values.
 
 A "step" is one pass of the whole hot path (kernel A: box + Sobel + fern hashing, kernel B: per-row
 matching, scans, kernel C: ordered support emission) over one batch of synthetic stereo pairs.
@@ -35,6 +41,12 @@ FORESTS = {"tau": os.path.join(ROOT, "forests", "defaultTauForest.txt"),
            "zero": os.path.join(ROOT, "forests", "defaultZeroForest.txt"),
            "deep": os.path.join(ROOT, "forests", "deepRandomForest16x12.txt")}
 METRIC = "stereo pairs/s (sparsematch: preprocessImage x2 + rectifiedMatch)"
+# BASELINE.json configs[i] -> (forest, shape, pairs per step per GPU)
+CONFIGS = {0: ("tau", "1024x436", 256), 1: ("zero", "1024x436", 256), 2: ("tau", "1920x1080", 32),
+           3: ("tau", "3840x2160", 1), 4: ("deep", "1920x1080", 32)}
+CONFIG_NAMES = {0: "sparsematch", 1: "sparsematch", 2: "batch of 1080p pairs, one pair stream per GPU",
+                3: "4-level pyramid (3840x2160, 1920x1080, 960x540, 480x270), per-level hashing and matching",
+                4: "deep random forest (16 trees x 12 tests, first 32 tests as in the reference) on a 1080p sequence"}
 
 
 def parse_args():
@@ -43,13 +55,19 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--forest", default="tau", choices=list(FORESTS))
-    ap.add_argument("--shape", default="1024x436")
-    ap.add_argument("--batch", type=int, default=256, help="pairs per step per GPU")
+    ap.add_argument("--config", type=int, default=1, choices=[0, 1, 2, 3, 4])
+    ap.add_argument("--forest", default=None, choices=list(FORESTS))
+    ap.add_argument("--shape", default=None)
+    ap.add_argument("--batch", type=int, default=None, help="pairs per step per GPU")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic pairs (seeds 1234+i), tiled to the batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    forest, shape, batch = CONFIGS[args.config]
+    args.forest = args.forest or forest
+    args.shape = args.shape or shape
+    args.batch = args.batch or batch
+    return args
 
 
 def peaks():
@@ -61,8 +79,20 @@ def peaks():
 
 
 def workload_name(args, w, h):
-    cfg = {"tau": "configs[0]", "zero": "configs[1]"}.get(args.forest, "configs[4] stand-in")
-    return f"{cfg}: sparsematch, forests/{os.path.basename(FORESTS[args.forest])}, synthetic {w}x{h} stereo pairs"
+    return (f"configs[{args.config}]: {CONFIG_NAMES[args.config]}, forests/{os.path.basename(FORESTS[args.forest])}, "
+            f"synthetic {w}x{h} stereo pairs")
+
+
+def ncu_traffic(kernel, n_pixels):
+    """DRAM bytes per launch from the committed ncu capture (profiles/traffic.json: bytes per pixel)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        t = json.load(f)
+    if kernel not in t.get("dram_bytes_per_pixel", {}):
+        return None, None
+    return t["dram_bytes_per_pixel"][kernel] * n_pixels, t.get("source")
 
 
 class ClockSampler:
@@ -170,6 +200,43 @@ def run_reference_arm(args, w, h):
     print(json.dumps(line), flush=True)
 
 
+def run_pyramid(args, g, ctx, images, w, h, world, rank, dist, torch):
+    """configs[3]: one 4K pair through 4 pyramid levels (gpc_match_pyramid, host buffers: the upload
+    of the pair and the download of every level's supports are inside the timed region)."""
+    settings = g.sparsematch_settings()
+    L, R = images[0, 0], images[0, 1]
+    levels = 4
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        supp, offs, _ = ctx.match_pyramid(L, R, levels, settings)
+    l0 = ctx.launches
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        supp, offs, _ = ctx.match_pyramid(L, R, levels, settings)
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    from opengpc_b200.shard import reduce_timing
+    ms, launches = reduce_timing(sec * 1e3, ctx.launches - l0, dist, "cuda")
+    clocks = sampler.stop()
+    if rank != 0:
+        return
+    value = world * args.steps / (ms / 1e3)
+    pix = sum(2 * (w >> l) * (h >> l) for l in range(levels))
+    line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "mpix_per_s": value * pix / 1e6,
+            "config": {"workload": workload_name(args, w, h), "levels": levels, "supports_per_level": np.diff(offs).tolist(),
+                       "note": "host-buffer API only: value == e2e (upload + per-level download inside the timed region)"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 2 * w * h, "d2h_bytes_per_step": int(len(supp)) * 12,
+                    "api": "gpc_match_pyramid"}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
     w, h = (int(v) for v in args.shape.lower().split("x"))
@@ -202,7 +269,10 @@ def main():
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
 
-    cap = (w - 26) * (h - 26) // 4                                # device-resident capacity per pair
+    if args.config == 3:
+        run_pyramid(args, g, ctx, images, w, h, world, rank, dist, torch)
+        return
+    cap = (w - 26) * (h - 26) * 6 // 10                           # device-resident capacity per pair
     with torch.cuda.stream(stream):
         d_img = torch.from_numpy(images).cuda(non_blocking=False)
         d_out = torch.empty((B, cap, 3), dtype=torch.int32, device="cuda")
@@ -220,14 +290,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ------------------------------------------------------------
+    sampler = ClockSampler(local_rank)                            # samples clocks from warm-up to the end of the timed work
+    sampler.start()
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
             step()
     barrier()
     n_sup = d_n.cpu().numpy().astype(np.int64)
     assert (n_sup <= cap).all(), "device capacity per pair too small for this workload"
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = ctx.launches
     ctx.enable_kernel_timing(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -242,14 +312,8 @@ def main():
     kms, kruns = ctx.kernel_times()
     ctx.enable_kernel_timing(False)
     launches = ctx.launches - launches0
-    clocks = sampler.stop()
-    if dist is not None:
-        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt.item())
+    from opengpc_b200.shard import reduce_timing
+    ms_total, launches = reduce_timing(ms_total, launches, dist, "cuda")     # max over ranks, sum over ranks
     ms_per_step = ms_total / args.steps
     value = world * B / (ms_per_step / 1e3)
 
@@ -277,9 +341,31 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             sec = float(t.item())
         assert int(h_off[B]) == tot_sup
+        clocks = sampler.stop()
         e2e = {"value": world * B * args.steps / sec, "unit": "pairs/s",
                "h2d_bytes_per_step": int(2 * B * P), "d2h_bytes_per_step": int(tot_sup * 12 + (B + 1) * 8),
-               "api": "gpc_match_batch (pinned host buffers, synchronous)"}
+               "api": "gpc_match_batch (pinned host buffers; upload, kernels and download pipelined over 3 streams)"}
+
+    if args.no_e2e:
+        clocks = sampler.stop()
+
+    # ---- the other Sintel forest, device-resident only (same run, fewer steps) ---------------------
+    other = None
+    if args.config in (0, 1) and world == 1 and not args.no_e2e:
+        of = "tau" if args.forest == "zero" else "zero"
+        ctx.set_forest(FORESTS[of])
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(max(3, args.steps // 2)):
+                step()
+            e1.record(stream)
+        barrier()
+        other = {f"configs[{1 - args.config}] ({os.path.basename(FORESTS[of])}) pairs/s, device-resident":
+                 B * max(3, args.steps // 2) / (e0.elapsed_time(e1) / 1e3)}
+        ctx.set_forest(FORESTS[args.forest])
 
     if rank != 0:
         if dist is not None:
@@ -297,8 +383,10 @@ def main():
     dom_ms = per_kernel_ms[dominant]
     achieved = alg_bytes[dominant] / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
     path_bytes = (10.0 * P + 12.0 * mean_sup)                     # B_alg per pair
+    traffic, traffic_src = ncu_traffic(dominant, (2 * B if dominant == "preprocess_hash" else B) * P)
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes[dominant],
                 "kernel_ms_per_step": per_kernel_ms,
                 "path_bytes_per_pair": path_bytes,
                 "path_frac": path_bytes * value / world / 1e9 / peak}
@@ -314,6 +402,8 @@ def main():
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
     if e2e:
         line["e2e"] = e2e
+    if other:
+        line["other_configs"] = other
 
     # ---- CPU baseline: the unmodified reference on this box's host cores -------------------------
     if not args.no_cpu_baseline and world == 1:

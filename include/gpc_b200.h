@@ -93,6 +93,15 @@ int gpc_match_batch(gpc_ctx* ctx, const uint8_t* images, int n_pairs, int w, int
                     const gpc_settings* s, gpc_support* out, int64_t cap, int64_t* offsets,
                     int32_t* n_cand);
 
+/* Multi-level matching (BASELINE.json configs[3]).  The reference has no pyramid; SURVEY.md 8d
+ * defines it: level l+1 = 2x2 floor-mean (a+b+c+d)/4 of the raw level-l images (built on the
+ * device), the single-level path of inference.hpp:302-393 per level with the same forest, and
+ * disp_high halved per level.  Level l's supports are out[level_offsets[l]..level_offsets[l+1]);
+ * level_offsets has n_levels+1 entries; n_cand (optional) = [n_levels][2]. */
+int gpc_match_pyramid(gpc_ctx* ctx, const uint8_t* left, const uint8_t* right, int w, int h, int stride,
+                      int n_levels, const gpc_settings* s, gpc_support* out, int64_t cap,
+                      int64_t* level_offsets, int32_t* n_cand);
+
 /* ---- whole path, device-resident, stream-ordered (no host synchronisation) ---------------
  * d_images = [n_pairs][2][h][w] uint8 in device memory; d_out = [n_pairs][cap_per_pair]
  * gpc_support in device memory; d_n_out = [n_pairs] int32 (true counts, may exceed the

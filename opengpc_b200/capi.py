@@ -23,7 +23,7 @@ SYMBOLS = ["gpc_create", "gpc_destroy", "gpc_last_error", "gpc_status_string", "
            "gpc_read_forest", "gpc_set_forest", "gpc_match_pair", "gpc_match_batch", "gpc_match_batch_device",
            "gpc_preprocess", "gpc_hash", "gpc_match_hash_images", "gpc_launch_count", "gpc_enable_kernel_timing",
            "gpc_kernel_times", "gpc_hash_smooth", "gpc_image_upload", "gpc_image_release", "gpc_image_preprocess",
-           "gpc_match_images", "gpc_correspond_images", "gpc_find_correspondences", "gpc_set_matcher"]
+           "gpc_match_images", "gpc_correspond_images", "gpc_find_correspondences", "gpc_set_matcher", "gpc_match_pyramid"]
 KERNEL_NAMES = ["preprocess_hash", "match_rows", "scans", "emit_supports"]
 
 
@@ -203,6 +203,19 @@ class Context:
         self._check(self.lib.gpc_match_batch_device(self._h, C.c_void_p(d_images), n_pairs, w, h, C.byref(settings),
                                                     C.c_void_p(d_out), C.c_int(cap_per_pair), C.c_void_p(d_n_out),
                                                     C.c_void_p(d_n_cand or 0)))
+
+    def match_pyramid(self, left, right, n_levels, settings, cap=None):
+        """Multi-level matching: (supports, level_offsets[n_levels+1], n_cand[n_levels,2])."""
+        left = np.ascontiguousarray(left, np.uint8)
+        right = np.ascontiguousarray(right, np.uint8)
+        h, w = left.shape
+        cap = max(2 * (w - 26) * (h - 26), 1) if cap is None else cap
+        out = np.empty(max(cap, 1), SUPPORT_DTYPE)
+        offsets = np.zeros(n_levels + 1, np.int64)
+        n_cand = np.zeros((n_levels, 2), np.int32)
+        self._check(self.lib.gpc_match_pyramid(self._h, _ptr(left), _ptr(right), w, h, w, int(n_levels), C.byref(settings),
+                                               _ptr(out), C.c_int64(cap), _ptr(offsets), _ptr(n_cand)))
+        return out[:offsets[-1]].copy(), offsets, n_cand
 
     # ---- stage seams ------------------------------------------------------------------------
     def preprocess(self, img, thr):

@@ -36,6 +36,7 @@ cudaError_t launch_match_keys(void* ws, long long max_records, int ns, int nt, i
                               int32_t* n_out, cudaStream_t stream, int* launches);
 void* global_key_buffer(void* ws, long long max_records);
 int32_t* global_nside_ptr(void* ws);
+cudaError_t launch_downsample2x(const uint8_t* src, uint8_t* dst, int sw, int sh, int n_img, cudaStream_t stream);
 }  // namespace gpc
 
 static thread_local std::string g_create_error;
@@ -73,6 +74,7 @@ struct gpc_ctx {
   // pinned host scratch for counts
   int32_t* h_counts = nullptr;     // totals [B] | ncand [2B]
   long long* h_pair_base = nullptr;  // [B+1]
+  uint8_t* d_pyr = nullptr;        // pyramid levels 1.. of one pair (lazily allocated)
   void* d_gws = nullptr;           // radix-sort matcher workspace (lazily allocated)
   long long gws_records = 0;
   int32_t* d_rowoff2 = nullptr;    // [2][H] candidate offsets of the sort matcher (lazily allocated)
@@ -379,7 +381,7 @@ void gpc_destroy(gpc_ctx* c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (cudaEvent_t e : c->ev_chunk) cudaEventDestroy(e);
   cudaFree(c->d_rowoff); cudaFree(c->d_totals); cudaFree(c->d_ncand); cudaFree(c->d_pair_base); cudaFree(c->d_out);
-  cudaFree(c->d_dbg8); cudaFree(c->d_mask); cudaFree(c->d_gws); cudaFree(c->d_rowoff2);
+  cudaFree(c->d_dbg8); cudaFree(c->d_mask); cudaFree(c->d_gws); cudaFree(c->d_rowoff2); cudaFree(c->d_pyr);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->h_pair_base) cudaFreeHost(c->h_pair_base);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -893,6 +895,63 @@ int gpc_find_correspondences(gpc_ctx* c, const uint64_t* src_keys, int n_src, co
   cudaFree(d_pairs);
   if (e != cudaSuccess) return fail(c, GPC_E_CUDA, std::string("gpc_find_correspondences: ") + cudaGetErrorString(e));
   if (*n_out > cap) return fail(c, GPC_E_CAPACITY, "pair buffer too small: need " + std::to_string(*n_out));
+  return GPC_OK;
+}
+
+// Multi-level matching (BASELINE.json configs[3]; definition in SURVEY.md 8d -- the reference has
+// no pyramid): level l+1 = 2x2 floor-mean of the raw level-l images, built on the device; the whole
+// single-level path runs per level with the same forest and disp_high halved per level.  Supports
+// of all levels are written back to back, level l in out[level_offsets[l] .. level_offsets[l+1]);
+// n_cand (optional) = [n_levels][2].  Every level width must stay a multiple of 16.
+int gpc_match_pyramid(gpc_ctx* c, const uint8_t* left, const uint8_t* right, int w, int h, int stride, int n_levels,
+                      const gpc_settings* s, gpc_support* out, int64_t cap, int64_t* level_offsets, int32_t* n_cand) {
+  if (!c || !left || !right || !level_offsets || cap < 0 || (cap > 0 && !out)) return fail(c, GPC_E_ARG, "null argument");
+  if (n_levels < 1 || n_levels > 16) return fail(c, GPC_E_ARG, "n_levels must be within 1...16");
+  if (stride < w) return fail(c, GPC_E_ARG, "stride smaller than width");
+  int rc = check_dims(c, w, h, 1); if (rc) return rc;
+  rc = check_settings(c, s); if (rc) return rc;
+  if (!c->has_forest) return fail(c, GPC_E_FOREST, "no forest set");
+  for (int l = 1; l < n_levels; l++)
+    if (((w >> l) % 16) != 0 || (w >> l) <= 0 || (h >> l) <= 0)
+      return fail(c, GPC_E_WIDTH16, "every pyramid level needs a positive width that is a multiple of 16");
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  const size_t P0 = (size_t)w * h;
+  if (n_levels > 1 && !c->d_pyr) GPC_CUDA(c, cudaMalloc(&c->d_pyr, (size_t)c->max_w * c->max_h));   // 2 * (P/4 + P/16 + ...) < P
+  GPC_CUDA(c, cudaMemcpy2DAsync(c->d_raw, w, left, stride, w, h, cudaMemcpyHostToDevice, c->stream));
+  GPC_CUDA(c, cudaMemcpy2DAsync(c->d_raw + P0, w, right, stride, w, h, cudaMemcpyHostToDevice, c->stream));
+  const uint8_t* level = c->d_raw;
+  uint8_t* next = c->d_pyr;
+  long long total = 0;
+  bool overflow = false;
+  level_offsets[0] = 0;
+  gpc_settings ls = *s;
+  for (int l = 0; l < n_levels; l++) {
+    const int lw = w >> l, lh = h >> l;
+    rc = run_preprocess(c, Slot{0, c->stream}, level, 2, lw, lh, ls.gradient_threshold, c->forest_dev, nullptr, nullptr);
+    if (rc) return rc;
+    rc = run_match(c, Slot{0, c->stream}, 1, lw, lh, &ls, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
+    if (rc) return rc;
+    if (l + 1 < n_levels) {                                     // next level from this level's raw images
+      GPC_CUDA(c, gpc::launch_downsample2x(level, next, lw, lh, 2, c->stream));
+      c->launches += 1;
+    }
+    GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_totals, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    GPC_CUDA(c, cudaMemcpyAsync(c->h_counts + 1, c->d_ncand, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int n = c->h_counts[0];
+    if (n_cand) { n_cand[2 * l] = c->h_counts[1]; n_cand[2 * l + 1] = c->h_counts[2]; }
+    if (total + n > cap) overflow = true;
+    else if (n > 0) GPC_CUDA(c, cudaMemcpyAsync(out + total, c->d_out, (size_t)n * sizeof(gpc_support), cudaMemcpyDeviceToHost, c->stream));
+    total += n;
+    level_offsets[l + 1] = total;
+    if (l + 1 < n_levels) {
+      level = next;
+      next += 2 * (size_t)(lw / 2) * (lh / 2);
+      ls.disp_high = ls.disp_high / 2;
+    }
+  }
+  GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (overflow) return fail(c, GPC_E_CAPACITY, "support buffer too small: need " + std::to_string(total));
   return GPC_OK;
 }
 

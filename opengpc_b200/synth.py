@@ -48,3 +48,10 @@ def sparsify(img, tile=64):
     keep = ((ty % 2) == 0) & ((tx % 2) == 0)
     out = np.where(keep, img, 128).astype(np.uint8)
     return np.ascontiguousarray(out)
+
+
+def downsample2x(img):
+    """Pyramid level l+1 from level l (SURVEY.md 8d): 2x2 mean with floor, (a + b + c + d) // 4."""
+    h, w = img.shape
+    v = img[:h // 2 * 2, :w // 2 * 2].astype(np.uint16)
+    return np.ascontiguousarray(((v[0::2, 0::2] + v[0::2, 1::2] + v[1::2, 0::2] + v[1::2, 1::2]) >> 2).astype(np.uint8))

@@ -186,3 +186,30 @@ def test_pipelined_batch(g, oracle, monkeypatch):
         assert e.value.status == capi.GPC_E_CAPACITY
         supp2, offsets2, _ = c.match_batch(imgs, s)          # the context stays usable afterwards
         assert np.array_equal(supp2, supp) and np.array_equal(offsets2, offsets)
+
+
+def test_pyramid_vs_golden_and_oracle(g, oracle):
+    """BASELINE configs[3]: levels built on the device, the single-level path per level.  Golden values come
+    from the unmodified reference run per level on identically down-sampled images (scripts/make_golden_pyramid.py)."""
+    import json
+    import os
+    from oraclelib import ROOT
+    from opengpc_b200.synth import downsample2x, synth_pair
+    with open(os.path.join(ROOT, "tests", "golden", "pyramid.json")) as f:
+        gold = json.load(f)
+    of = oracle.read_forest(FORESTS["tau"])
+    for case in gold["cases"]:
+        w, h, nl = case["w"], case["h"], len(case["levels"])
+        L, R = synth_pair(w, h, case["seed"])
+        with g.Context(device=0, max_w=w, max_h=h, max_batch=1) as c:
+            c.set_forest(FORESTS["tau"])
+            supp, offs, ncand = c.match_pyramid(L, R, nl, g.sparsematch_settings())
+        for rec in case["levels"]:
+            l = rec["level"]
+            lev = supp[offs[l]:offs[l + 1]]
+            assert (ncand[l, 0], ncand[l, 1], len(lev)) == (rec["n_cand_l"], rec["n_cand_r"], rec["n_supports"]), rec
+            assert "%016x" % oracle.digest(lev) == rec["digest"], rec
+            if w <= 1024:                                        # the oracle itself on the down-sampled images
+                ref, _, _ = oracle.pair(L, R, of, osettings(5, rec["disp_high"], 0, True))
+                assert np.array_equal(lev, ref)
+            L, R = downsample2x(L), downsample2x(R)
