@@ -115,11 +115,14 @@ match_rows_kernel(const MatchArgs args) {
         if (e & 1) rank[sd][e >> 1] |= r << 16; else rank[sd][e >> 1] = r;
       }
     __syncthreads();
-    // ---- exclusive scan: thread t owns buckets t, t + 256, ... (consecutive in the entry array) ------
+    // ---- exclusive scan over the buckets in "layout order": thread t owns the quads of buckets
+    // 4 * (k * 256 + t) .. + 3, k = 0, 1, ... (16-byte accesses, conflict free); the order of buckets
+    // in the entry array is free, it only has to be a partition ----------------------------------------
     {
-      const int per = nb / kThreadsB;              // nb >= 256 by construction
+      uint4* c4 = reinterpret_cast<uint4*>(cnt);
+      const int per = nb / (4 * kThreadsB);        // nb >= 1024 by construction
       uint32_t sum = 0;
-      for (int k = 0; k < per; k++) sum += cnt[k * kThreadsB + tid];
+      for (int k = 0; k < per; k++) { const uint4 q = c4[k * kThreadsB + tid]; sum += q.x + q.y + q.z + q.w; }
       uint32_t incl = sum;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
@@ -129,9 +132,13 @@ match_rows_kernel(const MatchArgs args) {
 #pragma unroll
       for (int w = 0; w < kThreadsB / 32; w++) if (w < wid) base += warp_tot[w];
       for (int k = 0; k < per; k++) {
-        const uint32_t c = cnt[k * kThreadsB + tid];
-        cnt[k * kThreadsB + tid] = base | (c << 16);
-        base += c;
+        uint4 q = c4[k * kThreadsB + tid];
+        uint4 o;
+        o.x = base | (q.x << 16); base += q.x;
+        o.y = base | (q.y << 16); base += q.y;
+        o.z = base | (q.z << 16); base += q.z;
+        o.w = base | (q.w << 16); base += q.w;
+        c4[k * kThreadsB + tid] = o;
       }
     }
     __syncthreads();
@@ -174,52 +181,62 @@ match_rows_kernel(const MatchArgs args) {
     // ---- resolve + emit: a left state that is unique in its bucket on both sides is a match ---------
     const uint32_t kmax = kmax_s;
     const int cmr = cmax_r, cml = cmax_l, xmin = xmin_s;
-    const uint32_t xmask = (1u << xb) - 1u;
+    const uint32_t XL = 1u << xb;
+    unsigned long long rec[4 * KQ];
+    uint32_t okmask = 0;
 #pragma unroll
     for (int e = 0; e < 4 * KQ; e++) {
-      bool ok = false;
-      unsigned long long rec = 0;
+      rec[e] = 0;
       if (v[0][e] >> 31) {
         const uint32_t key = v[0][e] & 0x7fffffffu;
         const uint32_t h = key * kHashMul;
         const uint32_t word = cnt[h >> rs];
         const uint32_t s0 = word & 0xffffu, n = word >> 16;
         const uint32_t mine = (h << log2nb) >> es;             // remainder field, side = 0, x = 0
+        // t = entry ^ mine: same state, left  <=> t < XL (t = its x);  same state, right <=> XL <= t < 2 XL
         uint32_t nl = 0, nr = 0, xr = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          if (j < (int)n) {
-            const uint32_t k = entry[s0 + j];
-            if (((k ^ mine) >> (xb + 1)) == 0u) {                // same state
-              if ((k >> xb) & 1u) { nr++; xr = k & xmask; } else nl++;
-            }
-          }
+          const uint32_t t = (j < (int)n) ? (entry[s0 + j] ^ mine) : 0xffffffffu;
+          const uint32_t u = t - XL;
+          nl += (t < XL) ? 1u : 0u;
+          nr += (u < XL) ? 1u : 0u;
+          xr = (u < XL) ? u : xr;
         }
         for (uint32_t j = 4; j < n && nl < 2u && nr < 2u; j++) { // rare: bucket longer than four entries
-          const uint32_t k = entry[s0 + j];
-          if (((k ^ mine) >> (xb + 1)) == 0u) {
-            if ((k >> xb) & 1u) { nr++; xr = k & xmask; } else nl++;
-          }
+          const uint32_t t = entry[s0 + j] ^ mine;
+          const uint32_t u = t - XL;
+          nl += (t < XL) ? 1u : 0u;
+          nr += (u < XL) ? 1u : 0u;
+          xr = (u < XL) ? u : xr;
         }
-        ok = (nl == 1u) && (nr == 1u);
+        bool ok = (nl == 1u) && (nr == 1u);
         const int xl = 4 * (tid + (e >> 2) * kThreadsB) + (e & 3);
         if (last_row && key == kmax) {         // inference.hpp:243-249 on the tail of the sorted right keys
           ok = (cml == 1) && (cmr == 2);       // 1 right: the last element never matches; >=3: duplicates
           xr = (uint32_t)xmin;                 // 2: "first of the two" := smaller x (stable order)
         }
+        const int dx = xl - (int)xr;
+        ok = ok && (dx <= args.disp_high && -dx <= args.disp_high) && (0 <= args.vertical_tolerance);
         if (ok) {
-          const int dx = xl - (int)xr;
-          ok = (dx <= args.disp_high && -dx <= args.disp_high) && (0 <= args.vertical_tolerance);
-          rec = ((unsigned long long)key << 32) | ((unsigned long long)xl << 16) | (unsigned long long)xr;
+          okmask |= 1u << e;
+          rec[e] = ((unsigned long long)key << 32) | ((unsigned long long)xl << 16) | (unsigned long long)xr;
         }
       }
-      const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-      if (bal) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&n_out, __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (ok) out[base + __popc(bal & ((1u << lane) - 1u))] = rec;
-      }
+    }
+    // one shared-memory reservation per warp for all of its matches
+    {
+      const int mine_n = __popc(okmask);
+      int incl = mine_n;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+      const int warp_n = __shfl_sync(0xffffffffu, incl, 31);
+      int base = 0;
+      if (lane == 31 && warp_n > 0) base = atomicAdd(&n_out, warp_n);
+      base = __shfl_sync(0xffffffffu, base, 31) + incl - mine_n;
+#pragma unroll
+      for (int e = 0; e < 4 * KQ; e++)
+        if ((okmask >> e) & 1u) out[base++] = rec[e];
     }
     __syncthreads();
     m = n_out;
