@@ -10,8 +10,9 @@
   4  deep random forest (16 x 12) on 1080p frames (32 per GPU)
 --forest / --shape / --batch override the configuration's values.
 
-A "step" is one pass of the whole hot path (kernel A: box + Sobel + fern hashing, kernel B: per-row
-matching, scans, kernel C: ordered support emission) over one batch of synthetic stereo pairs.
+A "step" is one pass of the whole hot path (kernel A1: box + Sobel, kernel A2: fern hashing on
+TMA-staged tiles, kernel B: per-row matching, scans, kernel C: ordered support emission) over one
+batch of synthetic stereo pairs.
 
   value      stereo pairs/s, inputs resident in HBM, timed with CUDA events on the launching
              stream (max over ranks); `mpix_per_s` = value * 2*W*H / 1e6 (BASELINE.json's second unit)
@@ -377,13 +378,14 @@ def main():
     per_kernel_ms = {k: v / max(kruns, 1) for k, v in kms.items()}
     dominant = max(per_kernel_ms, key=per_kernel_ms.get)
     mean_sup = float(n_sup.mean())
-    alg_bytes = {"preprocess_hash": 10.0 * P * B,                 # read 2 u8 images, write 2 u32 hash images
+    alg_bytes = {"smooth_sobel": 4.0 * P * B,                     # per pair: read 2 u8 images, write 2 u8 smoothed images
+                 "hash_tiles": 10.0 * P * B,                      # read 2 u8 smoothed images, write 2 u32 hash images
                  "match_rows": (8.0 * P + 4.0 * mean_sup) * B,    # read 2 hash images, write staged matches
                  "scans": 0.0, "emit_supports": 16.0 * mean_sup * B}
     dom_ms = per_kernel_ms[dominant]
     achieved = alg_bytes[dominant] / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
     path_bytes = (10.0 * P + 12.0 * mean_sup)                     # B_alg per pair
-    traffic, traffic_src = ncu_traffic(dominant, (2 * B if dominant == "preprocess_hash" else B) * P)
+    traffic, traffic_src = ncu_traffic(dominant, (2 * B if dominant in ("smooth_sobel", "hash_tiles") else B) * P)
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes[dominant],

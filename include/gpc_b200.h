@@ -170,11 +170,11 @@ int64_t gpc_launch_count(const gpc_ctx* ctx);
 
 /* Per-kernel device times, measured with CUDA events on the launching stream around each
  * kernel of the whole-path entry points (bench.py's roofline figures).  Slots:
- *   0 preprocess_hash (kernel A)   1 match_rows (kernel B)
- *   2 row/pair scans               3 emit_supports (kernel C)
+ *   0 smooth_sobel (kernel A1)     1 hash_tiles (kernel A2)      2 match_rows (kernel B)
+ *   3 row/pair scans               4 emit_supports (kernel C)
  * gpc_kernel_times synchronises the stream and returns accumulated milliseconds per slot and
  * the number of batch runs they cover. */
-#define GPC_N_KERNELS 4
+#define GPC_N_KERNELS 5
 int gpc_enable_kernel_timing(gpc_ctx* ctx, int on);
 int gpc_kernel_times(gpc_ctx* ctx, double* ms, int64_t* runs);
 

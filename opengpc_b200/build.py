@@ -11,7 +11,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libgpc_b200.so")
-SOURCES = ["gpc_capi.cu", "preprocess_hash.cu", "match_rows.cu", "match_global.cu", "pyramid.cu"]
+SOURCES = ["gpc_capi.cu", "smooth_sobel.cu", "hash_tiles.cu", "match_rows.cu", "match_global.cu", "pyramid.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall", "--shared", "-cudart", "static"]
 

@@ -24,7 +24,7 @@ SYMBOLS = ["gpc_create", "gpc_destroy", "gpc_last_error", "gpc_status_string", "
            "gpc_preprocess", "gpc_hash", "gpc_match_hash_images", "gpc_launch_count", "gpc_enable_kernel_timing",
            "gpc_kernel_times", "gpc_hash_smooth", "gpc_image_upload", "gpc_image_release", "gpc_image_preprocess",
            "gpc_match_images", "gpc_correspond_images", "gpc_find_correspondences", "gpc_set_matcher", "gpc_match_pyramid"]
-KERNEL_NAMES = ["preprocess_hash", "match_rows", "scans", "emit_supports"]
+KERNEL_NAMES = ["smooth_sobel", "hash_tiles", "match_rows", "scans", "emit_supports"]
 
 
 class GpcSettings(C.Structure):
@@ -148,7 +148,7 @@ class Context:
 
     def kernel_times(self):
         """(dict kernel -> accumulated ms, number of batch runs); synchronises the stream."""
-        ms = (C.c_double * 4)()
+        ms = (C.c_double * len(KERNEL_NAMES))()
         runs = C.c_int64(0)
         self._check(self.lib.gpc_kernel_times(self._h, ms, C.byref(runs)))
         return dict(zip(KERNEL_NAMES, list(ms))), runs.value

@@ -13,9 +13,12 @@
 #include <vector>
 
 namespace gpc {
-size_t preprocess_smem_bytes();
-cudaError_t configure_preprocess_hash();
-cudaError_t launch_preprocess_hash(const PreprocessArgs&, const ForestDev&, int n_img, int mode, cudaStream_t);
+cudaError_t launch_smooth_sobel(const PreprocessArgs&, int n_img, bool debug_out, cudaStream_t);
+cudaError_t launch_prep_from_smooth(const uint8_t* smooth, const uint8_t* flags, uint8_t* smooth_x, uint16_t* cand, int32_t* rowcnt,
+                                    int32_t* lastrow, int W, int H, cudaStream_t);
+cudaError_t configure_hash_tiles();
+int make_smooth_tensor_map(void* out_map, const uint8_t* base, int W, int H, int n_img);
+cudaError_t launch_hash_tiles(const void* tensor_map, const HashArgs&, const ForestDev&, int n_img, cudaStream_t);
 size_t match_smem_bytes(int wcap, int table_log2);
 cudaError_t configure_match_rows(int max_smem);
 cudaError_t launch_match_rows(const MatchArgs&, int n_pairs, cudaStream_t);
@@ -51,6 +54,10 @@ struct gpc_ctx {
   gpc::ForestDev forest_dev{};
   // resident device buffers
   uint8_t* d_raw = nullptr;        // [2B][H][W]
+  uint8_t* d_smooth = nullptr;     // [2B][H][W]  biased smoothed images (kernel A1 -> TMA -> kernel A2)
+  uint16_t* d_cand = nullptr;      // [2B][H][W/16] candidate masks
+  alignas(64) unsigned char tmap[128];   // CUtensorMap over d_smooth for images of tmap_w x tmap_h
+  int tmap_w = 0, tmap_h = 0;
   uint32_t* d_hash = nullptr;      // [2B][H][W]
   uint32_t* d_stage = nullptr;     // [B][H][W]
   int32_t* d_rows = nullptr;       // rowcnt [2B][H]   (cleared per launch)
@@ -85,7 +92,7 @@ struct gpc_ctx {
   bool timing = false;
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
-  double k_ms[GPC_N_KERNELS] = {0, 0, 0, 0};
+  double k_ms[GPC_N_KERNELS] = {0, 0, 0, 0, 0};
   int64_t k_runs = 0;
   std::string err;
 };
@@ -185,23 +192,42 @@ struct Slot {
 
 int mark_on(gpc_ctx* c, const Slot& sl) { return (sl.stream == c->stream) ? mark(c) : GPC_OK; }
 
-// Kernel A over n_img resident images of the slot; clears and fills rowcnt / lastrow.
+// Kernels A1 + A2 over n_img resident images of the slot; clears and fills rowcnt / lastrow.
+// d_flags != nullptr: d_images holds SMOOTHED images and d_flags the pixels to hash (gpc_hash_smooth).
 int run_preprocess(gpc_ctx* c, const Slot& sl, const uint8_t* d_images, int n_img, int w, int h, int thr,
-                   const gpc::ForestDev& forest, uint8_t* d_smooth, uint8_t* d_grad, const uint8_t* d_flags = nullptr) {
+                   const gpc::ForestDev& forest, uint8_t* d_smooth_out, uint8_t* d_grad_out, const uint8_t* d_flags = nullptr) {
   const size_t P = (size_t)w * h;
-  int32_t* rowcnt = c->d_rows + (size_t)(2 * sl.p0) * h;
-  int32_t* lastrow = c->d_lastrow + 2 * sl.p0;
+  const int img0 = 2 * sl.p0;
+  int32_t* rowcnt = c->d_rows + (size_t)img0 * h;
+  int32_t* lastrow = c->d_lastrow + img0;
   GPC_CUDA(c, cudaMemsetAsync(rowcnt, 0, (size_t)n_img * h * sizeof(int32_t), sl.stream));
   GPC_CUDA(c, cudaMemsetAsync(lastrow, 0xff, (size_t)n_img * sizeof(int32_t), sl.stream));   // -1
-  gpc::PreprocessArgs a{};
-  a.raw = d_images; a.hash = c->d_hash + (size_t)(2 * sl.p0) * P; a.rowcnt = rowcnt; a.lastrow = lastrow;
-  a.smooth_out = d_smooth; a.grad_out = d_grad; a.flags = d_flags; a.W = w; a.H = h;
-  a.thr2 = (int32_t)(int16_t)(thr * thr);                                          // filter.hpp:418
+  if (c->tmap_w != w || c->tmap_h != h) {
+    const int n_cap = (int)std::min<size_t>(2 * (size_t)c->max_batch * ((size_t)c->max_w * c->max_h / P), 1u << 30);
+    if (gpc::make_smooth_tensor_map(c->tmap, c->d_smooth, w, h, n_cap) != 0)
+      return fail(c, GPC_E_CUDA, "cuTensorMapEncodeTiled failed");
+    c->tmap_w = w; c->tmap_h = h;
+  }
+  uint8_t* smooth_x = c->d_smooth + (size_t)img0 * P;
+  uint16_t* cand = c->d_cand + (size_t)img0 * h * (w / 16);
   int rc = mark_on(c, sl); if (rc) return rc;                                      // event 0
-  const int mode = d_flags ? 2 : ((d_smooth || d_grad) ? 1 : 0);
-  GPC_CUDA(c, gpc::launch_preprocess_hash(a, forest, n_img, mode, sl.stream));
-  c->launches += 1;
-  return mark_on(c, sl);                                                           // event 1
+  if (d_flags) {
+    if (n_img != 1) return fail(c, GPC_E_ARG, "internal: the smooth seam handles one image");
+    GPC_CUDA(c, gpc::launch_prep_from_smooth(d_images, d_flags, smooth_x, cand, rowcnt, lastrow, w, h, sl.stream));
+  } else {
+    gpc::PreprocessArgs a{};
+    a.raw = d_images; a.smooth_x = smooth_x; a.cand = cand; a.rowcnt = rowcnt; a.lastrow = lastrow;
+    a.smooth_out = d_smooth_out; a.grad_out = d_grad_out; a.W = w; a.H = h;
+    a.thr2 = (int32_t)(int16_t)(thr * thr);                                        // filter.hpp:418
+    GPC_CUDA(c, gpc::launch_smooth_sobel(a, n_img, d_smooth_out || d_grad_out, sl.stream));
+  }
+  rc = mark_on(c, sl); if (rc) return rc;                                          // event 1
+  gpc::HashArgs ha{};
+  ha.cand = c->d_cand; ha.hash = c->d_hash;
+  ha.W = w; ha.H = h; ha.img0 = img0;
+  GPC_CUDA(c, gpc::launch_hash_tiles(c->tmap, ha, forest, n_img, sl.stream));
+  c->launches += 2;
+  return mark_on(c, sl);                                                           // event 2
 }
 
 int ensure_global_ws(gpc_ctx* c, long long records) {
@@ -245,7 +271,7 @@ int run_match(gpc_ctx* c, const Slot& sl, int n_pairs, int w, int h, const gpc_s
     // packed host entry points run one pair at a time)
     if (sl.stream != c->stream || sl.p0 != 0) return fail(c, GPC_E_ARG, "internal: sort matcher runs on the context stream");
     if (packed && n_pairs != 1) return fail(c, GPC_E_ARG, "internal: packed sort matcher handles one pair per call");
-    for (int k = 0; k < 2; k++) { int rc = mark(c); if (rc) return rc; }   // events 2, 3 (no row kernels here)
+    for (int k = 0; k < 2; k++) { int rc = mark(c); if (rc) return rc; }   // events 3, 4 (no row kernels here)
     for (int p = 0; p < n_pairs; p++) {
       int rc = run_match_sort_pair(c, hash, p, w, h, s, 0, d_out + (packed ? 0 : (size_t)p * cap), cap, d_n_out + p,
                                    d_n_cand ? d_n_cand + 2 * p : nullptr);
@@ -255,7 +281,7 @@ int run_match(gpc_ctx* c, const Slot& sl, int n_pairs, int w, int h, const gpc_s
       GPC_CUDA(c, gpc::launch_pair_scan(d_n_out, 1, c->d_pair_base, c->stream));
       c->launches += 1;
     }
-    return mark(c);                                                                // event 4
+    return mark(c);                                                                // event 5
   }
   const int32_t* rowcnt = c->d_rows + (size_t)(2 * sl.p0) * h;
   int32_t* rowmatch = c->d_rowmatch + (size_t)sl.p0 * h;
@@ -275,7 +301,7 @@ int run_match(gpc_ctx* c, const Slot& sl, int n_pairs, int w, int h, const gpc_s
     return fail(c, GPC_E_DIMS, "image too wide for the row matcher's shared memory");
   if (h - 2 * gpc::kRadius <= 0) GPC_CUDA(c, cudaMemsetAsync(rowmatch, 0, (size_t)n_pairs * h * sizeof(int32_t), sl.stream));
   GPC_CUDA(c, gpc::launch_match_rows(m, n_pairs, sl.stream));
-  int rc = mark_on(c, sl); if (rc) return rc;                                      // event 2
+  int rc = mark_on(c, sl); if (rc) return rc;                                      // event 3
   GPC_CUDA(c, gpc::launch_row_scan(rowmatch, rowcnt, h, n_pairs, rowoff, d_n_out, d_n_cand, sl.stream));
   c->launches += 2;
   const long long* pair_base = nullptr;
@@ -284,10 +310,10 @@ int run_match(gpc_ctx* c, const Slot& sl, int n_pairs, int w, int h, const gpc_s
     c->launches += 1;
     pair_base = c->d_pair_base + 2 * sl.p0;
   }
-  rc = mark_on(c, sl); if (rc) return rc;                                          // event 3
+  rc = mark_on(c, sl); if (rc) return rc;                                          // event 4
   GPC_CUDA(c, gpc::launch_emit_supports(stage, rowmatch, rowoff, pair_base, d_out, cap, w, h, n_pairs, sl.stream));
   if (h - 2 * gpc::kRadius > 0) c->launches += 1;
-  return mark_on(c, sl);                                                           // event 4
+  return mark_on(c, sl);                                                           // event 5
 }
 
 int ensure_debug_buffers(gpc_ctx* c) {
@@ -342,13 +368,15 @@ int gpc_create(gpc_ctx** out, int device, int max_w, int max_h, int max_batch) {
   TRY(cudaSetDevice(device));
   TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
-  TRY(gpc::configure_preprocess_hash());
+  TRY(gpc::configure_hash_tiles());
   int smem_optin = 0;
   TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   c->match_smem_max = smem_optin - 1024;
   TRY(gpc::configure_match_rows(c->match_smem_max));
   const size_t P = (size_t)max_w * max_h, B = (size_t)max_batch;
   TRY(cudaMalloc(&c->d_raw, 2 * B * P));
+  TRY(cudaMalloc(&c->d_smooth, 2 * B * P));
+  TRY(cudaMalloc(&c->d_cand, 2 * B * (size_t)max_h * (max_w / 16) * sizeof(uint16_t)));
   TRY(cudaMalloc(&c->d_hash, 2 * B * P * sizeof(uint32_t)));
   TRY(cudaMalloc(&c->d_stage, B * P * sizeof(uint32_t)));
   TRY(cudaMalloc(&c->d_rows, 2 * B * max_h * sizeof(int32_t)));
@@ -376,7 +404,7 @@ int gpc_create(gpc_ctx** out, int device, int max_w, int max_h, int max_batch) {
 void gpc_destroy(gpc_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaFree(c->d_raw); cudaFree(c->d_hash); cudaFree(c->d_stage); cudaFree(c->d_rows); cudaFree(c->d_lastrow); cudaFree(c->d_rowmatch);
+  cudaFree(c->d_raw); cudaFree(c->d_smooth); cudaFree(c->d_cand); cudaFree(c->d_hash); cudaFree(c->d_stage); cudaFree(c->d_rows); cudaFree(c->d_lastrow); cudaFree(c->d_rowmatch);
   for (int l = 0; l < gpc_ctx::kLanes; l++) if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (cudaEvent_t e : c->ev_chunk) cudaEventDestroy(e);
@@ -413,13 +441,13 @@ int gpc_enable_kernel_timing(gpc_ctx* c, int on) {
   return GPC_OK;
 }
 
-// Synchronises the stream, folds the recorded event quintuples into per-kernel sums and returns
+// Synchronises the stream, folds the recorded event groups into per-kernel sums and returns
 // the accumulated milliseconds per kernel and the number of batch runs they cover.
 int gpc_kernel_times(gpc_ctx* c, double* ms, int64_t* runs) {
   if (!c || !ms || !runs) return GPC_E_ARG;
   GPC_CUDA(c, cudaSetDevice(c->device));
   GPC_CUDA(c, cudaStreamSynchronize(c->stream));
-  for (size_t i = 0; i + 5 <= c->ev_used; i += 5) {
+  for (size_t i = 0; i + (GPC_N_KERNELS + 1) <= c->ev_used; i += GPC_N_KERNELS + 1) {
     for (int k = 0; k < GPC_N_KERNELS; k++) {
       float t = 0.f;
       GPC_CUDA(c, cudaEventElapsedTime(&t, c->ev_pool[i + k], c->ev_pool[i + k + 1]));

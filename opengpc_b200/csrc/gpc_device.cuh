@@ -2,6 +2,8 @@
 //
 // Data layout in HBM (all resident in the context, see gpc_capi.cu):
 //   raw    uint8  [n_img][H][W]        input images, image 2p = left, 2p+1 = right of pair p
+//   smooth uint8  [n_img][H][W]        biased smoothed images (s ^ 0x80), kernel A1 -> TMA -> kernel A2
+//   cand   uint16 [n_img][H][W/16]     candidate bit masks per 16-pixel segment
 //   hash   uint32 [n_img][H][W]        bit 31 = "candidate", bits 0..30 = fern state
 //   rowcnt int32  [n_img][H]           candidates per image row
 //   lastrow int32 [n_img]              largest row with a candidate (-1 if none)
@@ -17,9 +19,9 @@ constexpr int kRadius = 13;            // patch radius / candidate border (infer
 constexpr int kMaxTests = 32;          // inference.hpp:426
 constexpr uint32_t kCandFlag = 0x80000000u;
 
-// ---- kernel A tile geometry -------------------------------------------------------------
+// ---- kernel A2 (hash_tiles.cu) tile geometry ---------------------------------------------------
 #ifndef GPC_TILE_W
-#define GPC_TILE_W 256
+#define GPC_TILE_W 128
 #endif
 #ifndef GPC_TILE_H
 #define GPC_TILE_H 32
@@ -27,16 +29,16 @@ constexpr uint32_t kCandFlag = 0x80000000u;
 #ifndef GPC_THREADS_A
 #define GPC_THREADS_A 256
 #endif
-constexpr int kTileW = GPC_TILE_W;             // output pixels per tile row (multiple of 128)
+constexpr int kTileW = GPC_TILE_W;             // output pixels per tile row; kTileW + 32 <= 256 (TMA box limit)
 constexpr int kTileH = GPC_TILE_H;             // output rows per tile
 constexpr int kPitch = kTileW + 32;            // smem row pitch in bytes: image cols x0-16 .. x0+kTileW+15
 constexpr int kPitchW = kPitch / 4;            // ... in 32-bit words
-constexpr int kRawRows = kTileH + 2 * kRadius + 2;   // image rows y0-14 .. y0+kTileH+13
-constexpr int kSmRows = kTileH + 2 * kRadius;        // image rows y0-13 .. y0+kTileH+12
-constexpr int kCopyBytes = kSmRows * kPitch;   // one copy of the smoothed tile
+constexpr int kSmRows = kTileH + 2 * kRadius;  // image rows y0-13 .. y0+kTileH+12
+constexpr int kCopyBytes = (kSmRows * kPitch + 127) / 128 * 128;   // one copy of the smoothed tile (TMA destination: 128-byte aligned)
 constexpr int kThreadsA = GPC_THREADS_A;
 constexpr int kQuadsX = kTileW / 4;            // quads (4 pixels) per tile row
-static_assert(kThreadsA % kQuadsX == 0 && kThreadsA >= kPitchW, "thread block must cover whole quad rows");
+static_assert(kPitch <= 256 && kSmRows <= 256, "TMA box dimensions are limited to 256");
+static_assert(kThreadsA % kQuadsX == 0 && kTileH % (kThreadsA / kQuadsX) == 0, "thread block must tile the rows evenly");
 
 // Forest baked for the kernel's shared-memory layout (replaces the per-width baking of
 // inference.hpp:427-428).  The smoothed tile is kept four times, copy k shifted left by k bytes,
@@ -55,16 +57,23 @@ struct ForestDev {
                                  // is strength-reduced to five ALU-pipe instructions)
 };
 
-struct PreprocessArgs {
+struct PreprocessArgs {     // kernel A1; all pointers already offset to the first image of the launch
   const uint8_t* raw;      // [n_img][H][W]
-  uint32_t* hash;          // [n_img][H][W]
-  int32_t* rowcnt;         // [n_img][H]
-  int32_t* lastrow;        // [n_img]
-  uint8_t* smooth_out;     // optional [n_img][H][W]
-  uint8_t* grad_out;       // optional [n_img][H][W]
-  const uint8_t* flags;    // mode 2 only: [n_img][H][W], non-zero = hash this pixel
+  uint8_t* smooth_x;       // [n_img][H][W] biased smoothed image (s ^ 0x80)
+  uint16_t* cand;          // [n_img][H][W/16] candidate bit masks per 16-pixel segment
+  int32_t* rowcnt;         // [n_img][H] candidates per row (zeroed before the launch)
+  int32_t* lastrow;        // [n_img] largest row with a candidate (-1 before the launch)
+  uint8_t* smooth_out;     // optional [n_img][H][W] (debug seam: unbiased)
+  uint8_t* grad_out;       // optional [n_img][H][W] (debug seam: 0 / 255)
   int32_t W, H;
   int32_t thr2;            // (int16)(thr*thr), filter.hpp:418
+};
+
+struct HashArgs {           // kernel A2; pointers are buffer BASES, img0 = first image of the launch
+  const uint16_t* cand;    // [..][H][W/16]
+  uint32_t* hash;          // [..][H][W]
+  int32_t W, H;
+  int32_t img0;
 };
 
 struct MatchArgs {

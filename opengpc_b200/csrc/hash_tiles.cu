@@ -1,0 +1,213 @@
+// hash_tiles.cu -- kernel A2: fern hashing, one 128 x 32 pixel tile per CTA, operands staged by TMA.
+//
+// Replaces the reference's ndb::gpcFilter / gpcFilterTau (filter.hpp:547-606, :619-683) and the
+// gather of Forest::evalFastMaskOnSubsetSSE (inference.hpp:266-292).  Nothing here is a translation
+// of the SSE code.  The kernel is bound by the SM's ALU pipe (LOP3/SHF/PRMT: one warp instruction
+// per two cycles per scheduler), not by HBM, so everything is arranged to minimise ALU-pipe work:
+//   * the tile of the biased smoothed image (kernel A1), 13-pixel halo included, is fetched by ONE
+//     TMA tensor copy (zero fill outside the image, no staging instructions); the CTA then keeps it
+//     four times, copy k shifted left by k bytes (TMA itself needs 16-byte aligned source
+//     coordinates, so copies 1..3 are funnel-shifted out of copy 0 in shared memory), which makes
+//     the 4-pixel operand of every test ONE aligned LDS with a uniform offset;
+//   * in the biased domain the reference's "signed-saturating b - tau, then unsigned compare"
+//     (filter.hpp:647-652) is clamp(x - tau, 0, 255) -- two DPX VIADDMNMX on 16-bit lanes --
+//     followed by a SIGNED byte compare, which costs the same carry trick as the unsigned one;
+//   * result bits are accumulated with IMAD.WIDE on the otherwise idle FMA pipe:
+//     acc64 += (r & 0x80808080) * 2^p puts test p of pixel j at bit 8j+7+p without carries;
+//   * the tests of one state byte form a single basic block (no per-test guards: the forest is
+//     padded with never-true tests), so the compiler interleaves their dependency chains.
+// Each pixel's state is written once to the hash image (bit 31 = candidate).
+#include <cuda.h>
+
+#include "gpc_device.cuh"
+
+namespace gpc {
+
+constexpr uint32_t kMsb = 0x80808080u;
+constexpr uint32_t kLow7 = 0x7f7f7f7fu;
+
+// One fern test on 4 horizontally adjacent pixels; operands are BIASED bytes (pixel ^ 0x80).
+//   zero forest (filter.hpp:575):      a > b  unsigned           ==  xa > xb        signed
+//   tau forest  (filter.hpp:647-652):  a > (uint8)sat_int8((int8)b - tau)  unsigned
+//                                      ==  xa > clamp(xb - tau, 0, 255)    signed
+// Signed byte compare: msb = (~a7 & c7) | (~(a7 ^ c7) & carry7), carry from the low 7 bits.
+// The returned word is masked to the msbs.  A tau forest sends every test through the clamp
+// (tau == 0 leaves x unchanged).
+template <bool kTau>
+__device__ __forceinline__ uint32_t eval_test(const uint8_t* base, const ForestDev& forest, const int t) {
+  const uint32_t a = *reinterpret_cast<const uint32_t*>(base + forest.imm_a[t]);
+  uint32_t c = *reinterpret_cast<const uint32_t*>(base + forest.imm_b[t]);
+  if (kTau) {
+    const uint32_t mt = forest.mtau2[t];
+    const uint32_t lo = __viaddmin_s16x2_relu(__byte_perm(c, 0u, 0x4140), mt, 0x00ff00ffu);
+    const uint32_t hi = __viaddmin_s16x2_relu(__byte_perm(c, 0u, 0x4342), mt, 0x00ff00ffu);
+    c = __byte_perm(lo, hi, 0x6420);                                         // clamp(x - tau, 0, 255)
+  }
+  const uint32_t s = (a & kLow7) + (~c & kLow7);                             // bit 7: low7(a) > low7(c)
+  return ((~a & c) | (~(a ^ c) & s)) & kMsb;
+}
+
+// All tests of state byte G (filter.hpp:574-584: tests 0..8 -> byte 0 with test 8 OR-ed into bit 0
+// under m8, 9..16 -> byte 1, 17..24 -> byte 2, 25..31 -> byte 3).
+template <bool kTau, int G>
+__device__ __forceinline__ unsigned long long eval_group(const uint8_t* base, const ForestDev& forest, uint32_t m8) {
+  constexpr int t0 = (G == 0) ? 1 : 8 * G + 1;
+  constexpr int t1 = (G == 0) ? 8 : (G == 3) ? kMaxTests : 8 * G + 9;       // exclusive
+  unsigned long long acc = 0ull;
+  if (G == 0) {
+    const uint32_t r0 = eval_test<kTau>(base, forest, 0), r8 = eval_test<kTau>(base, forest, 8);
+    acc = (unsigned long long)(r0 | (r8 & m8));
+  }
+#pragma unroll
+  for (int t = t0; t < t1; t++)
+    acc += (unsigned long long)eval_test<kTau>(base, forest, t) * (unsigned long long)forest.pmul[t];
+  return acc;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+#ifndef GPC_MINB_A
+#define GPC_MINB_A 1
+#endif
+template <bool kTau>
+__global__ void __launch_bounds__(kThreadsA, GPC_MINB_A)
+hash_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const HashArgs args, const ForestDev forest) {
+  extern __shared__ __align__(128) uint8_t smem[];                // 4 copies of [kSmRows][kPitch] biased bytes
+  __shared__ __align__(8) unsigned long long mbar;
+
+  const int W = args.W, H = args.H;
+  const int img = args.img0 + blockIdx.z;
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  const int tid = threadIdx.x;
+  const size_t img_off = (size_t)img * W * H;
+
+  // ---- candidate masks of this thread's quads: issued first, consumed after the tile has landed --------
+  const int qx = tid % kQuadsX;
+  const int gx = x0 + 4 * qx;
+  constexpr int kRowStep = kThreadsA / kQuadsX;
+  constexpr int kIters = kTileH / kRowStep;
+  static_assert(kIters <= 8, "candidate nibbles of a thread are packed into one word");
+  uint32_t craw[kIters];
+#pragma unroll
+  for (int i = 0; i < kIters; i++) {
+    const int gy = y0 + tid / kQuadsX + i * kRowStep;
+    craw[i] = 0;
+    if (gy < H && gx < W) craw[i] = __ldg(args.cand + ((size_t)img * H + gy) * (W / 16) + (gx >> 4));
+  }
+
+  // ---- TMA: copy 0 = image columns x0 - 16 .., rows y0 - 13 ..; zero fill outside the image ---------
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(kSmRows * kPitch) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(smem)), "l"(&tmap), "r"(x0 - 16), "r"(y0 - kRadius), "r"(img), "r"(smem_u32(&mbar))
+        : "memory");
+  }
+  __syncthreads();                                                 // the initialised barrier is visible to all waiters
+
+  {                                                                // wait for the tile
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+  }
+
+  uint32_t cms = 0;                                                // nibble i = candidate bits of iteration i
+#pragma unroll
+  for (int i = 0; i < kIters; i++) cms |= ((craw[i] >> ((qx & 3) * 4)) & 15u) << (4 * i);
+
+  // ---- copies 1..3 = copy 0 shifted left by 1..3 bytes (two words per step) ----------------------------
+  {
+    static_assert(kPitchW % 2 == 0 && kCopyBytes % 8 == 0, "64-bit accesses");
+    const uint32_t* x32 = reinterpret_cast<const uint32_t*>(smem);
+    for (int i = tid; i < kSmRows * (kPitchW / 2); i += kThreadsA) {
+      const int r = i / (kPitchW / 2), q = 2 * (i - r * (kPitchW / 2));
+      const uint2 w = *reinterpret_cast<const uint2*>(x32 + r * kPitchW + q);
+      const uint32_t nx = (q + 2 < kPitchW) ? x32[r * kPitchW + q + 2] : 0u;
+      uint8_t* dst = smem + (r * kPitchW + q) * 4;
+      *reinterpret_cast<uint2*>(dst + 1 * kCopyBytes) = make_uint2(__funnelshift_r(w.x, w.y, 8), __funnelshift_r(w.y, nx, 8));
+      *reinterpret_cast<uint2*>(dst + 2 * kCopyBytes) = make_uint2(__funnelshift_r(w.x, w.y, 16), __funnelshift_r(w.y, nx, 16));
+      *reinterpret_cast<uint2*>(dst + 3 * kCopyBytes) = make_uint2(__funnelshift_r(w.x, w.y, 24), __funnelshift_r(w.y, nx, 24));
+    }
+  }
+  __syncthreads();
+
+  // ---- fern tests, 4 pixels per step ---------------------------------------------------------------------
+  uint32_t* __restrict__ hash = args.hash + img_off;
+  const uint32_t m8 = (gx & 4) ? kMsb : 0x80808000u;              // test #8: byte lanes x%8==0 dropped (filter.hpp:582)
+  const int T = forest.n_tests;
+  const int n_groups = (T <= 9) ? 1 : (T <= 17) ? 2 : (T <= 25) ? 3 : 4;
+#pragma unroll 1
+  for (int i = 0; i < kIters; i++) {
+    const int ry = tid / kQuadsX + i * kRowStep;
+    const int gy = y0 + ry;
+    const uint32_t cm = (cms >> (4 * i)) & 15u;
+    uint32_t st[4] = {0u, 0u, 0u, 0u};
+    if (cm != 0u && gy >= kRadius && gy < H - 15) {                // hashed rows (filter.hpp:601-604)
+      const uint8_t* base = smem + (ry + kRadius) * kPitch + 16 + 4 * qx;
+      unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+      acc[0] = eval_group<kTau, 0>(base, forest, m8);
+      if (n_groups > 1) acc[1] = eval_group<kTau, 1>(base, forest, m8);      // uniform branches
+      if (n_groups > 2) acc[2] = eval_group<kTau, 2>(base, forest, m8);
+      if (n_groups > 3) acc[3] = eval_group<kTau, 3>(base, forest, m8);
+      // byte j of (acc[g] >> 7) = state byte g of pixel j; 4x4 byte transpose -> one state per pixel
+      uint32_t w[4];
+#pragma unroll
+      for (int g = 0; g < 4; g++) w[g] = (uint32_t)(acc[g] >> 7);
+      uint32_t lo01 = __byte_perm(w[0], w[1], 0x5140), hi01 = __byte_perm(w[0], w[1], 0x7362);
+      uint32_t lo23 = __byte_perm(w[2], w[3], 0x5140), hi23 = __byte_perm(w[2], w[3], 0x7362);
+      st[0] = __byte_perm(lo01, lo23, 0x5410);
+      st[1] = __byte_perm(lo01, lo23, 0x7632);
+      st[2] = __byte_perm(hi01, hi23, 0x5410);
+      st[3] = __byte_perm(hi01, hi23, 0x7632);
+    }
+    uint4 o;
+    o.x = (cm & 1u) ? (st[0] | kCandFlag) : 0u;
+    o.y = (cm & 2u) ? (st[1] | kCandFlag) : 0u;
+    o.z = (cm & 4u) ? (st[2] | kCandFlag) : 0u;
+    o.w = (cm & 8u) ? (st[3] | kCandFlag) : 0u;
+    if (gx < W && gy < H) *reinterpret_cast<uint4*>(hash + (size_t)gy * W + gx) = o;
+  }
+}
+
+size_t hash_smem_bytes() { return (size_t)4 * kCopyBytes; }
+
+cudaError_t configure_hash_tiles() {   // per device: opt in to > 48 KB dynamic shared memory
+  cudaError_t e = cudaFuncSetAttribute(hash_tiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hash_smem_bytes());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(hash_tiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hash_smem_bytes());
+  return e;
+}
+
+// Tensor map over the biased smoothed images [n_img][H][W] u8; box = one operand tile.
+int make_smooth_tensor_map(void* out_map, const uint8_t* base, int W, int H, int n_img) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -1;
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
+  const cuuint64_t strides[2] = {(cuuint64_t)W, (cuuint64_t)W * (cuuint64_t)H};      // bytes, dims 1 and 2
+  const cuuint32_t box[3] = {(cuuint32_t)kPitch, (cuuint32_t)kSmRows, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims,
+                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+cudaError_t launch_hash_tiles(const void* tensor_map, const HashArgs& args, const ForestDev& forest, int n_img, cudaStream_t stream) {
+  dim3 grid((args.W + kTileW - 1) / kTileW, (args.H + kTileH - 1) / kTileH, n_img);
+  const CUtensorMap& tmap = *reinterpret_cast<const CUtensorMap*>(tensor_map);
+  if (forest.type != 0) hash_tiles_kernel<true><<<grid, kThreadsA, hash_smem_bytes(), stream>>>(tmap, args, forest);
+  else hash_tiles_kernel<false><<<grid, kThreadsA, hash_smem_bytes(), stream>>>(tmap, args, forest);
+  return cudaGetLastError();
+}
+
+}  // namespace gpc

@@ -1,0 +1,205 @@
+// smooth_sobel.cu -- kernel A1: box blur + Sobel candidate masks for a whole batch of images.
+//
+// Replaces the reference's
+//   ndb::box + Buffer::clearBoundary   (filter.hpp:293-392, buffer.hpp:630-654)
+//   ndb::sobel                         (filter.hpp:404-519, incl. the lane duplication at :504-507)
+//   ndb::arr2ind + border lambda       (filter.hpp:60-87, inference.hpp:318-330)
+// One CTA stages a (32+2) x (256+32) raw tile in shared memory and produces, for its 256 x 32
+// pixels, (a) the smoothed image in BIASED form (s ^ 0x80, the form kernel A2's signed byte
+// compares want) and (b) one 16-bit candidate mask per 16-pixel segment.  Every pixel of both
+// outputs is written exactly once, borders included, so kernel A2 can fetch arbitrary tiles of
+// the smoothed image with TMA.  Nothing here is a translation of the SSE code: the horizontal
+// floor-thirds are dp4a row sums, the vertical pass slides a 3-row register window.
+#include "gpc_device.cuh"
+
+namespace gpc {
+
+__device__ __forceinline__ uint32_t third(uint32_t s) { return __umulhi(s, 21846u << 16); }   // (s*21846)>>16
+__device__ __forceinline__ uint32_t ninth(uint32_t s) { return __umulhi(s, 7282u << 16); }    // (s*7282)>>16
+
+constexpr int kPreW = 256, kPreH = 32;             // output tile
+constexpr int kPrePitch = kPreW + 32;              // image cols x0-16 .. x0+kPreW+15
+constexpr int kPrePitchW = kPrePitch / 4;
+constexpr int kPreRows = kPreH + 2;                // image rows y0-1 .. y0+kPreH
+constexpr int kPreThreads = 256;
+constexpr int kPreSegRows = kPreH / (kPreThreads / (kPreW / 4));   // rows per thread in the vertical pass
+
+// Horizontal floor-thirds of 4 consecutive pixels: h[k] = (p[x+k-1] + p[x+k] + p[x+k+1]) / 3.
+__device__ __forceinline__ void hthirds(uint32_t wm1, uint32_t w, uint32_t wp1, uint32_t h[4]) {
+  h[0] = third(__dp4a(__funnelshift_r(wm1, w, 24), 0x00010101u, 0u));
+  h[1] = third(__dp4a(w, 0x00010101u, 0u));
+  h[2] = third(__dp4a(w, 0x01010100u, 0u));
+  h[3] = third(__dp4a(__funnelshift_r(w, wp1, 16), 0x00010101u, 0u));
+}
+
+// candidate border (inference.hpp:322): 13 <= x < W-13, 13 <= y < H-13, applied to a segment mask
+__device__ __forceinline__ uint32_t border_mask(uint32_t m, int gy, int gxs, int W, int H) {
+  if (gy < kRadius || gy >= H - kRadius) return 0u;
+  const int lowcut = kRadius - gxs;                 // columns below 13
+  if (lowcut >= 16) return 0u;
+  if (lowcut > 0) m &= ~((1u << lowcut) - 1u);
+  const int keep = W - kRadius - gxs;               // columns below W-13
+  if (keep <= 0) return 0u;
+  if (keep < 16) m &= (1u << keep) - 1u;
+  return m;
+}
+
+// kDebugOut: also writes the unbiased smooth image and the 0/255 grad image (gpc_preprocess seam)
+template <bool kDebugOut>
+__global__ void __launch_bounds__(kPreThreads)
+smooth_sobel_kernel(const PreprocessArgs args) {
+  __shared__ __align__(16) uint32_t raw32[kPreRows * kPrePitchW];
+  __shared__ int cta_last;                                   // largest row of this tile with a candidate
+  const int W = args.W, H = args.H;
+  const int img = blockIdx.z;
+  const int x0 = blockIdx.x * kPreW, y0 = blockIdx.y * kPreH;
+  const int tid = threadIdx.x;
+  const size_t img_off = (size_t)img * W * H;
+  const uint8_t* __restrict__ raw = args.raw + img_off;
+
+  if (threadIdx.x == 0) cta_last = -1;
+  // ---- stage the raw tile (zero outside the image) ---------------------------------------------
+  {
+    constexpr int kChunks = kPrePitch / 16;
+    uint4* dst = reinterpret_cast<uint4*>(raw32);
+    for (int c = tid; c < kPreRows * kChunks; c += kPreThreads) {
+      const int r = c / kChunks, k = c - r * kChunks;
+      const int gy = y0 - 1 + r, gx = x0 - 16 + 16 * k;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+        v = __ldg(reinterpret_cast<const uint4*>(raw + (size_t)gy * W + gx));
+      dst[c] = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- smoothed pixels: thread = (quad column, band of kPreSegRows rows), 3-row register window ---
+  {
+    const int q = tid % (kPreW / 4), band = tid / (kPreW / 4);
+    const int gxq = x0 + 4 * q;
+    if (gxq < W) {
+      const int last_written = (H & 1) ? H - 3 : H - 4;    // box writes rows 1..last (filter.hpp:307,388)
+      uint32_t colmask = 0xffffffffu;                      // clearBoundary: columns 0,1 and W-1
+      if (gxq == 0) colmask = 0xffff0000u;
+      if (gxq == W - 4) colmask &= 0x00ffffffu;
+      uint32_t ha[4], hb[4], hc[4];
+      auto load_h = [&](int r, uint32_t h[4]) {            // raw-tile row r = image row y0 - 1 + r
+        const uint32_t* row = raw32 + r * kPrePitchW + 4 + q;
+        hthirds(row[-1], row[0], row[1], h);
+      };
+      const int j0 = band * kPreSegRows;
+      load_h(j0, ha);
+      load_h(j0 + 1, hb);
+#pragma unroll 4
+      for (int j = j0; j < j0 + kPreSegRows; j++) {
+        load_h(j + 2, hc);
+        uint32_t v = third(ha[0] + hb[0] + hc[0]) | (third(ha[1] + hb[1] + hc[1]) << 8) |
+                     (third(ha[2] + hb[2] + hc[2]) << 16) | (third(ha[3] + hb[3] + hc[3]) << 24);
+        const int gy = y0 + j;
+        if (gy < 1 || gy > last_written) v = 0u; else v &= colmask;
+        if (gy < H) {
+          *reinterpret_cast<uint32_t*>(args.smooth_x + img_off + (size_t)gy * W + gxq) = v ^ 0x80808080u;
+          if (kDebugOut && args.smooth_out)
+            *reinterpret_cast<uint32_t*>(args.smooth_out + img_off + (size_t)gy * W + gxq) = v;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) { ha[k] = hb[k]; hb[k] = hc[k]; }
+      }
+    }
+  }
+
+  // ---- Sobel predicate per 16-pixel segment -> candidate bit masks, per-row candidate counts ----------
+  {
+    static_assert((kPreH * (kPreW / 16)) % kPreThreads == 0 && kPreW / 16 == 16, "uniform trip count, 16 segments per tile row");
+    const uint8_t* raw8 = reinterpret_cast<const uint8_t*>(raw32);
+    const int segs_per_row = W / 16;
+    for (int sr = tid; sr < kPreH * (kPreW / 16); sr += kPreThreads) {
+      const int ry = sr / (kPreW / 16), sg = sr - ry * (kPreW / 16);
+      const int gy = y0 + ry, gxs = x0 + 16 * sg;
+      const bool valid = gy < H && gxs < W;
+      uint32_t m = 0;
+      if (valid && gy >= 1 && gy < H - 3) {                // rows the reference writes (filter.hpp:517)
+        const uint8_t* r0 = raw8 + ry * kPrePitch + 16 + 16 * sg;            // image row gy-1, col gxs
+        const uint8_t* r1 = r0 + kPrePitch;
+        const uint8_t* r2 = r1 + kPrePitch;
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+          const int c = (g < 4) ? g : g + 4;              // true columns s..s+3 and s+8..s+11 survive :504-507
+          int p00 = r0[c - 1], p01 = r0[c], p02 = r0[c + 1];
+          int p10 = r1[c - 1], p12 = r1[c + 1];
+          int p20 = r2[c - 1], p21 = r2[c], p22 = r2[c + 1];
+          int a = (int)ninth(p00 + p20 + 2 * p10), b = (int)ninth(p02 + p22 + 2 * p12);
+          int cc = (int)ninth(p00 + p02 + 2 * p01), d = (int)ninth(p20 + p22 + 2 * p21);
+          int sum = (a - b) * (a - b) + (cc - d) * (cc - d);   // <= 25538, no int16 wrap / saturation
+          if (sum > args.thr2) m |= 3u << (2 * g);            // lane duplication: outputs 2g, 2g+1
+        }
+      }
+      if (kDebugOut && args.grad_out && valid) {
+        uint32_t wv[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          uint32_t nib = (m >> (4 * k)) & 15u;
+          wv[k] = ((nib & 1u) * 0xffu) | ((nib & 2u) * (0xff00u >> 1)) | ((nib & 4u) * (0xff0000u >> 2)) |
+                  ((nib & 8u) * (0xff000000u >> 3));
+        }
+        *reinterpret_cast<uint4*>(args.grad_out + img_off + (size_t)gy * W + gxs) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+      }
+      const uint32_t bm = valid ? border_mask(m, gy, gxs, W, H) : 0u;
+      if (valid) args.cand[((size_t)img * H + gy) * segs_per_row + (gxs >> 4)] = (uint16_t)bm;
+      // the 16 segments of one tile row sit in 16 consecutive lanes: one global atomic per tile row
+      int cnt = __popc(bm);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, 8);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+      if ((tid & 15) == 0 && cnt > 0) {
+        atomicAdd(args.rowcnt + (size_t)img * H + gy, cnt);
+        atomicMax(&cta_last, gy);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0 && cta_last >= 0 && cta_last > *reinterpret_cast<volatile int32_t*>(args.lastrow + img))
+    atomicMax(args.lastrow + img, cta_last);              // a stale read only costs a redundant atomic
+}
+
+cudaError_t launch_smooth_sobel(const PreprocessArgs& args, int n_img, bool debug_out, cudaStream_t stream) {
+  dim3 grid((args.W + kPreW - 1) / kPreW, (args.H + kPreH - 1) / kPreH, n_img);
+  if (debug_out) smooth_sobel_kernel<true><<<grid, kPreThreads, 0, stream>>>(args);
+  else smooth_sobel_kernel<false><<<grid, kPreThreads, 0, stream>>>(args);
+  return cudaGetLastError();
+}
+
+// gpc_hash_smooth seam: the caller provides the smoothed image and a u8 flag image; produce the
+// biased smooth image and the candidate masks kernel A2 consumes.  One thread per 16-pixel segment.
+__global__ void __launch_bounds__(256)
+prep_from_smooth_kernel(const uint8_t* __restrict__ smooth, const uint8_t* __restrict__ flags, uint8_t* __restrict__ smooth_x,
+                        uint16_t* __restrict__ cand, int32_t* __restrict__ rowcnt, int32_t* __restrict__ lastrow, int W, int H) {
+  const int segs_per_row = W / 16;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= segs_per_row * H) return;
+  const int gy = i / segs_per_row, gxs = 16 * (i - gy * segs_per_row);
+  uint4 v = __ldg(reinterpret_cast<const uint4*>(smooth + (size_t)gy * W + gxs));
+  v.x ^= 0x80808080u; v.y ^= 0x80808080u; v.z ^= 0x80808080u; v.w ^= 0x80808080u;
+  *reinterpret_cast<uint4*>(smooth_x + (size_t)gy * W + gxs) = v;
+  const uint4 f = __ldg(reinterpret_cast<const uint4*>(flags + (size_t)gy * W + gxs));
+  const uint32_t wv[4] = {f.x, f.y, f.z, f.w};
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+      if ((wv[k] >> (8 * b)) & 0xffu) m |= 1u << (4 * k + b);
+  const uint32_t bm = border_mask(m, gy, gxs, W, H);
+  cand[i] = (uint16_t)bm;
+  if (bm) { atomicAdd(rowcnt + gy, __popc(bm)); atomicMax(lastrow, gy); }
+}
+
+cudaError_t launch_prep_from_smooth(const uint8_t* smooth, const uint8_t* flags, uint8_t* smooth_x, uint16_t* cand, int32_t* rowcnt,
+                                    int32_t* lastrow, int W, int H, cudaStream_t stream) {
+  const int n = (W / 16) * H;
+  prep_from_smooth_kernel<<<(n + 255) / 256, 256, 0, stream>>>(smooth, flags, smooth_x, cand, rowcnt, lastrow, W, H);
+  return cudaGetLastError();
+}
+
+}  // namespace gpc

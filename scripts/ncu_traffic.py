@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MULT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 PIX = 1024 * 436
-UNITS = {"preprocess_hash": 64 * PIX, "match_rows": 32 * PIX}      # image pixels / pair pixels (one side) per launch at --batch 32
+UNITS = {"smooth_sobel": 64 * PIX, "hash_tiles": 64 * PIX, "match_rows": 32 * PIX}      # image pixels / pair pixels (one side) per launch at --batch 32
 out = {"source": f"ncu --set full, {sys.argv[1]} (profiles/), small bench --batch 32", "dram_bytes_per_pixel": {}}
 for rep in sys.argv[2:]:
     rows = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)))
