@@ -24,7 +24,7 @@ constexpr uint32_t kCandFlag = 0x80000000u;
 #define GPC_TILE_W 128
 #endif
 #ifndef GPC_TILE_H
-#define GPC_TILE_H 32
+#define GPC_TILE_H 64
 #endif
 #ifndef GPC_THREADS_A
 #define GPC_THREADS_A 256
