@@ -217,6 +217,12 @@ class Context:
                                                _ptr(out), C.c_int64(cap), _ptr(offsets), _ptr(n_cand)))
         return out[:offsets[-1]].copy(), offsets, n_cand
 
+    def match_pyramid_raw(self, left_ptr, right_ptr, w, h, n_levels, settings, out_ptr, cap, offsets_ptr, n_cand_ptr=None):
+        """Pointer-level gpc_match_pyramid (host buffers owned by the caller, ideally pinned)."""
+        self._check(self.lib.gpc_match_pyramid(self._h, C.c_void_p(left_ptr), C.c_void_p(right_ptr), w, h, w, int(n_levels),
+                                               C.byref(settings), C.c_void_p(out_ptr), C.c_int64(cap), C.c_void_p(offsets_ptr),
+                                               C.c_void_p(n_cand_ptr or 0)))
+
     # ---- stage seams ------------------------------------------------------------------------
     def preprocess(self, img, thr):
         img = np.ascontiguousarray(img, np.uint8)

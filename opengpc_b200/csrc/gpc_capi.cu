@@ -22,6 +22,7 @@ cudaError_t launch_hash_tiles(const void* tensor_map, const HashArgs&, const For
 size_t match_smem_bytes(int wcap, int table_log2);
 cudaError_t configure_match_rows(int max_smem);
 cudaError_t launch_match_rows(const MatchArgs&, int n_pairs, cudaStream_t);
+int match_rows_threads(int W);
 cudaError_t launch_row_scan(const int32_t* rowmatch, const int32_t* rowcnt, int H, int n_pairs, int32_t* rowoff,
                             int32_t* totals, int32_t* n_cand, cudaStream_t);
 cudaError_t launch_pair_scan(const int32_t* totals, int n_pairs, long long* pair_base, cudaStream_t);
@@ -177,9 +178,9 @@ int check_settings(gpc_ctx* c, const gpc_settings* s) {
 int ceil_log2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
 // log2 of the row matcher's bucket count: about half a candidate (left + right) per bucket, at
-// least 1024 (scan layout) and at least 2 * W (so that remainder + side + x fit one 32-bit entry)
+// least 4 per thread (scan layout) and at least 2 * W (so that remainder + side + x fit one 32-bit entry)
 int table_log2_for(int w, int wcap) {
-  int l = std::max(10, ceil_log2(w) + 1);
+  int l = std::max(ceil_log2(4 * gpc::match_rows_threads(w)), ceil_log2(w) + 1);
   while ((1 << l) < 4 * wcap) l++;
   return l;
 }
@@ -294,7 +295,8 @@ int run_match(gpc_ctx* c, const Slot& sl, int n_pairs, int w, int h, const gpc_s
   m.table_log2 = table_log2_for(w, m.wcap);
   m.x_bits = ceil_log2(w);
   m.pow2cap = 1 << ceil_log2(m.wcap);
-  while ((int)gpc::match_smem_bytes(m.wcap, m.table_log2) > 72 * 1024 && m.table_log2 > std::max(10, m.x_bits + 1))
+  while ((int)gpc::match_smem_bytes(m.wcap, m.table_log2) > 72 * 1024 &&
+         m.table_log2 > std::max(ceil_log2(4 * gpc::match_rows_threads(w)), m.x_bits + 1))
     m.table_log2--;                                  // wide rows: fewer, longer buckets keep >= 3 CTAs per SM
   m.key_bits = 31;   // hash images may come from the caller (gpc_match_hash_images): assume full 31-bit states
   if ((int)gpc::match_smem_bytes(m.wcap, m.table_log2) > c->match_smem_max)

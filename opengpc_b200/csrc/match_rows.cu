@@ -17,7 +17,6 @@
 
 namespace gpc {
 
-constexpr int kThreadsB = 256;
 constexpr int kBuckets = 256;                 // ordering pass: counting sort on the top 8 state bits
 constexpr int kBucketLimit = 64;              // above this the in-bucket rank pass falls back to a bitonic network
 
@@ -49,7 +48,7 @@ size_t match_smem_bytes(int wcap, int table_log2) {
 //   scatter : entry stored at start[bucket] + rank
 //   resolve : every left candidate reads its bucket (<= 4 entries in one unrolled step, longer
 //             buckets in a loop) counting equal states per side; unique on both sides = match
-template <int KQ>
+template <int KQ, int kThreadsB>
 __global__ void __launch_bounds__(kThreadsB)
 match_rows_kernel(const MatchArgs args) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -304,24 +303,37 @@ match_rows_kernel(const MatchArgs args) {
   if (tid == 0) args.rowmatch[(size_t)pair * H + y] = m;
 }
 
+// Launch shapes: every thread owns 4 * KQ pixels per side.  Rows up to 1024 pixels run 256 threads,
+// wider rows 512 or 1024 threads with KQ = 1 (wide rows need large tables, so few CTAs fit an SM and
+// each has to bring more warps); beyond 4096 pixels KQ grows.
+template <int KQ, int T>
+static cudaError_t configure_one(int max_smem) {
+  return cudaFuncSetAttribute(match_rows_kernel<KQ, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+}
+
 cudaError_t configure_match_rows(int max_smem) {
-  cudaError_t e = cudaFuncSetAttribute(match_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(match_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(match_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(match_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaError_t e = configure_one<1, 256>(max_smem);
+  if (e == cudaSuccess) e = configure_one<1, 512>(max_smem);
+  if (e == cudaSuccess) e = configure_one<1, 1024>(max_smem);
+  if (e == cudaSuccess) e = configure_one<2, 1024>(max_smem);
   return e;
+}
+
+int match_rows_threads(int W) {
+  const int quads = W / 4;
+  return quads <= 256 ? 256 : quads <= 512 ? 512 : 1024;
 }
 
 cudaError_t launch_match_rows(const MatchArgs& args, int n_pairs, cudaStream_t stream) {
   int rows = args.H - 2 * kRadius;
   if (rows <= 0 || n_pairs <= 0) return cudaSuccess;
   size_t smem = match_smem_bytes(args.wcap, args.table_log2);
-  const int kq = (args.W / 4 + kThreadsB - 1) / kThreadsB;
+  const int quads = args.W / 4;
   dim3 grid(rows, n_pairs);
-  if (kq <= 1) match_rows_kernel<1><<<grid, kThreadsB, smem, stream>>>(args);
-  else if (kq <= 2) match_rows_kernel<2><<<grid, kThreadsB, smem, stream>>>(args);
-  else if (kq <= 4) match_rows_kernel<4><<<grid, kThreadsB, smem, stream>>>(args);
-  else if (kq <= 8) match_rows_kernel<8><<<grid, kThreadsB, smem, stream>>>(args);
+  if (quads <= 256) match_rows_kernel<1, 256><<<grid, 256, smem, stream>>>(args);
+  else if (quads <= 512) match_rows_kernel<1, 512><<<grid, 512, smem, stream>>>(args);
+  else if (quads <= 1024) match_rows_kernel<1, 1024><<<grid, 1024, smem, stream>>>(args);
+  else if (quads <= 2048) match_rows_kernel<2, 1024><<<grid, 1024, smem, stream>>>(args);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }

@@ -213,3 +213,61 @@ def test_pyramid_vs_golden_and_oracle(g, oracle):
                 ref, _, _ = oracle.pair(L, R, of, osettings(5, rec["disp_high"], 0, True))
                 assert np.array_equal(lev, ref)
             L, R = downsample2x(L), downsample2x(R)
+
+
+def test_device_batch_global_mode(g, oracle):
+    """gpc_match_batch_device with epipolarMode(false): the radix-sort matcher pair by pair, strided output."""
+    import torch
+    from opengpc_b200.synth import synth_batch
+    imgs = synth_batch(256, 80, 3, seed0=41)
+    of = oracle.read_forest(FORESTS["tau"])
+    cap = 6000
+    s = g.make_settings(thr=5, disp_high=100, vt=2, epipolar=False)
+    with g.Context(device=0, max_w=256, max_h=80, max_batch=3) as ctx:
+        ctx.set_forest(FORESTS["tau"])
+        d_img = torch.from_numpy(imgs).cuda()
+        d_out = torch.zeros((3, cap, 3), dtype=torch.int32, device="cuda")
+        d_n = torch.zeros(3, dtype=torch.int32, device="cuda")
+        d_nc = torch.zeros((3, 2), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        ctx.match_batch_device(d_img.data_ptr(), 3, 256, 80, s, d_out.data_ptr(), cap, d_n.data_ptr(), d_nc.data_ptr())
+        ctx.synchronize()
+        n, out, nc = d_n.cpu().numpy(), d_out.cpu().numpy(), d_nc.cpu().numpy()
+    for p in range(3):
+        ref, ocl, ocr = oracle.pair(imgs[p, 0], imgs[p, 1], of, osettings(5, 100, 2, False))
+        assert n[p] == len(ref) and (nc[p, 0], nc[p, 1]) == (ocl, ocr)
+        assert np.array_equal(out[p, :n[p]].copy().view(g.SUPPORT_DTYPE).reshape(-1), ref)
+
+
+def test_edge_shapes(g, oracle):
+    """Minimum and ragged sizes: width 32 (one tile column, mostly border), heights with 0 / 1 / 2 candidate
+    rows, odd heights, a row stride larger than the width, and a width that is not a tile multiple."""
+    rng = np.random.default_rng(21)
+    of = oracle.read_forest(FORESTS["tau"])
+    with g.Context(device=0, max_w=1040, max_h=70, max_batch=1) as ctx:
+        ctx.set_forest(FORESTS["tau"])
+        for (w, h) in [(32, 40), (48, 26), (48, 27), (64, 28), (144, 29), (1040, 31), (400, 69), (16, 64)]:
+            L = rng.integers(0, 256, (h, w), dtype=np.uint8)
+            R = np.roll(L, -2, axis=1)
+            for epi in (True, False):
+                ref, ocl, ocr = oracle.pair(L, R, of, osettings(5, 128, 1 if not epi else 0, epi))
+                supp, ncl, ncr = ctx.match_pair(L, R, g.make_settings(thr=5, disp_high=128, vt=1 if not epi else 0, epipolar=epi))
+                assert (ncl, ncr) == (ocl, ocr), (w, h, epi)
+                assert np.array_equal(supp, ref), (w, h, epi, len(supp), len(ref))
+            sm, gr, mk = ctx.preprocess(L, 5)
+            osm, ogr, omk, _ = oracle.stages(L, of, 5)
+            assert np.array_equal(sm, osm) and np.array_equal(gr, ogr) and np.array_equal(mk, omk), (w, h)
+        # strided input rows (gpc_match_pair's stride argument)
+        import ctypes as C
+        from opengpc_b200 import capi
+        w, h, stride = 96, 50, 128
+        big_l = rng.integers(0, 256, (h, stride), dtype=np.uint8)
+        big_r = np.roll(big_l, -3, axis=1)
+        L, R = np.ascontiguousarray(big_l[:, :w]), np.ascontiguousarray(big_r[:, :w])
+        ref, _, _ = oracle.pair(L, R, of, osettings())
+        out = np.empty(w * h, g.SUPPORT_DTYPE)
+        n = C.c_int(0)
+        s = g.sparsematch_settings()
+        rc = ctx.lib.gpc_match_pair(ctx._h, C.c_void_p(big_l.ctypes.data), C.c_void_p(big_r.ctypes.data), w, h, stride, C.byref(s),
+                                    C.c_void_p(out.ctypes.data), C.c_int(len(out)), C.byref(n), None, None)
+        assert rc == capi.GPC_OK and np.array_equal(out[:n.value], ref)
