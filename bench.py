@@ -353,8 +353,16 @@ def main():
             sec = float(t.item())
         assert int(h_off[B]) == tot_sup
         clocks = sampler.stop()
+        # single-pair latency through the same API (SURVEY.md 8d asks for it beside the batched throughput)
+        lat = []
+        for _ in range(12):
+            t1 = time.perf_counter()
+            ctx.match_batch_raw(h_img.data_ptr(), 1, w, h, settings, h_out.data_ptr(), h_out.shape[0], h_off.data_ptr())
+            lat.append(time.perf_counter() - t1)
+        single_pair_ms = 1e3 * float(np.median(lat[2:]))
         e2e = {"value": world * B * args.steps / sec, "unit": "pairs/s",
                "h2d_bytes_per_step": int(2 * B * P), "d2h_bytes_per_step": int(tot_sup * 12 + (B + 1) * 8),
+               "single_pair_latency_ms": single_pair_ms,
                "api": "gpc_match_batch (pinned host buffers; upload, kernels and download pipelined over 3 streams)"}
 
     if args.no_e2e:

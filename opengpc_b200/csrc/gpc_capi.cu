@@ -63,8 +63,8 @@ struct gpc_ctx {
   uint32_t* d_stage = nullptr;     // [B][H][W]
   int32_t* d_rows = nullptr;       // rowcnt [2B][H]   (cleared per launch)
   int32_t* d_lastrow = nullptr;    // [2B]             (cleared per launch)
-  // gpc_match_batch pipelines chunks of pairs over these lanes: H2D of chunk k+2, kernels of chunk
-  // k+1 and D2H of chunk k overlap (every chunk works on its own slice of the resident buffers)
+  // gpc_match_batch pipelines chunks of pairs over these lanes (upload / kernels / download); every
+  // chunk works on its own slice of the resident buffers
   static constexpr int kLanes = 3;
   cudaStream_t lane_stream[kLanes] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr;
@@ -521,29 +521,68 @@ int gpc_match_batch_device(gpc_ctx* c, const uint8_t* d_images, int n_pairs, int
   return run_match(c, Slot{0, c->stream}, n_pairs, w, h, s, d_out, cap_per_pair, false, d_n_out, d_n_cand);
 }
 
-// Pipelined body of gpc_match_batch (row matcher): chunks of pairs rotate over kLanes streams, each
-// chunk on its own slice of the resident buffers, so that the upload of chunk k+2, the kernels of
-// chunk k+1 and the download of chunk k's supports overlap (PCIe is full duplex).
+// Pipelined body of gpc_match_batch (row matcher): the batch is cut into chunks of pairs, each on its
+// own slice of the resident buffers; one stream uploads all chunks back to back, a second runs the
+// kernels chunk after chunk, a third downloads each chunk's supports as soon as its count is known --
+// upload, kernels and download overlap (PCIe is full duplex).
 static int match_batch_pipelined(gpc_ctx* c, const uint8_t* images, int n_pairs, int w, int h, const gpc_settings* s,
                                  gpc_support* out, int64_t cap, int64_t* offsets, int32_t* n_cand) {
   const size_t P = (size_t)w * h;
   const int CH = c->chunk_pairs;
-  const int nch = (n_pairs + CH - 1) / CH;
   const long long per_pair = c->out_cap / c->max_batch;
-  while ((int)c->ev_chunk.size() < nch) {
+  // chunk sizes ramp up at the start and down at the end (CH/4, CH/2, CH, ..., CH, CH/2, CH/4): the
+  // first upload and the last kernels + download are the only parts of the pipeline nothing overlaps
+  std::vector<int> sizes;
+  {
+    std::vector<int> ramp;
+    for (int v = std::max(1, CH / 4); v < CH; v *= 2) ramp.push_back(v);
+    int ramp_sum = 0;
+    for (int v : ramp) ramp_sum += v;
+    int rest = n_pairs;
+    if (n_pairs >= 2 * ramp_sum + CH) { sizes = ramp; rest -= 2 * ramp_sum; }
+    for (; rest > 0; rest -= CH) sizes.push_back(std::min(CH, rest));
+    if (n_pairs >= 2 * ramp_sum + CH) sizes.insert(sizes.end(), ramp.rbegin(), ramp.rend());
+  }
+  const int nch = (int)sizes.size();
+  std::vector<int> first(nch + 1, 0);
+  for (int k = 0; k < nch; k++) first[k + 1] = first[k] + sizes[k];
+  while ((int)c->ev_chunk.size() < 2 * nch) {
     cudaEvent_t e;
     GPC_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->ev_chunk.push_back(e);
   }
+  // lane 0: every upload, back to back; lane 1: the kernels, chunk after chunk; lane 2: the downloads
+  cudaStream_t s_up = c->lane_stream[0], s_run = c->lane_stream[1], s_down = c->lane_stream[2];
   GPC_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));               // order after earlier work of the context
   for (int l = 0; l < gpc_ctx::kLanes; l++) GPC_CUDA(c, cudaStreamWaitEvent(c->lane_stream[l], c->ev_fork, 0));
+  for (int k = 0; k < nch; k++) {
+    const int p0 = first[k], n = sizes[k];
+    GPC_CUDA(c, cudaMemcpyAsync(c->d_raw + (size_t)(2 * p0) * P, images + (size_t)(2 * p0) * P, 2 * (size_t)n * P,
+                                cudaMemcpyHostToDevice, s_up));
+    GPC_CUDA(c, cudaEventRecord(c->ev_chunk[2 * k], s_up));
+  }
+  for (int k = 0; k < nch; k++) {
+    const int p0 = first[k], n = sizes[k];
+    const Slot sl{p0, s_run};
+    GPC_CUDA(c, cudaStreamWaitEvent(s_run, c->ev_chunk[2 * k], 0));
+    int rc = run_preprocess(c, sl, c->d_raw + (size_t)(2 * p0) * P, 2 * n, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
+    if (rc) return rc;
+    rc = run_match(c, sl, n, w, h, s, c->d_out + (size_t)p0 * per_pair, (long long)n * per_pair, true, c->d_totals + p0,
+                   c->d_ncand + 2 * p0);
+    if (rc) return rc;
+    GPC_CUDA(c, cudaMemcpyAsync(c->h_pair_base + 2 * p0, c->d_pair_base + 2 * p0, (size_t)(n + 1) * sizeof(long long),
+                                cudaMemcpyDeviceToHost, s_run));
+    if (n_cand)
+      GPC_CUDA(c, cudaMemcpyAsync(c->h_counts + 2 * p0, c->d_ncand + 2 * p0, 2 * (size_t)n * sizeof(int32_t),
+                                  cudaMemcpyDeviceToHost, s_run));
+    GPC_CUDA(c, cudaEventRecord(c->ev_chunk[2 * k + 1], s_run));
+  }
   long long total = 0;
   bool overflow = false;
   offsets[0] = 0;
-  auto drain = [&](int k) -> int {                                     // download the supports of chunk k
-    const int p0 = k * CH, n = std::min(CH, n_pairs - p0);
-    cudaStream_t st = c->lane_stream[k % gpc_ctx::kLanes];
-    GPC_CUDA(c, cudaEventSynchronize(c->ev_chunk[k]));
+  for (int k = 0; k < nch; k++) {                                      // downloads follow the kernels chunk by chunk
+    const int p0 = first[k], n = sizes[k];
+    GPC_CUDA(c, cudaEventSynchronize(c->ev_chunk[2 * k + 1]));
     const long long* pb = c->h_pair_base + 2 * p0;
     for (int i = 0; i < n; i++) offsets[p0 + i + 1] = total + pb[i + 1];
     if (n_cand) std::memcpy(n_cand + 2 * p0, c->h_counts + 2 * p0, 2 * (size_t)n * sizeof(int32_t));
@@ -551,29 +590,9 @@ static int match_batch_pipelined(gpc_ctx* c, const uint8_t* images, int n_pairs,
     if (total + m > cap) overflow = true;
     else if (m > 0)
       GPC_CUDA(c, cudaMemcpyAsync(out + total, c->d_out + (size_t)p0 * per_pair, (size_t)m * sizeof(gpc_support),
-                                  cudaMemcpyDeviceToHost, st));
+                                  cudaMemcpyDeviceToHost, s_down));
     total += m;
-    return GPC_OK;
-  };
-  for (int k = 0; k < nch; k++) {
-    const int p0 = k * CH, n = std::min(CH, n_pairs - p0);
-    const Slot sl{p0, c->lane_stream[k % gpc_ctx::kLanes]};
-    uint8_t* d_img = c->d_raw + (size_t)(2 * p0) * P;
-    GPC_CUDA(c, cudaMemcpyAsync(d_img, images + (size_t)(2 * p0) * P, 2 * (size_t)n * P, cudaMemcpyHostToDevice, sl.stream));
-    int rc = run_preprocess(c, sl, d_img, 2 * n, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
-    if (rc) return rc;
-    rc = run_match(c, sl, n, w, h, s, c->d_out + (size_t)p0 * per_pair, (long long)n * per_pair, true, c->d_totals + p0,
-                   c->d_ncand + 2 * p0);
-    if (rc) return rc;
-    GPC_CUDA(c, cudaMemcpyAsync(c->h_pair_base + 2 * p0, c->d_pair_base + 2 * p0, (size_t)(n + 1) * sizeof(long long),
-                                cudaMemcpyDeviceToHost, sl.stream));
-    if (n_cand)
-      GPC_CUDA(c, cudaMemcpyAsync(c->h_counts + 2 * p0, c->d_ncand + 2 * p0, 2 * (size_t)n * sizeof(int32_t),
-                                  cudaMemcpyDeviceToHost, sl.stream));
-    GPC_CUDA(c, cudaEventRecord(c->ev_chunk[k], sl.stream));
-    if (k >= gpc_ctx::kLanes - 1) { rc = drain(k - (gpc_ctx::kLanes - 1)); if (rc) return rc; }
   }
-  for (int k = std::max(0, nch - (gpc_ctx::kLanes - 1)); k < nch; k++) { int rc = drain(k); if (rc) return rc; }
   for (int l = 0; l < gpc_ctx::kLanes; l++) GPC_CUDA(c, cudaStreamSynchronize(c->lane_stream[l]));
   if (overflow) return fail(c, GPC_E_CAPACITY, "support buffer too small: need " + std::to_string(total));
   return GPC_OK;
