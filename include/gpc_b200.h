@@ -165,6 +165,11 @@ int gpc_find_correspondences(gpc_ctx* ctx, const uint64_t* src_keys, int n_src, 
 #define GPC_MATCHER_SORT 1
 int gpc_set_matcher(gpc_ctx* ctx, int matcher);
 
+/* After gpc_set_forest the hashing kernel is rebuilt with the forest baked into its code (NVRTC,
+ * loaded with dlopen; about 1 s).  Returns "specialised", or "generic: <reason>" when the
+ * precompiled kernel is in use (NVRTC absent, build failure, GPC_JIT=0).  Results are identical. */
+const char* gpc_jit_status(const gpc_ctx* ctx);
+
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t gpc_launch_count(const gpc_ctx* ctx);
 

@@ -23,7 +23,7 @@ SYMBOLS = ["gpc_create", "gpc_destroy", "gpc_last_error", "gpc_status_string", "
            "gpc_read_forest", "gpc_set_forest", "gpc_match_pair", "gpc_match_batch", "gpc_match_batch_device",
            "gpc_preprocess", "gpc_hash", "gpc_match_hash_images", "gpc_launch_count", "gpc_enable_kernel_timing",
            "gpc_kernel_times", "gpc_hash_smooth", "gpc_image_upload", "gpc_image_release", "gpc_image_preprocess",
-           "gpc_match_images", "gpc_correspond_images", "gpc_find_correspondences", "gpc_set_matcher", "gpc_match_pyramid"]
+           "gpc_match_images", "gpc_correspond_images", "gpc_find_correspondences", "gpc_set_matcher", "gpc_match_pyramid", "gpc_jit_status"]
 KERNEL_NAMES = ["smooth_sobel", "hash_tiles", "match_rows", "scans", "emit_supports"]
 
 
@@ -60,6 +60,8 @@ def load_library():
     lib.gpc_last_error.restype = C.c_char_p
     lib.gpc_last_error.argtypes = [C.c_void_p]
     lib.gpc_status_string.restype = C.c_char_p
+    lib.gpc_jit_status.restype = C.c_char_p
+    lib.gpc_jit_status.argtypes = [C.c_void_p]
     lib.gpc_launch_count.restype = C.c_int64
     lib.gpc_launch_count.argtypes = [C.c_void_p]
     lib.gpc_destroy.restype = None
@@ -142,6 +144,11 @@ class Context:
     @property
     def launches(self):
         return int(self.lib.gpc_launch_count(self._h))
+
+    @property
+    def jit_status(self):
+        """'specialised' if kernel A2 was rebuilt for the current forest, else 'generic: <reason>'."""
+        return self.lib.gpc_jit_status(self._h).decode()
 
     def enable_kernel_timing(self, on=True):
         self._check(self.lib.gpc_enable_kernel_timing(self._h, int(bool(on))))

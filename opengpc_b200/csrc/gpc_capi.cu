@@ -41,6 +41,11 @@ cudaError_t launch_match_keys(void* ws, long long max_records, int ns, int nt, i
 void* global_key_buffer(void* ws, long long max_records);
 int32_t* global_nside_ptr(void* ws);
 cudaError_t launch_downsample2x(const uint8_t* src, uint8_t* dst, int sw, int sh, int n_img, cudaStream_t stream);
+struct JitKernel;
+JitKernel* jit_build_hash_tiles(const ForestDev& f, std::string* why);
+void jit_destroy(JitKernel* k);
+cudaError_t jit_launch_hash_tiles(JitKernel* k, const void* tensor_map, const HashArgs& args, const ForestDev& forest, int n_img,
+                                  cudaStream_t stream);
 }  // namespace gpc
 
 static thread_local std::string g_create_error;
@@ -53,6 +58,8 @@ struct gpc_ctx {
   bool has_forest = false;
   gpc_forest forest_host{};
   gpc::ForestDev forest_dev{};
+  gpc::JitKernel* jit = nullptr;   // kernel A2 specialised for forest_dev (NVRTC), or nullptr -> generic kernel
+  std::string jit_note = "no forest set";
   // resident device buffers
   uint8_t* d_raw = nullptr;        // [2B][H][W]
   uint8_t* d_smooth = nullptr;     // [2B][H][W]  biased smoothed images (kernel A1 -> TMA -> kernel A2)
@@ -181,7 +188,8 @@ int ceil_log2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 // least 4 per thread (scan layout) and at least 2 * W (so that remainder + side + x fit one 32-bit entry)
 int table_log2_for(int w, int wcap) {
   int l = std::max(ceil_log2(4 * gpc::match_rows_threads(w)), ceil_log2(w) + 1);
-  while ((1 << l) < 4 * wcap) l++;
+  static const int mult = std::getenv("GPC_B_BUCKET_MULT") ? std::max(1, std::atoi(std::getenv("GPC_B_BUCKET_MULT"))) : 4;
+  while ((1 << l) < mult * wcap) l++;
   return l;
 }
 
@@ -226,7 +234,10 @@ int run_preprocess(gpc_ctx* c, const Slot& sl, const uint8_t* d_images, int n_im
   gpc::HashArgs ha{};
   ha.cand = c->d_cand; ha.hash = c->d_hash;
   ha.W = w; ha.H = h; ha.img0 = img0;
-  GPC_CUDA(c, gpc::launch_hash_tiles(c->tmap, ha, forest, n_img, sl.stream));
+  if (c->jit && &forest == &c->forest_dev)
+    GPC_CUDA(c, gpc::jit_launch_hash_tiles(c->jit, c->tmap, ha, forest, n_img, sl.stream));
+  else
+    GPC_CUDA(c, gpc::launch_hash_tiles(c->tmap, ha, forest, n_img, sl.stream));
   c->launches += 2;
   return mark_on(c, sl);                                                           // event 2
 }
@@ -411,6 +422,7 @@ void gpc_destroy(gpc_ctx* c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (cudaEvent_t e : c->ev_chunk) cudaEventDestroy(e);
   cudaFree(c->d_rowoff); cudaFree(c->d_totals); cudaFree(c->d_ncand); cudaFree(c->d_pair_base); cudaFree(c->d_out);
+  gpc::jit_destroy(c->jit);
   cudaFree(c->d_dbg8); cudaFree(c->d_mask); cudaFree(c->d_gws); cudaFree(c->d_rowoff2); cudaFree(c->d_pyr);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->h_pair_base) cudaFreeHost(c->h_pair_base);
@@ -433,6 +445,8 @@ int gpc_synchronize(gpc_ctx* c) {
 }
 
 int64_t gpc_launch_count(const gpc_ctx* c) { return c ? c->launches : 0; }
+
+const char* gpc_jit_status(const gpc_ctx* c) { return c ? c->jit_note.c_str() : ""; }
 
 int gpc_enable_kernel_timing(gpc_ctx* c, int on) {
   if (!c) return GPC_E_ARG;
@@ -503,9 +517,17 @@ int gpc_set_forest(gpc_ctx* c, const gpc_forest* f) {
       if (v[k] < -GPC_PATCH_RADIUS || v[k] > GPC_PATCH_RADIUS)
         return fail(c, GPC_E_FOREST, "test offset outside the 27x27 patch (|offset| <= 13)");
   }
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  GPC_CUDA(c, cudaStreamSynchronize(c->stream));     // earlier launches may still use the previous specialised kernel
+  for (int l = 0; l < gpc_ctx::kLanes; l++) GPC_CUDA(c, cudaStreamSynchronize(c->lane_stream[l]));
+  gpc::jit_destroy(c->jit);
+  c->jit = nullptr;
   c->forest_host = *f;
   bake_forest(*f, &c->forest_dev);
   c->has_forest = true;
+  std::string why;
+  c->jit = gpc::jit_build_hash_tiles(c->forest_dev, &why);
+  c->jit_note = c->jit ? "specialised" : ("generic: " + why);
   return GPC_OK;
 }
 

@@ -10,8 +10,18 @@
 //   stage  uint32 [n_pair][H][W]       per-row match lists, xL<<16 | xR, sorted by state
 //   rowmatch int32 [n_pair][H]         matches per row
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdint>
 #include <cuda_runtime.h>
+#else   // NVRTC (forest-specialised kernel A2, see jit.cu): no host headers
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+typedef unsigned long size_t;
+#endif
 
 namespace gpc {
 

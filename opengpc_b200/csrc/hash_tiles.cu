@@ -17,7 +17,12 @@
 //   * the tests of one state byte form a single basic block (no per-test guards: the forest is
 //     padded with never-true tests), so the compiler interleaves their dependency chains.
 // Each pixel's state is written once to the hash image (bit 31 = candidate).
+#ifndef __CUDACC_RTC__
 #include <cuda.h>
+#else
+struct alignas(64) CUtensorMap_st { unsigned long long opaque[16]; };
+typedef CUtensorMap_st CUtensorMap;
+#endif
 
 #include "gpc_device.cuh"
 
@@ -33,12 +38,24 @@ constexpr uint32_t kLow7 = 0x7f7f7f7fu;
 // Signed byte compare: msb = (~a7 & c7) | (~(a7 ^ c7) & carry7), carry from the low 7 bits.
 // The returned word is masked to the msbs.  A tau forest sends every test through the clamp
 // (tau == 0 leaves x unchanged).
+#ifdef GPC_JIT_HEADER
+#include GPC_JIT_HEADER      // forest baked into the code: jit_imm_a(t), jit_imm_b(t), jit_mtau2(t), kJitTests
+#endif
+
 template <bool kTau>
 __device__ __forceinline__ uint32_t eval_test(const uint8_t* base, const ForestDev& forest, const int t) {
+#ifdef GPC_JIT_HEADER
+  if (t >= kJitTests) return 0u;                                             // compile time after unrolling
+  const uint32_t a = *reinterpret_cast<const uint32_t*>(base + jit_imm_a(t));
+  uint32_t c = *reinterpret_cast<const uint32_t*>(base + jit_imm_b(t));
+  if (kTau && jit_mtau2(t) != 0u) {
+    const uint32_t mt = jit_mtau2(t);
+#else
   const uint32_t a = *reinterpret_cast<const uint32_t*>(base + forest.imm_a[t]);
   uint32_t c = *reinterpret_cast<const uint32_t*>(base + forest.imm_b[t]);
   if (kTau) {
     const uint32_t mt = forest.mtau2[t];
+#endif
     const uint32_t lo = __viaddmin_s16x2_relu(__byte_perm(c, 0u, 0x4140), mt, 0x00ff00ffu);
     const uint32_t hi = __viaddmin_s16x2_relu(__byte_perm(c, 0u, 0x4342), mt, 0x00ff00ffu);
     c = __byte_perm(lo, hi, 0x6420);                                         // clamp(x - tau, 0, 255)
@@ -70,8 +87,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 #define GPC_MINB_A 1
 #endif
 template <bool kTau>
-__global__ void __launch_bounds__(kThreadsA, GPC_MINB_A)
-hash_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const HashArgs args, const ForestDev forest) {
+__device__ __forceinline__ void hash_tiles_body(const CUtensorMap& tmap, const HashArgs& args, const ForestDev& forest) {
   extern __shared__ __align__(128) uint8_t smem[];                // 4 copies of [kSmRows][kPitch] biased bytes
   __shared__ __align__(8) unsigned long long mbar;
 
@@ -172,6 +188,21 @@ hash_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const HashArgs args,
   }
 }
 
+template <bool kTau>
+__global__ void __launch_bounds__(kThreadsA, GPC_MINB_A)
+hash_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const HashArgs args, const ForestDev forest) {
+  hash_tiles_body<kTau>(tmap, args, forest);
+}
+
+#ifdef GPC_JIT_HEADER
+// Entry point of the forest-specialised build (NVRTC, jit.cu): unmangled name, forest baked in.
+extern "C" __global__ void __launch_bounds__(kThreadsA, GPC_MINB_A)
+gpc_hash_tiles_jit(const __grid_constant__ CUtensorMap tmap, const HashArgs args, const ForestDev forest) {
+  hash_tiles_body<kJitTau>(tmap, args, forest);
+}
+#endif
+
+#ifndef __CUDACC_RTC__
 size_t hash_smem_bytes() { return (size_t)4 * kCopyBytes; }
 
 cudaError_t configure_hash_tiles() {   // per device: opt in to > 48 KB dynamic shared memory
@@ -209,5 +240,6 @@ cudaError_t launch_hash_tiles(const void* tensor_map, const HashArgs& args, cons
   else hash_tiles_kernel<false><<<grid, kThreadsA, hash_smem_bytes(), stream>>>(tmap, args, forest);
   return cudaGetLastError();
 }
+#endif   // !__CUDACC_RTC__
 
 }  // namespace gpc

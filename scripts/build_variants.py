@@ -18,7 +18,8 @@ os.makedirs(out_dir, exist_ok=True)
 def build(spec):
     w, h, t = spec.split(",")[:3]
     extra = spec.split(",")[3:]
-    lib = os.path.join(out_dir, f"libgpc_{spec.replace(',', '_').replace('=', '')}.so")
+    import re
+    lib = os.path.join(out_dir, "libgpc_" + re.sub(r"[^A-Za-z0-9_]", "", spec.replace(",", "_")) + ".so")
     cmd = [_nvcc()] + NVCC_FLAGS + [f"-DGPC_TILE_W={w}", f"-DGPC_TILE_H={h}", f"-DGPC_THREADS_A={t}"] + \
           [f"-D{e}" for e in extra] + ["-I", os.path.join(ROOT, "include"), "-o", lib] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -271,3 +271,27 @@ def test_edge_shapes(g, oracle):
         rc = ctx.lib.gpc_match_pair(ctx._h, C.c_void_p(big_l.ctypes.data), C.c_void_p(big_r.ctypes.data), w, h, stride, C.byref(s),
                                     C.c_void_p(out.ctypes.data), C.c_int(len(out)), C.byref(n), None, None)
         assert rc == capi.GPC_OK and np.array_equal(out[:n.value], ref)
+
+
+def test_forest_specialised_kernel(g, oracle, monkeypatch):
+    """gpc_set_forest rebuilds the hashing kernel with the forest baked in (NVRTC).  The specialised
+    and the generic precompiled kernel must both be bit-exact, for every forest type."""
+    from opengpc_b200.synth import synth_pair
+    L, R = synth_pair(640, 150, 8)
+    rng = np.random.default_rng(4)
+    forests = {n: (FORESTS[n], oracle.read_forest(FORESTS[n])) for n in ("tau", "zero", "deep")}
+    tests = [tuple(int(v) for v in rng.integers(-13, 14, 4)) for _ in range(11)]
+    taus = [0, -128, 127, 0, 3, 0, 0, -1, 0, 0, 55]
+    with g.Context(device=0, max_w=640, max_h=150, max_batch=1) as c:
+        for jit in ("1", "0"):
+            monkeypatch.setenv("GPC_JIT", jit)
+            for name, (path, of) in forests.items():
+                c.set_forest(path)
+                assert c.jit_status == ("specialised" if jit == "1" else "generic: disabled by GPC_JIT=0"), c.jit_status
+                ref, ocl, ocr = oracle.pair(L, R, of, osettings())
+                supp, ncl, ncr = c.match_pair(L, R, g.sparsematch_settings())
+                assert (ncl, ncr) == (ocl, ocr) and np.array_equal(supp, ref), (jit, name)
+            c.set_forest(g.make_forest(tests, taus))
+            st, mk = c.hash(L, 5)
+            _, _, omk, ost = oracle.stages(L, oracle.make_forest(tests, taus), 5)
+            assert np.array_equal(mk, omk) and np.array_equal(st, ost), jit
