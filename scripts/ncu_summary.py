@@ -105,7 +105,7 @@ def main():
             if n not in agg:
                 order.append(n)
             agg[n].append(float(r["Metric Value"]))
-        ours = [n for n in order if "gpc::" in n]
+        ours = [n for n in order if "gpc" in n]
         tot = sum(sum(agg[n]) for n in ours)
         print(f"## launch list `{sys.argv[2].split('/')[-1]}` (gpu__time_duration.sum, ns)\n")
         print("| kernel | launches | mean ns | share of the step (our kernels) |")
