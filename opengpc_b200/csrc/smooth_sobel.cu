@@ -32,6 +32,39 @@ __device__ __forceinline__ void hthirds(uint32_t wm1, uint32_t w, uint32_t wp1, 
   h[3] = third(__dp4a(__funnelshift_r(w, wp1, 16), 0x00010101u, 0u));
 }
 
+// Sobel predicate (filter.hpp:466-503) for the 4 pixels of word `w` (image columns x0..x0+3); wl / wr are the
+// words left and right of it; index 0..2 = image rows y-1, y, y+1.  With P = raw pixel,
+//   A = ninth(col(x-1)), B = ninth(col(x+1)), col(x) = P[y-1][x] + 2 P[y][x] + P[y+1][x]
+//   C = ninth(row(y-1)), D = ninth(row(y+1)), row(y) = P[y][x-1] + 2 P[y][x] + P[y][x+1]
+// and bit j of the result = ((A-B)^2 + (C-D)^2 > thr2) for pixel x0+j.  Row sums are dp4a on (funnel-shifted)
+// words, column sums are formed for two pixels at a time in 16-bit lanes.
+__device__ __forceinline__ uint32_t sobel_quad(const uint32_t wl[3], const uint32_t w[3], const uint32_t wr[3], int thr2) {
+  uint32_t c[4], d[4];
+  {
+    const uint32_t t0 = __funnelshift_r(wl[0], w[0], 24), t3 = __funnelshift_r(w[0], wr[0], 16);
+    c[0] = ninth(__dp4a(t0, 0x00010201u, 0u)); c[1] = ninth(__dp4a(w[0], 0x00010201u, 0u));
+    c[2] = ninth(__dp4a(w[0], 0x01020100u, 0u)); c[3] = ninth(__dp4a(t3, 0x00010201u, 0u));
+    const uint32_t b0 = __funnelshift_r(wl[2], w[2], 24), b3 = __funnelshift_r(w[2], wr[2], 16);
+    d[0] = ninth(__dp4a(b0, 0x00010201u, 0u)); d[1] = ninth(__dp4a(w[2], 0x00010201u, 0u));
+    d[2] = ninth(__dp4a(w[2], 0x01020100u, 0u)); d[3] = ninth(__dp4a(b3, 0x00010201u, 0u));
+  }
+  // column sums: lanes of colE = (col(x0), col(x0+2)), of colO = (col(x0+1), col(x0+3)); each <= 1020
+  const uint32_t colE = (w[0] & 0x00ff00ffu) + (w[2] & 0x00ff00ffu) + 2u * (w[1] & 0x00ff00ffu);
+  const uint32_t colO = __byte_perm(w[0], 0u, 0x4341) + __byte_perm(w[2], 0u, 0x4341) + 2u * __byte_perm(w[1], 0u, 0x4341);
+  const uint32_t colL = (wl[0] >> 24) + (wl[2] >> 24) + 2u * (wl[1] >> 24);                  // col(x0-1)
+  const uint32_t colR = (wr[0] & 0xffu) + (wr[2] & 0xffu) + 2u * (wr[1] & 0xffu);            // col(x0+4)
+  const int nL = (int)ninth(colL), n0 = (int)ninth(colE & 0xffffu), n1 = (int)ninth(colO & 0xffffu);
+  const int n2 = (int)ninth(colE >> 16), n3 = (int)ninth(colO >> 16), nR = (int)ninth(colR);
+  const int ab[4] = {nL - n1, n0 - n2, n1 - n3, n2 - nR};
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int cd = (int)c[j] - (int)d[j];
+    if (ab[j] * ab[j] + cd * cd > thr2) m |= 1u << j;        // <= 25538, no int16 wrap / saturation
+  }
+  return m;
+}
+
 // candidate border (inference.hpp:322): 13 <= x < W-13, 13 <= y < H-13, applied to a segment mask
 __device__ __forceinline__ uint32_t border_mask(uint32_t m, int gy, int gxs, int W, int H) {
   if (gy < kRadius || gy >= H - kRadius) return 0u;
@@ -111,7 +144,6 @@ smooth_sobel_kernel(const PreprocessArgs args) {
   // ---- Sobel predicate per 16-pixel segment -> candidate bit masks, per-row candidate counts ----------
   {
     static_assert((kPreH * (kPreW / 16)) % kPreThreads == 0 && kPreW / 16 == 16, "uniform trip count, 16 segments per tile row");
-    const uint8_t* raw8 = reinterpret_cast<const uint8_t*>(raw32);
     const int segs_per_row = W / 16;
     for (int sr = tid; sr < kPreH * (kPreW / 16); sr += kPreThreads) {
       const int ry = sr / (kPreW / 16), sg = sr - ry * (kPreW / 16);
@@ -119,19 +151,20 @@ smooth_sobel_kernel(const PreprocessArgs args) {
       const bool valid = gy < H && gxs < W;
       uint32_t m = 0;
       if (valid && gy >= 1 && gy < H - 3) {                // rows the reference writes (filter.hpp:517)
-        const uint8_t* r0 = raw8 + ry * kPrePitch + 16 + 16 * sg;            // image row gy-1, col gxs
-        const uint8_t* r1 = r0 + kPrePitch;
-        const uint8_t* r2 = r1 + kPrePitch;
+        // words wi0-1 .. wi0+3 of tile rows ry, ry+1, ry+2 (image rows gy-1, gy, gy+1); wi0 = image column gxs
+        uint32_t wm[3], q0[3], q1[3], q2[3], q3[3];
 #pragma unroll
-        for (int g = 0; g < 8; g++) {
-          const int c = (g < 4) ? g : g + 4;              // true columns s..s+3 and s+8..s+11 survive :504-507
-          int p00 = r0[c - 1], p01 = r0[c], p02 = r0[c + 1];
-          int p10 = r1[c - 1], p12 = r1[c + 1];
-          int p20 = r2[c - 1], p21 = r2[c], p22 = r2[c + 1];
-          int a = (int)ninth(p00 + p20 + 2 * p10), b = (int)ninth(p02 + p22 + 2 * p12);
-          int cc = (int)ninth(p00 + p02 + 2 * p01), d = (int)ninth(p20 + p22 + 2 * p21);
-          int sum = (a - b) * (a - b) + (cc - d) * (cc - d);   // <= 25538, no int16 wrap / saturation
-          if (sum > args.thr2) m |= 3u << (2 * g);            // lane duplication: outputs 2g, 2g+1
+        for (int k = 0; k < 3; k++) {
+          const uint32_t* row = raw32 + (ry + k) * kPrePitchW + 4 + 4 * sg;
+          const uint4 v = *reinterpret_cast<const uint4*>(row);
+          wm[k] = row[-1]; q0[k] = v.x; q1[k] = v.y; q2[k] = v.z; q3[k] = v.w;
+        }
+        // true columns s..s+3 and s+8..s+11 survive the lane duplication (filter.hpp:504-507): output bits 2g, 2g+1
+        const uint32_t ma = sobel_quad(wm, q0, q1, args.thr2), mb = sobel_quad(q1, q2, q3, args.thr2);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if ((ma >> j) & 1u) m |= 3u << (2 * j);
+          if ((mb >> j) & 1u) m |= 3u << (2 * (4 + j));
         }
       }
       if (kDebugOut && args.grad_out && valid) {
