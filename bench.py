@@ -143,6 +143,31 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_near_gpu(index):
+    """Pin this rank's host thread (and so, by first touch, its pinned staging buffers) to the CPU cores of
+    the GPU's NUMA node: the end-to-end number is bound by host-memory / PCIe traffic when several ranks
+    stream at once.  Best effort; returns a note for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, b, rest = bus.split(":")
+        path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{b.lower()}:{rest.lower()}/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"host thread bound to {len(cpus)} cores local to GPU {index}"
+    except Exception as e:                                        # noqa: BLE001 - measurement nicety only
+        return f"no NUMA binding ({type(e).__name__})"
+    return "no NUMA binding"
+
+
 def make_images(w, h, batch, distinct):
     from opengpc_b200.synth import synth_batch
     base = synth_batch(w, h, min(distinct, batch), seed0=1234)
@@ -264,6 +289,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa_note = bind_near_gpu(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -417,7 +443,7 @@ def main():
             "mpix_per_s": value * 2 * P / 1e6,
             "config": {"workload": workload_name(args, w, h), "pairs_per_step_per_gpu": B,
                        "distinct_pairs": min(args.distinct, B), "sharding": f"pairs round-robin over {world} GPU(s), no collective",
-                       "supports_per_pair": mean_sup,
+                       "supports_per_pair": mean_sup, "host": numa_note,
                        "l2": f"inputs larger than L2: {2 * B * P / 1e6:.0f} MB raw + {8 * B * P / 1e6:.0f} MB hash per step vs 126 MB L2"},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
     if e2e:
