@@ -295,3 +295,26 @@ def test_forest_specialised_kernel(g, oracle, monkeypatch):
             st, mk = c.hash(L, 5)
             _, _, omk, ost = oracle.stages(L, oracle.make_forest(tests, taus), 5)
             assert np.array_equal(mk, omk) and np.array_equal(st, ost), jit
+
+
+def test_degenerate_states(g, oracle):
+    """Rows where nearly every candidate carries the same state (periodic texture, short forests): the row
+    matcher's buckets hold hundreds of equal entries and its ordering pass takes the skewed-state path."""
+    w, h = 1024, 60
+    x = np.arange(w)[None, :]
+    y = np.arange(h)[:, None]
+    stripes = (((x // 3) % 2) * 200 + (y % 2) * 30).astype(np.uint8) * np.ones((h, 1), np.uint8)
+    rng = np.random.default_rng(9)
+    noisy = stripes.copy()
+    noisy[rng.random((h, w)) < 0.02] ^= 0x40
+    with g.Context(device=0, max_w=w, max_h=h, max_batch=1) as ctx:
+        for tests, taus in (([(1, 0, -1, 0)], [0]), ([(2, 1, -3, 0), (0, 2, 1, -2), (5, 5, -5, -5)], [3, -2, 0]),
+                            ([tuple(int(v) for v in rng.integers(-13, 14, 4)) for _ in range(12)], [0] * 12)):
+            ctx.set_forest(g.make_forest(tests, taus))
+            of = oracle.make_forest(tests, taus)
+            for L, R in ((stripes, np.roll(stripes, -6, axis=1)), (noisy, np.roll(noisy, -4, axis=1)), (noisy, stripes)):
+                for epi in (True, False):
+                    ref, ocl, ocr = oracle.pair(L, R, of, osettings(5, 128, 0 if epi else 1, epi))
+                    supp, ncl, ncr = ctx.match_pair(L, R, g.make_settings(thr=5, disp_high=128, vt=0 if epi else 1, epipolar=epi))
+                    assert (ncl, ncr) == (ocl, ocr)
+                    assert np.array_equal(supp, ref), (len(tests), epi, len(supp), len(ref))
