@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--shape", default=None)
     ap.add_argument("--batch", type=int, default=None, help="pairs per step per GPU")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic pairs (seeds 1234+i), tiled to the batch")
+    ap.add_argument("--sparse", action="store_true", help="low-texture variant of the synthetic pairs (SURVEY.md 8d): ~25 %% of the candidates")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -81,7 +82,7 @@ def peaks():
 
 def workload_name(args, w, h):
     return (f"configs[{args.config}]: {CONFIG_NAMES[args.config]}, forests/{os.path.basename(FORESTS[args.forest])}, "
-            f"synthetic {w}x{h} stereo pairs")
+            f"synthetic {w}x{h} stereo pairs" + (" (low-texture variant)" if args.sparse else ""))
 
 
 def ncu_traffic(kernel, n_pixels):
@@ -168,9 +169,9 @@ def bind_near_gpu(index):
     return "no NUMA binding"
 
 
-def make_images(w, h, batch, distinct):
+def make_images(w, h, batch, distinct, sparse=False):
     from opengpc_b200.synth import synth_batch
-    base = synth_batch(w, h, min(distinct, batch), seed0=1234)
+    base = synth_batch(w, h, min(distinct, batch), seed0=1234, sparse=sparse)
     reps = (batch + len(base) - 1) // len(base)
     return np.ascontiguousarray(np.tile(base, (reps, 1, 1, 1))[:batch])
 
@@ -200,7 +201,7 @@ def run_reference_arm(args, w, h):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    images = make_images(w, h, min(args.distinct, 8), args.distinct)
+    images = make_images(w, h, min(args.distinct, 8), args.distinct, args.sparse)
     # one step = every host thread runs the sparsematch window on one pair (bounded sample)
     rates = []
     for _ in range(args.warmup):
@@ -297,7 +298,7 @@ def main():
 
     B = args.batch
     P = w * h
-    images = make_images(w, h, B, args.distinct)                  # [B, 2, h, w] uint8
+    images = make_images(w, h, B, args.distinct, args.sparse)     # [B, 2, h, w] uint8
     if world > 1:   # each rank gets its own pairs (seeds shifted) -- independent units, no collective
         images = np.roll(images, rank, axis=0)
     settings = g.sparsematch_settings()
