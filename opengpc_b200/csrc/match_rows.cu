@@ -415,9 +415,12 @@ struct EmitArgs {
   int32_t W, H;
 };
 
-__global__ void __launch_bounds__(128)
+constexpr int kEmitRows = 8;       // rows per CTA, one warp each
+
+__global__ void __launch_bounds__(32 * kEmitRows)
 emit_supports_kernel(const EmitArgs a) {
-  const int y = kRadius + blockIdx.x, pair = blockIdx.y;
+  const int y = kRadius + blockIdx.x * kEmitRows + (threadIdx.x >> 5), pair = blockIdx.y, lane = threadIdx.x & 31;
+  if (y >= a.H - kRadius) return;
   const int m = a.rowmatch[(size_t)pair * a.H + y];
   if (m == 0) return;
   const long long off = a.rowoff[(size_t)pair * a.H + y];
@@ -425,7 +428,7 @@ emit_supports_kernel(const EmitArgs a) {
   if (a.pair_base) { base = a.pair_base[pair]; limit = a.cap; }
   else { base = (long long)pair * a.cap; limit = base + a.cap; }
   const uint32_t* stage = a.stage + ((size_t)pair * a.H + y) * a.W;
-  for (int k = threadIdx.x; k < m; k += blockDim.x) {
+  for (int k = lane; k < m; k += 32) {
     const long long idx = base + off + k;
     if (idx >= limit) break;
     const uint32_t u = stage[k];
@@ -443,7 +446,7 @@ cudaError_t launch_emit_supports(const uint32_t* stage, const int32_t* rowmatch,
   int rows = H - 2 * kRadius;
   if (rows <= 0 || n_pairs <= 0) return cudaSuccess;
   EmitArgs a{stage, rowmatch, rowoff, pair_base, reinterpret_cast<float*>(out), cap, W, H};
-  emit_supports_kernel<<<dim3(rows, n_pairs), 128, 0, stream>>>(a);
+  emit_supports_kernel<<<dim3((rows + kEmitRows - 1) / kEmitRows, n_pairs), 32 * kEmitRows, 0, stream>>>(a);
   return cudaGetLastError();
 }
 
