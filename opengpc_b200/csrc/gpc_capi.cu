@@ -634,24 +634,27 @@ int gpc_match_batch(gpc_ctx* c, const uint8_t* images, int n_pairs, int w, int h
   rc = run_preprocess(c, Slot{0, c->stream}, c->d_raw, 2 * n_pairs, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
   if (rc) return rc;
   if (use_sort_matcher(c, s) && n_pairs > 1) {
-    // radix-sort matcher: one pair at a time, results appended on the host
+    // radix-sort matcher: the pairs run back to back on the stream (no host round trip in between), each
+    // into its own region of d_out; one synchronisation, then the regions are packed on the way to the host
+    const long long per_pair = c->out_cap / c->max_batch;
+    for (int p = 0; p < n_pairs; p++) {
+      rc = run_match_sort_pair(c, c->d_hash, p, w, h, s, 0, c->d_out + (size_t)p * per_pair, per_pair, c->d_totals + p,
+                               c->d_ncand + 2 * p);
+      if (rc) return rc;
+    }
+    GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_totals, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    GPC_CUDA(c, cudaMemcpyAsync(c->h_counts + n_pairs, c->d_ncand, 2 * (size_t)n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    GPC_CUDA(c, cudaStreamSynchronize(c->stream));
     long long total = 0;
     offsets[0] = 0;
-    bool overflow = false;
-    for (int p = 0; p < n_pairs; p++) {
-      rc = run_match_sort_pair(c, c->d_hash, p, w, h, s, 0, c->d_out, c->out_cap, c->d_totals, c->d_ncand);
-      if (rc) return rc;
-      GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_totals, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-      GPC_CUDA(c, cudaMemcpyAsync(c->h_counts + 1, c->d_ncand, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-      GPC_CUDA(c, cudaStreamSynchronize(c->stream));
-      const int n = c->h_counts[0];
-      if (n_cand) { n_cand[2 * p] = c->h_counts[1]; n_cand[2 * p + 1] = c->h_counts[2]; }
-      if (total + n > cap) overflow = true;
-      else if (n > 0) GPC_CUDA(c, cudaMemcpy(out + total, c->d_out, (size_t)n * sizeof(gpc_support), cudaMemcpyDeviceToHost));
-      total += n;
-      offsets[p + 1] = total;
-    }
-    if (overflow) return fail(c, GPC_E_CAPACITY, "support buffer too small: need " + std::to_string(total));
+    for (int p = 0; p < n_pairs; p++) { total += c->h_counts[p]; offsets[p + 1] = total; }
+    if (n_cand) std::memcpy(n_cand, c->h_counts + n_pairs, 2 * (size_t)n_pairs * sizeof(int32_t));
+    if (total > cap) return fail(c, GPC_E_CAPACITY, "support buffer too small: need " + std::to_string(total));
+    for (int p = 0; p < n_pairs; p++)
+      if (c->h_counts[p] > 0)
+        GPC_CUDA(c, cudaMemcpyAsync(out + offsets[p], c->d_out + (size_t)p * per_pair, (size_t)c->h_counts[p] * sizeof(gpc_support),
+                                    cudaMemcpyDeviceToHost, c->stream));
+    GPC_CUDA(c, cudaStreamSynchronize(c->stream));
     return GPC_OK;
   }
   rc = run_match(c, Slot{0, c->stream}, n_pairs, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
