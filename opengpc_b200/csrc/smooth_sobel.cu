@@ -4,7 +4,7 @@
 //   ndb::box + Buffer::clearBoundary   (filter.hpp:293-392, buffer.hpp:630-654)
 //   ndb::sobel                         (filter.hpp:404-519, incl. the lane duplication at :504-507)
 //   ndb::arr2ind + border lambda       (filter.hpp:60-87, inference.hpp:318-330)
-// One CTA stages a (32+2) x (256+32) raw tile in shared memory and produces, for its 256 x 32
+// One CTA stages a (64+2) x (256+32) raw tile in shared memory and produces, for its 256 x 64
 // pixels, (a) the smoothed image in BIASED form (s ^ 0x80, the form kernel A2's signed byte
 // compares want) and (b) one 16-bit candidate mask per 16-pixel segment.  Every pixel of both
 // outputs is written exactly once, borders included, so kernel A2 can fetch arbitrary tiles of
@@ -17,7 +17,7 @@ namespace gpc {
 __device__ __forceinline__ uint32_t third(uint32_t s) { return __umulhi(s, 21846u << 16); }   // (s*21846)>>16
 __device__ __forceinline__ uint32_t ninth(uint32_t s) { return __umulhi(s, 7282u << 16); }    // (s*7282)>>16
 
-constexpr int kPreW = 256, kPreH = 32;             // output tile
+constexpr int kPreW = 256, kPreH = 64;             // output tile
 constexpr int kPrePitch = kPreW + 32;              // image cols x0-16 .. x0+kPreW+15
 constexpr int kPrePitchW = kPrePitch / 4;
 constexpr int kPreRows = kPreH + 2;                // image rows y0-1 .. y0+kPreH
