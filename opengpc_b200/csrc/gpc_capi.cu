@@ -517,6 +517,7 @@ int gpc_set_forest(gpc_ctx* c, const gpc_forest* f) {
       if (v[k] < -GPC_PATCH_RADIUS || v[k] > GPC_PATCH_RADIUS)
         return fail(c, GPC_E_FOREST, "test offset outside the 27x27 patch (|offset| <= 13)");
   }
+  if (c->has_forest && std::memcmp(&c->forest_host, f, sizeof(gpc_forest)) == 0) return GPC_OK;   // unchanged: keep the kernel
   GPC_CUDA(c, cudaSetDevice(c->device));
   GPC_CUDA(c, cudaStreamSynchronize(c->stream));     // earlier launches may still use the previous specialised kernel
   for (int l = 0; l < gpc_ctx::kLanes; l++) GPC_CUDA(c, cudaStreamSynchronize(c->lane_stream[l]));
