@@ -318,3 +318,27 @@ def test_degenerate_states(g, oracle):
                     supp, ncl, ncr = ctx.match_pair(L, R, g.make_settings(thr=5, disp_high=128, vt=0 if epi else 1, epipolar=epi))
                     assert (ncl, ncr) == (ocl, ocr)
                     assert np.array_equal(supp, ref), (len(tests), epi, len(supp), len(ref))
+
+
+def test_very_wide_rows(g, oracle):
+    """Rows wider than 4096 pixels take the 2-quads-per-thread / 1024-thread shape of the row matcher; 8192 is
+    the widest supported row (13-bit column fields)."""
+    from opengpc_b200 import capi
+    rng = np.random.default_rng(33)
+    of = oracle.read_forest(FORESTS["tau"])
+    with g.Context(device=0, max_w=8192, max_h=48, max_batch=1) as ctx:
+        ctx.set_forest(FORESTS["tau"])
+        for (w, h) in [(4112, 45), (6016, 40), (8192, 48)]:
+            b = 5
+            L = rng.integers(0, 256, (h // b + 1, w // b + 1), dtype=np.uint8).repeat(b, 0).repeat(b, 1)[:h, :w].copy()
+            R = np.roll(L, -9, axis=1)
+            R[rng.random((h, w)) < 0.02] ^= 0x11
+            for epi in (True, False):
+                ref, ocl, ocr = oracle.pair(L, R, of, osettings(5, 128, 0 if epi else 1, epi))
+                supp, ncl, ncr = ctx.match_pair(L, R, g.make_settings(thr=5, disp_high=128, vt=0 if epi else 1, epipolar=epi))
+                assert (ncl, ncr) == (ocl, ocr), (w, h, epi)
+                assert np.array_equal(supp, ref), (w, h, epi, len(supp), len(ref))
+    with pytest.raises(g.GpcError) as e:
+        g.Context(device=0, max_w=8208, max_h=32, max_batch=1).match_pair(np.zeros((32, 8208), np.uint8), np.zeros((32, 8208), np.uint8),
+                                                                       g.sparsematch_settings())
+    assert e.value.status == capi.GPC_E_DIMS
