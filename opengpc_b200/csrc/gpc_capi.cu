@@ -31,15 +31,14 @@ cudaError_t launch_emit_supports(const uint32_t* stage, const int32_t* rowmatch,
                                  cudaStream_t);
 cudaError_t launch_mask_list(const uint32_t* hash, const int32_t* rowcnt, int32_t* rowoff, int W, int H, int32_t* mask,
                              int cap, cudaStream_t);
-size_t global_workspace_bytes_padded(long long max_records, int key_bytes);
-cudaError_t launch_match_global(const uint32_t* hash_l, const uint32_t* hash_r, const int32_t* rowcnt, int32_t* rowoff2,
-                                int W, int H, int epipolar, int key_bits, int disp_high, int vertical_tolerance, int mode,
-                                void* ws, long long max_records, void* out, long long cap, int32_t* n_out,
-                                cudaStream_t stream, int* launches);
+size_t global_workspace_bytes(long long max_records, int n_pairs, int H);
+cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int W, int H, int n_pairs, int epipolar, int key_bits,
+                                int disp_high, int vertical_tolerance, int mode, void* ws, long long max_records, void* out,
+                                long long out_stride, long long cap, int32_t* n_out, int32_t* n_cand, cudaStream_t stream,
+                                int* launches);
 cudaError_t launch_match_keys(void* ws, long long max_records, int ns, int nt, int key_bits, int32_t* out_pairs, long long cap,
                               int32_t* n_out, cudaStream_t stream, int* launches);
 void* global_key_buffer(void* ws, long long max_records);
-int32_t* global_nside_ptr(void* ws);
 cudaError_t launch_downsample2x(const uint8_t* src, uint8_t* dst, int sw, int sh, int n_img, cudaStream_t stream);
 struct JitKernel;
 JitKernel* jit_build_hash_tiles(const ForestDev& f, std::string* why);
@@ -90,9 +89,8 @@ struct gpc_ctx {
   int32_t* h_counts = nullptr;     // totals [B] | ncand [2B]
   long long* h_pair_base = nullptr;  // [B+1]
   uint8_t* d_pyr = nullptr;        // pyramid levels 1.. of one pair (lazily allocated)
-  void* d_gws = nullptr;           // radix-sort matcher workspace (lazily allocated)
-  long long gws_records = 0;
-  int32_t* d_rowoff2 = nullptr;    // [2][H] candidate offsets of the sort matcher (lazily allocated)
+  void* d_gws = nullptr;           // radix-sort matcher workspace (lazily allocated, grown on demand)
+  size_t gws_bytes = 0;
   int matcher = GPC_MATCHER_AUTO;
   int64_t launches = 0;
   int match_smem_max = 0;
@@ -242,31 +240,34 @@ int run_preprocess(gpc_ctx* c, const Slot& sl, const uint8_t* d_images, int n_im
   return mark_on(c, sl);                                                           // event 2
 }
 
-int ensure_global_ws(gpc_ctx* c, long long records) {
-  if (records > c->gws_records) {
-    if (c->d_gws) { GPC_CUDA(c, cudaStreamSynchronize(c->stream)); cudaFree(c->d_gws); c->d_gws = nullptr; c->gws_records = 0; }
-    GPC_CUDA(c, cudaMalloc(&c->d_gws, gpc::global_workspace_bytes_padded(records, 8)));
-    c->gws_records = records;
+int ensure_global_ws(gpc_ctx* c, size_t bytes) {
+  if (bytes > c->gws_bytes) {
+    if (c->d_gws) { GPC_CUDA(c, cudaStreamSynchronize(c->stream)); cudaFree(c->d_gws); c->d_gws = nullptr; c->gws_bytes = 0; }
+    GPC_CUDA(c, cudaMalloc(&c->d_gws, bytes));
+    c->gws_bytes = bytes;
   }
-  if (!c->d_rowoff2) GPC_CUDA(c, cudaMalloc(&c->d_rowoff2, 2 * (size_t)c->max_h * sizeof(int32_t)));
   return GPC_OK;
 }
 
-// Radix-sort matcher (match_global.cu) for ONE pair whose hash images / rowcnt sit at index `p`.
-// mode 0: filtered supports, 1: unfiltered correspondences.  Output goes to d_out[0..cap), the
-// count to d_n_out[0].
-int run_match_sort_pair(gpc_ctx* c, const uint32_t* hash, int p, int w, int h, const gpc_settings* s, int mode, void* d_out,
-                        long long cap, int32_t* d_n_out, int32_t* d_n_cand) {
+// Radix-sort matcher (match_global.cu) for pairs p0 .. p0 + n of the resident hash images, a chunk of pairs
+// per launch sequence.  mode 0: filtered supports, 1: unfiltered correspondences.  Pair p0 + i writes at
+// d_out + i * out_stride records (capacity cap each), its count to d_n_out[i], candidate counts to d_n_cand[2i..].
+int run_match_sort(gpc_ctx* c, const uint32_t* hash, int p0, int n, int w, int h, const gpc_settings* s, int mode, void* d_out,
+                   size_t record_bytes, long long out_stride, long long cap, int32_t* d_n_out, int32_t* d_n_cand) {
   const size_t P = (size_t)w * h;
   const long long records = 2ll * std::max(w - 2 * gpc::kRadius, 0) * std::max(h - 2 * gpc::kRadius, 0) + 2;
-  int rc = ensure_global_ws(c, records); if (rc) return rc;
-  int launches = 0;
-  GPC_CUDA(c, gpc::launch_match_global(hash + (size_t)(2 * p) * P, hash + (size_t)(2 * p + 1) * P, c->d_rows + (size_t)(2 * p) * h,
-                                       c->d_rowoff2, w, h, s->epipolar_mode ? 1 : 0, 31, s->disp_high, s->vertical_tolerance,
-                                       mode, c->d_gws, c->gws_records, d_out, cap, d_n_out, c->stream, &launches));
-  c->launches += launches;
-  if (d_n_cand)
-    GPC_CUDA(c, cudaMemcpyAsync(d_n_cand, gpc::global_nside_ptr(c->d_gws), 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+  const size_t per_pair = gpc::global_workspace_bytes(records, 1, h);
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)1 << 30) / per_pair));
+  for (int q0 = 0; q0 < n; q0 += chunk) {
+    const int m = std::min(chunk, n - q0);
+    int rc = ensure_global_ws(c, gpc::global_workspace_bytes(records, m, h)); if (rc) return rc;
+    int launches = 0;
+    GPC_CUDA(c, gpc::launch_match_global(hash + (size_t)(2 * (p0 + q0)) * P, c->d_rows + (size_t)(2 * (p0 + q0)) * h, w, h, m,
+                                         s->epipolar_mode ? 1 : 0, 31, s->disp_high, s->vertical_tolerance, mode, c->d_gws, records,
+                                         reinterpret_cast<uint8_t*>(d_out) + (size_t)q0 * (size_t)out_stride * record_bytes, out_stride,
+                                         cap, d_n_out + q0, d_n_cand ? d_n_cand + 2 * q0 : nullptr, c->stream, &launches));
+    c->launches += launches;
+  }
   return GPC_OK;
 }
 
@@ -284,9 +285,8 @@ int run_match(gpc_ctx* c, const Slot& sl, int n_pairs, int w, int h, const gpc_s
     if (sl.stream != c->stream || sl.p0 != 0) return fail(c, GPC_E_ARG, "internal: sort matcher runs on the context stream");
     if (packed && n_pairs != 1) return fail(c, GPC_E_ARG, "internal: packed sort matcher handles one pair per call");
     for (int k = 0; k < 2; k++) { int rc = mark(c); if (rc) return rc; }   // events 3, 4 (no row kernels here)
-    for (int p = 0; p < n_pairs; p++) {
-      int rc = run_match_sort_pair(c, hash, p, w, h, s, 0, d_out + (packed ? 0 : (size_t)p * cap), cap, d_n_out + p,
-                                   d_n_cand ? d_n_cand + 2 * p : nullptr);
+    {
+      int rc = run_match_sort(c, c->d_hash, 0, n_pairs, w, h, s, 0, d_out, sizeof(gpc_support), packed ? 0 : cap, cap, d_n_out, d_n_cand);
       if (rc) return rc;
     }
     if (packed) {
@@ -423,7 +423,7 @@ void gpc_destroy(gpc_ctx* c) {
   for (cudaEvent_t e : c->ev_chunk) cudaEventDestroy(e);
   cudaFree(c->d_rowoff); cudaFree(c->d_totals); cudaFree(c->d_ncand); cudaFree(c->d_pair_base); cudaFree(c->d_out);
   gpc::jit_destroy(c->jit);
-  cudaFree(c->d_dbg8); cudaFree(c->d_mask); cudaFree(c->d_gws); cudaFree(c->d_rowoff2); cudaFree(c->d_pyr);
+  cudaFree(c->d_dbg8); cudaFree(c->d_mask); cudaFree(c->d_gws); cudaFree(c->d_pyr);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->h_pair_base) cudaFreeHost(c->h_pair_base);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -638,11 +638,8 @@ int gpc_match_batch(gpc_ctx* c, const uint8_t* images, int n_pairs, int w, int h
     // radix-sort matcher: the pairs run back to back on the stream (no host round trip in between), each
     // into its own region of d_out; one synchronisation, then the regions are packed on the way to the host
     const long long per_pair = c->out_cap / c->max_batch;
-    for (int p = 0; p < n_pairs; p++) {
-      rc = run_match_sort_pair(c, c->d_hash, p, w, h, s, 0, c->d_out + (size_t)p * per_pair, per_pair, c->d_totals + p,
-                               c->d_ncand + 2 * p);
-      if (rc) return rc;
-    }
+    rc = run_match_sort(c, c->d_hash, 0, n_pairs, w, h, s, 0, c->d_out, sizeof(gpc_support), per_pair, per_pair, c->d_totals, c->d_ncand);
+    if (rc) return rc;
     GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_totals, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     GPC_CUDA(c, cudaMemcpyAsync(c->h_counts + n_pairs, c->d_ncand, 2 * (size_t)n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     GPC_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -925,7 +922,7 @@ int gpc_correspond_images(gpc_ctx* c, const gpc_image* l, const gpc_image* r, co
   if (rc) return rc;
   // a correspondence is 16 bytes, a support 12: d_out holds out_cap * 12 / 16 correspondences
   const long long dcap = c->out_cap * 12 / 16;
-  rc = run_match_sort_pair(c, c->d_hash, 0, w, h, s, 1, c->d_out, dcap, c->d_totals, nullptr);
+  rc = run_match_sort(c, c->d_hash, 0, 1, w, h, s, 1, c->d_out, sizeof(gpc_correspondence), 0, dcap, c->d_totals, nullptr);
   if (rc) return rc;
   GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_totals, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   GPC_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -946,20 +943,20 @@ int gpc_find_correspondences(gpc_ctx* c, const uint64_t* src_keys, int n_src, co
   if ((long long)n_src + n_tar >= 0x7fffffffll) return fail(c, GPC_E_DIMS, "too many descriptors");
   GPC_CUDA(c, cudaSetDevice(c->device));
   const long long n = (long long)n_src + n_tar;
-  int rc = ensure_global_ws(c, n + 2); if (rc) return rc;
+  int rc = ensure_global_ws(c, gpc::global_workspace_bytes(n + 2, 1, 0)); if (rc) return rc;
   uint64_t kmax = 0;
   for (int i = 0; i < n_src; i++) kmax = std::max(kmax, src_keys[i]);
   for (int i = 0; i < n_tar; i++) kmax = std::max(kmax, tar_keys[i]);
   int key_bits = 8;
   while (key_bits < 64 && (kmax >> key_bits) != 0) key_bits += 8;
-  uint64_t* d_keys = reinterpret_cast<uint64_t*>(gpc::global_key_buffer(c->d_gws, c->gws_records));
+  uint64_t* d_keys = reinterpret_cast<uint64_t*>(gpc::global_key_buffer(c->d_gws, n + 2));
   GPC_CUDA(c, cudaMemcpyAsync(d_keys, src_keys, (size_t)n_src * 8, cudaMemcpyHostToDevice, c->stream));
   GPC_CUDA(c, cudaMemcpyAsync(d_keys + n_src, tar_keys, (size_t)n_tar * 8, cudaMemcpyHostToDevice, c->stream));
   const long long need = std::min<long long>(n_src, n_tar);
   int32_t* d_pairs = nullptr;
   GPC_CUDA(c, cudaMalloc(&d_pairs, (size_t)std::max<long long>(need, 1) * 2 * sizeof(int32_t)));
   int launches = 0;
-  cudaError_t e = gpc::launch_match_keys(c->d_gws, c->gws_records, n_src, n_tar, key_bits, d_pairs, need, c->d_totals, c->stream, &launches);
+  cudaError_t e = gpc::launch_match_keys(c->d_gws, n + 2, n_src, n_tar, key_bits, d_pairs, need, c->d_totals, c->stream, &launches);
   c->launches += launches;
   if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_counts, c->d_totals, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);

@@ -15,6 +15,11 @@
 //               the first R (the reference's one implementation-defined case);
 //               a single R at the very tail never matches (inference.hpp:243-249).
 // Output order = position in the sorted array = ascending key, as std::sort gives the reference.
+//
+// Every kernel carries a pair dimension (blockIdx.y): a chunk of independent pairs is sorted by the
+// same launches, each pair in its own slice of the workspace.
+#include <algorithm>
+
 #include "gpc_device.cuh"
 
 namespace gpc {
@@ -23,20 +28,35 @@ constexpr int kSortThreads = 1024;          // one key per thread, 32 warps
 constexpr int kDigits = 256;
 constexpr uint32_t kSideBit = 0x80000000u;
 
+// Workspace of a chunk of pairs (device pointers; slice `pair` starts at pair * stride of each array).
+template <typename KeyT>
+struct SortWs {
+  KeyT* keys[2];                 // [n_pairs][rec_stride] ping-pong
+  uint32_t* vals[2];             // [n_pairs][rec_stride] side << 31 | index
+  uint32_t* blockhist;           // [n_pairs][kDigits][nb_max]
+  uint32_t* digit_tot;           // [n_pairs][kDigits]
+  int32_t* blockcount;           // [n_pairs][nb_max + 1]
+  int32_t* n_side;               // [n_pairs][2] left / right record counts
+  unsigned long long* tmax;      // [n_pairs] largest right key + 1 (0: no right record)
+  int32_t* rowoff;               // [n_pairs][2][H] candidate offsets (hash-image input only)
+  long long rec_stride;
+  int nb_max;
+};
+
 // ---- record gathering from hash images ----------------------------------------------------------
-// One warp per (side, row): candidates in raster order.  rowoff[side][y] = exclusive prefix of the
-// row's candidate count inside its image; n_side[0..1] = totals.
+// rowoff[pair][side][y] = exclusive prefix of the row's candidate count inside its image.
 __global__ void __launch_bounds__(1024)
-global_rowoff_kernel(const int32_t* __restrict__ rowcnt, int H, int32_t* __restrict__ rowoff, int32_t* __restrict__ n_side) {
-  // blockIdx.x = side; single block scan over H rows
+global_rowoff_kernel(const int32_t* __restrict__ rowcnt, int H, int32_t* __restrict__ rowoff_all, int32_t* __restrict__ n_side_all) {
   __shared__ int warp_sums[32];
   __shared__ int carry;
-  const int side = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int side = blockIdx.x, pair = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int32_t* cnt = rowcnt + ((size_t)2 * pair + side) * H;
+  int32_t* rowoff = rowoff_all + ((size_t)2 * pair + side) * H;
   if (tid == 0) carry = 0;
   __syncthreads();
   for (int y0 = 0; y0 < H; y0 += 1024) {
     const int y = y0 + tid;
-    const int v = (y < H) ? rowcnt[(size_t)side * H + y] : 0;
+    const int v = (y < H) ? cnt[y] : 0;
     int incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
@@ -50,24 +70,26 @@ global_rowoff_kernel(const int32_t* __restrict__ rowcnt, int H, int32_t* __restr
     }
     __syncthreads();
     const int base = carry + warp_sums[wid];
-    if (y < H) rowoff[(size_t)side * H + y] = base + incl - v;
+    if (y < H) rowoff[y] = base + incl - v;
     __syncthreads();
     if (tid == 1023) carry = base + incl;
     __syncthreads();
   }
-  if (tid == 0) n_side[side] = carry;
+  if (tid == 0) n_side_all[2 * pair + side] = carry;
 }
 
+// One warp per (side, row): candidates in raster order.
 template <typename KeyT>
 __global__ void __launch_bounds__(128)
-global_gather_kernel(const uint32_t* __restrict__ hash_l, const uint32_t* __restrict__ hash_r, const int32_t* __restrict__ rowoff,
-                     const int32_t* __restrict__ n_side, int W, int H, int epipolar, KeyT* __restrict__ keys,
-                     uint32_t* __restrict__ vals, unsigned long long* __restrict__ tmax) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+global_gather_kernel(const uint32_t* __restrict__ hash, int W, int H, int epipolar, const SortWs<KeyT> ws) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, pair = blockIdx.y;
   if (warp >= 2 * H) return;
   const int side = warp / H, y = warp - side * H;
-  const uint32_t* row = (side ? hash_r : hash_l) + (size_t)y * W;
-  int off = rowoff[(size_t)side * H + y] + (side ? n_side[0] : 0);
+  const uint32_t* row = hash + ((size_t)(2 * pair + side) * H + y) * W;
+  const int32_t* n_side = ws.n_side + 2 * pair;
+  KeyT* keys = ws.keys[0] + (size_t)pair * ws.rec_stride;
+  uint32_t* vals = ws.vals[0] + (size_t)pair * ws.rec_stride;
+  int off = ws.rowoff[((size_t)2 * pair + side) * H + y] + (side ? n_side[0] : 0);
   unsigned long long kmax = 0;
   bool any = false;
   for (int x0 = 0; x0 < W; x0 += 32) {
@@ -86,18 +108,19 @@ global_gather_kernel(const uint32_t* __restrict__ hash_l, const uint32_t* __rest
     }
     off += __popc(b);
   }
-  if (side == 1 && any) atomicMax(tmax, kmax + 1ull);     // stored as key+1 so that 0 means "no right record"
+  if (side == 1 && any) atomicMax(ws.tmax + pair, kmax + 1ull);     // stored as key+1 so that 0 means "no right record"
 }
 
 // ---- LSD radix sort, 8-bit digits, one key per thread ---------------------------------------------
 template <typename KeyT>
 __global__ void __launch_bounds__(kSortThreads)
-radix_hist_kernel(const KeyT* __restrict__ keys, const int32_t* __restrict__ n_ptr, int shift, int nb_max,
-                  uint32_t* __restrict__ blockhist) {
+radix_hist_kernel(const SortWs<KeyT> ws, int cur, int shift) {
   __shared__ uint32_t hist[kDigits];
-  const int n = n_ptr[0] + n_ptr[1];
+  const int pair = blockIdx.y;
+  const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
   const int nb = (n + kSortThreads - 1) / kSortThreads;
   if ((int)blockIdx.x >= nb) return;
+  const KeyT* keys = ws.keys[cur] + (size_t)pair * ws.rec_stride;
   if (threadIdx.x < kDigits) hist[threadIdx.x] = 0u;
   __syncthreads();
   const int i = blockIdx.x * kSortThreads + threadIdx.x;
@@ -107,19 +130,21 @@ radix_hist_kernel(const KeyT* __restrict__ keys, const int32_t* __restrict__ n_p
     if (old == 0xffffffffu) __trap();                    // value-returning form (see match_rows.cu note)
   }
   __syncthreads();
-  if (threadIdx.x < kDigits) blockhist[(size_t)threadIdx.x * nb_max + blockIdx.x] = hist[threadIdx.x];
+  if (threadIdx.x < kDigits)
+    ws.blockhist[((size_t)pair * kDigits + threadIdx.x) * ws.nb_max + blockIdx.x] = hist[threadIdx.x];
 }
 
 // per-digit exclusive scan over the nb active blocks (one warp per digit, coalesced 32-wide
 // chunks); digit_tot[d] = number of keys with digit d.  The cross-digit base is added by the
-// scatter kernel.
+// scatter kernel.  Grid (kDigits / 32, n_pairs).
+template <typename KeyT>
 __global__ void __launch_bounds__(1024)
-radix_scan_kernel(const int32_t* __restrict__ n_ptr, int nb_max, uint32_t* __restrict__ blockhist,
-                  uint32_t* __restrict__ digit_tot) {
-  const int n = n_ptr[0] + n_ptr[1];
+radix_scan_kernel(const SortWs<KeyT> ws) {
+  const int pair = blockIdx.y;
+  const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
   const int nb = (n + kSortThreads - 1) / kSortThreads;
   const int d = blockIdx.x * 32 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  uint32_t* row = blockhist + (size_t)d * nb_max;
+  uint32_t* row = ws.blockhist + ((size_t)pair * kDigits + d) * ws.nb_max;
   uint32_t carry = 0;
   for (int b0 = 0; b0 < nb; b0 += 32) {
     const int b = b0 + lane;
@@ -130,19 +155,23 @@ radix_scan_kernel(const int32_t* __restrict__ n_ptr, int nb_max, uint32_t* __res
     if (b < nb) row[b] = carry + incl - c;
     carry += __shfl_sync(0xffffffffu, incl, 31);
   }
-  if (lane == 0) digit_tot[d] = carry;
+  if (lane == 0) ws.digit_tot[(size_t)pair * kDigits + d] = carry;
 }
 
 template <typename KeyT>
 __global__ void __launch_bounds__(kSortThreads)
-radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
-                     uint32_t* __restrict__ vals_out, const int32_t* __restrict__ n_ptr, int shift, int nb_max,
-                     const uint32_t* __restrict__ blockhist, const uint32_t* __restrict__ digit_tot) {
+radix_scatter_kernel(const SortWs<KeyT> ws, int cur, int shift) {
   __shared__ uint32_t whist[32][kDigits];                // per-warp digit counts -> exclusive prefix over warps
   __shared__ uint32_t dbase[kDigits];                    // exclusive prefix of the digit totals
-  const int n = n_ptr[0] + n_ptr[1];
+  const int pair = blockIdx.y;
+  const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
   const int nb = (n + kSortThreads - 1) / kSortThreads;
   if ((int)blockIdx.x >= nb) return;
+  const KeyT* keys_in = ws.keys[cur] + (size_t)pair * ws.rec_stride;
+  const uint32_t* vals_in = ws.vals[cur] + (size_t)pair * ws.rec_stride;
+  KeyT* keys_out = ws.keys[cur ^ 1] + (size_t)pair * ws.rec_stride;
+  uint32_t* vals_out = ws.vals[cur ^ 1] + (size_t)pair * ws.rec_stride;
+  const uint32_t* digit_tot = ws.digit_tot + (size_t)pair * kDigits;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int k = tid; k < 32 * kDigits; k += kSortThreads) (&whist[0][0])[k] = 0u;
   __syncthreads();
@@ -175,7 +204,7 @@ radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restric
   }
   __syncthreads();
   if (active) {
-    const uint32_t pos = dbase[d] + blockhist[(size_t)d * nb_max + blockIdx.x] + whist[wid][d] + rank;
+    const uint32_t pos = dbase[d] + ws.blockhist[((size_t)pair * kDigits + d) * ws.nb_max + blockIdx.x] + whist[wid][d] + rank;
     keys_out[pos] = key;
     vals_out[pos] = val;
   }
@@ -183,16 +212,12 @@ radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restric
 
 // ---- segmented scan over the sorted records ---------------------------------------------------------
 struct GlobalEmitArgs {
-  const uint32_t* vals;
-  const int32_t* n_ptr;
-  const unsigned long long* tmax;    // largest right key + 1 (0: no right record)
-  int32_t* blockcount;               // [nb_max + 1]
   int32_t W;
   int32_t disp_high, vertical_tolerance;
   int32_t mode;                      // 0 supports (filtered), 1 correspondences (unfiltered), 2 index pairs
-  void* out;
-  long long cap;
-  int32_t* n_out;
+  void* out;                         // pair p writes at out + p * out_stride records
+  long long out_stride, cap;         // records per pair region, capacity of one region
+  int32_t* n_out;                    // [n_pairs]
 };
 
 template <typename KeyT>
@@ -223,40 +248,56 @@ __device__ __forceinline__ bool is_match(const KeyT* __restrict__ keys, const ui
 
 template <typename KeyT>
 __global__ void __launch_bounds__(kSortThreads)
-global_count_kernel(const KeyT* __restrict__ keys, const GlobalEmitArgs a) {
+global_count_kernel(const SortWs<KeyT> ws, int cur, const GlobalEmitArgs a) {
   __shared__ int cnt;
-  const int n = a.n_ptr[0] + a.n_ptr[1];
+  const int pair = blockIdx.y;
+  const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
   const int nb = (n + kSortThreads - 1) / kSortThreads;
   if ((int)blockIdx.x >= nb) return;
   if (threadIdx.x == 0) cnt = 0;
   __syncthreads();
   uint32_t vl, vr;
-  const bool m = is_match(keys, a.vals, blockIdx.x * kSortThreads + threadIdx.x, n, *a.tmax, a, &vl, &vr);
+  const bool m = is_match(ws.keys[cur] + (size_t)pair * ws.rec_stride, ws.vals[cur] + (size_t)pair * ws.rec_stride,
+                          blockIdx.x * kSortThreads + threadIdx.x, n, ws.tmax[pair], a, &vl, &vr);
   const uint32_t b = __ballot_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0 && b) { if (atomicAdd(&cnt, __popc(b)) < 0) __trap(); }
   __syncthreads();
-  if (threadIdx.x == 0) a.blockcount[blockIdx.x] = cnt;
+  if (threadIdx.x == 0) ws.blockcount[(size_t)pair * (ws.nb_max + 1) + blockIdx.x] = cnt;
 }
 
-__global__ void global_blockscan_kernel(const GlobalEmitArgs a) {
-  if (threadIdx.x != 0) return;
-  const int n = a.n_ptr[0] + a.n_ptr[1];
+// exclusive scan of a pair's block counts (one warp per pair), total -> n_out[pair]
+template <typename KeyT>
+__global__ void __launch_bounds__(32)
+global_blockscan_kernel(const SortWs<KeyT> ws, const GlobalEmitArgs a) {
+  const int pair = blockIdx.x, lane = threadIdx.x;
+  const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
   const int nb = (n + kSortThreads - 1) / kSortThreads;
-  int acc = 0;
-  for (int b = 0; b < nb; b++) { const int c = a.blockcount[b]; a.blockcount[b] = acc; acc += c; }
-  *a.n_out = acc;
+  int32_t* bc = ws.blockcount + (size_t)pair * (ws.nb_max + 1);
+  int carry = 0;
+  for (int b0 = 0; b0 < nb; b0 += 32) {
+    const int b = b0 + lane;
+    const int c = (b < nb) ? bc[b] : 0;
+    int incl = c;
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, k); if (lane >= k) incl += t; }
+    if (b < nb) bc[b] = carry + incl - c;
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) a.n_out[pair] = carry;
 }
 
 template <typename KeyT>
 __global__ void __launch_bounds__(kSortThreads)
-global_emit_kernel(const KeyT* __restrict__ keys, const GlobalEmitArgs a) {
+global_emit_kernel(const SortWs<KeyT> ws, int cur, const GlobalEmitArgs a) {
   __shared__ int warp_base[32];
-  const int n = a.n_ptr[0] + a.n_ptr[1];
+  const int pair = blockIdx.y;
+  const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
   const int nb = (n + kSortThreads - 1) / kSortThreads;
   if ((int)blockIdx.x >= nb) return;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   uint32_t vl = 0, vr = 0;
-  const bool m = is_match(keys, a.vals, blockIdx.x * kSortThreads + tid, n, *a.tmax, a, &vl, &vr);
+  const bool m = is_match(ws.keys[cur] + (size_t)pair * ws.rec_stride, ws.vals[cur] + (size_t)pair * ws.rec_stride,
+                          blockIdx.x * kSortThreads + tid, n, ws.tmax[pair], a, &vl, &vr);
   const uint32_t b = __ballot_sync(0xffffffffu, m);
   if (lane == 0) warp_base[wid] = __popc(b);
   __syncthreads();
@@ -268,8 +309,9 @@ global_emit_kernel(const KeyT* __restrict__ keys, const GlobalEmitArgs a) {
   }
   __syncthreads();
   if (!m) return;
-  const long long idx = (long long)a.blockcount[blockIdx.x] + warp_base[wid] + __popc(b & ((1u << lane) - 1u));
-  if (idx >= a.cap) return;
+  const long long k = (long long)ws.blockcount[(size_t)pair * (ws.nb_max + 1) + blockIdx.x] + warp_base[wid] + __popc(b & ((1u << lane) - 1u));
+  if (k >= a.cap) return;
+  const long long idx = (long long)pair * a.out_stride + k;
   if (a.mode == 2) {
     int32_t* o = reinterpret_cast<int32_t*>(a.out) + 2 * idx;
     o[0] = (int32_t)vl; o[1] = (int32_t)vr;
@@ -287,127 +329,116 @@ global_emit_kernel(const KeyT* __restrict__ keys, const GlobalEmitArgs a) {
 }
 
 // ---- host-side launch sequences -----------------------------------------------------------------------
-size_t global_workspace_bytes(long long max_records, int key_bytes) {
-  const long long nb = (max_records + kSortThreads - 1) / kSortThreads + 1;
-  size_t b = 0;
-  b += 2 * (size_t)max_records * key_bytes;       // key ping-pong
-  b += 2 * (size_t)max_records * 4;               // value ping-pong
-  b += (size_t)kDigits * nb * 4 + kDigits * 4;    // block histograms + digit totals
-  b += (size_t)(nb + 1) * 4;                      // block counts
-  b += 64;                                        // n_side[2], tmax
-  return b + 1024;
+static size_t pad256(size_t b) { return (b + 255) / 256 * 256; }
+
+// bytes of workspace for n_pairs pairs of up to max_records records each, H rows (0 for explicit keys)
+size_t global_workspace_bytes(long long max_records, int n_pairs, int H) {
+  const size_t nb = (size_t)((max_records + kSortThreads - 1) / kSortThreads + 1);
+  const size_t np = (size_t)n_pairs;
+  return pad256(np * 8) + pad256(np * 2 * 4) + 2 * pad256(np * (size_t)max_records * 8) + 2 * pad256(np * (size_t)max_records * 4) +
+         pad256(np * kDigits * nb * 4) + pad256(np * kDigits * 4) + pad256(np * (nb + 1) * 4) + pad256(np * 2 * (size_t)std::max(H, 1) * 4) + 256;
 }
 
 template <typename KeyT>
-struct GlobalWs {
-  KeyT* keys[2]; uint32_t* vals[2]; uint32_t* blockhist; uint32_t* digit_tot; int32_t* blockcount; int32_t* n_side;
-  unsigned long long* tmax;
-  int nb_max;
-};
-
-template <typename KeyT>
-static GlobalWs<KeyT> carve(void* ws, long long max_records) {
-  GlobalWs<KeyT> w;
+static SortWs<KeyT> carve(void* ws, long long max_records, int n_pairs, int H) {
+  SortWs<KeyT> w;
   uint8_t* p = reinterpret_cast<uint8_t*>(ws);
-  auto take = [&p](size_t bytes) { uint8_t* r = p; p += (bytes + 255) / 256 * 256; return r; };
+  auto take = [&p](size_t bytes) { uint8_t* r = p; p += pad256(bytes); return r; };
+  const size_t np = (size_t)n_pairs;
   w.nb_max = (int)((max_records + kSortThreads - 1) / kSortThreads + 1);
-  w.tmax = reinterpret_cast<unsigned long long*>(take(8));
-  w.n_side = reinterpret_cast<int32_t*>(take(8));
-  w.keys[0] = reinterpret_cast<KeyT*>(take((size_t)max_records * sizeof(KeyT)));
-  w.keys[1] = reinterpret_cast<KeyT*>(take((size_t)max_records * sizeof(KeyT)));
-  w.vals[0] = reinterpret_cast<uint32_t*>(take((size_t)max_records * 4));
-  w.vals[1] = reinterpret_cast<uint32_t*>(take((size_t)max_records * 4));
-  w.blockhist = reinterpret_cast<uint32_t*>(take((size_t)kDigits * w.nb_max * 4));
-  w.digit_tot = reinterpret_cast<uint32_t*>(take((size_t)kDigits * 4));
-  w.blockcount = reinterpret_cast<int32_t*>(take((size_t)(w.nb_max + 1) * 4));
+  w.rec_stride = max_records;
+  w.tmax = reinterpret_cast<unsigned long long*>(take(np * 8));
+  w.n_side = reinterpret_cast<int32_t*>(take(np * 2 * 4));
+  w.keys[0] = reinterpret_cast<KeyT*>(take(np * (size_t)max_records * 8));        // sized for 64-bit keys either way
+  w.keys[1] = reinterpret_cast<KeyT*>(take(np * (size_t)max_records * 8));
+  w.vals[0] = reinterpret_cast<uint32_t*>(take(np * (size_t)max_records * 4));
+  w.vals[1] = reinterpret_cast<uint32_t*>(take(np * (size_t)max_records * 4));
+  w.blockhist = reinterpret_cast<uint32_t*>(take(np * kDigits * (size_t)w.nb_max * 4));
+  w.digit_tot = reinterpret_cast<uint32_t*>(take(np * kDigits * 4));
+  w.blockcount = reinterpret_cast<int32_t*>(take(np * ((size_t)w.nb_max + 1) * 4));
+  w.rowoff = reinterpret_cast<int32_t*>(take(np * 2 * (size_t)std::max(H, 1) * 4));
   return w;
 }
 
-size_t global_workspace_bytes_padded(long long max_records, int key_bytes) {
-  return global_workspace_bytes(max_records, key_bytes) + 10 * 256;
-}
-
 template <typename KeyT>
-static cudaError_t sort_and_emit(GlobalWs<KeyT>& w, long long max_records, int key_bits, GlobalEmitArgs ea, cudaStream_t stream,
-                                 int* launches) {
+static cudaError_t sort_and_emit(SortWs<KeyT>& w, long long max_records, int n_pairs, int key_bits, const GlobalEmitArgs& ea,
+                                 cudaStream_t stream, int* launches) {
   const int nb = (int)((max_records + kSortThreads - 1) / kSortThreads);
-  if (nb <= 0) return cudaSuccess;
+  if (nb <= 0 || n_pairs <= 0) return cudaSuccess;
+  const dim3 grid(nb, n_pairs);
   int cur = 0;
   for (int shift = 0; shift < key_bits; shift += 8) {
-    radix_hist_kernel<KeyT><<<nb, kSortThreads, 0, stream>>>(w.keys[cur], w.n_side, shift, w.nb_max, w.blockhist);
-    radix_scan_kernel<<<kDigits / 32, 1024, 0, stream>>>(w.n_side, w.nb_max, w.blockhist, w.digit_tot);
-    radix_scatter_kernel<KeyT><<<nb, kSortThreads, 0, stream>>>(w.keys[cur], w.vals[cur], w.keys[cur ^ 1], w.vals[cur ^ 1],
-                                                               w.n_side, shift, w.nb_max, w.blockhist, w.digit_tot);
+    radix_hist_kernel<KeyT><<<grid, kSortThreads, 0, stream>>>(w, cur, shift);
+    radix_scan_kernel<KeyT><<<dim3(kDigits / 32, n_pairs), 1024, 0, stream>>>(w);
+    radix_scatter_kernel<KeyT><<<grid, kSortThreads, 0, stream>>>(w, cur, shift);
     cur ^= 1;
     *launches += 3;
   }
-  ea.vals = w.vals[cur]; ea.n_ptr = w.n_side; ea.tmax = w.tmax; ea.blockcount = w.blockcount;
-  global_count_kernel<KeyT><<<nb, kSortThreads, 0, stream>>>(w.keys[cur], ea);
-  global_blockscan_kernel<<<1, 32, 0, stream>>>(ea);
-  global_emit_kernel<KeyT><<<nb, kSortThreads, 0, stream>>>(w.keys[cur], ea);
+  global_count_kernel<KeyT><<<grid, kSortThreads, 0, stream>>>(w, cur, ea);
+  global_blockscan_kernel<KeyT><<<n_pairs, 32, 0, stream>>>(w, ea);
+  global_emit_kernel<KeyT><<<grid, kSortThreads, 0, stream>>>(w, cur, ea);
   *launches += 3;
   return cudaGetLastError();
 }
 
-// Hash images (one pair) -> ordered supports (mode 0) or correspondences (mode 1).
-// rowcnt = [2][H] candidate counts of the two images; ws from global_workspace_bytes_padded.
-cudaError_t launch_match_global(const uint32_t* hash_l, const uint32_t* hash_r, const int32_t* rowcnt, int32_t* rowoff2,
-                                int W, int H, int epipolar, int key_bits, int disp_high, int vertical_tolerance, int mode,
-                                void* ws, long long max_records, void* out, long long cap, int32_t* n_out,
-                                cudaStream_t stream, int* launches) {
+// Hash images of n_pairs pairs ([2 * n_pairs][H][W], rowcnt [2 * n_pairs][H]) -> ordered supports (mode 0)
+// or correspondences (mode 1); pair p writes at out + p * out_stride records, count to n_out[p], candidate
+// counts to n_cand[2p], n_cand[2p+1] (optional).  ws from global_workspace_bytes(max_records, n_pairs, H).
+cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int W, int H, int n_pairs, int epipolar, int key_bits,
+                                int disp_high, int vertical_tolerance, int mode, void* ws, long long max_records, void* out,
+                                long long out_stride, long long cap, int32_t* n_out, int32_t* n_cand, cudaStream_t stream,
+                                int* launches) {
   GlobalEmitArgs ea{};
   ea.W = W; ea.disp_high = disp_high; ea.vertical_tolerance = vertical_tolerance; ea.mode = mode;
-  ea.out = out; ea.cap = cap; ea.n_out = n_out;
-  const int gather_blocks = (2 * H * 32 + 127) / 128;
+  ea.out = out; ea.out_stride = out_stride; ea.cap = cap; ea.n_out = n_out;
+  const dim3 gather_grid((2 * H * 32 + 127) / 128, n_pairs);
   cudaError_t e;
   if (epipolar) {
-    GlobalWs<unsigned long long> w = carve<unsigned long long>(ws, max_records);
-    if ((e = cudaMemsetAsync(w.tmax, 0, 8, stream)) != cudaSuccess) return e;
-    global_rowoff_kernel<<<2, 1024, 0, stream>>>(rowcnt, H, rowoff2, w.n_side);
-    global_gather_kernel<unsigned long long><<<gather_blocks, 128, 0, stream>>>(hash_l, hash_r, rowoff2, w.n_side, W, H, 1,
-                                                                                  w.keys[0], w.vals[0], w.tmax);
+    SortWs<unsigned long long> w = carve<unsigned long long>(ws, max_records, n_pairs, H);
+    if ((e = cudaMemsetAsync(w.tmax, 0, (size_t)n_pairs * 8, stream)) != cudaSuccess) return e;
+    global_rowoff_kernel<<<dim3(2, n_pairs), 1024, 0, stream>>>(rowcnt, H, w.rowoff, w.n_side);
+    global_gather_kernel<unsigned long long><<<gather_grid, 128, 0, stream>>>(hash, W, H, 1, w);
     *launches += 2;
     int hb = 1; while ((1 << hb) < H) hb++;
-    return sort_and_emit(w, max_records, 32 + hb, ea, stream, launches);
+    e = sort_and_emit(w, max_records, n_pairs, 32 + hb, ea, stream, launches);
+    if (e == cudaSuccess && n_cand) e = cudaMemcpyAsync(n_cand, w.n_side, (size_t)n_pairs * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
+    return e;
   }
-  GlobalWs<uint32_t> w = carve<uint32_t>(ws, max_records);
-  if ((e = cudaMemsetAsync(w.tmax, 0, 8, stream)) != cudaSuccess) return e;
-  global_rowoff_kernel<<<2, 1024, 0, stream>>>(rowcnt, H, rowoff2, w.n_side);
-  global_gather_kernel<uint32_t><<<gather_blocks, 128, 0, stream>>>(hash_l, hash_r, rowoff2, w.n_side, W, H, 0, w.keys[0],
-                                                                      w.vals[0], w.tmax);
+  SortWs<uint32_t> w = carve<uint32_t>(ws, max_records, n_pairs, H);
+  if ((e = cudaMemsetAsync(w.tmax, 0, (size_t)n_pairs * 8, stream)) != cudaSuccess) return e;
+  global_rowoff_kernel<<<dim3(2, n_pairs), 1024, 0, stream>>>(rowcnt, H, w.rowoff, w.n_side);
+  global_gather_kernel<uint32_t><<<gather_grid, 128, 0, stream>>>(hash, W, H, 0, w);
   *launches += 2;
-  return sort_and_emit(w, max_records, key_bits, ea, stream, launches);
+  e = sort_and_emit(w, max_records, n_pairs, key_bits, ea, stream, launches);
+  if (e == cudaSuccess && n_cand) e = cudaMemcpyAsync(n_cand, w.n_side, (size_t)n_pairs * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
+  return e;
 }
 
-// Explicit key lists (device copies made by the caller into ws): keys laid out src then tar.
-__global__ void keys_prepare_kernel(const unsigned long long* __restrict__ keys, int ns, int nt, uint32_t* __restrict__ vals,
-                                    int32_t* __restrict__ n_side, unsigned long long* __restrict__ tmax) {
+// Explicit key lists: the caller has copied n_src + n_tar 64-bit keys (src then tar) into global_key_buffer().
+__global__ void keys_prepare_kernel(SortWs<unsigned long long> ws, int ns, int nt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { n_side[0] = ns; n_side[1] = nt; }
+  if (i == 0) { ws.n_side[0] = ns; ws.n_side[1] = nt; }
   if (i >= ns + nt) return;
   const bool tar = i >= ns;
-  vals[i] = tar ? (kSideBit | (uint32_t)(i - ns)) : (uint32_t)i;
-  if (tar) atomicMax(tmax, keys[i] + 1ull);
+  ws.vals[0][i] = tar ? (kSideBit | (uint32_t)(i - ns)) : (uint32_t)i;
+  if (tar) atomicMax(ws.tmax, ws.keys[0][i] + 1ull);
 }
 
-// keys_host_order: device pointer to ns + nt 64-bit keys already copied into the workspace's first key buffer.
 cudaError_t launch_match_keys(void* ws, long long max_records, int ns, int nt, int key_bits, int32_t* out_pairs, long long cap,
                               int32_t* n_out, cudaStream_t stream, int* launches) {
-  GlobalWs<unsigned long long> w = carve<unsigned long long>(ws, max_records);
+  SortWs<unsigned long long> w = carve<unsigned long long>(ws, max_records, 1, 0);
   cudaError_t e = cudaMemsetAsync(w.tmax, 0, 8, stream);
   if (e != cudaSuccess) return e;
   const int n = ns + nt;
-  keys_prepare_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w.keys[0], ns, nt, w.vals[0], w.n_side, w.tmax);
+  keys_prepare_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w, ns, nt);
   *launches += 1;
   GlobalEmitArgs ea{};
-  ea.W = 1; ea.mode = 2; ea.out = out_pairs; ea.cap = cap; ea.n_out = n_out;
-  return sort_and_emit(w, n, key_bits, ea, stream, launches);
+  ea.W = 1; ea.mode = 2; ea.out = out_pairs; ea.out_stride = 0; ea.cap = cap; ea.n_out = n_out;
+  return sort_and_emit(w, n, 1, key_bits, ea, stream, launches);
 }
 
-int32_t* global_nside_ptr(void* ws) { return carve<uint32_t>(ws, 1).n_side; }
-
 void* global_key_buffer(void* ws, long long max_records) {
-  return carve<unsigned long long>(ws, max_records).keys[0];
+  return carve<unsigned long long>(ws, max_records, 1, 0).keys[0];
 }
 
 }  // namespace gpc
