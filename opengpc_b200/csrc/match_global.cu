@@ -24,7 +24,11 @@
 
 namespace gpc {
 
-constexpr int kSortThreads = 1024;          // one key per thread, 32 warps
+constexpr int kSortThreads = 512;           // 16 warps; two to four blocks per SM
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kRounds = 8;                  // keys per thread: a block owns a tile of kRounds * 512 keys; warp w takes the
+                                            // w-th run of 32 * kRounds consecutive keys, 32 per round
+constexpr int kTile = kSortThreads * kRounds;
 constexpr int kDigits = 256;
 constexpr uint32_t kSideBit = 0x80000000u;
 
@@ -90,48 +94,95 @@ global_gather_kernel(const uint32_t* __restrict__ hash, int W, int H, int epipol
   KeyT* keys = ws.keys[0] + (size_t)pair * ws.rec_stride;
   uint32_t* vals = ws.vals[0] + (size_t)pair * ws.rec_stride;
   int off = ws.rowoff[((size_t)2 * pair + side) * H + y] + (side ? n_side[0] : 0);
-  unsigned long long kmax = 0;
-  bool any = false;
-  for (int x0 = 0; x0 < W; x0 += 32) {
-    const int x = x0 + lane;
-    const uint32_t v = (x < W) ? row[x] : 0u;
-    const bool c = (v >> 31) != 0u;
-    const uint32_t b = __ballot_sync(0xffffffffu, c);
-    if (c) {
-      const int p = off + __popc(b & ((1u << lane) - 1u));
-      unsigned long long k = v & 0x7fffffffu;
-      if (epipolar) k |= (unsigned long long)y << 32;
-      keys[p] = (KeyT)k;
-      vals[p] = (side ? kSideBit : 0u) | (uint32_t)(y * W + x);
-      kmax = k > kmax ? k : kmax;
-      any = true;
+  for (int x0 = 0; x0 < W; x0 += 128) {                  // four 32-pixel groups per trip, their loads issued together
+    uint32_t v4[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { const int x = x0 + 32 * q + lane; v4[q] = (x < W) ? row[x] : 0u; }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int x = x0 + 32 * q + lane;
+      const uint32_t v = v4[q];
+      const bool c = (v >> 31) != 0u;
+      const uint32_t b = __ballot_sync(0xffffffffu, c);
+      if (c) {
+        const int p = off + __popc(b & ((1u << lane) - 1u));
+        unsigned long long k = v & 0x7fffffffu;
+        if (epipolar) k |= (unsigned long long)y << 32;
+        keys[p] = (KeyT)k;
+        vals[p] = (side ? kSideBit : 0u) | (uint32_t)(y * W + x);
+      }
+      off += __popc(b);
     }
-    off += __popc(b);
   }
-  if (side == 1 && any) atomicMax(ws.tmax + pair, kmax + 1ull);     // stored as key+1 so that 0 means "no right record"
 }
 
-// ---- LSD radix sort, 8-bit digits, one key per thread ---------------------------------------------
+// Lanes of the warp (among `amask`) holding the same 8-bit digit.  Eight ballots instead of match.any, which
+// iterates once per distinct value (a warp of hash digits has ~30): measured 153 vs 183 us per scatter pass.
+__device__ __forceinline__ uint32_t digit_peers(uint32_t amask, uint32_t d) {
+  uint32_t peers = amask;
+#pragma unroll
+  for (int b = 0; b < 8; b++) {
+    const bool bit = (d >> b) & 1u;
+    const uint32_t bal = __ballot_sync(amask, bit);
+    peers &= bit ? bal : ~bal;
+  }
+  return peers;
+}
+
+// kRounds consecutive keys from a 16-byte aligned address.
+__device__ __forceinline__ void load_keys16(const uint32_t* p, uint32_t (&k)[kRounds]) {
+#pragma unroll
+  for (int q = 0; q < kRounds / 4; q++) {
+    const uint4 v = reinterpret_cast<const uint4*>(p)[q];
+    k[4 * q] = v.x; k[4 * q + 1] = v.y; k[4 * q + 2] = v.z; k[4 * q + 3] = v.w;
+  }
+}
+__device__ __forceinline__ void load_keys16(const unsigned long long* p, unsigned long long (&k)[kRounds]) {
+#pragma unroll
+  for (int q = 0; q < kRounds / 2; q++) {
+    const ulonglong2 v = reinterpret_cast<const ulonglong2*>(p)[q];
+    k[2 * q] = v.x; k[2 * q + 1] = v.y;
+  }
+}
+
+// ---- LSD radix sort, 8-bit digits; a block owns a tile of kTile keys, visited in kRounds rounds of 1024
+// consecutive keys (round-major order = input order, which keeps the sort stable) ------------------------
 template <typename KeyT>
 __global__ void __launch_bounds__(kSortThreads)
 radix_hist_kernel(const SortWs<KeyT> ws, int cur, int shift) {
-  __shared__ uint32_t hist[kDigits];
+  __shared__ uint32_t tot[kDigits];
   const int pair = blockIdx.y;
   const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
-  const int nb = (n + kSortThreads - 1) / kSortThreads;
+  const int nb = (n + kTile - 1) / kTile;
   if ((int)blockIdx.x >= nb) return;
-  const KeyT* keys = ws.keys[cur] + (size_t)pair * ws.rec_stride;
-  if (threadIdx.x < kDigits) hist[threadIdx.x] = 0u;
-  __syncthreads();
-  const int i = blockIdx.x * kSortThreads + threadIdx.x;
-  if (i < n) {
-    const uint32_t d = (uint32_t)(keys[i] >> shift) & 0xffu;
-    const uint32_t old = atomicAdd(&hist[d], 1u);
-    if (old == 0xffffffffu) __trap();                    // value-returning form (see match_rows.cu note)
+  const KeyT* keys = (cur ? ws.keys[1] : ws.keys[0]) + (size_t)pair * ws.rec_stride;
+  const int tid = threadIdx.x;
+  if (tid < kDigits) tot[tid] = 0u;
+  // the histogram does not care about order: each thread takes kRounds consecutive keys with 16-byte loads
+  const int i0 = blockIdx.x * kTile + kRounds * tid;
+  KeyT k[kRounds];
+  const bool full = i0 + kRounds <= n && (reinterpret_cast<uintptr_t>(keys + i0) & 15u) == 0u;
+  if (full) {
+    load_keys16(keys + i0, k);
+  } else {
+#pragma unroll
+    for (int r = 0; r < kRounds; r++) k[r] = (i0 + r < n) ? keys[i0 + r] : (KeyT)0;
   }
   __syncthreads();
-  if (threadIdx.x < kDigits)
-    ws.blockhist[((size_t)pair * kDigits + threadIdx.x) * ws.nb_max + blockIdx.x] = hist[threadIdx.x];
+#pragma unroll
+  for (int r = 0; r < kRounds; r++) {
+    const bool active = i0 + r < n;
+    // plain shared-memory atomics: measured 30 us per 26 M keys against 76 us with one atomic per distinct digit
+    // (the peer search costs more ALU work than the conflicts it avoids); a warp-uniform digit -- key bits the
+    // forest never sets -- would serialise 32-fold and is counted by one lane instead
+    const uint32_t d = (uint32_t)(k[r] >> shift) & 0xffu;
+    int uniform = 0;
+    __match_all_sync(0xffffffffu, active ? d : 0x100u, &uniform);
+    if (uniform) { if ((tid & 31) == 0 && active) atomicAdd(&tot[d], 32u); }
+    else if (active) atomicAdd(&tot[d], 1u);
+  }
+  __syncthreads();
+  if (tid < kDigits) ws.blockhist[((size_t)pair * kDigits + tid) * ws.nb_max + blockIdx.x] = tot[tid];
 }
 
 // per-digit exclusive scan over the nb active blocks (one warp per digit, coalesced 32-wide
@@ -142,7 +193,7 @@ __global__ void __launch_bounds__(1024)
 radix_scan_kernel(const SortWs<KeyT> ws) {
   const int pair = blockIdx.y;
   const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
-  const int nb = (n + kSortThreads - 1) / kSortThreads;
+  const int nb = (n + kTile - 1) / kTile;
   const int d = blockIdx.x * 32 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   uint32_t* row = ws.blockhist + ((size_t)pair * kDigits + d) * ws.nb_max;
   uint32_t carry = 0;
@@ -158,56 +209,161 @@ radix_scan_kernel(const SortWs<KeyT> ws) {
   if (lane == 0) ws.digit_tot[(size_t)pair * kDigits + d] = carry;
 }
 
+// Shared memory of the scatter kernel: a region used first as per-warp digit counters, then as the staging
+// area of the tile sorted by digit, followed by four 256-entry tables.
 template <typename KeyT>
-__global__ void __launch_bounds__(kSortThreads)
+__host__ __device__ constexpr int scatter_region_bytes() {
+  return (kSortWarps * kDigits * 4 > kTile * ((int)sizeof(KeyT) + 4)) ? kSortWarps * kDigits * 4 : kTile * ((int)sizeof(KeyT) + 4);
+}
+template <typename KeyT>
+__host__ __device__ constexpr int scatter_smem_bytes() { return scatter_region_bytes<KeyT>() + (kSortWarps / 8 + 3) * kDigits * 4; }
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortThreads, 2)
 radix_scatter_kernel(const SortWs<KeyT> ws, int cur, int shift) {
-  __shared__ uint32_t whist[32][kDigits];                // per-warp digit counts -> exclusive prefix over warps
-  __shared__ uint32_t dbase[kDigits];                    // exclusive prefix of the digit totals
+  extern __shared__ __align__(16) uint8_t smem[];
+  constexpr int kGroups = kSortWarps / 8;                // warps are prefix-summed in groups of eight
+  static_assert(kGroups * kDigits == kSortThreads, "one thread per (digit, group of warps)");
+  uint32_t (*whist)[kDigits] = reinterpret_cast<uint32_t (*)[kDigits]>(smem);          // [warp][digit] counts -> exclusive prefix
+  KeyT* skeys = reinterpret_cast<KeyT*>(smem);                                            // later: tile sorted by digit
+  uint32_t* svals = reinterpret_cast<uint32_t*>(smem + kTile * sizeof(KeyT));
+  uint32_t* gtot = reinterpret_cast<uint32_t*>(smem + scatter_region_bytes<KeyT>());      // [group][digit]
+  uint32_t* racc = gtot + kGroups * kDigits;             // the tile's keys with digit d
+  uint32_t* loff = racc + kDigits;                       // exclusive scan of racc
+  uint32_t* dbase = loff + kDigits;                      // global position of the tile's first key with digit d
   const int pair = blockIdx.y;
   const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
-  const int nb = (n + kSortThreads - 1) / kSortThreads;
+  const int nb = (n + kTile - 1) / kTile;
   if ((int)blockIdx.x >= nb) return;
-  const KeyT* keys_in = ws.keys[cur] + (size_t)pair * ws.rec_stride;
-  const uint32_t* vals_in = ws.vals[cur] + (size_t)pair * ws.rec_stride;
-  KeyT* keys_out = ws.keys[cur ^ 1] + (size_t)pair * ws.rec_stride;
-  uint32_t* vals_out = ws.vals[cur ^ 1] + (size_t)pair * ws.rec_stride;
+  const KeyT* keys_in = (cur ? ws.keys[1] : ws.keys[0]) + (size_t)pair * ws.rec_stride;
+  const uint32_t* vals_in = (cur ? ws.vals[1] : ws.vals[0]) + (size_t)pair * ws.rec_stride;
+  KeyT* keys_out = (cur ? ws.keys[0] : ws.keys[1]) + (size_t)pair * ws.rec_stride;
+  uint32_t* vals_out = (cur ? ws.vals[0] : ws.vals[1]) + (size_t)pair * ws.rec_stride;
   const uint32_t* digit_tot = ws.digit_tot + (size_t)pair * kDigits;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  for (int k = tid; k < 32 * kDigits; k += kSortThreads) (&whist[0][0])[k] = 0u;
-  __syncthreads();
-  const int i = blockIdx.x * kSortThreads + tid;
-  const bool active = i < n;
-  KeyT key = 0;
-  uint32_t val = 0, d = 0, rank = 0;
-  const uint32_t amask = __ballot_sync(0xffffffffu, active);
-  if (active) {
-    key = keys_in[i]; val = vals_in[i];
-    d = (uint32_t)(key >> shift) & 0xffu;
-    const uint32_t peers = __match_any_sync(amask, d);
-    rank = __popc(peers & ((1u << lane) - 1u));
-    if (rank == 0) whist[wid][d] = __popc(peers);
+  const int tile0 = blockIdx.x * kTile;
+  const int w0 = tile0 + wid * (32 * kRounds) + lane;    // the thread's record of round r is w0 + 32 r
+  // all of the thread's records first, so that every load is in flight at once
+  KeyT k[kRounds];
+  uint32_t v[kRounds], lr[kRounds];
+#pragma unroll
+  for (int r = 0; r < kRounds; r++) {
+    const int i = w0 + 32 * r;
+    k[r] = (i < n) ? keys_in[i] : (KeyT)0;
+    v[r] = (i < n) ? vals_in[i] : 0u;
   }
-  __syncthreads();
-  if (tid < kDigits) {
-    uint32_t acc = 0;
-    for (int w = 0; w < 32; w++) { const uint32_t c = whist[w][tid]; whist[w][tid] = acc; acc += c; }
-  } else if (wid == 8) {                                 // one warp: exclusive scan of the 256 digit totals
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+#pragma unroll
+    for (int q = 0; q < kSortWarps * kDigits / 4 / kSortThreads; q++) z[q * kSortThreads + tid] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (wid == kSortWarps - 1) {                           // one warp: exclusive scan of the 256 digit totals
     uint32_t c[8], sum = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { c[k] = digit_tot[8 * lane + k]; sum += c[k]; }
+    for (int q = 0; q < 8; q++) { c[q] = digit_tot[8 * lane + q]; sum += c[q]; }
     uint32_t incl = sum;
 #pragma unroll
-    for (int k = 1; k < 32; k <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, k); if (lane >= k) incl += t; }
+    for (int q = 1; q < 32; q <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, q); if (lane >= q) incl += t; }
     uint32_t run = incl - sum;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { dbase[8 * lane + k] = run; run += c[k]; }
+    for (int q = 0; q < 8; q++) {
+      dbase[8 * lane + q] = run + ws.blockhist[((size_t)pair * kDigits + 8 * lane + q) * ws.nb_max + blockIdx.x];
+      run += c[q];
+    }
   }
   __syncthreads();
-  if (active) {
-    const uint32_t pos = dbase[d] + ws.blockhist[((size_t)pair * kDigits + d) * ws.nb_max + blockIdx.x] + whist[wid][d] + rank;
-    keys_out[pos] = key;
-    vals_out[pos] = val;
+  // ranking inside the warp's own run of keys: the warp's counters need no block-wide barrier
+#pragma unroll
+  for (int r = 0; r < kRounds; r++) {
+    const bool active = w0 + 32 * r < n;
+    const uint32_t amask = __ballot_sync(0xffffffffu, active);
+    const uint32_t d = (uint32_t)(k[r] >> shift) & 0xffu;
+    uint32_t rank = 0, prev = 0, peers = 0;
+    if (active) {
+      peers = digit_peers(amask, d);
+      rank = __popc(peers & ((1u << lane) - 1u));
+      prev = whist[wid][d];
+    }
+    __syncwarp();
+    if (active && rank == 0) whist[wid][d] = prev + __popc(peers);
+    __syncwarp();
+    lr[r] = prev + rank;                                 // rank among the warp's records with this digit
   }
+  __syncthreads();
+  const int pd = tid & (kDigits - 1), pg = tid >> 8;     // digit pd, warps 8 * pg .. 8 * pg + 7
+  {                                                      // exclusive prefix over the warps, in two levels
+    uint32_t acc = 0;
+#pragma unroll
+    for (int w = 8 * pg; w < 8 * pg + 8; w++) { const uint32_t c = whist[w][pd]; whist[w][pd] = acc; acc += c; }
+    gtot[pg * kDigits + pd] = acc;
+  }
+  __syncthreads();
+  {
+    uint32_t total = 0, base = 0;
+#pragma unroll
+    for (int g = 0; g < kGroups; g++) { const uint32_t c = gtot[g * kDigits + pd]; if (g < pg) base += c; total += c; }
+    if (base)
+#pragma unroll
+      for (int w = 8 * pg; w < 8 * pg + 8; w++) whist[w][pd] += base;
+    if (pg == 0) racc[pd] = total;
+  }
+  __syncthreads();
+  if (wid == 0) {                                        // exclusive scan of the tile's digit counts
+    uint32_t c[8], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) { c[q] = racc[8 * lane + q]; sum += c[q]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int q = 1; q < 32; q <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, q); if (lane >= q) incl += t; }
+    uint32_t run = incl - sum;
+#pragma unroll
+    for (int q = 0; q < 8; q++) { loff[8 * lane + q] = run; run += c[q]; }
+  }
+#pragma unroll
+  for (int r = 0; r < kRounds; r++) lr[r] += whist[wid][(uint32_t)(k[r] >> shift) & 0xffu];
+  __syncthreads();                                       // whist is dead from here: the region becomes the staging area
+#pragma unroll
+  for (int r = 0; r < kRounds; r++) {
+    if (w0 + 32 * r < n) {
+      const uint32_t pos = loff[(uint32_t)(k[r] >> shift) & 0xffu] + lr[r];
+      skeys[pos] = k[r];
+      svals[pos] = v[r];
+    }
+  }
+  __syncthreads();
+  const int tile_n = min(kTile, n - tile0);
+#pragma unroll
+  for (int r = 0; r < kRounds; r++) {                    // runs of equal digits leave as contiguous stores
+    const int j = r * kSortThreads + tid;
+    if (j < tile_n) {
+      const KeyT key = skeys[j];
+      const uint32_t d = (uint32_t)(key >> shift) & 0xffu;
+      const uint32_t pos = dbase[d] + ((uint32_t)j - loff[d]);
+      keys_out[pos] = key;
+      vals_out[pos] = svals[j];
+    }
+  }
+}
+
+// tmax[pair] = 1 + the largest key carried by a right record = the key of the last right record of the
+// sorted array (0: no right record).  One warp per pair, scanning backwards; it normally stops at once.
+template <typename KeyT>
+__global__ void __launch_bounds__(32)
+global_tmax_kernel(const SortWs<KeyT> ws, int cur) {
+  const int pair = blockIdx.x, lane = threadIdx.x;
+  const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
+  const KeyT* keys = (cur ? ws.keys[1] : ws.keys[0]) + (size_t)pair * ws.rec_stride;
+  const uint32_t* vals = (cur ? ws.vals[1] : ws.vals[0]) + (size_t)pair * ws.rec_stride;
+  for (int hi = n; hi > 0; hi -= 32) {
+    const int i = hi - 1 - lane;
+    const bool right = i >= 0 && (vals[i] & kSideBit) != 0u;
+    const uint32_t b = __ballot_sync(0xffffffffu, right);
+    if (b) {
+      if (lane == __ffs(b) - 1) ws.tmax[pair] = (unsigned long long)keys[i] + 1ull;
+      return;
+    }
+  }
+  if (lane == 0) ws.tmax[pair] = 0ull;
 }
 
 // ---- segmented scan over the sorted records ---------------------------------------------------------
@@ -220,30 +376,52 @@ struct GlobalEmitArgs {
   int32_t* n_out;                    // [n_pairs]
 };
 
+// Matches among the kRounds consecutive sorted records i0 .. i0 + kRounds - 1 (i0 a multiple of kRounds): bit j of
+// the result is set when record i0 + j is the left record of a match; V[j] / V[j + 1] are then its value and
+// its partner's.  The window (one record before, three after) is loaded with 16-byte loads where it can be.
 template <typename KeyT>
-__device__ __forceinline__ bool is_match(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, int i, int n,
-                                         unsigned long long tmax1, const GlobalEmitArgs& a, uint32_t* vl, uint32_t* vr) {
-  if (i >= n) return false;
-  const uint32_t v = vals[i];
-  if (v & kSideBit) return false;
-  const KeyT k = keys[i];
-  if (i > 0 && keys[i - 1] == k) return false;
-  if (i + 1 >= n || keys[i + 1] != k || !(vals[i + 1] & kSideBit)) return false;
-  const bool is_tail = (tmax1 != 0ull) && ((unsigned long long)k == tmax1 - 1ull);
-  if (!is_tail) {
-    if (i + 2 < n && keys[i + 2] == k) return false;
+__device__ __forceinline__ uint32_t window_matches(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, int i0, int n,
+                                                   unsigned long long tmax1, const GlobalEmitArgs& a, uint32_t (&V)[kRounds + 1]) {
+  if (i0 >= n) return 0u;
+  KeyT K[kRounds + 4];                                   // K[j] = key of record i0 - 1 + j
+  const bool full = i0 + kRounds <= n && (reinterpret_cast<uintptr_t>(keys + i0) & 15u) == 0u &&
+                    (reinterpret_cast<uintptr_t>(vals + i0) & 15u) == 0u;
+  if (full) {
+    KeyT kk[kRounds];
+    load_keys16(keys + i0, kk);
+    uint32_t vv[kRounds];
+    load_keys16(vals + i0, vv);
+#pragma unroll
+    for (int j = 0; j < kRounds; j++) { K[j + 1] = kk[j]; V[j] = vv[j]; }
   } else {
-    if (i + 2 >= n || keys[i + 2] != k) return false;     // a single right record at the tail never matches
-    if (i + 3 < n && keys[i + 3] == k) return false;      // three or more: duplicates
+#pragma unroll
+    for (int j = 0; j < kRounds; j++) { const int i = min(i0 + j, n - 1); K[j + 1] = keys[i]; V[j] = vals[i]; }
   }
-  *vl = v; *vr = vals[i + 1] & ~kSideBit;
-  if (a.mode == 0) {
-    const int xl = (int)(*vl % (uint32_t)a.W), yl = (int)(*vl / (uint32_t)a.W);
-    const int xr = (int)(*vr % (uint32_t)a.W), yr = (int)(*vr / (uint32_t)a.W);
-    const int dx = xl - xr, dy = yl - yr;
-    if (!(dy <= a.vertical_tolerance && -dy <= a.vertical_tolerance && dx <= a.disp_high && -dx <= a.disp_high)) return false;
+  K[0] = keys[max(i0 - 1, 0)];
+#pragma unroll
+  for (int j = kRounds; j < kRounds + 3; j++) K[j + 1] = keys[min(i0 + j, n - 1)];
+  V[kRounds] = vals[min(i0 + kRounds, n - 1)];
+  uint32_t bits = 0;
+#pragma unroll
+  for (int j = 0; j < kRounds; j++) {
+    const int i = i0 + j;
+    const KeyT k = K[j + 1];
+    bool m = i < n && !(V[j] & kSideBit);                                  // a left record ...
+    m = m && !(i > 0 && K[j] == k);                                        // ... the first of its run ...
+    m = m && i + 1 < n && K[j + 2] == k && (V[j + 1] & kSideBit);          // ... followed by a right record
+    const bool is_tail = (tmax1 != 0ull) && ((unsigned long long)k == tmax1 - 1ull);
+    const bool k2 = i + 2 < n && K[j + 3] == k, k3 = i + 3 < n && K[j + 4] == k;
+    m = m && (is_tail ? (k2 && !k3) : !k2);              // tail key: exactly {L, R, R}; elsewhere exactly {L, R}
+    if (m && a.mode == 0) {
+      const uint32_t vl = V[j], vr = V[j + 1] & ~kSideBit;
+      const int xl = (int)(vl % (uint32_t)a.W), yl = (int)(vl / (uint32_t)a.W);
+      const int xr = (int)(vr % (uint32_t)a.W), yr = (int)(vr / (uint32_t)a.W);
+      const int dx = xl - xr, dy = yl - yr;
+      m = dy <= a.vertical_tolerance && -dy <= a.vertical_tolerance && dx <= a.disp_high && -dx <= a.disp_high;
+    }
+    bits |= (m ? 1u : 0u) << j;
   }
-  return true;
+  return bits;
 }
 
 template <typename KeyT>
@@ -252,15 +430,16 @@ global_count_kernel(const SortWs<KeyT> ws, int cur, const GlobalEmitArgs a) {
   __shared__ int cnt;
   const int pair = blockIdx.y;
   const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
-  const int nb = (n + kSortThreads - 1) / kSortThreads;
+  const int nb = (n + kTile - 1) / kTile;
   if ((int)blockIdx.x >= nb) return;
   if (threadIdx.x == 0) cnt = 0;
   __syncthreads();
-  uint32_t vl, vr;
-  const bool m = is_match(ws.keys[cur] + (size_t)pair * ws.rec_stride, ws.vals[cur] + (size_t)pair * ws.rec_stride,
-                          blockIdx.x * kSortThreads + threadIdx.x, n, ws.tmax[pair], a, &vl, &vr);
-  const uint32_t b = __ballot_sync(0xffffffffu, m);
-  if ((threadIdx.x & 31) == 0 && b) { if (atomicAdd(&cnt, __popc(b)) < 0) __trap(); }
+  uint32_t V[kRounds + 1];
+  const uint32_t bits = window_matches((cur ? ws.keys[1] : ws.keys[0]) + (size_t)pair * ws.rec_stride,
+                                       (cur ? ws.vals[1] : ws.vals[0]) + (size_t)pair * ws.rec_stride,
+                                       blockIdx.x * kTile + kRounds * threadIdx.x, n, ws.tmax[pair], a, V);
+  const int mine = __reduce_add_sync(0xffffffffu, __popc(bits));
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&cnt, mine);
   __syncthreads();
   if (threadIdx.x == 0) ws.blockcount[(size_t)pair * (ws.nb_max + 1) + blockIdx.x] = cnt;
 }
@@ -271,7 +450,7 @@ __global__ void __launch_bounds__(32)
 global_blockscan_kernel(const SortWs<KeyT> ws, const GlobalEmitArgs a) {
   const int pair = blockIdx.x, lane = threadIdx.x;
   const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
-  const int nb = (n + kSortThreads - 1) / kSortThreads;
+  const int nb = (n + kTile - 1) / kTile;
   int32_t* bc = ws.blockcount + (size_t)pair * (ws.nb_max + 1);
   int carry = 0;
   for (int b0 = 0; b0 < nb; b0 += 32) {
@@ -289,42 +468,53 @@ global_blockscan_kernel(const SortWs<KeyT> ws, const GlobalEmitArgs a) {
 template <typename KeyT>
 __global__ void __launch_bounds__(kSortThreads)
 global_emit_kernel(const SortWs<KeyT> ws, int cur, const GlobalEmitArgs a) {
-  __shared__ int warp_base[32];
+  __shared__ int warp_base[kSortWarps];
   const int pair = blockIdx.y;
   const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
-  const int nb = (n + kSortThreads - 1) / kSortThreads;
+  const int nb = (n + kTile - 1) / kTile;
   if ((int)blockIdx.x >= nb) return;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  uint32_t vl = 0, vr = 0;
-  const bool m = is_match(ws.keys[cur] + (size_t)pair * ws.rec_stride, ws.vals[cur] + (size_t)pair * ws.rec_stride,
-                          blockIdx.x * kSortThreads + tid, n, ws.tmax[pair], a, &vl, &vr);
-  const uint32_t b = __ballot_sync(0xffffffffu, m);
-  if (lane == 0) warp_base[wid] = __popc(b);
+  uint32_t V[kRounds + 1];
+  const uint32_t bits = window_matches((cur ? ws.keys[1] : ws.keys[0]) + (size_t)pair * ws.rec_stride,
+                                       (cur ? ws.vals[1] : ws.vals[0]) + (size_t)pair * ws.rec_stride,
+                                       blockIdx.x * kTile + kRounds * tid, n, ws.tmax[pair], a, V);
+  // thread order = record order: exclusive scan of the per-thread match counts
+  const int c = __popc(bits);
+  int incl = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+  if (lane == 31) warp_base[wid] = incl;
   __syncthreads();
   if (wid == 0) {
-    int v = warp_base[lane], incl = v;
+    const int v = lane < kSortWarps ? warp_base[lane] : 0;
+    int wi = v;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-    warp_base[lane] = incl - v;
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += t; }
+    if (lane < kSortWarps) warp_base[lane] = wi - v;
   }
   __syncthreads();
-  if (!m) return;
-  const long long k = (long long)ws.blockcount[(size_t)pair * (ws.nb_max + 1) + blockIdx.x] + warp_base[wid] + __popc(b & ((1u << lane) - 1u));
-  if (k >= a.cap) return;
-  const long long idx = (long long)pair * a.out_stride + k;
-  if (a.mode == 2) {
-    int32_t* o = reinterpret_cast<int32_t*>(a.out) + 2 * idx;
-    o[0] = (int32_t)vl; o[1] = (int32_t)vr;
-    return;
-  }
-  const int xl = (int)(vl % (uint32_t)a.W), yl = (int)(vl / (uint32_t)a.W);
-  const int xr = (int)(vr % (uint32_t)a.W), yr = (int)(vr / (uint32_t)a.W);
-  if (a.mode == 0) {
-    float* o = reinterpret_cast<float*>(a.out) + 3 * idx;
-    o[0] = __int_as_float(xl); o[1] = __int_as_float(yl); o[2] = (float)(xl - xr);
-  } else {
-    int32_t* o = reinterpret_cast<int32_t*>(a.out) + 4 * idx;
-    o[0] = xl; o[1] = yl; o[2] = xr; o[3] = yr;
+  long long k = (long long)ws.blockcount[(size_t)pair * (ws.nb_max + 1) + blockIdx.x] + warp_base[wid] + (incl - c);
+#pragma unroll
+  for (int j = 0; j < kRounds; j++) {
+    if (!((bits >> j) & 1u)) continue;
+    const long long slot = k++;
+    if (slot >= a.cap) continue;
+    const uint32_t vl = V[j], vr = V[j + 1] & ~kSideBit;
+    const long long idx = (long long)pair * a.out_stride + slot;
+    if (a.mode == 2) {
+      int32_t* o = reinterpret_cast<int32_t*>(a.out) + 2 * idx;
+      o[0] = (int32_t)vl; o[1] = (int32_t)vr;
+    } else {
+      const int xl = (int)(vl % (uint32_t)a.W), yl = (int)(vl / (uint32_t)a.W);
+      const int xr = (int)(vr % (uint32_t)a.W), yr = (int)(vr / (uint32_t)a.W);
+      if (a.mode == 0) {
+        float* o = reinterpret_cast<float*>(a.out) + 3 * idx;
+        o[0] = __int_as_float(xl); o[1] = __int_as_float(yl); o[2] = (float)(xl - xr);
+      } else {
+        int32_t* o = reinterpret_cast<int32_t*>(a.out) + 4 * idx;
+        o[0] = xl; o[1] = yl; o[2] = xr; o[3] = yr;
+      }
+    }
   }
 }
 
@@ -333,7 +523,7 @@ static size_t pad256(size_t b) { return (b + 255) / 256 * 256; }
 
 // bytes of workspace for n_pairs pairs of up to max_records records each, H rows (0 for explicit keys)
 size_t global_workspace_bytes(long long max_records, int n_pairs, int H) {
-  const size_t nb = (size_t)((max_records + kSortThreads - 1) / kSortThreads + 1);
+  const size_t nb = (size_t)((max_records + kTile - 1) / kTile + 1);
   const size_t np = (size_t)n_pairs;
   return pad256(np * 8) + pad256(np * 2 * 4) + 2 * pad256(np * (size_t)max_records * 8) + 2 * pad256(np * (size_t)max_records * 4) +
          pad256(np * kDigits * nb * 4) + pad256(np * kDigits * 4) + pad256(np * (nb + 1) * 4) + pad256(np * 2 * (size_t)std::max(H, 1) * 4) + 256;
@@ -345,7 +535,7 @@ static SortWs<KeyT> carve(void* ws, long long max_records, int n_pairs, int H) {
   uint8_t* p = reinterpret_cast<uint8_t*>(ws);
   auto take = [&p](size_t bytes) { uint8_t* r = p; p += pad256(bytes); return r; };
   const size_t np = (size_t)n_pairs;
-  w.nb_max = (int)((max_records + kSortThreads - 1) / kSortThreads + 1);
+  w.nb_max = (int)((max_records + kTile - 1) / kTile + 1);
   w.rec_stride = max_records;
   w.tmax = reinterpret_cast<unsigned long long*>(take(np * 8));
   w.n_side = reinterpret_cast<int32_t*>(take(np * 2 * 4));
@@ -363,21 +553,26 @@ static SortWs<KeyT> carve(void* ws, long long max_records, int n_pairs, int H) {
 template <typename KeyT>
 static cudaError_t sort_and_emit(SortWs<KeyT>& w, long long max_records, int n_pairs, int key_bits, const GlobalEmitArgs& ea,
                                  cudaStream_t stream, int* launches) {
-  const int nb = (int)((max_records + kSortThreads - 1) / kSortThreads);
+  const int nb = (int)((max_records + kTile - 1) / kTile);
   if (nb <= 0 || n_pairs <= 0) return cudaSuccess;
   const dim3 grid(nb, n_pairs);
+  {                                                       // per device and per call: cheap next to the sort itself
+    cudaError_t e = cudaFuncSetAttribute(radix_scatter_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_smem_bytes<KeyT>());
+    if (e != cudaSuccess) return e;
+  }
   int cur = 0;
   for (int shift = 0; shift < key_bits; shift += 8) {
     radix_hist_kernel<KeyT><<<grid, kSortThreads, 0, stream>>>(w, cur, shift);
     radix_scan_kernel<KeyT><<<dim3(kDigits / 32, n_pairs), 1024, 0, stream>>>(w);
-    radix_scatter_kernel<KeyT><<<grid, kSortThreads, 0, stream>>>(w, cur, shift);
+    radix_scatter_kernel<KeyT><<<grid, kSortThreads, scatter_smem_bytes<KeyT>(), stream>>>(w, cur, shift);
     cur ^= 1;
     *launches += 3;
   }
+  global_tmax_kernel<KeyT><<<n_pairs, 32, 0, stream>>>(w, cur);
   global_count_kernel<KeyT><<<grid, kSortThreads, 0, stream>>>(w, cur, ea);
   global_blockscan_kernel<KeyT><<<n_pairs, 32, 0, stream>>>(w, ea);
   global_emit_kernel<KeyT><<<grid, kSortThreads, 0, stream>>>(w, cur, ea);
-  *launches += 3;
+  *launches += 4;
   return cudaGetLastError();
 }
 
@@ -395,7 +590,6 @@ cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int
   cudaError_t e;
   if (epipolar) {
     SortWs<unsigned long long> w = carve<unsigned long long>(ws, max_records, n_pairs, H);
-    if ((e = cudaMemsetAsync(w.tmax, 0, (size_t)n_pairs * 8, stream)) != cudaSuccess) return e;
     global_rowoff_kernel<<<dim3(2, n_pairs), 1024, 0, stream>>>(rowcnt, H, w.rowoff, w.n_side);
     global_gather_kernel<unsigned long long><<<gather_grid, 128, 0, stream>>>(hash, W, H, 1, w);
     *launches += 2;
@@ -405,7 +599,6 @@ cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int
     return e;
   }
   SortWs<uint32_t> w = carve<uint32_t>(ws, max_records, n_pairs, H);
-  if ((e = cudaMemsetAsync(w.tmax, 0, (size_t)n_pairs * 8, stream)) != cudaSuccess) return e;
   global_rowoff_kernel<<<dim3(2, n_pairs), 1024, 0, stream>>>(rowcnt, H, w.rowoff, w.n_side);
   global_gather_kernel<uint32_t><<<gather_grid, 128, 0, stream>>>(hash, W, H, 0, w);
   *launches += 2;
@@ -421,14 +614,11 @@ __global__ void keys_prepare_kernel(SortWs<unsigned long long> ws, int ns, int n
   if (i >= ns + nt) return;
   const bool tar = i >= ns;
   ws.vals[0][i] = tar ? (kSideBit | (uint32_t)(i - ns)) : (uint32_t)i;
-  if (tar) atomicMax(ws.tmax, ws.keys[0][i] + 1ull);
 }
 
 cudaError_t launch_match_keys(void* ws, long long max_records, int ns, int nt, int key_bits, int32_t* out_pairs, long long cap,
                               int32_t* n_out, cudaStream_t stream, int* launches) {
   SortWs<unsigned long long> w = carve<unsigned long long>(ws, max_records, 1, 0);
-  cudaError_t e = cudaMemsetAsync(w.tmax, 0, 8, stream);
-  if (e != cudaSuccess) return e;
   const int n = ns + nt;
   keys_prepare_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w, ns, nt);
   *launches += 1;
