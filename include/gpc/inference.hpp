@@ -21,8 +21,9 @@
 //     are filled for API parity (sparsematch prints mask.size()); editing them does not change
 //     what the resident path computes.  PreprocessedImage objects built by hand (no handle) go
 //     through evalFastMaskOnSubsetSSE + findCorrespondences on the caller's smooth / mask data.
-//   * useHashtable(true) throws (GPC_E_UNSUPPORTED): the reference's hashtable matcher returns a
-//     different, smaller match set by construction.
+//   * useHashtable(true) reproduces the reference's hashtable matcher (hashmatch.hpp:48-272: 214673 buckets of
+//     at most 10 elements, a different and smaller match set) for images that carry their device handle;
+//     with hand-built PreprocessedImages it throws GPC_E_UNSUPPORTED.
 //   * numThreads is accepted and ignored.
 #ifndef GPC_B200_INFERENCE_HPP
 #define GPC_B200_INFERENCE_HPP
@@ -244,8 +245,6 @@ class Forest {
   // inference.hpp:184-226
   std::vector<ndb::Correspondence> depthPriorFast(PreprocessedImage& src, PreprocessedImage& tar, FilterMask& fastmask,
                                                   InferenceSettings& settings) {
-    if (settings.useHashtable_)
-      throw GpcError(GPC_E_UNSUPPORTED, "useHashtable(true) is not supported (sort-path semantics only)");
     if (resident_pair(src, tar)) {
       gpc_ctx* c = src.resident->ctx;
       upload_forest(c, fastmask);
@@ -261,6 +260,8 @@ class Forest {
         corr.push_back(ndb::Correspondence(ndb::Point(raw[i].xs, raw[i].ys), ndb::Point(raw[i].xt, raw[i].yt)));
       return corr;
     }
+    if (settings.useHashtable_)
+      throw GpcError(GPC_E_UNSUPPORTED, "useHashtable(true) needs images preprocessed by preprocessImage (device handle)");
     std::vector<ndb::Descriptor> a = evalFastMaskOnSubsetSSE(src.smooth, src.grad, src.mask, fastmask, settings);
     std::vector<ndb::Descriptor> b = evalFastMaskOnSubsetSSE(tar.smooth, tar.grad, tar.mask, fastmask, settings);
     if (settings.epipolarMode_) {

@@ -34,7 +34,7 @@ typedef enum {
   GPC_E_DIMS = 3,         /* exceeds the context's max_w / max_h / max_batch */
   GPC_E_CUDA = 4,         /* CUDA runtime error or no device */
   GPC_E_CAPACITY = 5,     /* output buffer too small; counts still report the need */
-  GPC_E_UNSUPPORTED = 6,  /* useHashtable(true) (inference.hpp:204-225), out of scope */
+  GPC_E_UNSUPPORTED = 6,  /* a combination this library does not implement (see the entry point's comment) */
   GPC_E_FOREST = 7,       /* no forest set / more than 32 tests / offset outside +-13 */
   GPC_E_IO = 8            /* forest file cannot be opened (inference.hpp:409-412) */
 } gpc_status;
@@ -48,7 +48,8 @@ typedef struct {
   int32_t disp_high;            /* dispHigh_ */
   int32_t vertical_tolerance;   /* verticalTolerance_ */
   int32_t epipolar_mode;        /* epipolarMode_ */
-  int32_t use_hashtable;        /* useHashtable_: must be 0 */
+  int32_t use_hashtable;        /* useHashtable_: 1 = the reference's hashtable matcher (inference.hpp:204-225,
+                                   hashmatch.hpp:48-272), reproduced bucket by bucket; a different, smaller set */
   int32_t num_threads;          /* numThreads_: accepted, ignored */
 } gpc_settings;
 

@@ -35,7 +35,7 @@ size_t global_workspace_bytes(long long max_records, int n_pairs, int H);
 cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int W, int H, int n_pairs, int epipolar, int key_bits,
                                 int disp_high, int vertical_tolerance, int mode, void* ws, long long max_records, void* out,
                                 long long out_stride, long long cap, int32_t* n_out, int32_t* n_cand, cudaStream_t stream,
-                                int* launches);
+                                int* launches, int hashtable);
 cudaError_t launch_match_keys(void* ws, long long max_records, int ns, int nt, int key_bits, int32_t* out_pairs, long long cap,
                               int32_t* n_out, cudaStream_t stream, int* launches);
 void* global_key_buffer(void* ws, long long max_records);
@@ -174,7 +174,6 @@ int check_dims(gpc_ctx* c, int w, int h, int n_pairs) {
 
 int check_settings(gpc_ctx* c, const gpc_settings* s) {
   if (!s) return fail(c, GPC_E_ARG, "settings is NULL");
-  if (s->use_hashtable) return fail(c, GPC_E_UNSUPPORTED, "useHashtable(true) is not supported (sort-path semantics only)");
   if (s->gradient_threshold < 0 || s->gradient_threshold > 255)
     return fail(c, GPC_E_ARG, "gradientThreshold needs to be within 0...255");     // inference.hpp:303
   return GPC_OK;
@@ -265,13 +264,18 @@ int run_match_sort(gpc_ctx* c, const uint32_t* hash, int p0, int n, int w, int h
     GPC_CUDA(c, gpc::launch_match_global(hash + (size_t)(2 * (p0 + q0)) * P, c->d_rows + (size_t)(2 * (p0 + q0)) * h, w, h, m,
                                          s->epipolar_mode ? 1 : 0, 31, s->disp_high, s->vertical_tolerance, mode, c->d_gws, records,
                                          reinterpret_cast<uint8_t*>(d_out) + (size_t)q0 * (size_t)out_stride * record_bytes, out_stride,
-                                         cap, d_n_out + q0, d_n_cand ? d_n_cand + 2 * q0 : nullptr, c->stream, &launches));
+                                         cap, d_n_out + q0, d_n_cand ? d_n_cand + 2 * q0 : nullptr, c->stream, &launches,
+                                         s->use_hashtable ? 1 : 0));
     c->launches += launches;
   }
   return GPC_OK;
 }
 
-bool use_sort_matcher(const gpc_ctx* c, const gpc_settings* s) { return !s->epipolar_mode || c->matcher == GPC_MATCHER_SORT; }
+// the per-row matcher covers the sort path's semantics in epipolar mode only; global mode and the reference's
+// hashtable matcher (useHashtable, inference.hpp:204-225) go through the device-wide sort
+bool use_sort_matcher(const gpc_ctx* c, const gpc_settings* s) {
+  return !s->epipolar_mode || s->use_hashtable || c->matcher == GPC_MATCHER_SORT;
+}
 
 // Kernels B, scan, C over the slot's hash images.  packed: supports of the slot's pairs back to back
 // from d_out[0], prefix in d_pair_base + 2 * p0; else pair i at d_out + i * cap.

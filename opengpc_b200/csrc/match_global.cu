@@ -16,6 +16,11 @@
 //               a single R at the very tail never matches (inference.hpp:243-249).
 // Output order = position in the sorted array = ascending key, as std::sort gives the reference.
 //
+// useHashtable(true) (inference.hpp:204-225, ndb::Hashmatch hashmatch.hpp:48-272) runs on the same machinery:
+// the sort key is the bucket index key % 214673, the stable sort leaves each bucket's records in insertion
+// order (all left, then all right, each in raster order), and one thread replays the bucket: the first 10
+// records in stable ascending key order, walked by the reference's pairing rules.
+//
 // Every kernel carries a pair dimension (blockIdx.y): a chunk of independent pairs is sorted by the
 // same launches, each pair in its own slice of the workspace.
 #include <algorithm>
@@ -31,6 +36,8 @@ constexpr int kRounds = 8;                  // keys per thread: a block owns a t
 constexpr int kTile = kSortThreads * kRounds;
 constexpr int kDigits = 256;
 constexpr uint32_t kSideBit = 0x80000000u;
+constexpr uint32_t kHtBuckets = 214673u;    // inference.hpp:212
+constexpr int kHtDepth = 10;                // hashmatch.hpp:95: a bucket keeps the first 10 elements offered to it
 
 // Workspace of a chunk of pairs (device pointers; slice `pair` starts at pair * stride of each array).
 template <typename KeyT>
@@ -85,7 +92,7 @@ global_rowoff_kernel(const int32_t* __restrict__ rowcnt, int H, int32_t* __restr
 // One warp per (side, row): candidates in raster order.
 template <typename KeyT>
 __global__ void __launch_bounds__(128)
-global_gather_kernel(const uint32_t* __restrict__ hash, int W, int H, int epipolar, const SortWs<KeyT> ws) {
+global_gather_kernel(const uint32_t* __restrict__ hash, int W, int H, int epipolar, int hashtable, const SortWs<KeyT> ws) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, pair = blockIdx.y;
   if (warp >= 2 * H) return;
   const int side = warp / H, y = warp - side * H;
@@ -108,6 +115,7 @@ global_gather_kernel(const uint32_t* __restrict__ hash, int W, int H, int epipol
         const int p = off + __popc(b & ((1u << lane) - 1u));
         unsigned long long k = v & 0x7fffffffu;
         if (epipolar) k |= (unsigned long long)y << 32;
+        if (hashtable) k %= kHtBuckets;                  // buffer.hpp:84-86
         keys[p] = (KeyT)k;
         vals[p] = (side ? kSideBit : 0u) | (uint32_t)(y * W + x);
       }
@@ -518,6 +526,130 @@ global_emit_kernel(const SortWs<KeyT> ws, int cur, const GlobalEmitArgs a) {
   }
 }
 
+// ---- useHashtable(true): replay of the reference's buckets -------------------------------------------
+struct HtArgs {
+  const uint32_t* hash;              // hash images of the chunk's first pair
+  int32_t W, H, epipolar;
+};
+
+__device__ __forceinline__ void write_match(const GlobalEmitArgs& a, int pair, long long slot, uint32_t vl, uint32_t vr) {
+  if (slot >= a.cap) return;
+  const long long idx = (long long)pair * a.out_stride + slot;
+  const int xl = (int)(vl % (uint32_t)a.W), yl = (int)(vl / (uint32_t)a.W);
+  const int xr = (int)(vr % (uint32_t)a.W), yr = (int)(vr / (uint32_t)a.W);
+  if (a.mode == 0) {
+    float* o = reinterpret_cast<float*>(a.out) + 3 * idx;
+    o[0] = __int_as_float(xl); o[1] = __int_as_float(yl); o[2] = (float)(xl - xr);
+  } else {
+    int32_t* o = reinterpret_cast<int32_t*>(a.out) + 4 * idx;
+    o[0] = xl; o[1] = yl; o[2] = xr; o[3] = yr;
+  }
+}
+
+__device__ __forceinline__ bool passes_filter(const GlobalEmitArgs& a, uint32_t vl, uint32_t vr) {
+  if (a.mode != 0) return true;
+  const int xl = (int)(vl % (uint32_t)a.W), yl = (int)(vl / (uint32_t)a.W);
+  const int xr = (int)(vr % (uint32_t)a.W), yr = (int)(vr / (uint32_t)a.W);
+  const int dx = xl - xr, dy = yl - yr;
+  return dy <= a.vertical_tolerance && -dy <= a.vertical_tolerance && dx <= a.disp_high && -dx <= a.disp_high;
+}
+
+// Record i of the bucket-sorted array: if it opens a bucket, replay that bucket and return its number of
+// matches (written from `slot` on when kWrite).  keys = bucket indices, vals = side << 31 | pixel index.
+template <bool kWrite>
+__device__ int ht_bucket(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int i, int n, const HtArgs& h,
+                         int pair, const GlobalEmitArgs& a, long long slot) {
+  if (i >= n) return 0;
+  const uint32_t b = keys[i];
+  if (i > 0 && keys[i - 1] == b) return 0;
+  const uint32_t* img = h.hash + (size_t)(2 * pair) * h.H * h.W;
+  unsigned long long lk[kHtDepth];                       // the bucket's list: keys ascending, ties in insertion order
+  uint32_t lv[kHtDepth];
+  int m = 0;
+  for (int j = i; j < n && m < kHtDepth && keys[j] == b; j++) {        // hashmatch.hpp:101: a full bucket drops the rest
+    const uint32_t v = vals[j], pix = v & ~kSideBit;
+    unsigned long long k = img[(size_t)(v >> 31) * h.H * h.W + pix] & 0x7fffffffu;
+    if (h.epipolar) k |= (unsigned long long)(pix / (uint32_t)h.W) << 32;
+    int pos = m;                                         // :112-116: behind every element with key <= k
+    while (pos > 0 && lk[pos - 1] > k) { lk[pos] = lk[pos - 1]; lv[pos] = lv[pos - 1]; pos--; }
+    lk[pos] = k; lv[pos] = v;
+    m++;
+  }
+  int found = 0, j = 0;
+  while (j < m) {                                        // getDuplicates, hashmatch.hpp:162-198
+    const int p = j;
+    j = j + 1;
+    if (j < m && lk[p] == lk[j]) {
+      if ((lv[p] ^ lv[j]) & kSideBit) {                  // from different images
+        bool emit, stop = false;
+        if (j + 1 < m) { emit = lk[j + 1] != lk[j]; stop = j + 2 >= m; }     // :174-180
+        else emit = true;                                                     // :181-183
+        if (emit) {
+          const uint32_t vl = lv[p] & ~kSideBit, vr = lv[j] & ~kSideBit;      // left records precede equal right ones
+          if (passes_filter(a, vl, vr)) {
+            if (kWrite) write_match(a, pair, slot + found, vl, vr);
+            found++;
+          }
+        }
+        if (stop) break;
+      } else if (j + 1 < m && ((lv[j] ^ lv[j + 1]) & kSideBit)) {
+        j = j + 1;                                       // :189-193: step over the false pair
+      }
+    }
+  }
+  return found;
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+ht_count_kernel(const SortWs<uint32_t> ws, int cur, const HtArgs h, const GlobalEmitArgs a) {
+  __shared__ int cnt;
+  const int pair = blockIdx.y;
+  const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
+  const int nb = (n + kTile - 1) / kTile;
+  if ((int)blockIdx.x >= nb) return;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  const uint32_t* keys = (cur ? ws.keys[1] : ws.keys[0]) + (size_t)pair * ws.rec_stride;
+  const uint32_t* vals = (cur ? ws.vals[1] : ws.vals[0]) + (size_t)pair * ws.rec_stride;
+  int mine = 0;
+  for (int r = 0; r < kRounds; r++) mine += ht_bucket<false>(keys, vals, blockIdx.x * kTile + kRounds * threadIdx.x + r, n, h, pair, a, 0);
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&cnt, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) ws.blockcount[(size_t)pair * (ws.nb_max + 1) + blockIdx.x] = cnt;
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+ht_emit_kernel(const SortWs<uint32_t> ws, int cur, const HtArgs h, const GlobalEmitArgs a) {
+  __shared__ int warp_base[kSortWarps];
+  const int pair = blockIdx.y;
+  const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
+  const int nb = (n + kTile - 1) / kTile;
+  if ((int)blockIdx.x >= nb) return;
+  const uint32_t* keys = (cur ? ws.keys[1] : ws.keys[0]) + (size_t)pair * ws.rec_stride;
+  const uint32_t* vals = (cur ? ws.vals[1] : ws.vals[0]) + (size_t)pair * ws.rec_stride;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int i0 = blockIdx.x * kTile + kRounds * tid;     // thread order = record order = bucket order
+  int c = 0;
+  for (int r = 0; r < kRounds; r++) c += ht_bucket<false>(keys, vals, i0 + r, n, h, pair, a, 0);
+  int incl = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+  if (lane == 31) warp_base[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    const int v = lane < kSortWarps ? warp_base[lane] : 0;
+    int wi = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += t; }
+    if (lane < kSortWarps) warp_base[lane] = wi - v;
+  }
+  __syncthreads();
+  long long slot = (long long)ws.blockcount[(size_t)pair * (ws.nb_max + 1) + blockIdx.x] + warp_base[wid] + (incl - c);
+  if (c == 0) return;
+  for (int r = 0; r < kRounds; r++) slot += ht_bucket<true>(keys, vals, i0 + r, n, h, pair, a, slot);
+}
+
 // ---- host-side launch sequences -----------------------------------------------------------------------
 static size_t pad256(size_t b) { return (b + 255) / 256 * 256; }
 
@@ -551,10 +683,9 @@ static SortWs<KeyT> carve(void* ws, long long max_records, int n_pairs, int H) {
 }
 
 template <typename KeyT>
-static cudaError_t sort_and_emit(SortWs<KeyT>& w, long long max_records, int n_pairs, int key_bits, const GlobalEmitArgs& ea,
-                                 cudaStream_t stream, int* launches) {
+static cudaError_t sort_passes(SortWs<KeyT>& w, long long max_records, int n_pairs, int key_bits, cudaStream_t stream, int* launches,
+                               int* cur_out) {
   const int nb = (int)((max_records + kTile - 1) / kTile);
-  if (nb <= 0 || n_pairs <= 0) return cudaSuccess;
   const dim3 grid(nb, n_pairs);
   {                                                       // per device and per call: cheap next to the sort itself
     cudaError_t e = cudaFuncSetAttribute(radix_scatter_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_smem_bytes<KeyT>());
@@ -567,6 +698,21 @@ static cudaError_t sort_and_emit(SortWs<KeyT>& w, long long max_records, int n_p
     radix_scatter_kernel<KeyT><<<grid, kSortThreads, scatter_smem_bytes<KeyT>(), stream>>>(w, cur, shift);
     cur ^= 1;
     *launches += 3;
+  }
+  *cur_out = cur;
+  return cudaGetLastError();
+}
+
+template <typename KeyT>
+static cudaError_t sort_and_emit(SortWs<KeyT>& w, long long max_records, int n_pairs, int key_bits, const GlobalEmitArgs& ea,
+                                 cudaStream_t stream, int* launches) {
+  const int nb = (int)((max_records + kTile - 1) / kTile);
+  if (nb <= 0 || n_pairs <= 0) return cudaSuccess;
+  const dim3 grid(nb, n_pairs);
+  int cur = 0;
+  {
+    cudaError_t e = sort_passes(w, max_records, n_pairs, key_bits, stream, launches, &cur);
+    if (e != cudaSuccess) return e;
   }
   global_tmax_kernel<KeyT><<<n_pairs, 32, 0, stream>>>(w, cur);
   global_count_kernel<KeyT><<<grid, kSortThreads, 0, stream>>>(w, cur, ea);
@@ -582,16 +728,35 @@ static cudaError_t sort_and_emit(SortWs<KeyT>& w, long long max_records, int n_p
 cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int W, int H, int n_pairs, int epipolar, int key_bits,
                                 int disp_high, int vertical_tolerance, int mode, void* ws, long long max_records, void* out,
                                 long long out_stride, long long cap, int32_t* n_out, int32_t* n_cand, cudaStream_t stream,
-                                int* launches) {
+                                int* launches, int hashtable) {
   GlobalEmitArgs ea{};
   ea.W = W; ea.disp_high = disp_high; ea.vertical_tolerance = vertical_tolerance; ea.mode = mode;
   ea.out = out; ea.out_stride = out_stride; ea.cap = cap; ea.n_out = n_out;
   const dim3 gather_grid((2 * H * 32 + 127) / 128, n_pairs);
   cudaError_t e;
+  if (hashtable) {                                       // inference.hpp:204-225: sort by bucket, then replay the buckets
+    SortWs<uint32_t> w = carve<uint32_t>(ws, max_records, n_pairs, H);
+    global_rowoff_kernel<<<dim3(2, n_pairs), 1024, 0, stream>>>(rowcnt, H, w.rowoff, w.n_side);
+    global_gather_kernel<uint32_t><<<gather_grid, 128, 0, stream>>>(hash, W, H, epipolar, 1, w);
+    *launches += 2;
+    const int nb = (int)((max_records + kTile - 1) / kTile);
+    if (nb <= 0 || n_pairs <= 0) return cudaGetLastError();
+    int cur = 0;
+    if ((e = sort_passes(w, max_records, n_pairs, 18, stream, launches, &cur)) != cudaSuccess) return e;   // 214673 < 2^18
+    HtArgs h{hash, W, H, epipolar};
+    const dim3 grid(nb, n_pairs);
+    ht_count_kernel<<<grid, kSortThreads, 0, stream>>>(w, cur, h, ea);
+    global_blockscan_kernel<uint32_t><<<n_pairs, 32, 0, stream>>>(w, ea);
+    ht_emit_kernel<<<grid, kSortThreads, 0, stream>>>(w, cur, h, ea);
+    *launches += 3;
+    e = cudaGetLastError();
+    if (e == cudaSuccess && n_cand) e = cudaMemcpyAsync(n_cand, w.n_side, (size_t)n_pairs * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
+    return e;
+  }
   if (epipolar) {
     SortWs<unsigned long long> w = carve<unsigned long long>(ws, max_records, n_pairs, H);
     global_rowoff_kernel<<<dim3(2, n_pairs), 1024, 0, stream>>>(rowcnt, H, w.rowoff, w.n_side);
-    global_gather_kernel<unsigned long long><<<gather_grid, 128, 0, stream>>>(hash, W, H, 1, w);
+    global_gather_kernel<unsigned long long><<<gather_grid, 128, 0, stream>>>(hash, W, H, 1, 0, w);
     *launches += 2;
     int hb = 1; while ((1 << hb) < H) hb++;
     e = sort_and_emit(w, max_records, n_pairs, 32 + hb, ea, stream, launches);
@@ -600,7 +765,7 @@ cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int
   }
   SortWs<uint32_t> w = carve<uint32_t>(ws, max_records, n_pairs, H);
   global_rowoff_kernel<<<dim3(2, n_pairs), 1024, 0, stream>>>(rowcnt, H, w.rowoff, w.n_side);
-  global_gather_kernel<uint32_t><<<gather_grid, 128, 0, stream>>>(hash, W, H, 0, w);
+  global_gather_kernel<uint32_t><<<gather_grid, 128, 0, stream>>>(hash, W, H, 0, 0, w);
   *launches += 2;
   e = sort_and_emit(w, max_records, n_pairs, key_bits, ea, stream, launches);
   if (e == cudaSuccess && n_cand) e = cudaMemcpyAsync(n_cand, w.n_side, (size_t)n_pairs * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);

@@ -276,6 +276,108 @@ int gpco_match(const int32_t* mask_l, const uint32_t* st_l, int nl,
 }
 
 /* ------------------------------------------------------------------------------------------
+ * useHashtable(true): ndb::Hashmatch (hashmatch.hpp:48-272) as driven by depthPriorFast
+ * (inference.hpp:204-225).  214673 buckets, bucket = key % 214673 (buffer.hpp:84-86); all src
+ * descriptors are inserted first, then all tar descriptors, each in list order.
+ *
+ * A bucket is a linked list kept ascending by key.  insert() (hashmatch.hpp:93-134) drops the
+ * element when the bucket already holds 10, otherwise places it behind every element whose key
+ * is <= its own: the bucket is the stable ascending order of the first 10 elements offered to it.
+ * getDuplicates() (:162-198) walks the list once; restated on an array below.
+ * ---------------------------------------------------------------------------------------- */
+#define GPCO_HT_BUCKETS 214673   /* inference.hpp:212 */
+#define GPCO_HT_DEPTH 10         /* hashmatch.hpp:95 terminateAfter */
+
+typedef struct { uint64_t key; int32_t idx; int32_t is_src; } ht_item;
+
+/* walk of one bucket (hashmatch.hpp:162-198); L = list in order, m = its length */
+static int ht_walk(const ht_item* L, int m, int32_t* out_pairs, int n_out) {
+  int j = 0;
+  while (j < m) {
+    int p = j;                         /* prev = next; next = next->next  (:167-168) */
+    j = j + 1;
+    if (j < m && L[p].key == L[j].key) {                       /* :171 */
+      if (L[p].is_src != L[j].is_src) {                        /* :172 diffImgs */
+        if (j + 1 < m) {                                       /* :174 a third element exists */
+          if (L[j + 1].key != L[j].key) {                      /* :176 */
+            out_pairs[2 * n_out] = L[p].idx; out_pairs[2 * n_out + 1] = L[j].idx; n_out++;
+          }
+          if (j + 2 >= m) return n_out;                        /* :179 the last triplet was just checked */
+        } else {                                               /* :181 */
+          out_pairs[2 * n_out] = L[p].idx; out_pairs[2 * n_out + 1] = L[j].idx; n_out++;
+        }
+      } else if (j + 1 < m && L[j].is_src != L[j + 1].is_src) { /* :189 skip over the false pair */
+        j = j + 1;
+      }
+    }
+  }
+  return n_out;
+}
+
+int gpco_hashmatch(const uint64_t* src, int ns, const uint64_t* tar, int nt, int32_t* out_pairs) {
+  int n = ns + nt;
+  /* bucket contents in insertion order: counting sort of the insertion sequence by bucket */
+  int32_t* start = (int32_t*)calloc((size_t)GPCO_HT_BUCKETS + 1, sizeof(int32_t));
+  int32_t* order = (int32_t*)malloc((size_t)(n > 0 ? n : 1) * sizeof(int32_t));
+  for (int i = 0; i < n; i++) start[(i < ns ? src[i] : tar[i - ns]) % GPCO_HT_BUCKETS + 1]++;
+  for (int b = 0; b < GPCO_HT_BUCKETS; b++) start[b + 1] += start[b];
+  int32_t* fill = (int32_t*)malloc((size_t)GPCO_HT_BUCKETS * sizeof(int32_t));
+  memcpy(fill, start, (size_t)GPCO_HT_BUCKETS * sizeof(int32_t));
+  for (int i = 0; i < n; i++) order[fill[(i < ns ? src[i] : tar[i - ns]) % GPCO_HT_BUCKETS]++] = i;
+  int n_out = 0;
+  for (int b = 0; b < GPCO_HT_BUCKETS; b++) {                  /* hashmatch.hpp:254-259: buckets in index order */
+    ht_item L[GPCO_HT_DEPTH];
+    int m = 0;
+    for (int q = start[b]; q < start[b + 1] && m < GPCO_HT_DEPTH; q++) {   /* :101 a full bucket drops the rest */
+      int i = order[q];
+      ht_item e;
+      e.is_src = i < ns; e.idx = e.is_src ? i : i - ns; e.key = e.is_src ? src[i] : tar[i - ns];
+      int pos = m;                                             /* :112-116 behind every element <= e */
+      while (pos > 0 && L[pos - 1].key > e.key) { L[pos] = L[pos - 1]; pos--; }
+      L[pos] = e;
+      m++;
+    }
+    n_out = ht_walk(L, m, out_pairs, n_out);
+  }
+  free(start); free(order); free(fill);
+  return n_out;
+}
+
+/* depthPriorFast with useHashtable_ (inference.hpp:204-225) + rectifiedMatch (:375-393).  A pair is
+ * (first, second) in list order; src elements precede equal tar elements, so first is always src. */
+int gpco_match_hashtable(const int32_t* mask_l, const uint32_t* st_l, int nl,
+                         const int32_t* mask_r, const uint32_t* st_r, int nr,
+                         int w, const gpco_settings* s,
+                         gpco_correspondence* corr, int* n_corr, gpco_support* supp) {
+  uint64_t* kl = (uint64_t*)malloc((size_t)(nl > 0 ? nl : 1) * 8);
+  uint64_t* kr = (uint64_t*)malloc((size_t)(nr > 0 ? nr : 1) * 8);
+  for (int i = 0; i < nl; i++) {
+    kl[i] = st_l[i];
+    if (s->epipolar_mode) kl[i] |= (uint64_t)(uint32_t)(mask_l[i] / w) << 32;
+  }
+  for (int i = 0; i < nr; i++) {
+    kr[i] = st_r[i];
+    if (s->epipolar_mode) kr[i] |= (uint64_t)(uint32_t)(mask_r[i] / w) << 32;
+  }
+  int cap = nl < nr ? nl : nr;
+  int32_t* pairs = (int32_t*)malloc((size_t)(cap > 0 ? cap : 1) * 8);
+  int m = gpco_hashmatch(kl, nl, kr, nr, pairs);
+  int ns = 0;
+  for (int i = 0; i < m; i++) {
+    int ks = mask_l[pairs[2 * i]], kt = mask_r[pairs[2 * i + 1]];
+    int xs = ks % w, ys = ks / w, xt = kt % w, yt = kt / w;
+    if (corr) { corr[i].xs = xs; corr[i].ys = ys; corr[i].xt = xt; corr[i].yt = yt; }
+    if (abs(ys - yt) <= s->vertical_tolerance && abs(xs - xt) <= s->disp_high) {
+      supp[ns].x = xs; supp[ns].y = ys; supp[ns].d = (float)(xs - xt);
+      ns++;
+    }
+  }
+  if (n_corr) *n_corr = m;
+  free(kl); free(kr); free(pairs);
+  return ns;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Row R: Forest::readForest (inference.hpp:404-446)
  * ---------------------------------------------------------------------------------------- */
 int gpco_read_forest(const char* path, gpco_forest* f) {
@@ -306,8 +408,8 @@ int gpco_read_forest(const char* path, gpco_forest* f) {
 }
 
 /* sparsematch.cpp:46-51 */
-int gpco_pair(const uint8_t* L, const uint8_t* R, int w, int h, const gpco_forest* f,
-              const gpco_settings* s, gpco_support* supp, int* n_cand_l, int* n_cand_r) {
+static int pair_impl(const uint8_t* L, const uint8_t* R, int w, int h, const gpco_forest* f,
+                     const gpco_settings* s, gpco_support* supp, int* n_cand_l, int* n_cand_r, int use_hashtable) {
   size_t P = (size_t)w * h;
   uint8_t* sm[2]; uint8_t* gr[2]; int32_t* mk[2]; uint32_t* st[2]; int n[2];
   const uint8_t* img[2] = { L, R };
@@ -320,9 +422,20 @@ int gpco_pair(const uint8_t* L, const uint8_t* R, int w, int h, const gpco_fores
     st[k] = (uint32_t*)malloc((size_t)(n[k] > 0 ? n[k] : 1) * 4);
     gpco_hash(sm[k], w, h, f, mk[k], n[k], st[k]);
   }
-  int ns = gpco_match(mk[0], st[0], n[0], mk[1], st[1], n[1], w, s, NULL, NULL, supp);
+  int ns = use_hashtable ? gpco_match_hashtable(mk[0], st[0], n[0], mk[1], st[1], n[1], w, s, NULL, NULL, supp)
+                         : gpco_match(mk[0], st[0], n[0], mk[1], st[1], n[1], w, s, NULL, NULL, supp);
   if (n_cand_l) *n_cand_l = n[0];
   if (n_cand_r) *n_cand_r = n[1];
   for (int k = 0; k < 2; k++) { free(sm[k]); free(gr[k]); free(mk[k]); free(st[k]); }
   return ns;
+}
+
+int gpco_pair(const uint8_t* L, const uint8_t* R, int w, int h, const gpco_forest* f,
+              const gpco_settings* s, gpco_support* supp, int* n_cand_l, int* n_cand_r) {
+  return pair_impl(L, R, w, h, f, s, supp, n_cand_l, n_cand_r, 0);
+}
+
+int gpco_pair_hashtable(const uint8_t* L, const uint8_t* R, int w, int h, const gpco_forest* f,
+                        const gpco_settings* s, gpco_support* supp, int* n_cand_l, int* n_cand_r) {
+  return pair_impl(L, R, w, h, f, s, supp, n_cand_l, n_cand_r, 1);
 }

@@ -70,6 +70,14 @@ int gpco_match(const int32_t* mask_l, const uint32_t* st_l, int nl,
                int w, const gpco_settings* s,
                gpco_correspondence* corr, int* n_corr,   /* may be NULL */
                gpco_support* supp);                       /* capacity >= min(nl,nr) */
+/* useHashtable(true): ndb::Hashmatch (hashmatch.hpp:48-272) driven as in inference.hpp:204-225, on bare keys;
+ * out = (index into src, index into tar) pairs in the reference's output order (bucket index, then list order) */
+int gpco_hashmatch(const uint64_t* src, int ns, const uint64_t* tar, int nt, int32_t* out_pairs);
+/* gpco_match with the hashtable matcher in place of findCorrespondences */
+int gpco_match_hashtable(const int32_t* mask_l, const uint32_t* st_l, int nl,
+                         const int32_t* mask_r, const uint32_t* st_r, int nr,
+                         int w, const gpco_settings* s,
+                         gpco_correspondence* corr, int* n_corr, gpco_support* supp);
 /* inference.hpp:404-446; returns 0 ok, -1 cannot open */
 int gpco_read_forest(const char* path, gpco_forest* f);
 
@@ -77,6 +85,10 @@ int gpco_read_forest(const char* path, gpco_forest* f);
  * Any of the optional outputs may be NULL.  Returns number of supports. */
 int gpco_pair(const uint8_t* L, const uint8_t* R, int w, int h, const gpco_forest* f,
               const gpco_settings* s, gpco_support* supp, int* n_cand_l, int* n_cand_r);
+
+/* gpco_pair with InferenceSettings::useHashtable(true) */
+int gpco_pair_hashtable(const uint8_t* L, const uint8_t* R, int w, int h, const gpco_forest* f,
+                        const gpco_settings* s, gpco_support* supp, int* n_cand_l, int* n_cand_r);
 
 #ifdef __cplusplus
 }

@@ -112,6 +112,39 @@ int ref_find_correspondences(const uint64_t* src, int ns, const uint64_t* tar, i
   return (int)c.size();
 }
 
+// ndb::Hashmatch driven exactly as depthPriorFast drives it (inference.hpp:204-225) on bare keys;
+// point.x carries the input index.
+int ref_hashmatch(const uint64_t* src, int ns, const uint64_t* tar, int nt, int32_t* out_pairs) {
+  ndb::Hashmatch<ndb::Descriptor> hm(214673, ns + nt);
+  for (int i = 0; i < ns; i++) { ndb::Descriptor d(ndb::Point(i, 0), src[i]); d.srcDescr = true; hm.insert(d); }
+  for (int i = 0; i < nt; i++) { ndb::Descriptor d(ndb::Point(i, 0), tar[i]); d.srcDescr = false; hm.insert(d); }
+  std::vector<std::pair<ndb::Descriptor, ndb::Descriptor>> corr;
+  hm.getDuplicates(corr);
+  for (size_t i = 0; i < corr.size(); i++) {
+    out_pairs[2 * i] = corr[i].first.point.x;
+    out_pairs[2 * i + 1] = corr[i].second.point.x;
+  }
+  return (int)corr.size();
+}
+
+// ref_pair with InferenceSettings::useHashtable(true) (inference.hpp:204-225).
+int ref_pair_hashtable(const uint8_t* L, const uint8_t* R, int w, int h, const char* forest_path,
+                       int thr, int disp_high, int vt, int epipolar, ref_support* supp, int cap) {
+  Quiet q;
+  Forest forest;
+  Settings s = make_settings(thr, disp_high, vt, epipolar, 1).useHashtable(true);
+  ndb::Buffer<uint8_t> simg = to_buffer(L, w, h), timg = to_buffer(R, w, h);
+  Forest::FilterMask fm = forest.readForest(forest_path, (int)simg.cols(), (int)simg.rows());
+  Forest::PreprocessedImage sp = forest.preprocessImage(simg, s);
+  Forest::PreprocessedImage tp = forest.preprocessImage(timg, s);
+  zero_unwritten_row(sp);
+  zero_unwritten_row(tp);
+  std::vector<ndb::Support> out = forest.rectifiedMatch(sp, tp, fm, s);
+  if ((int)out.size() > cap) return -(int)out.size();
+  for (size_t i = 0; i < out.size(); i++) { supp[i].x = out[i].x; supp[i].y = out[i].y; supp[i].d = out[i].d; }
+  return (int)out.size();
+}
+
 // The sparsematch.cpp:42-51 window.  Returns the support count (or -required if cap is too small).
 int ref_pair(const uint8_t* L, const uint8_t* R, int w, int h, const char* forest_path,
              int thr, int disp_high, int vt, int epipolar, int num_threads,

@@ -27,19 +27,23 @@ int main(int argc, char** argv) {
     gi::Forest::PreprocessedImage lq(lp.smooth, lp.grad, lp.mask), rq(rp.smooth, rp.grad, rp.mask);
     std::vector<ndb::Support> supp2 = forest.rectifiedMatch(lq, rq, fm, st);
     std::vector<ndb::Descriptor> desc = forest.evalFastMaskOnSubsetSSE(lp.smooth, lp.grad, lp.mask, fm, st);
-    // useHashtable must be refused, not silently mapped to the sort path
+    // useHashtable(true): the reference's hashtable matcher on resident images; refused for hand-built ones
+    gi::InferenceSettings hs = st;
+    hs.useHashtable(true);
+    std::vector<ndb::Support> supp_ht = forest.rectifiedMatch(lp, rp, fm, hs);
     bool refused = false;
-    try { gi::InferenceSettings h = st; h.useHashtable(true); forest.rectifiedMatch(lp, rp, fm, h); }
+    try { forest.rectifiedMatch(lq, rq, fm, hs); }
     catch (const gi::GpcError& e) { refused = (e.status == GPC_E_UNSUPPORTED); }
-    if (!refused) { std::cerr << "useHashtable(true) was not refused\n"; return 4; }
+    if (!refused) { std::cerr << "useHashtable(true) on hand-built images was not refused\n"; return 4; }
     std::vector<int32_t> out = {(int32_t)lp.mask.size(), (int32_t)rp.mask.size(), (int32_t)supp.size(), (int32_t)corr.size(),
-                                (int32_t)supp2.size(), (int32_t)desc.size()};
+                                (int32_t)supp2.size(), (int32_t)desc.size(), (int32_t)supp_ht.size()};
     for (int v : lp.mask) out.push_back(v);
     for (int v : rp.mask) out.push_back(v);
     for (auto& s : supp) { out.push_back(s.x); out.push_back(s.y); out.push_back((int32_t)s.d); }
     for (auto& c : corr) { out.push_back(c.srcPt.x); out.push_back(c.srcPt.y); out.push_back(c.tarPt.x); out.push_back(c.tarPt.y); }
     for (auto& s : supp2) { out.push_back(s.x); out.push_back(s.y); out.push_back((int32_t)s.d); }
     for (auto& d : desc) out.push_back((int32_t)(uint32_t)d.state);
+    for (auto& s : supp_ht) { out.push_back(s.x); out.push_back(s.y); out.push_back((int32_t)s.d); }
     FILE* fp = std::fopen(argv[4], "wb");
     if (!fp) return 5;
     std::fwrite(out.data(), sizeof(int32_t), out.size(), fp);

@@ -136,6 +136,34 @@ class Oracle:
         m = self.lib.gpco_find_correspondences(_p(src), C.c_int(len(src)), _p(tar), C.c_int(len(tar)), _p(out))
         return out[:2 * m].reshape(-1, 2).copy()
 
+    def hashmatch(self, src, tar):
+        """useHashtable(true) matcher on bare keys: (src index, tar index) pairs in the reference's order."""
+        src = np.ascontiguousarray(src, np.uint64)
+        tar = np.ascontiguousarray(tar, np.uint64)
+        out = np.empty(2 * max(min(len(src), len(tar)), 1), np.int32)
+        m = self.lib.gpco_hashmatch(_p(src), C.c_int(len(src)), _p(tar), C.c_int(len(tar)), _p(out))
+        return out[:2 * m].reshape(-1, 2).copy()
+
+    def pair_hashtable(self, Lm, Rm, forest, s):
+        h, w = Lm.shape
+        supp = np.empty(max((w - 26) * (h - 26), 1), SUPPORT_DTYPE)
+        n = self.lib.gpco_pair_hashtable(_p(np.ascontiguousarray(Lm)), _p(np.ascontiguousarray(Rm)), C.c_int(w),
+                                         C.c_int(h), C.byref(forest), C.byref(s), _p(supp), None, None)
+        return supp[:n].copy()
+
+    def correspondences_hashtable(self, Lm, Rm, forest, s):
+        h, w = Lm.shape
+        thr = s.gradient_threshold
+        _, _, mkl, stl = self.stages(Lm, forest, thr)
+        _, _, mkr, str_ = self.stages(Rm, forest, thr)
+        cap = max(min(len(mkl), len(mkr)), 1)
+        corr = np.empty((cap, 4), np.int32)
+        supp = np.empty(cap, SUPPORT_DTYPE)
+        nc = C.c_int(0)
+        self.lib.gpco_match_hashtable(_p(mkl), _p(stl), C.c_int(len(mkl)), _p(mkr), _p(str_), C.c_int(len(mkr)),
+                                      C.c_int(w), C.byref(s), _p(corr), C.byref(nc), _p(supp))
+        return corr[:nc.value].copy()
+
     def match(self, mask_l, st_l, mask_r, st_r, w, s):
         mask_l = np.ascontiguousarray(mask_l, np.int32)
         mask_r = np.ascontiguousarray(mask_r, np.int32)
@@ -227,6 +255,23 @@ class Reference:
         out = np.empty(2 * max(min(len(src), len(tar)), 1), np.int32)
         m = self.lib.ref_find_correspondences(_p(src), C.c_int(len(src)), _p(tar), C.c_int(len(tar)), _p(out))
         return out[:2 * m].reshape(-1, 2).copy()
+
+    def hashmatch(self, src, tar):
+        src = np.ascontiguousarray(src, np.uint64)
+        tar = np.ascontiguousarray(tar, np.uint64)
+        out = np.empty(2 * max(min(len(src), len(tar)), 1), np.int32)
+        m = self.lib.ref_hashmatch(_p(src), C.c_int(len(src)), _p(tar), C.c_int(len(tar)), _p(out))
+        return out[:2 * m].reshape(-1, 2).copy()
+
+    def pair_hashtable(self, Lm, Rm, forest_path, thr=5, disp_high=128, vt=0, epipolar=True):
+        h, w = Lm.shape
+        cap = max((w - 26) * (h - 26), 1)
+        supp = np.empty(cap, SUPPORT_DTYPE)
+        n = self.lib.ref_pair_hashtable(_p(np.ascontiguousarray(Lm)), _p(np.ascontiguousarray(Rm)), C.c_int(w),
+                                        C.c_int(h), forest_path.encode(), C.c_int(thr), C.c_int(disp_high),
+                                        C.c_int(vt), C.c_int(int(epipolar)), _p(supp), C.c_int(cap))
+        assert n >= 0
+        return supp[:n].copy()
 
     def pair(self, Lm, Rm, forest_path, thr=5, disp_high=128, vt=0, epipolar=True, num_threads=1):
         h, w = Lm.shape

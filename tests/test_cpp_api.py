@@ -97,14 +97,15 @@ def test_cpp_api_vs_oracle(oracle, forest, epipolar, vt, dh, thr, w, h):
             assert r.stdout.count("Note: A maximum of 32 fern features") == 160
         assert "number of ferns:" in r.stdout
         v = np.fromfile(pout, np.int32)
-    nL, nR, nS, nC, nS2, nD = v[:6]
-    p = 6
+    nL, nR, nS, nC, nS2, nD, nH = v[:7]
+    p = 7
     maskL = v[p:p + nL]; p += nL
     maskR = v[p:p + nR]; p += nR
     supp = v[p:p + 3 * nS].reshape(-1, 3); p += 3 * nS
     corr = v[p:p + 4 * nC].reshape(-1, 4); p += 4 * nC
     supp2 = v[p:p + 3 * nS2].reshape(-1, 3); p += 3 * nS2
-    states = v[p:p + nD].view(np.uint32)
+    states = v[p:p + nD].view(np.uint32); p += nD
+    supp_ht = v[p:p + 3 * nH].reshape(-1, 3)
     _, _, omkL, ostL = oracle.stages(Lp, of, thr)
     _, _, omkR, _ = oracle.stages(Rp, of, thr)
     assert np.array_equal(maskL, omkL) and np.array_equal(maskR, omkR)
@@ -114,6 +115,8 @@ def test_cpp_api_vs_oracle(oracle, forest, epipolar, vt, dh, thr, w, h):
     assert np.array_equal(supp, want)
     assert np.array_equal(supp2, want), "hand-built PreprocessedImage path differs"
     assert np.array_equal(corr, oracle.correspondences(Lp, Rp, of, s))
+    ht = oracle.pair_hashtable(Lp, Rp, of, s)
+    assert np.array_equal(supp_ht, np.stack([ht["x"], ht["y"], ht["d"].astype(np.int32)], 1)), "useHashtable(true) differs"
 
 
 @pytest.mark.gpu

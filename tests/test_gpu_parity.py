@@ -205,9 +205,6 @@ def test_error_codes(g, ctx_small):
     assert e.value.status == capi.GPC_E_DIMS
     img = np.zeros((64, 64), np.uint8)
     with pytest.raises(g.GpcError) as e:
-        ctx_small.match_pair(img, img, g.make_settings(epipolar=True, use_hashtable=True))
-    assert e.value.status == capi.GPC_E_UNSUPPORTED
-    with pytest.raises(g.GpcError) as e:
         ctx_small.match_pair(img, img, s, cap=0) if False else ctx_small.set_forest(g.make_forest([(14, 0, 0, 0)], [0]))
     assert e.value.status == capi.GPC_E_FOREST
 
