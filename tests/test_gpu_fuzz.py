@@ -1,5 +1,6 @@
 """Randomised parity campaign (pytest -m gpu): random shapes, textures, thresholds, forests and settings
-against the oracle, every case through the whole path in both matching modes.  GPC_FUZZ_CASES scales it up."""
+against the oracle, every case through the whole path in both matching modes, every third also through the
+hashtable matcher.  GPC_FUZZ_CASES scales it up."""
 import os
 
 import numpy as np
@@ -62,3 +63,7 @@ def test_fuzz_vs_oracle(oracle):
             info = (it, w, h, nt, tkind, thr, dh, epi, vt, mode)
             assert (ncl, ncr) == (ocl, ocr), info
             assert np.array_equal(supp, ref), info + (len(supp), len(ref))
+            if it % 3 == 0:                                         # the same case through useHashtable(true)
+                ref_h = oracle.pair_hashtable(L, R, of, osettings(thr, dh, vt, epi))
+                supp_h, _, _ = ctx.match_pair(L, R, g.make_settings(thr=thr, disp_high=dh, vt=vt, epipolar=epi, use_hashtable=True))
+                assert np.array_equal(supp_h, ref_h), info + ("hashtable", len(supp_h), len(ref_h))
