@@ -22,8 +22,7 @@
 //     what the resident path computes.  PreprocessedImage objects built by hand (no handle) go
 //     through evalFastMaskOnSubsetSSE + findCorrespondences on the caller's smooth / mask data.
 //   * useHashtable(true) reproduces the reference's hashtable matcher (hashmatch.hpp:48-272: 214673 buckets of
-//     at most 10 elements, a different and smaller match set) for images that carry their device handle;
-//     with hand-built PreprocessedImages it throws GPC_E_UNSUPPORTED.
+//     at most 10 elements, a different and smaller match set than the sort path).
 //   * numThreads is accepted and ignored.
 #ifndef GPC_B200_INFERENCE_HPP
 #define GPC_B200_INFERENCE_HPP
@@ -260,14 +259,13 @@ class Forest {
         corr.push_back(ndb::Correspondence(ndb::Point(raw[i].xs, raw[i].ys), ndb::Point(raw[i].xt, raw[i].yt)));
       return corr;
     }
-    if (settings.useHashtable_)
-      throw GpcError(GPC_E_UNSUPPORTED, "useHashtable(true) needs images preprocessed by preprocessImage (device handle)");
     std::vector<ndb::Descriptor> a = evalFastMaskOnSubsetSSE(src.smooth, src.grad, src.mask, fastmask, settings);
     std::vector<ndb::Descriptor> b = evalFastMaskOnSubsetSSE(tar.smooth, tar.grad, tar.mask, fastmask, settings);
     if (settings.epipolarMode_) {
       for (auto& el : a) el.state |= uint64_t(el.point.y) << 32;
       for (auto& el : b) el.state |= uint64_t(el.point.y) << 32;
     }
+    if (settings.useHashtable_) return hashMatch(a, b);          // inference.hpp:204-225
     return findCorrespondences(a, b);
   }
 
@@ -304,6 +302,24 @@ class Forest {
     int n = 0;
     detail::check(c, gpc_find_correspondences(c, ks.data(), (int)ks.size(), kt.data(), (int)kt.size(), pairs.data(),
                                               (int)(pairs.size() / 2), &n), "gpc_find_correspondences");
+    corr.reserve((size_t)n);
+    for (int i = 0; i < n; i++) corr.push_back(ndb::Correspondence(srcStates[pairs[2 * i]].point, tarStates[pairs[2 * i + 1]].point));
+    return corr;
+  }
+
+  // ndb::Hashmatch<Descriptor> as depthPriorFast drives it (inference.hpp:204-225; CUDA, gpc_hashmatch).
+  std::vector<ndb::Correspondence> hashMatch(std::vector<ndb::Descriptor>& srcStates, std::vector<ndb::Descriptor>& tarStates) {
+    std::vector<ndb::Correspondence> corr;
+    if (srcStates.empty() || tarStates.empty()) return corr;
+    auto rt = detail::runtime();
+    gpc_ctx* c = rt->get(std::max(rt->max_w, 16), std::max(rt->max_h, 1));
+    std::vector<uint64_t> ks(srcStates.size()), kt(tarStates.size());
+    for (size_t i = 0; i < ks.size(); i++) ks[i] = srcStates[i].state;
+    for (size_t i = 0; i < kt.size(); i++) kt[i] = tarStates[i].state;
+    std::vector<int32_t> pairs(2 * std::min(ks.size(), kt.size()));
+    int n = 0;
+    detail::check(c, gpc_hashmatch(c, ks.data(), (int)ks.size(), kt.data(), (int)kt.size(), pairs.data(), (int)(pairs.size() / 2), &n),
+                  "gpc_hashmatch");
     corr.reserve((size_t)n);
     for (int i = 0; i < n; i++) corr.push_back(ndb::Correspondence(srcStates[pairs[2 * i]].point, tarStates[pairs[2 * i + 1]].point));
     return corr;

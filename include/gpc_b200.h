@@ -158,6 +158,13 @@ int gpc_correspond_images(gpc_ctx* ctx, const gpc_image* left, const gpc_image* 
  * reference) yields no matches. */
 int gpc_find_correspondences(gpc_ctx* ctx, const uint64_t* src_keys, int n_src, const uint64_t* tar_keys,
                              int n_tar, int32_t* out_pairs, int cap, int* n_out);
+/* ndb::Hashmatch<Descriptor> (hashmatch.hpp:208-272) driven as depthPriorFast does with useHashtable
+ * (inference.hpp:204-225) on explicit 64-bit keys: 214673 buckets (key % 214673), all src keys inserted
+ * first, then all tar keys; a bucket keeps the first 10 elements offered to it in stable ascending key
+ * order and is walked by getDuplicates' rules (hashmatch.hpp:162-198).  out_pairs as above, in the
+ * reference's output order: bucket index, then list order. */
+int gpc_hashmatch(gpc_ctx* ctx, const uint64_t* src_keys, int n_src, const uint64_t* tar_keys, int n_tar,
+                  int32_t* out_pairs, int cap, int* n_out);
 
 /* Matcher selection.  AUTO: epipolar mode uses the per-row shared-memory matcher, global mode the
  * device-wide radix sort + segmented scan.  SORT forces the radix-sort matcher for both (same

@@ -36,6 +36,8 @@ cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int
                                 int disp_high, int vertical_tolerance, int mode, void* ws, long long max_records, void* out,
                                 long long out_stride, long long cap, int32_t* n_out, int32_t* n_cand, cudaStream_t stream,
                                 int* launches, int hashtable);
+cudaError_t launch_hashmatch_keys(void* ws, long long max_records, const unsigned long long* d_keys64, int ns, int nt, int32_t* out_pairs,
+                                  long long cap, int32_t* n_out, cudaStream_t stream, int* launches);
 cudaError_t launch_match_keys(void* ws, long long max_records, int ns, int nt, int key_bits, int32_t* out_pairs, long long cap,
                               int32_t* n_out, cudaStream_t stream, int* launches);
 void* global_key_buffer(void* ws, long long max_records);
@@ -970,6 +972,40 @@ int gpc_find_correspondences(gpc_ctx* c, const uint64_t* src_keys, int n_src, co
   }
   cudaFree(d_pairs);
   if (e != cudaSuccess) return fail(c, GPC_E_CUDA, std::string("gpc_find_correspondences: ") + cudaGetErrorString(e));
+  if (*n_out > cap) return fail(c, GPC_E_CAPACITY, "pair buffer too small: need " + std::to_string(*n_out));
+  return GPC_OK;
+}
+
+// ndb::Hashmatch as depthPriorFast drives it with useHashtable (inference.hpp:204-225, hashmatch.hpp:48-272)
+// on explicit 64-bit keys: all src keys inserted, then all tar keys; pairs in bucket order, then list order.
+int gpc_hashmatch(gpc_ctx* c, const uint64_t* src_keys, int n_src, const uint64_t* tar_keys, int n_tar,
+                  int32_t* out_pairs, int cap, int* n_out) {
+  if (!c || !n_out || n_src < 0 || n_tar < 0 || cap < 0 || (cap > 0 && !out_pairs)) return fail(c, GPC_E_ARG, "null argument");
+  *n_out = 0;
+  if (n_src == 0 || n_tar == 0) return GPC_OK;                 // a match needs one element of each list
+  if (!src_keys || !tar_keys) return fail(c, GPC_E_ARG, "null argument");
+  if ((long long)n_src + n_tar >= 0x7fffffffll) return fail(c, GPC_E_DIMS, "too many descriptors");
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  const long long n = (long long)n_src + n_tar;
+  int rc = ensure_global_ws(c, gpc::global_workspace_bytes(n + 2, 1, 0)); if (rc) return rc;
+  const long long need = std::min<long long>(n_src, n_tar);
+  uint8_t* d_tmp = nullptr;                                    // keys, then the output pairs
+  GPC_CUDA(c, cudaMalloc(&d_tmp, (size_t)n * 8 + (size_t)std::max<long long>(need, 1) * 2 * sizeof(int32_t)));
+  unsigned long long* d_keys = reinterpret_cast<unsigned long long*>(d_tmp);
+  int32_t* d_pairs = reinterpret_cast<int32_t*>(d_tmp + (size_t)n * 8);
+  cudaError_t e = cudaMemcpyAsync(d_keys, src_keys, (size_t)n_src * 8, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_keys + n_src, tar_keys, (size_t)n_tar * 8, cudaMemcpyHostToDevice, c->stream);
+  int launches = 0;
+  if (e == cudaSuccess) e = gpc::launch_hashmatch_keys(c->d_gws, n + 2, d_keys, n_src, n_tar, d_pairs, need, c->d_totals, c->stream, &launches);
+  c->launches += launches;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_counts, c->d_totals, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess) {
+    *n_out = c->h_counts[0];
+    if (*n_out <= cap && *n_out > 0) e = cudaMemcpy(out_pairs, d_pairs, (size_t)*n_out * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d_tmp);
+  if (e != cudaSuccess) return fail(c, GPC_E_CUDA, std::string("gpc_hashmatch: ") + cudaGetErrorString(e));
   if (*n_out > cap) return fail(c, GPC_E_CAPACITY, "pair buffer too small: need " + std::to_string(*n_out));
   return GPC_OK;
 }

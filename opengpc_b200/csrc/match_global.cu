@@ -528,13 +528,19 @@ global_emit_kernel(const SortWs<KeyT> ws, int cur, const GlobalEmitArgs a) {
 
 // ---- useHashtable(true): replay of the reference's buckets -------------------------------------------
 struct HtArgs {
-  const uint32_t* hash;              // hash images of the chunk's first pair
-  int32_t W, H, epipolar;
+  const uint32_t* hash;              // hash images of the chunk's first pair, or
+  const unsigned long long* keys64;  // explicit keys (src then tar); vals then index this list
+  int32_t W, H, epipolar, n_src;
 };
 
 __device__ __forceinline__ void write_match(const GlobalEmitArgs& a, int pair, long long slot, uint32_t vl, uint32_t vr) {
   if (slot >= a.cap) return;
   const long long idx = (long long)pair * a.out_stride + slot;
+  if (a.mode == 2) {
+    int32_t* o = reinterpret_cast<int32_t*>(a.out) + 2 * idx;
+    o[0] = (int32_t)vl; o[1] = (int32_t)vr;
+    return;
+  }
   const int xl = (int)(vl % (uint32_t)a.W), yl = (int)(vl / (uint32_t)a.W);
   const int xr = (int)(vr % (uint32_t)a.W), yr = (int)(vr / (uint32_t)a.W);
   if (a.mode == 0) {
@@ -562,14 +568,19 @@ __device__ int ht_bucket(const uint32_t* __restrict__ keys, const uint32_t* __re
   if (i >= n) return 0;
   const uint32_t b = keys[i];
   if (i > 0 && keys[i - 1] == b) return 0;
-  const uint32_t* img = h.hash + (size_t)(2 * pair) * h.H * h.W;
+  const uint32_t* img = h.keys64 ? nullptr : h.hash + (size_t)(2 * pair) * h.H * h.W;
   unsigned long long lk[kHtDepth];                       // the bucket's list: keys ascending, ties in insertion order
   uint32_t lv[kHtDepth];
   int m = 0;
   for (int j = i; j < n && m < kHtDepth && keys[j] == b; j++) {        // hashmatch.hpp:101: a full bucket drops the rest
     const uint32_t v = vals[j], pix = v & ~kSideBit;
-    unsigned long long k = img[(size_t)(v >> 31) * h.H * h.W + pix] & 0x7fffffffu;
-    if (h.epipolar) k |= (unsigned long long)(pix / (uint32_t)h.W) << 32;
+    unsigned long long k;
+    if (h.keys64) {
+      k = h.keys64[(v >> 31) ? h.n_src + pix : pix];
+    } else {
+      k = img[(size_t)(v >> 31) * h.H * h.W + pix] & 0x7fffffffu;
+      if (h.epipolar) k |= (unsigned long long)(pix / (uint32_t)h.W) << 32;
+    }
     int pos = m;                                         // :112-116: behind every element with key <= k
     while (pos > 0 && lk[pos - 1] > k) { lk[pos] = lk[pos - 1]; lv[pos] = lv[pos - 1]; pos--; }
     lk[pos] = k; lv[pos] = v;
@@ -743,7 +754,7 @@ cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int
     if (nb <= 0 || n_pairs <= 0) return cudaGetLastError();
     int cur = 0;
     if ((e = sort_passes(w, max_records, n_pairs, 18, stream, launches, &cur)) != cudaSuccess) return e;   // 214673 < 2^18
-    HtArgs h{hash, W, H, epipolar};
+    HtArgs h{hash, nullptr, W, H, epipolar, 0};
     const dim3 grid(nb, n_pairs);
     ht_count_kernel<<<grid, kSortThreads, 0, stream>>>(w, cur, h, ea);
     global_blockscan_kernel<uint32_t><<<n_pairs, 32, 0, stream>>>(w, ea);
@@ -790,6 +801,35 @@ cudaError_t launch_match_keys(void* ws, long long max_records, int ns, int nt, i
   GlobalEmitArgs ea{};
   ea.W = 1; ea.mode = 2; ea.out = out_pairs; ea.out_stride = 0; ea.cap = cap; ea.n_out = n_out;
   return sort_and_emit(w, n, 1, key_bits, ea, stream, launches);
+}
+
+// ndb::Hashmatch on explicit keys: d_keys64 holds n_src + n_tar keys (src then tar), outside the workspace.
+__global__ void ht_keys_prepare_kernel(SortWs<uint32_t> ws, const unsigned long long* __restrict__ keys64, int ns, int nt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { ws.n_side[0] = ns; ws.n_side[1] = nt; }
+  if (i >= ns + nt) return;
+  ws.keys[0][i] = (uint32_t)(keys64[i] % kHtBuckets);
+  ws.vals[0][i] = i >= ns ? (kSideBit | (uint32_t)(i - ns)) : (uint32_t)i;
+}
+
+cudaError_t launch_hashmatch_keys(void* ws, long long max_records, const unsigned long long* d_keys64, int ns, int nt, int32_t* out_pairs,
+                                  long long cap, int32_t* n_out, cudaStream_t stream, int* launches) {
+  SortWs<uint32_t> w = carve<uint32_t>(ws, max_records, 1, 0);
+  const int n = ns + nt;
+  ht_keys_prepare_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w, d_keys64, ns, nt);
+  *launches += 1;
+  GlobalEmitArgs ea{};
+  ea.W = 1; ea.mode = 2; ea.out = out_pairs; ea.out_stride = 0; ea.cap = cap; ea.n_out = n_out;
+  const int nb = (int)((n + kTile - 1) / kTile);
+  int cur = 0;
+  cudaError_t e = sort_passes(w, n, 1, 18, stream, launches, &cur);
+  if (e != cudaSuccess) return e;
+  HtArgs h{nullptr, d_keys64, 1, 1, 0, ns};
+  ht_count_kernel<<<dim3(nb, 1), kSortThreads, 0, stream>>>(w, cur, h, ea);
+  global_blockscan_kernel<uint32_t><<<1, 32, 0, stream>>>(w, ea);
+  ht_emit_kernel<<<dim3(nb, 1), kSortThreads, 0, stream>>>(w, cur, h, ea);
+  *launches += 3;
+  return cudaGetLastError();
 }
 
 void* global_key_buffer(void* ws, long long max_records) {

@@ -129,3 +129,26 @@ def test_hashtable_batch_and_correspondences(g, ctx, oracle):
         supp1, _, _ = ctx.match_images(il, ir, s)
         assert np.array_equal(supp1, supp[offs[0]:offs[1]])
         il.release(); ir.release()
+
+
+@pytest.mark.gpu
+def test_hashmatch_explicit_keys(g, ctx, oracle, ht_golden):
+    """gpc_hashmatch: the reference's known answers, then random key lists with heavy bucket collisions."""
+    for k in ht_golden["kats"]:
+        got = ctx.hashmatch(np.array(k["src"], np.uint64), np.array(k["tar"], np.uint64))
+        assert got.tolist() == k["pairs"], (k["src"], k["tar"])
+    rng = np.random.default_rng(21)
+    B = np.uint64(214673)
+    for case in range(40):
+        ns, nt = int(rng.integers(1, 20000)), int(rng.integers(1, 20000))
+        kind = case % 4
+        if kind == 0:
+            pool = rng.integers(0, 2 ** 40, size=3000, dtype=np.uint64)
+        elif kind == 1:
+            pool = rng.integers(0, 300, size=200, dtype=np.uint64) * B + rng.integers(0, 9, size=200, dtype=np.uint64)
+        elif kind == 2:
+            pool = rng.integers(0, 2 ** 63, size=100000, dtype=np.uint64)
+        else:
+            pool = rng.integers(0, 2 ** 20, size=5000, dtype=np.uint64)
+        src, tar = rng.choice(pool, ns), rng.choice(pool, nt)
+        assert np.array_equal(ctx.hashmatch(src, tar), oracle.hashmatch(src, tar)), case
