@@ -5,6 +5,7 @@
 #include "gpc_device.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -374,7 +375,7 @@ int gpc_create(gpc_ctx** out, int device, int max_w, int max_h, int max_batch) {
     return fail(nullptr, GPC_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
                                          " (libgpc_b200 has no CPU fallback)");
   if (device < 0 || device >= n_dev) return fail(nullptr, GPC_E_ARG, "device index out of range");
-  static long long next_id = 1;
+  static std::atomic<long long> next_id{1};                // contexts may be created from several host threads
   gpc_ctx* c = new gpc_ctx();
   c->id = next_id++;
   c->device = device; c->max_w = max_w; c->max_h = max_h; c->max_batch = max_batch;

@@ -342,3 +342,37 @@ def test_very_wide_rows(g, oracle):
         g.Context(device=0, max_w=8208, max_h=32, max_batch=1).match_pair(np.zeros((32, 8208), np.uint8), np.zeros((32, 8208), np.uint8),
                                                                        g.sparsematch_settings())
     assert e.value.status == capi.GPC_E_DIMS
+
+
+def test_contexts_on_two_host_threads(g, oracle):
+    """One context per host thread (SURVEY.md 8b threading contract): two threads create their contexts, load
+    different forests (two NVRTC builds racing for the cubin cache) and match concurrently; ctypes drops the GIL
+    inside the library calls."""
+    import threading
+    from opengpc_b200.synth import synth_pair
+    cases = [("tau", 1234, 512, 200), ("zero", 99, 768, 150)]
+    want, got, errs = {}, {}, []
+    for name, seed, w, h in cases:
+        L, R = synth_pair(w, h, seed)
+        want[name] = oracle.pair(L, R, oracle.read_forest(FORESTS[name]), osettings(5, 128, 0, True))[0]
+
+    def work(name, seed, w, h):
+        try:
+            L, R = synth_pair(w, h, seed)
+            with g.Context(device=0, max_w=w, max_h=h, max_batch=2) as c:
+                c.set_forest(FORESTS[name])
+                outs = []
+                for _ in range(20):
+                    outs.append(c.match_pair(L, R, g.sparsematch_settings())[0])
+                got[name] = outs
+        except Exception as e:                                  # surfaced in the main thread below
+            errs.append((name, repr(e)))
+
+    threads = [threading.Thread(target=work, args=c) for c in cases]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    for name, _, _, _ in cases:
+        assert all(np.array_equal(o, want[name]) for o in got[name]), name
