@@ -38,6 +38,75 @@ size_t match_smem_bytes(int wcap, int table_log2) {
   return pow2 * 8 + nb * 4 + body + 3 * kBuckets * 4 + 64;
 }
 
+// Orders the m matches of a row (records key << 32 | xl << 16 | xr in out[]) by state -- the keys are
+// unique -- and writes xl << 16 | xr to the row's slice of `stage`.  Counting pass on the top 8 state bits,
+// then an exact rank inside each (tiny) bucket; bitonic network for skewed states.
+template <int kThreadsB>
+__device__ __forceinline__ void order_and_stage(const MatchArgs& args, unsigned long long* out, unsigned long long* out2,
+                                                uint32_t* bcnt, uint32_t* bstart, uint32_t* bfill, uint32_t* big_bucket,
+                                                int m, int pair, int y) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  // ---- order the matches by state (unique keys) and stage them ------------------------------------------
+  uint32_t* stage = args.stage + ((size_t)pair * args.H + y) * args.W;
+  if (m > 1) {
+    // counting pass on the top 8 state bits, then an exact rank inside each (tiny) bucket
+    const int shift = args.key_bits > 8 ? args.key_bits - 8 : 0;
+    uint32_t seen = 0;
+    for (int i = tid; i < m; i += kThreadsB) seen |= atomic_inc_ret(&bcnt[(uint32_t)(out[i] >> 32) >> shift]);
+    if (seen == 0xffffffffu) __trap();
+    __syncthreads();
+    if (tid < 32) {                                   // exclusive scan of 256 counters: 8 per lane
+      uint32_t c[8], sum = 0, mx = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) { c[k] = bcnt[8 * tid + k]; sum += c[k]; mx = max(mx, c[k]); }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+      uint32_t run = incl - sum;
+#pragma unroll
+      for (int k = 0; k < 8; k++) { bstart[8 * tid + k] = run; run += c[k]; }
+      mx = __reduce_max_sync(0xffffffffu, mx);
+      if (tid == 0) *big_bucket = (mx > (uint32_t)kBucketLimit) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!*big_bucket) {
+      for (int i = tid; i < m; i += kThreadsB) {      // scatter into bucket segments (arbitrary order inside)
+        const unsigned long long rec = out[i];
+        const uint32_t b = (uint32_t)(rec >> 32) >> shift;
+        out2[bstart[b] + atomic_inc_ret(&bfill[b])] = rec;
+      }
+      __syncthreads();
+      for (int i = tid; i < m; i += kThreadsB) {      // rank inside the bucket, write to the final position
+        const unsigned long long rec = out2[i];
+        const uint32_t b = (uint32_t)(rec >> 32) >> shift;
+        const uint32_t s0 = bstart[b], n = bcnt[b];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < n; j++) rank += (out2[s0 + j] < rec) ? 1u : 0u;
+        stage[s0 + rank] = (uint32_t)(rec & 0xffffffffull);
+      }
+    } else {                                          // skewed states: bitonic network over all matches
+      int p2 = 1; while (p2 < m) p2 <<= 1;
+      for (int i = m + tid; i < p2; i += kThreadsB) out[i] = ~0ull;
+      __syncthreads();
+      for (int k = 2; k <= p2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = tid; i < p2; i += kThreadsB) {
+            const int l = i ^ j;
+            if (l > i) {
+              const unsigned long long a = out[i], b2 = out[l];
+              const bool up = ((i & k) == 0);
+              if ((a > b2) == up) { out[i] = b2; out[l] = a; }
+            }
+          }
+          __syncthreads();
+        }
+      for (int i = tid; i < m; i += kThreadsB) stage[i] = (uint32_t)(out[i] & 0xffffffffull);
+    }
+  } else if (m == 1 && tid == 0) {
+    stage[0] = (uint32_t)(out[0] & 0xffffffffull);
+  }
+}
+
 // One CTA per (row, pair).  Every thread keeps its 4*KQ left and right pixels of the row in
 // registers.  h = state * odd constant (a bijection on 32-bit words): the top log2(nb) bits pick
 // the bucket, so inside a bucket two states are equal iff the remaining low bits of h are.  An
@@ -241,65 +310,7 @@ match_rows_kernel(const MatchArgs args) {
     m = n_out;
   }
 
-  // ---- order the matches by state (unique keys) and stage them ------------------------------------------
-  uint32_t* stage = args.stage + ((size_t)pair * H + y) * W;
-  if (m > 1) {
-    // counting pass on the top 8 state bits, then an exact rank inside each (tiny) bucket
-    const int shift = args.key_bits > 8 ? args.key_bits - 8 : 0;
-    uint32_t seen = 0;
-    for (int i = tid; i < m; i += kThreadsB) seen |= atomic_inc_ret(&bcnt[(uint32_t)(out[i] >> 32) >> shift]);
-    if (seen == 0xffffffffu) __trap();
-    __syncthreads();
-    if (tid < 32) {                                   // exclusive scan of 256 counters: 8 per lane
-      uint32_t c[8], sum = 0, mx = 0;
-#pragma unroll
-      for (int k = 0; k < 8; k++) { c[k] = bcnt[8 * tid + k]; sum += c[k]; mx = max(mx, c[k]); }
-      uint32_t incl = sum;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-      uint32_t run = incl - sum;
-#pragma unroll
-      for (int k = 0; k < 8; k++) { bstart[8 * tid + k] = run; run += c[k]; }
-      mx = __reduce_max_sync(0xffffffffu, mx);
-      if (tid == 0) big_bucket = (mx > (uint32_t)kBucketLimit) ? 1u : 0u;
-    }
-    __syncthreads();
-    if (!big_bucket) {
-      for (int i = tid; i < m; i += kThreadsB) {      // scatter into bucket segments (arbitrary order inside)
-        const unsigned long long rec = out[i];
-        const uint32_t b = (uint32_t)(rec >> 32) >> shift;
-        out2[bstart[b] + atomic_inc_ret(&bfill[b])] = rec;
-      }
-      __syncthreads();
-      for (int i = tid; i < m; i += kThreadsB) {      // rank inside the bucket, write to the final position
-        const unsigned long long rec = out2[i];
-        const uint32_t b = (uint32_t)(rec >> 32) >> shift;
-        const uint32_t s0 = bstart[b], n = bcnt[b];
-        uint32_t rank = 0;
-        for (uint32_t j = 0; j < n; j++) rank += (out2[s0 + j] < rec) ? 1u : 0u;
-        stage[s0 + rank] = (uint32_t)(rec & 0xffffffffull);
-      }
-    } else {                                          // skewed states: bitonic network over all matches
-      int p2 = 1; while (p2 < m) p2 <<= 1;
-      for (int i = m + tid; i < p2; i += kThreadsB) out[i] = ~0ull;
-      __syncthreads();
-      for (int k = 2; k <= p2; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int i = tid; i < p2; i += kThreadsB) {
-            const int l = i ^ j;
-            if (l > i) {
-              const unsigned long long a = out[i], b2 = out[l];
-              const bool up = ((i & k) == 0);
-              if ((a > b2) == up) { out[i] = b2; out[l] = a; }
-            }
-          }
-          __syncthreads();
-        }
-      for (int i = tid; i < m; i += kThreadsB) stage[i] = (uint32_t)(out[i] & 0xffffffffull);
-    }
-  } else if (m == 1 && tid == 0) {
-    stage[0] = (uint32_t)(out[0] & 0xffffffffull);
-  }
+  order_and_stage<kThreadsB>(args, out, out2, bcnt, bstart, bfill, &big_bucket, m, pair, y);
   if (tid == 0) args.rowmatch[(size_t)pair * H + y] = m;
 }
 
@@ -327,9 +338,9 @@ int match_rows_threads(int W) {
 cudaError_t launch_match_rows(const MatchArgs& args, int n_pairs, cudaStream_t stream) {
   int rows = args.H - 2 * kRadius;
   if (rows <= 0 || n_pairs <= 0) return cudaSuccess;
-  size_t smem = match_smem_bytes(args.wcap, args.table_log2);
   const int quads = args.W / 4;
   dim3 grid(rows, n_pairs);
+  size_t smem = match_smem_bytes(args.wcap, args.table_log2);
   if (quads <= 256) match_rows_kernel<1, 256><<<grid, 256, smem, stream>>>(args);
   else if (quads <= 512) match_rows_kernel<1, 512><<<grid, 512, smem, stream>>>(args);
   else if (quads <= 1024) match_rows_kernel<1, 1024><<<grid, 1024, smem, stream>>>(args);
