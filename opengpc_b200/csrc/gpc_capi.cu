@@ -36,7 +36,7 @@ size_t global_workspace_bytes(long long max_records, int n_pairs, int H);
 cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int W, int H, int n_pairs, int epipolar, int key_bits,
                                 int disp_high, int vertical_tolerance, int mode, void* ws, long long max_records, void* out,
                                 long long out_stride, long long cap, int32_t* n_out, int32_t* n_cand, cudaStream_t stream,
-                                int* launches, int hashtable);
+                                int* launches, int hashtable, long long* pair_base, int first_chunk);
 cudaError_t launch_hashmatch_keys(void* ws, long long max_records, const unsigned long long* d_keys64, int ns, int nt, int32_t* out_pairs,
                                   long long cap, int32_t* n_out, cudaStream_t stream, int* launches);
 cudaError_t launch_match_keys(void* ws, long long max_records, int ns, int nt, int key_bits, int32_t* out_pairs, long long cap,
@@ -244,7 +244,7 @@ int run_preprocess(gpc_ctx* c, const Slot& sl, const uint8_t* d_images, int n_im
 
 int ensure_global_ws(gpc_ctx* c, size_t bytes) {
   if (bytes > c->gws_bytes) {
-    if (c->d_gws) { GPC_CUDA(c, cudaStreamSynchronize(c->stream)); cudaFree(c->d_gws); c->d_gws = nullptr; c->gws_bytes = 0; }
+    if (c->d_gws) { GPC_CUDA(c, cudaDeviceSynchronize()); cudaFree(c->d_gws); c->d_gws = nullptr; c->gws_bytes = 0; }   // any lane may still use it
     GPC_CUDA(c, cudaMalloc(&c->d_gws, bytes));
     c->gws_bytes = bytes;
   }
@@ -252,14 +252,25 @@ int ensure_global_ws(gpc_ctx* c, size_t bytes) {
 }
 
 // Radix-sort matcher (match_global.cu) for pairs p0 .. p0 + n of the resident hash images, a chunk of pairs
-// per launch sequence.  mode 0: filtered supports, 1: unfiltered correspondences.  Pair p0 + i writes at
-// d_out + i * out_stride records (capacity cap each), its count to d_n_out[i], candidate counts to d_n_cand[2i..].
-int run_match_sort(gpc_ctx* c, const uint32_t* hash, int p0, int n, int w, int h, const gpc_settings* s, int mode, void* d_out,
-                   size_t record_bytes, long long out_stride, long long cap, int32_t* d_n_out, int32_t* d_n_cand) {
-  const size_t P = (size_t)w * h;
+// per launch sequence, on `stream`.  mode 0: filtered supports, 1: unfiltered correspondences.  Strided output
+// (pair_base == nullptr): pair p0 + i writes at d_out + i * out_stride records (capacity cap each).  Packed
+// output: the pairs' records back to back from d_out (capacity cap in total), prefix in pair_base[0 .. n].
+// Counts to d_n_out[i], candidate counts to d_n_cand[2i..].
+size_t sort_workspace_bytes(int w, int h, int n, int* chunk_out) {
   const long long records = 2ll * std::max(w - 2 * gpc::kRadius, 0) * std::max(h - 2 * gpc::kRadius, 0) + 2;
   const size_t per_pair = gpc::global_workspace_bytes(records, 1, h);
   const int chunk = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)1 << 30) / per_pair));
+  if (chunk_out) *chunk_out = chunk;
+  return gpc::global_workspace_bytes(records, std::min(chunk, std::max(n, 1)), h);
+}
+
+int run_match_sort(gpc_ctx* c, const uint32_t* hash, int p0, int n, int w, int h, const gpc_settings* s, int mode, void* d_out,
+                   size_t record_bytes, long long out_stride, long long cap, int32_t* d_n_out, int32_t* d_n_cand,
+                   cudaStream_t stream, long long* pair_base) {
+  const size_t P = (size_t)w * h;
+  const long long records = 2ll * std::max(w - 2 * gpc::kRadius, 0) * std::max(h - 2 * gpc::kRadius, 0) + 2;
+  int chunk = 1;
+  sort_workspace_bytes(w, h, n, &chunk);
   for (int q0 = 0; q0 < n; q0 += chunk) {
     const int m = std::min(chunk, n - q0);
     int rc = ensure_global_ws(c, gpc::global_workspace_bytes(records, m, h)); if (rc) return rc;
@@ -267,8 +278,8 @@ int run_match_sort(gpc_ctx* c, const uint32_t* hash, int p0, int n, int w, int h
     GPC_CUDA(c, gpc::launch_match_global(hash + (size_t)(2 * (p0 + q0)) * P, c->d_rows + (size_t)(2 * (p0 + q0)) * h, w, h, m,
                                          s->epipolar_mode ? 1 : 0, 31, s->disp_high, s->vertical_tolerance, mode, c->d_gws, records,
                                          reinterpret_cast<uint8_t*>(d_out) + (size_t)q0 * (size_t)out_stride * record_bytes, out_stride,
-                                         cap, d_n_out + q0, d_n_cand ? d_n_cand + 2 * q0 : nullptr, c->stream, &launches,
-                                         s->use_hashtable ? 1 : 0));
+                                         cap, d_n_out + q0, d_n_cand ? d_n_cand + 2 * q0 : nullptr, stream, &launches,
+                                         s->use_hashtable ? 1 : 0, pair_base ? pair_base + q0 : nullptr, q0 == 0 ? 1 : 0));
     c->launches += launches;
   }
   return GPC_OK;
@@ -287,20 +298,12 @@ int run_match(gpc_ctx* c, const Slot& sl, int n_pairs, int w, int h, const gpc_s
   const size_t P = (size_t)w * h;
   const uint32_t* hash = c->d_hash + (size_t)(2 * sl.p0) * P;
   if (use_sort_matcher(c, s)) {
-    // radix sort + segmented scan, pair by pair on the context's stream (strided output only; the
-    // packed host entry points run one pair at a time)
-    if (sl.stream != c->stream || sl.p0 != 0) return fail(c, GPC_E_ARG, "internal: sort matcher runs on the context stream");
-    if (packed && n_pairs != 1) return fail(c, GPC_E_ARG, "internal: packed sort matcher handles one pair per call");
-    for (int k = 0; k < 2; k++) { int rc = mark(c); if (rc) return rc; }   // events 3, 4 (no row kernels here)
-    {
-      int rc = run_match_sort(c, c->d_hash, 0, n_pairs, w, h, s, 0, d_out, sizeof(gpc_support), packed ? 0 : cap, cap, d_n_out, d_n_cand);
-      if (rc) return rc;
-    }
-    if (packed) {
-      GPC_CUDA(c, gpc::launch_pair_scan(d_n_out, 1, c->d_pair_base, c->stream));
-      c->launches += 1;
-    }
-    return mark(c);                                                                // event 5
+    // radix sort + segmented scan over the slot's pairs (match_global.cu); same output contract as the row path
+    for (int k = 0; k < 2; k++) { int rc = mark_on(c, sl); if (rc) return rc; }   // events 3, 4 (no row kernels here)
+    int rc = run_match_sort(c, c->d_hash, sl.p0, n_pairs, w, h, s, 0, d_out, sizeof(gpc_support), packed ? 0 : cap, cap, d_n_out,
+                            d_n_cand, sl.stream, packed ? c->d_pair_base + 2 * sl.p0 : nullptr);
+    if (rc) return rc;
+    return mark_on(c, sl);                                                         // event 5
   }
   const int32_t* rowcnt = c->d_rows + (size_t)(2 * sl.p0) * h;
   int32_t* rowmatch = c->d_rowmatch + (size_t)sl.p0 * h;
@@ -636,32 +639,15 @@ int gpc_match_batch(gpc_ctx* c, const uint8_t* images, int n_pairs, int w, int h
   if (!c->has_forest) return fail(c, GPC_E_FOREST, "no forest set");
   GPC_CUDA(c, cudaSetDevice(c->device));
   const size_t P = (size_t)w * h;
-  if (!use_sort_matcher(c, s) && !c->timing && n_pairs >= 2 * c->chunk_pairs && h > 2 * gpc::kRadius)
+  if (!c->timing && n_pairs >= 2 * c->chunk_pairs && h > 2 * gpc::kRadius) {
+    if (use_sort_matcher(c, s)) {                                  // size the sort workspace before the lanes start
+      rc = ensure_global_ws(c, sort_workspace_bytes(w, h, c->chunk_pairs, nullptr)); if (rc) return rc;
+    }
     return match_batch_pipelined(c, images, n_pairs, w, h, s, out, cap, offsets, n_cand);
+  }
   GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, images, 2 * (size_t)n_pairs * P, cudaMemcpyHostToDevice, c->stream));
   rc = run_preprocess(c, Slot{0, c->stream}, c->d_raw, 2 * n_pairs, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
   if (rc) return rc;
-  if (use_sort_matcher(c, s) && n_pairs > 1) {
-    // radix-sort matcher: the pairs run back to back on the stream (no host round trip in between), each
-    // into its own region of d_out; one synchronisation, then the regions are packed on the way to the host
-    const long long per_pair = c->out_cap / c->max_batch;
-    rc = run_match_sort(c, c->d_hash, 0, n_pairs, w, h, s, 0, c->d_out, sizeof(gpc_support), per_pair, per_pair, c->d_totals, c->d_ncand);
-    if (rc) return rc;
-    GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_totals, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    GPC_CUDA(c, cudaMemcpyAsync(c->h_counts + n_pairs, c->d_ncand, 2 * (size_t)n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    GPC_CUDA(c, cudaStreamSynchronize(c->stream));
-    long long total = 0;
-    offsets[0] = 0;
-    for (int p = 0; p < n_pairs; p++) { total += c->h_counts[p]; offsets[p + 1] = total; }
-    if (n_cand) std::memcpy(n_cand, c->h_counts + n_pairs, 2 * (size_t)n_pairs * sizeof(int32_t));
-    if (total > cap) return fail(c, GPC_E_CAPACITY, "support buffer too small: need " + std::to_string(total));
-    for (int p = 0; p < n_pairs; p++)
-      if (c->h_counts[p] > 0)
-        GPC_CUDA(c, cudaMemcpyAsync(out + offsets[p], c->d_out + (size_t)p * per_pair, (size_t)c->h_counts[p] * sizeof(gpc_support),
-                                    cudaMemcpyDeviceToHost, c->stream));
-    GPC_CUDA(c, cudaStreamSynchronize(c->stream));
-    return GPC_OK;
-  }
   rc = run_match(c, Slot{0, c->stream}, n_pairs, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
   if (rc) return rc;
   GPC_CUDA(c, cudaMemcpyAsync(c->h_pair_base, c->d_pair_base, (size_t)(n_pairs + 1) * sizeof(long long),
@@ -929,7 +915,7 @@ int gpc_correspond_images(gpc_ctx* c, const gpc_image* l, const gpc_image* r, co
   if (rc) return rc;
   // a correspondence is 16 bytes, a support 12: d_out holds out_cap * 12 / 16 correspondences
   const long long dcap = c->out_cap * 12 / 16;
-  rc = run_match_sort(c, c->d_hash, 0, 1, w, h, s, 1, c->d_out, sizeof(gpc_correspondence), 0, dcap, c->d_totals, nullptr);
+  rc = run_match_sort(c, c->d_hash, 0, 1, w, h, s, 1, c->d_out, sizeof(gpc_correspondence), 0, dcap, c->d_totals, nullptr, c->stream, nullptr);
   if (rc) return rc;
   GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_totals, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   GPC_CUDA(c, cudaStreamSynchronize(c->stream));

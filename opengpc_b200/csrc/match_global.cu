@@ -379,8 +379,9 @@ struct GlobalEmitArgs {
   int32_t W;
   int32_t disp_high, vertical_tolerance;
   int32_t mode;                      // 0 supports (filtered), 1 correspondences (unfiltered), 2 index pairs
-  void* out;                         // pair p writes at out + p * out_stride records
-  long long out_stride, cap;         // records per pair region, capacity of one region
+  void* out;                         // strided: pair p writes at out + p * out_stride records, at most cap of them
+  long long out_stride, cap;         // packed (pair_base != nullptr): pair p writes from out + pair_base[p], cap = total capacity
+  const long long* pair_base;        // [n_pairs + 1] exclusive prefix of n_out (filled between the count and the emit step)
   int32_t* n_out;                    // [n_pairs]
 };
 
@@ -473,6 +474,16 @@ global_blockscan_kernel(const SortWs<KeyT> ws, const GlobalEmitArgs a) {
   if (lane == 0) a.n_out[pair] = carry;
 }
 
+// packed output: pair_base[p + 1] = pair_base[p] + n_out[p]; `first` starts the prefix at 0, otherwise it continues
+// from pair_base[0] (left there by the previous chunk of pairs)
+__global__ void global_pairbase_kernel(const int32_t* __restrict__ n_out, int n_pairs, long long* __restrict__ pair_base, int first) {
+  if (threadIdx.x == 0) {
+    long long acc = first ? 0ll : pair_base[0];
+    for (int p = 0; p < n_pairs; p++) { pair_base[p] = acc; acc += n_out[p]; }
+    pair_base[n_pairs] = acc;
+  }
+}
+
 template <typename KeyT>
 __global__ void __launch_bounds__(kSortThreads)
 global_emit_kernel(const SortWs<KeyT> ws, int cur, const GlobalEmitArgs a) {
@@ -506,9 +517,9 @@ global_emit_kernel(const SortWs<KeyT> ws, int cur, const GlobalEmitArgs a) {
   for (int j = 0; j < kRounds; j++) {
     if (!((bits >> j) & 1u)) continue;
     const long long slot = k++;
-    if (slot >= a.cap) continue;
+    const long long idx = a.pair_base ? a.pair_base[pair] + slot : (long long)pair * a.out_stride + slot;
+    if ((a.pair_base ? idx : slot) >= a.cap) continue;
     const uint32_t vl = V[j], vr = V[j + 1] & ~kSideBit;
-    const long long idx = (long long)pair * a.out_stride + slot;
     if (a.mode == 2) {
       int32_t* o = reinterpret_cast<int32_t*>(a.out) + 2 * idx;
       o[0] = (int32_t)vl; o[1] = (int32_t)vr;
@@ -534,8 +545,8 @@ struct HtArgs {
 };
 
 __device__ __forceinline__ void write_match(const GlobalEmitArgs& a, int pair, long long slot, uint32_t vl, uint32_t vr) {
-  if (slot >= a.cap) return;
-  const long long idx = (long long)pair * a.out_stride + slot;
+  const long long idx = a.pair_base ? a.pair_base[pair] + slot : (long long)pair * a.out_stride + slot;
+  if ((a.pair_base ? idx : slot) >= a.cap) return;
   if (a.mode == 2) {
     int32_t* o = reinterpret_cast<int32_t*>(a.out) + 2 * idx;
     o[0] = (int32_t)vl; o[1] = (int32_t)vr;
@@ -716,7 +727,7 @@ static cudaError_t sort_passes(SortWs<KeyT>& w, long long max_records, int n_pai
 
 template <typename KeyT>
 static cudaError_t sort_and_emit(SortWs<KeyT>& w, long long max_records, int n_pairs, int key_bits, const GlobalEmitArgs& ea,
-                                 cudaStream_t stream, int* launches) {
+                                 cudaStream_t stream, int* launches, int first_chunk = 1) {
   const int nb = (int)((max_records + kTile - 1) / kTile);
   if (nb <= 0 || n_pairs <= 0) return cudaSuccess;
   const dim3 grid(nb, n_pairs);
@@ -728,21 +739,23 @@ static cudaError_t sort_and_emit(SortWs<KeyT>& w, long long max_records, int n_p
   global_tmax_kernel<KeyT><<<n_pairs, 32, 0, stream>>>(w, cur);
   global_count_kernel<KeyT><<<grid, kSortThreads, 0, stream>>>(w, cur, ea);
   global_blockscan_kernel<KeyT><<<n_pairs, 32, 0, stream>>>(w, ea);
+  if (ea.pair_base) { global_pairbase_kernel<<<1, 32, 0, stream>>>(ea.n_out, n_pairs, const_cast<long long*>(ea.pair_base), first_chunk); *launches += 1; }
   global_emit_kernel<KeyT><<<grid, kSortThreads, 0, stream>>>(w, cur, ea);
   *launches += 4;
   return cudaGetLastError();
 }
 
 // Hash images of n_pairs pairs ([2 * n_pairs][H][W], rowcnt [2 * n_pairs][H]) -> ordered supports (mode 0)
-// or correspondences (mode 1); pair p writes at out + p * out_stride records, count to n_out[p], candidate
-// counts to n_cand[2p], n_cand[2p+1] (optional).  ws from global_workspace_bytes(max_records, n_pairs, H).
+// or correspondences (mode 1); pair p writes at out + p * out_stride records (pair_base == nullptr) or packed
+// from out + pair_base[p] (pair_base filled here; first_chunk = 0 continues the prefix of an earlier call), count to
+// n_out[p], candidate counts to n_cand[2p], n_cand[2p+1] (optional).  ws from global_workspace_bytes(max_records, n_pairs, H).
 cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int W, int H, int n_pairs, int epipolar, int key_bits,
                                 int disp_high, int vertical_tolerance, int mode, void* ws, long long max_records, void* out,
                                 long long out_stride, long long cap, int32_t* n_out, int32_t* n_cand, cudaStream_t stream,
-                                int* launches, int hashtable) {
+                                int* launches, int hashtable, long long* pair_base, int first_chunk) {
   GlobalEmitArgs ea{};
   ea.W = W; ea.disp_high = disp_high; ea.vertical_tolerance = vertical_tolerance; ea.mode = mode;
-  ea.out = out; ea.out_stride = out_stride; ea.cap = cap; ea.n_out = n_out;
+  ea.out = out; ea.out_stride = out_stride; ea.cap = cap; ea.n_out = n_out; ea.pair_base = pair_base;
   const dim3 gather_grid((2 * H * 32 + 127) / 128, n_pairs);
   cudaError_t e;
   if (hashtable) {                                       // inference.hpp:204-225: sort by bucket, then replay the buckets
@@ -758,6 +771,7 @@ cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int
     const dim3 grid(nb, n_pairs);
     ht_count_kernel<<<grid, kSortThreads, 0, stream>>>(w, cur, h, ea);
     global_blockscan_kernel<uint32_t><<<n_pairs, 32, 0, stream>>>(w, ea);
+    if (ea.pair_base) { global_pairbase_kernel<<<1, 32, 0, stream>>>(n_out, n_pairs, pair_base, first_chunk); *launches += 1; }
     ht_emit_kernel<<<grid, kSortThreads, 0, stream>>>(w, cur, h, ea);
     *launches += 3;
     e = cudaGetLastError();
@@ -770,7 +784,7 @@ cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int
     global_gather_kernel<unsigned long long><<<gather_grid, 128, 0, stream>>>(hash, W, H, 1, 0, w);
     *launches += 2;
     int hb = 1; while ((1 << hb) < H) hb++;
-    e = sort_and_emit(w, max_records, n_pairs, 32 + hb, ea, stream, launches);
+    e = sort_and_emit(w, max_records, n_pairs, 32 + hb, ea, stream, launches, first_chunk);
     if (e == cudaSuccess && n_cand) e = cudaMemcpyAsync(n_cand, w.n_side, (size_t)n_pairs * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
     return e;
   }
@@ -778,7 +792,7 @@ cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int
   global_rowoff_kernel<<<dim3(2, n_pairs), 1024, 0, stream>>>(rowcnt, H, w.rowoff, w.n_side);
   global_gather_kernel<uint32_t><<<gather_grid, 128, 0, stream>>>(hash, W, H, 0, 0, w);
   *launches += 2;
-  e = sort_and_emit(w, max_records, n_pairs, key_bits, ea, stream, launches);
+  e = sort_and_emit(w, max_records, n_pairs, key_bits, ea, stream, launches, first_chunk);
   if (e == cudaSuccess && n_cand) e = cudaMemcpyAsync(n_cand, w.n_side, (size_t)n_pairs * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
   return e;
 }
