@@ -412,6 +412,20 @@ def main():
         other = {f"configs[{1 - args.config}] ({os.path.basename(FORESTS[of])}) pairs/s, device-resident":
                  B * max(3, args.steps // 2) / (e0.elapsed_time(e1) / 1e3)}
         ctx.set_forest(FORESTS[args.forest])
+        # the two other matching modes of the reference API, end to end through gpc_match_batch (pinned host buffers)
+        nb = min(B, 64)
+        for label, st in (("global mode (library defaults: epipolarMode(false), verticalTolerance 1, threshold 10)",
+                           g.make_settings(thr=10, disp_high=128, vt=1, epipolar=False)),
+                          ("useHashtable(true), sparsematch settings",
+                           g.make_settings(thr=5, disp_high=128, vt=0, epipolar=True, use_hashtable=True))):
+            for _ in range(2):
+                ctx.match_batch_raw(h_img.data_ptr(), nb, w, h, st, h_out.data_ptr(), h_out.shape[0], h_off.data_ptr())
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                ctx.match_batch_raw(h_img.data_ptr(), nb, w, h, st, h_out.data_ptr(), h_out.shape[0], h_off.data_ptr())
+            barrier()
+            other[f"{label}: pairs/s end to end, batch {nb}"] = 3 * nb / (time.perf_counter() - t0)
 
     if rank != 0:
         if dist is not None:

@@ -571,20 +571,20 @@ __device__ __forceinline__ bool passes_filter(const GlobalEmitArgs& a, uint32_t 
   return dy <= a.vertical_tolerance && -dy <= a.vertical_tolerance && dx <= a.disp_high && -dx <= a.disp_high;
 }
 
-// Record i of the bucket-sorted array: if it opens a bucket, replay that bucket and return its number of
-// matches (written from `slot` on when kWrite).  keys = bucket indices, vals = side << 31 | pixel index.
-template <bool kWrite>
-__device__ int ht_bucket(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int i, int n, const HtArgs& h,
-                         int pair, const GlobalEmitArgs& a, long long slot) {
-  if (i >= n) return 0;
-  const uint32_t b = keys[i];
-  if (i > 0 && keys[i - 1] == b) return 0;
+// The 64-bit key of every bucket-sorted record, gathered once (one thread per record) into the idle half of the
+// ping-pong key buffer, so that the bucket replay below reads consecutive memory.
+__global__ void __launch_bounds__(kSortThreads)
+ht_keys_kernel(const SortWs<uint32_t> ws, int cur, const HtArgs h) {
+  const int pair = blockIdx.y;
+  const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
+  const uint32_t* vals = (cur ? ws.vals[1] : ws.vals[0]) + (size_t)pair * ws.rec_stride;
+  unsigned long long* skey = reinterpret_cast<unsigned long long*>(cur ? ws.keys[0] : ws.keys[1]) + (size_t)pair * ws.rec_stride;
   const uint32_t* img = h.keys64 ? nullptr : h.hash + (size_t)(2 * pair) * h.H * h.W;
-  unsigned long long lk[kHtDepth];                       // the bucket's list: keys ascending, ties in insertion order
-  uint32_t lv[kHtDepth];
-  int m = 0;
-  for (int j = i; j < n && m < kHtDepth && keys[j] == b; j++) {        // hashmatch.hpp:101: a full bucket drops the rest
-    const uint32_t v = vals[j], pix = v & ~kSideBit;
+#pragma unroll
+  for (int r = 0; r < kRounds; r++) {
+    const int i = blockIdx.x * kTile + r * kSortThreads + threadIdx.x;
+    if (i >= n) continue;
+    const uint32_t v = vals[i], pix = v & ~kSideBit;
     unsigned long long k;
     if (h.keys64) {
       k = h.keys64[(v >> 31) ? h.n_src + pix : pix];
@@ -592,6 +592,24 @@ __device__ int ht_bucket(const uint32_t* __restrict__ keys, const uint32_t* __re
       k = img[(size_t)(v >> 31) * h.H * h.W + pix] & 0x7fffffffu;
       if (h.epipolar) k |= (unsigned long long)(pix / (uint32_t)h.W) << 32;
     }
+    skey[i] = k;
+  }
+}
+
+// Record i of the bucket-sorted array: if it opens a bucket, replay that bucket and return its number of
+// matches (written from `slot` on when kWrite).  keys = bucket indices, skey = full keys, vals = side << 31 | index.
+template <bool kWrite>
+__device__ int ht_bucket(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                         const unsigned long long* __restrict__ skey, int i, int n, int pair, const GlobalEmitArgs& a, long long slot) {
+  if (i >= n) return 0;
+  const uint32_t b = keys[i];
+  if (i > 0 && keys[i - 1] == b) return 0;
+  unsigned long long lk[kHtDepth];                       // the bucket's list: keys ascending, ties in insertion order
+  uint32_t lv[kHtDepth];
+  int m = 0;
+  for (int j = i; j < n && m < kHtDepth && keys[j] == b; j++) {        // hashmatch.hpp:101: a full bucket drops the rest
+    const uint32_t v = vals[j];
+    const unsigned long long k = skey[j];
     int pos = m;                                         // :112-116: behind every element with key <= k
     while (pos > 0 && lk[pos - 1] > k) { lk[pos] = lk[pos - 1]; lv[pos] = lv[pos - 1]; pos--; }
     lk[pos] = k; lv[pos] = v;
@@ -622,8 +640,9 @@ __device__ int ht_bucket(const uint32_t* __restrict__ keys, const uint32_t* __re
   return found;
 }
 
+// Matches per record (non-zero only where a bucket opens) into the idle half of the value buffer, and per tile.
 __global__ void __launch_bounds__(kSortThreads)
-ht_count_kernel(const SortWs<uint32_t> ws, int cur, const HtArgs h, const GlobalEmitArgs a) {
+ht_count_kernel(const SortWs<uint32_t> ws, int cur, const GlobalEmitArgs a) {
   __shared__ int cnt;
   const int pair = blockIdx.y;
   const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
@@ -633,8 +652,16 @@ ht_count_kernel(const SortWs<uint32_t> ws, int cur, const HtArgs h, const Global
   __syncthreads();
   const uint32_t* keys = (cur ? ws.keys[1] : ws.keys[0]) + (size_t)pair * ws.rec_stride;
   const uint32_t* vals = (cur ? ws.vals[1] : ws.vals[0]) + (size_t)pair * ws.rec_stride;
+  const unsigned long long* skey = reinterpret_cast<const unsigned long long*>(cur ? ws.keys[0] : ws.keys[1]) + (size_t)pair * ws.rec_stride;
+  uint8_t* found = reinterpret_cast<uint8_t*>((cur ? ws.vals[0] : ws.vals[1]) + (size_t)pair * ws.rec_stride);
   int mine = 0;
-  for (int r = 0; r < kRounds; r++) mine += ht_bucket<false>(keys, vals, blockIdx.x * kTile + kRounds * threadIdx.x + r, n, h, pair, a, 0);
+#pragma unroll 1
+  for (int r = 0; r < kRounds; r++) {                    // round-major: neighbouring lanes replay neighbouring buckets
+    const int i = blockIdx.x * kTile + r * kSortThreads + threadIdx.x;
+    const int c = ht_bucket<false>(keys, vals, skey, i, n, pair, a, 0);
+    if (i < n) found[i] = (uint8_t)c;
+    mine += c;
+  }
   mine = __reduce_add_sync(0xffffffffu, mine);
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&cnt, mine);
   __syncthreads();
@@ -642,7 +669,7 @@ ht_count_kernel(const SortWs<uint32_t> ws, int cur, const HtArgs h, const Global
 }
 
 __global__ void __launch_bounds__(kSortThreads)
-ht_emit_kernel(const SortWs<uint32_t> ws, int cur, const HtArgs h, const GlobalEmitArgs a) {
+ht_emit_kernel(const SortWs<uint32_t> ws, int cur, const GlobalEmitArgs a) {
   __shared__ int warp_base[kSortWarps];
   const int pair = blockIdx.y;
   const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
@@ -650,10 +677,13 @@ ht_emit_kernel(const SortWs<uint32_t> ws, int cur, const HtArgs h, const GlobalE
   if ((int)blockIdx.x >= nb) return;
   const uint32_t* keys = (cur ? ws.keys[1] : ws.keys[0]) + (size_t)pair * ws.rec_stride;
   const uint32_t* vals = (cur ? ws.vals[1] : ws.vals[0]) + (size_t)pair * ws.rec_stride;
+  const unsigned long long* skey = reinterpret_cast<const unsigned long long*>(cur ? ws.keys[0] : ws.keys[1]) + (size_t)pair * ws.rec_stride;
+  const uint8_t* found = reinterpret_cast<const uint8_t*>((cur ? ws.vals[0] : ws.vals[1]) + (size_t)pair * ws.rec_stride);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int i0 = blockIdx.x * kTile + kRounds * tid;     // thread order = record order = bucket order
-  int c = 0;
-  for (int r = 0; r < kRounds; r++) c += ht_bucket<false>(keys, vals, i0 + r, n, h, pair, a, 0);
+  int cr[kRounds], c = 0;
+#pragma unroll
+  for (int r = 0; r < kRounds; r++) { cr[r] = (i0 + r < n) ? found[i0 + r] : 0; c += cr[r]; }
   int incl = c;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
@@ -668,8 +698,9 @@ ht_emit_kernel(const SortWs<uint32_t> ws, int cur, const HtArgs h, const GlobalE
   }
   __syncthreads();
   long long slot = (long long)ws.blockcount[(size_t)pair * (ws.nb_max + 1) + blockIdx.x] + warp_base[wid] + (incl - c);
-  if (c == 0) return;
-  for (int r = 0; r < kRounds; r++) slot += ht_bucket<true>(keys, vals, i0 + r, n, h, pair, a, slot);
+#pragma unroll 1
+  for (int r = 0; r < kRounds; r++)
+    if (cr[r]) slot += ht_bucket<true>(keys, vals, skey, i0 + r, n, pair, a, slot);      // only buckets that hold a match
 }
 
 // ---- host-side launch sequences -----------------------------------------------------------------------
@@ -769,11 +800,12 @@ cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int
     if ((e = sort_passes(w, max_records, n_pairs, 18, stream, launches, &cur)) != cudaSuccess) return e;   // 214673 < 2^18
     HtArgs h{hash, nullptr, W, H, epipolar, 0};
     const dim3 grid(nb, n_pairs);
-    ht_count_kernel<<<grid, kSortThreads, 0, stream>>>(w, cur, h, ea);
+    ht_keys_kernel<<<grid, kSortThreads, 0, stream>>>(w, cur, h);
+    ht_count_kernel<<<grid, kSortThreads, 0, stream>>>(w, cur, ea);
     global_blockscan_kernel<uint32_t><<<n_pairs, 32, 0, stream>>>(w, ea);
     if (ea.pair_base) { global_pairbase_kernel<<<1, 32, 0, stream>>>(n_out, n_pairs, pair_base, first_chunk); *launches += 1; }
-    ht_emit_kernel<<<grid, kSortThreads, 0, stream>>>(w, cur, h, ea);
-    *launches += 3;
+    ht_emit_kernel<<<grid, kSortThreads, 0, stream>>>(w, cur, ea);
+    *launches += 4;
     e = cudaGetLastError();
     if (e == cudaSuccess && n_cand) e = cudaMemcpyAsync(n_cand, w.n_side, (size_t)n_pairs * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
     return e;
@@ -839,10 +871,11 @@ cudaError_t launch_hashmatch_keys(void* ws, long long max_records, const unsigne
   cudaError_t e = sort_passes(w, n, 1, 18, stream, launches, &cur);
   if (e != cudaSuccess) return e;
   HtArgs h{nullptr, d_keys64, 1, 1, 0, ns};
-  ht_count_kernel<<<dim3(nb, 1), kSortThreads, 0, stream>>>(w, cur, h, ea);
+  ht_keys_kernel<<<dim3(nb, 1), kSortThreads, 0, stream>>>(w, cur, h);
+  ht_count_kernel<<<dim3(nb, 1), kSortThreads, 0, stream>>>(w, cur, ea);
   global_blockscan_kernel<uint32_t><<<1, 32, 0, stream>>>(w, ea);
-  ht_emit_kernel<<<dim3(nb, 1), kSortThreads, 0, stream>>>(w, cur, h, ea);
-  *launches += 3;
+  ht_emit_kernel<<<dim3(nb, 1), kSortThreads, 0, stream>>>(w, cur, ea);
+  *launches += 4;
   return cudaGetLastError();
 }
 
