@@ -160,25 +160,35 @@ def test_resident_images(g, ctx, oracle):
         io.release()
 
 
-def test_pipelined_batch(g, oracle, monkeypatch):
+@pytest.mark.parametrize("mode", ["rows", "global", "hashtable"])
+def test_pipelined_batch(g, oracle, monkeypatch, mode):
     """gpc_match_batch splits large batches into chunks that rotate over three streams (upload,
     kernels and download overlap).  Chunk size 2 forces that path on a 7-pair batch, including a
-    pair without candidates and a too-small output buffer."""
+    pair without candidates and a too-small output buffer; per-row matcher, radix-sort matcher (global
+    mode) and the hashtable matcher all run through it."""
     from opengpc_b200 import capi
     from opengpc_b200.synth import synth_batch
     monkeypatch.setenv("GPC_CHUNK_PAIRS", "2")
     imgs = synth_batch(320, 90, 7, seed0=300)
     imgs[3] = 50
     of = oracle.read_forest(FORESTS["tau"])
+    if mode == "rows":
+        s, os_ = g.sparsematch_settings(), osettings()
+    elif mode == "global":
+        s, os_ = g.make_settings(thr=5, disp_high=128, vt=1, epipolar=False), osettings(5, 128, 1, False)
+    else:
+        s, os_ = g.make_settings(thr=5, disp_high=128, vt=0, epipolar=True, use_hashtable=True), osettings()
     with g.Context(device=0, max_w=320, max_h=90, max_batch=7) as c:
         c.set_forest(FORESTS["tau"])
-        s = g.sparsematch_settings()
         for rep in range(3):
             supp, offsets, ncand = c.match_batch(imgs, s)
             for p in range(7):
-                ref, ocl, ocr = oracle.pair(imgs[p, 0], imgs[p, 1], of, osettings())
-                assert (ncand[p, 0], ncand[p, 1]) == (ocl, ocr)
-                assert np.array_equal(supp[offsets[p]:offsets[p + 1]], ref), (rep, p)
+                if mode == "hashtable":
+                    ref = oracle.pair_hashtable(imgs[p, 0], imgs[p, 1], of, os_)
+                else:
+                    ref, ocl, ocr = oracle.pair(imgs[p, 0], imgs[p, 1], of, os_)
+                    assert (ncand[p, 0], ncand[p, 1]) == (ocl, ocr)
+                assert np.array_equal(supp[offsets[p]:offsets[p + 1]], ref), (mode, rep, p)
         assert offsets[4] == offsets[3]
         small = np.empty(10, g.SUPPORT_DTYPE)
         with pytest.raises(g.GpcError) as e:
