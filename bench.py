@@ -426,6 +426,20 @@ def main():
                 ctx.match_batch_raw(h_img.data_ptr(), nb, w, h, st, h_out.data_ptr(), h_out.shape[0], h_off.data_ptr())
             barrier()
             other[f"{label}: pairs/s end to end, batch {nb}"] = 3 * nb / (time.perf_counter() - t0)
+        # the reference's SSE=OFF result mode (GPC_RESULTS_NAIVE), device-resident like `value`
+        ctx.set_result_mode(True)
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(max(3, args.steps // 2)):
+                step()
+            e1.record(stream)
+        barrier()
+        other["GPC_RESULTS_NAIVE (the reference's SSE=OFF build), same forest: pairs/s, device-resident"] = \
+            B * max(3, args.steps // 2) / (e0.elapsed_time(e1) / 1e3)
+        ctx.set_result_mode(False)
 
     if rank != 0:
         if dist is not None:

@@ -23,6 +23,9 @@
 //     through evalFastMaskOnSubsetSSE + findCorrespondences on the caller's smooth / mask data.
 //   * useHashtable(true) reproduces the reference's hashtable matcher (hashmatch.hpp:48-272: 214673 buckets of
 //     at most 10 elements, a different and smaller match set than the sort path).
+//   * Results are those of the reference's default build (-D_INTRINSICS_SSE) whether or not that macro is
+//     defined here.  Define GPC_B200_NAIVE_RESULTS before including this header to get the results of the
+//     reference's SSE=OFF build instead (boxNaive, sobelNaive, gpcFilter[Tau]Naive; forests of at most 31 tests).
 //   * numThreads is accepted and ignored.
 #ifndef GPC_B200_INFERENCE_HPP
 #define GPC_B200_INFERENCE_HPP
@@ -114,6 +117,9 @@ struct Runtime {
     max_w = std::max(w, max_w); max_h = std::max(h, max_h);
     const int rc = gpc_create(&ctx, device, max_w, max_h, 1);
     if (rc != GPC_OK) throw GpcError(rc, std::string("gpc_create: ") + gpc_last_error(nullptr));
+#ifdef GPC_B200_NAIVE_RESULTS
+    gpc_set_result_mode(ctx, GPC_RESULTS_NAIVE);   // the reference's SSE=OFF build (filter.hpp *Naive functions)
+#endif
     return ctx;
   }
 };

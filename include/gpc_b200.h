@@ -166,6 +166,18 @@ int gpc_find_correspondences(gpc_ctx* ctx, const uint64_t* src_keys, int n_src, 
 int gpc_hashmatch(gpc_ctx* ctx, const uint64_t* src_keys, int n_src, const uint64_t* tar_keys, int n_tar,
                   int32_t* out_pairs, int cap, int* n_out);
 
+/* Which build of the reference the results reproduce.  GPC_RESULTS_SSE (default): the reference compiled with
+ * -D_INTRINSICS_SSE, its default (samples/CMakeLists.txt:13-17) and the build SURVEY.md 8a describes.
+ * GPC_RESULTS_NAIVE: its SSE=OFF build, whose box, sobel and gpcFilter[Tau] forward to boxNaive, sobelNaive and
+ * gpcFilter[Tau]Naive (filter.hpp:295-296, :406-407, :550-551, :622-623; bodies at :157-293): S = sum3x3 / 9,
+ * signed Sobel responses divided towards zero, `a > b - tau` in int, first test in the highest state bit, every
+ * candidate row hashed.  Different smooth / grad images, candidates, states and supports; matching is shared.
+ * Forests of 32 tests are refused in this mode (GPC_E_UNSUPPORTED: bit 31 of a hash word is the candidate flag).
+ * A forest set earlier is re-baked.  The fern hashing kernel runs un-specialised (no NVRTC build) in this mode. */
+#define GPC_RESULTS_SSE 0
+#define GPC_RESULTS_NAIVE 1
+int gpc_set_result_mode(gpc_ctx* ctx, int mode);
+
 /* Matcher selection.  AUTO: epipolar mode uses the per-row shared-memory matcher, global mode the
  * device-wide radix sort + segmented scan.  SORT forces the radix-sort matcher for both (same
  * results; used to cross-check the two implementations). */

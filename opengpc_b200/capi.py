@@ -23,7 +23,7 @@ SYMBOLS = ["gpc_create", "gpc_destroy", "gpc_last_error", "gpc_status_string", "
            "gpc_read_forest", "gpc_set_forest", "gpc_match_pair", "gpc_match_batch", "gpc_match_batch_device",
            "gpc_preprocess", "gpc_hash", "gpc_match_hash_images", "gpc_launch_count", "gpc_enable_kernel_timing",
            "gpc_kernel_times", "gpc_hash_smooth", "gpc_image_upload", "gpc_image_release", "gpc_image_preprocess",
-           "gpc_match_images", "gpc_correspond_images", "gpc_find_correspondences", "gpc_hashmatch", "gpc_set_matcher", "gpc_match_pyramid", "gpc_jit_status"]
+           "gpc_match_images", "gpc_correspond_images", "gpc_find_correspondences", "gpc_hashmatch", "gpc_set_result_mode", "gpc_set_matcher", "gpc_match_pyramid", "gpc_jit_status"]
 KERNEL_NAMES = ["smooth_sobel", "hash_tiles", "match_rows", "scans", "emit_supports"]
 
 
@@ -288,6 +288,10 @@ class Context:
         self._check(self.lib.gpc_find_correspondences(self._h, _ptr(src_keys), C.c_int(len(src_keys)), _ptr(tar_keys),
                                                       C.c_int(len(tar_keys)), _ptr(out), C.c_int(cap), C.byref(n)))
         return out[:n.value].copy()
+
+    def set_result_mode(self, naive):
+        """False: the reference's default (SSE) build; True: its SSE=OFF build (the *Naive functions)."""
+        self._check(self.lib.gpc_set_result_mode(self._h, C.c_int(1 if naive else 0)))
 
     def hashmatch(self, src_keys, tar_keys):
         """The reference's hashtable matcher (useHashtable) on explicit 64-bit keys -> int32 [n, 2]."""

@@ -16,7 +16,7 @@
 namespace gpc {
 cudaError_t launch_smooth_sobel(const PreprocessArgs&, int n_img, bool debug_out, cudaStream_t);
 cudaError_t launch_prep_from_smooth(const uint8_t* smooth, const uint8_t* flags, uint8_t* smooth_x, uint16_t* cand, int32_t* rowcnt,
-                                    int32_t* lastrow, int W, int H, cudaStream_t);
+                                    int32_t* lastrow, int W, int H, int naive, cudaStream_t);
 cudaError_t configure_hash_tiles();
 int make_smooth_tensor_map(void* out_map, const uint8_t* base, int W, int H, int n_img);
 cudaError_t launch_hash_tiles(const void* tensor_map, const HashArgs&, const ForestDev&, int n_img, cudaStream_t);
@@ -59,6 +59,7 @@ struct gpc_ctx {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   bool has_forest = false;
   gpc_forest forest_host{};
+  int result_mode = GPC_RESULTS_SSE;   // gpc_set_result_mode
   gpc::ForestDev forest_dev{};
   gpc::JitKernel* jit = nullptr;   // kernel A2 specialised for forest_dev (NVRTC), or nullptr -> generic kernel
   std::string jit_note = "no forest set";
@@ -142,27 +143,44 @@ int mark(gpc_ctx* c) {
 
 // Bake the forest for the kernel's shared-memory layout (the reference bakes it for the image
 // width instead, inference.hpp:427-428): see ForestDev.
-void bake_forest(const gpc_forest& f, gpc::ForestDev* d) {
+void bake_forest(const gpc_forest& f, gpc::ForestDev* d, int result_mode) {
   std::memset(d, 0, sizeof(*d));
   d->n_tests = f.n_tests;
   d->type = f.type;
+  d->naive = (result_mode == GPC_RESULTS_NAIVE) ? gpc::kResultsNaive : gpc::kResultsSse;
   auto imm = [](int dx, int dy) {
     const int o = dy * gpc::kPitch + dx;
     const int k = ((o % 4) + 4) % 4;
     return k * gpc::kCopyBytes + (o - k);
   };
+  // test slots the forest does not fill compare a pixel with itself: never true, state bit 0 (kernel A evaluates
+  // whole groups of tests without per-test guards); imm 0 = the quad's own word in copy 0
+  for (int t = 0; t < gpc::kMaxTests; t++) {                 // filter.hpp:574-584: t < 8 -> bit t, t >= 9 -> bit t - 1
+    const int p = (t < 8) ? t : t - 1;
+    d->pmul[t] = (t == 8) ? 1u : (1u << (p & 7));
+    if (d->naive) d->mtau2[t] = 0x80008000u;                 // 32768 - 0 in both lanes: "a + 0 > a" is false
+  }
+  if (d->naive) {
+    // gpcFilterNaive / gpcFilterTauNaive (filter.hpp:245-293): test t of T lands in bit T-1-t.  The kernel's slot s
+    // feeds state bit s (s < 8) or s - 1 (s > 8); slot 8 (the SSE build's ninth test, OR-ed into bit 0) stays empty.
+    const int T = f.n_tests;
+    for (int t = 0; t < T; t++) {
+      const int bit = T - 1 - t, slot = (bit < 8) ? bit : bit + 1;
+      d->imm_a[slot] = imm(f.ix[t], f.iy[t]);
+      d->imm_b[slot] = imm(f.jx[t], f.jy[t]);
+      const int tau = std::max(-256, std::min(256, (int)f.tau[t]));          // beyond +-255 the comparison is constant
+      const uint32_t k = (uint32_t)(32768 - (f.type == 1 ? tau : 0));
+      d->mtau2[slot] = k | (k << 16);
+    }
+    d->n_tests = (T <= 8) ? T : T + 1;                       // highest slot in use + 1
+    return;
+  }
   for (int t = 0; t < f.n_tests; t++) {
     d->imm_a[t] = imm(f.ix[t], f.iy[t]);
     d->imm_b[t] = imm(f.jx[t], f.jy[t]);
     int tau8 = (int)(int8_t)f.tau[t];                        // _mm_set1_epi8(tau): low 8 bits, signed
     uint32_t m = (uint32_t)(uint16_t)(int16_t)(-tau8);
     d->mtau2[t] = (f.type == 1) ? (m | (m << 16)) : 0u;
-  }
-  // tests beyond n_tests compare a pixel with itself: never true, state bit 0 (kernel A evaluates
-  // whole groups of tests without per-test guards); imm 0 = the quad's own word in copy 0
-  for (int t = 0; t < gpc::kMaxTests; t++) {                 // filter.hpp:574-584: t < 8 -> bit t, t >= 9 -> bit t - 1
-    const int p = (t < 8) ? t : t - 1;
-    d->pmul[t] = (t == 8) ? 1u : (1u << (p & 7));
   }
 }
 
@@ -222,18 +240,20 @@ int run_preprocess(gpc_ctx* c, const Slot& sl, const uint8_t* d_images, int n_im
   int rc = mark_on(c, sl); if (rc) return rc;                                      // event 0
   if (d_flags) {
     if (n_img != 1) return fail(c, GPC_E_ARG, "internal: the smooth seam handles one image");
-    GPC_CUDA(c, gpc::launch_prep_from_smooth(d_images, d_flags, smooth_x, cand, rowcnt, lastrow, w, h, sl.stream));
+    GPC_CUDA(c, gpc::launch_prep_from_smooth(d_images, d_flags, smooth_x, cand, rowcnt, lastrow, w, h, forest.naive, sl.stream));
   } else {
     gpc::PreprocessArgs a{};
     a.raw = d_images; a.smooth_x = smooth_x; a.cand = cand; a.rowcnt = rowcnt; a.lastrow = lastrow;
     a.smooth_out = d_smooth_out; a.grad_out = d_grad_out; a.W = w; a.H = h;
-    a.thr2 = (int32_t)(int16_t)(thr * thr);                                        // filter.hpp:418
+    a.naive = forest.naive;
+    a.thr2 = forest.naive ? thr * thr : (int32_t)(int16_t)(thr * thr);             // filter.hpp:159 / :418
     GPC_CUDA(c, gpc::launch_smooth_sobel(a, n_img, d_smooth_out || d_grad_out, sl.stream));
   }
   rc = mark_on(c, sl); if (rc) return rc;                                          // event 1
   gpc::HashArgs ha{};
   ha.cand = c->d_cand; ha.hash = c->d_hash;
   ha.W = w; ha.H = h; ha.img0 = img0;
+  ha.hash_y_end = forest.naive ? h - gpc::kRadius : h - 15;                       // filter.hpp:601-604; the naive filters hash every candidate
   if (c->jit && &forest == &c->forest_dev)
     GPC_CUDA(c, gpc::jit_launch_hash_tiles(c->jit, c->tmap, ha, forest, n_img, sl.stream));
   else
@@ -531,15 +551,34 @@ int gpc_set_forest(gpc_ctx* c, const gpc_forest* f) {
   GPC_CUDA(c, cudaSetDevice(c->device));
   GPC_CUDA(c, cudaStreamSynchronize(c->stream));     // earlier launches may still use the previous specialised kernel
   for (int l = 0; l < gpc_ctx::kLanes; l++) GPC_CUDA(c, cudaStreamSynchronize(c->lane_stream[l]));
+  if (c->result_mode == GPC_RESULTS_NAIVE && f->n_tests > 31)
+    return fail(c, GPC_E_UNSUPPORTED, "GPC_RESULTS_NAIVE supports forests of at most 31 tests (bit 31 of a hash word is the candidate flag)");
   gpc::jit_destroy(c->jit);
   c->jit = nullptr;
   c->forest_host = *f;
-  bake_forest(*f, &c->forest_dev);
+  bake_forest(*f, &c->forest_dev, c->result_mode);
   c->has_forest = true;
+  if (c->result_mode == GPC_RESULTS_NAIVE) { c->jit_note = "generic: naive result mode"; return GPC_OK; }
   std::string why;
   c->jit = gpc::jit_build_hash_tiles(c->forest_dev, &why);
   c->jit_note = c->jit ? "specialised" : ("generic: " + why);
   return GPC_OK;
+}
+
+// Which build of the reference the results reproduce: GPC_RESULTS_SSE (default; the reference built with
+// -D_INTRINSICS_SSE, samples/CMakeLists.txt:13-17) or GPC_RESULTS_NAIVE (its SSE=OFF build: boxNaive, sobelNaive,
+// gpcFilterNaive / gpcFilterTauNaive, filter.hpp:157-293).  A forest set earlier is re-baked for the new mode.
+int gpc_set_result_mode(gpc_ctx* c, int mode) {
+  if (!c) return GPC_E_ARG;
+  if (mode != GPC_RESULTS_SSE && mode != GPC_RESULTS_NAIVE) return fail(c, GPC_E_ARG, "unknown result mode");
+  if (mode == c->result_mode) return GPC_OK;
+  if (mode == GPC_RESULTS_NAIVE && c->has_forest && c->forest_host.n_tests > 31)
+    return fail(c, GPC_E_UNSUPPORTED, "GPC_RESULTS_NAIVE supports forests of at most 31 tests (bit 31 of a hash word is the candidate flag)");
+  c->result_mode = mode;
+  if (!c->has_forest) return GPC_OK;
+  const gpc_forest f = c->forest_host;
+  c->has_forest = false;                              // defeat the "unchanged forest" shortcut
+  return gpc_set_forest(c, &f);
 }
 
 int gpc_match_batch_device(gpc_ctx* c, const uint8_t* d_images, int n_pairs, int w, int h, const gpc_settings* s,
@@ -804,6 +843,7 @@ static int preprocess_device(gpc_ctx* c, const uint8_t* d_img, int w, int h, int
   int rc = ensure_debug_buffers(c); if (rc) return rc;
   const size_t P = (size_t)w * h;
   gpc::ForestDev none{};                           // no tests: hash image carries the candidate flag only
+  none.naive = (c->result_mode == GPC_RESULTS_NAIVE) ? gpc::kResultsNaive : gpc::kResultsSse;
   uint8_t* d_smooth = c->d_dbg8;
   uint8_t* d_grad = c->d_dbg8 + (size_t)c->max_w * c->max_h;
   rc = run_preprocess(c, Slot{0, c->stream}, d_img, 1, w, h, thr, none, d_smooth, d_grad);

@@ -56,12 +56,20 @@ static_assert(kThreadsA % kQuadsX == 0 && kTileH % (kThreadsA / kQuadsX) == 0, "
 // (dy * kPitch + dx - k) with k = (dy * kPitch + dx) mod 4.  Passed by value as a kernel
 // parameter: with the test loop fully unrolled every field is read from a fixed constant-bank
 // address (uniform datapath), never through an indexed load.
+// Result modes.  kResultsSse: the reference's default build (-D_INTRINSICS_SSE).  kResultsNaive: its SSE=OFF build
+// (the *Naive functions of filter.hpp: 3x3 sum / 9, signed Sobel, plain int tau compare, first test in the
+// highest bit, every candidate row hashed); the smoothed image is then kept UNBIASED and the fern tests are
+// assigned to the kernel's test slots by bit position.
+constexpr int kResultsSse = 0, kResultsNaive = 1;
+
 struct ForestDev {
-  int32_t n_tests;
-  int32_t type;                  // 0: a > b ; 1: a > sat_int8(b - tau)
+  int32_t n_tests;               // test slots in use (naive mode: highest slot + 1)
+  int32_t type;                  // 0: a > b ; 1: a > sat_int8(b - tau)  (naive mode: a > b - tau in int)
+  int32_t naive;                 // kResultsSse / kResultsNaive
   int32_t imm_a[kMaxTests];      // byte offset of operand a's word relative to the quad's word in copy 0
   int32_t imm_b[kMaxTests];
   uint32_t mtau2[kMaxTests];     // -tau (int8 tau) as int16 replicated into both 16-bit lanes; 0 = no tau
+                                 // (naive mode: 32768 - tau in both lanes, tau clamped to +-256)
   uint32_t pmul[kMaxTests];      // 1 << (bit position of the test inside its state byte); kept in the constant
                                  // bank so that the accumulate stays one IMAD.WIDE (an immediate power of two
                                  // is strength-reduced to five ALU-pipe instructions)
@@ -76,7 +84,8 @@ struct PreprocessArgs {     // kernel A1; all pointers already offset to the fir
   uint8_t* smooth_out;     // optional [n_img][H][W] (debug seam: unbiased)
   uint8_t* grad_out;       // optional [n_img][H][W] (debug seam: 0 / 255)
   int32_t W, H;
-  int32_t thr2;            // (int16)(thr*thr), filter.hpp:418
+  int32_t thr2;            // (int16)(thr*thr), filter.hpp:418  (naive mode: thr*thr as int, filter.hpp:159)
+  int32_t naive;           // kResultsNaive: boxNaive / sobelNaive semantics, smooth_x unbiased
 };
 
 struct HashArgs {           // kernel A2; pointers are buffer BASES, img0 = first image of the launch
@@ -84,6 +93,7 @@ struct HashArgs {           // kernel A2; pointers are buffer BASES, img0 = firs
   uint32_t* hash;          // [..][H][W]
   int32_t W, H;
   int32_t img0;
+  int32_t hash_y_end;      // rows kRadius <= y < hash_y_end are hashed: H - 15 (filter.hpp:601-604), naive mode H - 13
 };
 
 struct MatchArgs {

@@ -42,18 +42,34 @@ constexpr uint32_t kLow7 = 0x7f7f7f7fu;
 #include GPC_JIT_HEADER      // forest baked into the code: jit_imm_a(t), jit_imm_b(t), jit_mtau2(t), kJitTests
 #endif
 
-template <bool kTau>
+// kMode: 0 = a > b (biased bytes, signed compare), 1 = tau forest of the SSE build, 2 / 3 = the same two for the
+// reference's SSE=OFF build (unbiased bytes; gpcFilterNaive / gpcFilterTauNaive, filter.hpp:245-293).
+constexpr int kModeZero = 0, kModeTau = 1, kModeNaiveZero = 2, kModeNaiveTau = 3;
+
+template <int kMode>
 __device__ __forceinline__ uint32_t eval_test(const uint8_t* base, const ForestDev& forest, const int t) {
 #ifdef GPC_JIT_HEADER
   if (t >= kJitTests) return 0u;                                             // compile time after unrolling
   const uint32_t a = *reinterpret_cast<const uint32_t*>(base + jit_imm_a(t));
   uint32_t c = *reinterpret_cast<const uint32_t*>(base + jit_imm_b(t));
-  if (kTau && jit_mtau2(t) != 0u) {
+  if (kMode == kModeTau && jit_mtau2(t) != 0u) {
     const uint32_t mt = jit_mtau2(t);
 #else
   const uint32_t a = *reinterpret_cast<const uint32_t*>(base + forest.imm_a[t]);
   uint32_t c = *reinterpret_cast<const uint32_t*>(base + forest.imm_b[t]);
-  if (kTau) {
+  if (kMode == kModeNaiveTau) {
+    // a > b - tau in plain int arithmetic, two pixels per word in 16-bit lanes: lane = b + (32768 - tau) - a stays
+    // inside 16 bits, and its bit 15 is CLEAR exactly when a + tau > b
+    const uint32_t k2 = forest.mtau2[t];
+    const uint32_t lo = __byte_perm(c, 0u, 0x4140) + k2 - __byte_perm(a, 0u, 0x4140);
+    const uint32_t hi = __byte_perm(c, 0u, 0x4342) + k2 - __byte_perm(a, 0u, 0x4342);
+    return ~__byte_perm(lo, hi, 0x7531) & kMsb;
+  }
+  if (kMode == kModeNaiveZero) {                                             // unsigned a > c on unbiased bytes
+    const uint32_t s = (a & kLow7) + (~c & kLow7);
+    return ((a & ~c) | (~(a ^ c) & s)) & kMsb;
+  }
+  if (kMode == kModeTau) {
     const uint32_t mt = forest.mtau2[t];
 #endif
     const uint32_t lo = __viaddmin_s16x2_relu(__byte_perm(c, 0u, 0x4140), mt, 0x00ff00ffu);
@@ -66,18 +82,18 @@ __device__ __forceinline__ uint32_t eval_test(const uint8_t* base, const ForestD
 
 // All tests of state byte G (filter.hpp:574-584: tests 0..8 -> byte 0 with test 8 OR-ed into bit 0
 // under m8, 9..16 -> byte 1, 17..24 -> byte 2, 25..31 -> byte 3).
-template <bool kTau, int G>
+template <int kMode, int G>
 __device__ __forceinline__ unsigned long long eval_group(const uint8_t* base, const ForestDev& forest, uint32_t m8) {
   constexpr int t0 = (G == 0) ? 1 : 8 * G + 1;
   constexpr int t1 = (G == 0) ? 8 : (G == 3) ? kMaxTests : 8 * G + 9;       // exclusive
   unsigned long long acc = 0ull;
   if (G == 0) {
-    const uint32_t r0 = eval_test<kTau>(base, forest, 0), r8 = eval_test<kTau>(base, forest, 8);
+    const uint32_t r0 = eval_test<kMode>(base, forest, 0), r8 = eval_test<kMode>(base, forest, 8);
     acc = (unsigned long long)(r0 | (r8 & m8));
   }
 #pragma unroll
   for (int t = t0; t < t1; t++)
-    acc += (unsigned long long)eval_test<kTau>(base, forest, t) * (unsigned long long)forest.pmul[t];
+    acc += (unsigned long long)eval_test<kMode>(base, forest, t) * (unsigned long long)forest.pmul[t];
   return acc;
 }
 
@@ -86,7 +102,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 #ifndef GPC_MINB_A
 #define GPC_MINB_A 1
 #endif
-template <bool kTau>
+template <int kMode>
 __device__ __forceinline__ void hash_tiles_body(const CUtensorMap& tmap, const HashArgs& args, const ForestDev& forest) {
   extern __shared__ __align__(128) uint8_t smem[];                // 4 copies of [kSmRows][kPitch] biased bytes
   __shared__ __align__(8) unsigned long long mbar;
@@ -152,7 +168,7 @@ __device__ __forceinline__ void hash_tiles_body(const CUtensorMap& tmap, const H
 
   // ---- fern tests, 4 pixels per step ---------------------------------------------------------------------
   uint32_t* __restrict__ hash = args.hash + img_off;
-  const uint32_t m8 = (gx & 4) ? kMsb : 0x80808000u;              // test #8: byte lanes x%8==0 dropped (filter.hpp:582)
+  const uint32_t m8 = (gx & 4) ? kMsb : 0x80808000u;              // test #8: byte lanes x%8==0 dropped (filter.hpp:582); naive mode: slot 8 is a dummy
   const int T = forest.n_tests;
   const int n_groups = (T <= 9) ? 1 : (T <= 17) ? 2 : (T <= 25) ? 3 : 4;
 #pragma unroll 1
@@ -161,13 +177,13 @@ __device__ __forceinline__ void hash_tiles_body(const CUtensorMap& tmap, const H
     const int gy = y0 + ry;
     const uint32_t cm = (cms >> (4 * i)) & 15u;
     uint32_t st[4] = {0u, 0u, 0u, 0u};
-    if (cm != 0u && gy >= kRadius && gy < H - 15) {                // hashed rows (filter.hpp:601-604)
+    if (cm != 0u && gy >= kRadius && gy < args.hash_y_end) {       // hashed rows (filter.hpp:601-604)
       const uint8_t* base = smem + (ry + kRadius) * kPitch + 16 + 4 * qx;
       unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
-      acc[0] = eval_group<kTau, 0>(base, forest, m8);
-      if (n_groups > 1) acc[1] = eval_group<kTau, 1>(base, forest, m8);      // uniform branches
-      if (n_groups > 2) acc[2] = eval_group<kTau, 2>(base, forest, m8);
-      if (n_groups > 3) acc[3] = eval_group<kTau, 3>(base, forest, m8);
+      acc[0] = eval_group<kMode, 0>(base, forest, m8);
+      if (n_groups > 1) acc[1] = eval_group<kMode, 1>(base, forest, m8);      // uniform branches
+      if (n_groups > 2) acc[2] = eval_group<kMode, 2>(base, forest, m8);
+      if (n_groups > 3) acc[3] = eval_group<kMode, 3>(base, forest, m8);
       // byte j of (acc[g] >> 7) = state byte g of pixel j; 4x4 byte transpose -> one state per pixel
       uint32_t w[4];
 #pragma unroll
@@ -188,17 +204,17 @@ __device__ __forceinline__ void hash_tiles_body(const CUtensorMap& tmap, const H
   }
 }
 
-template <bool kTau>
+template <int kMode>
 __global__ void __launch_bounds__(kThreadsA, GPC_MINB_A)
 hash_tiles_kernel(const __grid_constant__ CUtensorMap tmap, const HashArgs args, const ForestDev forest) {
-  hash_tiles_body<kTau>(tmap, args, forest);
+  hash_tiles_body<kMode>(tmap, args, forest);
 }
 
 #ifdef GPC_JIT_HEADER
 // Entry point of the forest-specialised build (NVRTC, jit.cu): unmangled name, forest baked in.
 extern "C" __global__ void __launch_bounds__(kThreadsA, GPC_MINB_A)
 gpc_hash_tiles_jit(const __grid_constant__ CUtensorMap tmap, const HashArgs args, const ForestDev forest) {
-  hash_tiles_body<kJitTau>(tmap, args, forest);
+  hash_tiles_body<kJitTau ? kModeTau : kModeZero>(tmap, args, forest);
 }
 #endif
 
@@ -206,8 +222,10 @@ gpc_hash_tiles_jit(const __grid_constant__ CUtensorMap tmap, const HashArgs args
 size_t hash_smem_bytes() { return (size_t)4 * kCopyBytes; }
 
 cudaError_t configure_hash_tiles() {   // per device: opt in to > 48 KB dynamic shared memory
-  cudaError_t e = cudaFuncSetAttribute(hash_tiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hash_smem_bytes());
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(hash_tiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hash_smem_bytes());
+  cudaError_t e = cudaFuncSetAttribute(hash_tiles_kernel<kModeZero>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hash_smem_bytes());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(hash_tiles_kernel<kModeTau>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hash_smem_bytes());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(hash_tiles_kernel<kModeNaiveZero>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hash_smem_bytes());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(hash_tiles_kernel<kModeNaiveTau>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hash_smem_bytes());
   return e;
 }
 
@@ -236,8 +254,11 @@ int make_smooth_tensor_map(void* out_map, const uint8_t* base, int W, int H, int
 cudaError_t launch_hash_tiles(const void* tensor_map, const HashArgs& args, const ForestDev& forest, int n_img, cudaStream_t stream) {
   dim3 grid((args.W + kTileW - 1) / kTileW, (args.H + kTileH - 1) / kTileH, n_img);
   const CUtensorMap& tmap = *reinterpret_cast<const CUtensorMap*>(tensor_map);
-  if (forest.type != 0) hash_tiles_kernel<true><<<grid, kThreadsA, hash_smem_bytes(), stream>>>(tmap, args, forest);
-  else hash_tiles_kernel<false><<<grid, kThreadsA, hash_smem_bytes(), stream>>>(tmap, args, forest);
+  if (forest.naive) {
+    if (forest.type != 0) hash_tiles_kernel<kModeNaiveTau><<<grid, kThreadsA, hash_smem_bytes(), stream>>>(tmap, args, forest);
+    else hash_tiles_kernel<kModeNaiveZero><<<grid, kThreadsA, hash_smem_bytes(), stream>>>(tmap, args, forest);
+  } else if (forest.type != 0) hash_tiles_kernel<kModeTau><<<grid, kThreadsA, hash_smem_bytes(), stream>>>(tmap, args, forest);
+  else hash_tiles_kernel<kModeZero><<<grid, kThreadsA, hash_smem_bytes(), stream>>>(tmap, args, forest);
   return cudaGetLastError();
 }
 #endif   // !__CUDACC_RTC__

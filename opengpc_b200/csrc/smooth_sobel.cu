@@ -196,8 +196,143 @@ smooth_sobel_kernel(const PreprocessArgs args) {
     atomicMax(args.lastrow + img, cta_last);              // a stale read only costs a redundant atomic
 }
 
+// ---- the reference's SSE=OFF build: boxNaive + clearBoundary, sobelNaive (filter.hpp:157-231) --------------------
+// Same tile, same outputs, different arithmetic: S = (sum of the 3x3 neighbourhood) / 9 on rows 1..H-3, columns
+// 2..W-2; Sobel responses are signed, divided by 9 towards zero, compared in int, one result per pixel (no lane
+// duplication).  The reference walks the image as one linear array, so the neighbours of the first / last column
+// are the adjacent rows' bytes: the tile is staged by LINEAR address (zero outside the image) to reproduce that in
+// the gradient image.  The smoothed image is written UNBIASED (kernel A2's naive modes compare unsigned bytes).
+__device__ __forceinline__ int div9_toward_zero(int v) {                     // |v| <= 1020
+  const int q = (int)ninth((uint32_t)abs(v));
+  return v < 0 ? -q : q;
+}
+
+template <bool kDebugOut>
+__global__ void __launch_bounds__(kPreThreads)
+smooth_sobel_naive_kernel(const PreprocessArgs args) {
+  __shared__ __align__(16) uint32_t raw32[kPreRows * kPrePitchW];
+  __shared__ int cta_last;
+  const int W = args.W, H = args.H;
+  const int img = blockIdx.z;
+  const int x0 = blockIdx.x * kPreW, y0 = blockIdx.y * kPreH;
+  const int tid = threadIdx.x;
+  const size_t img_off = (size_t)img * W * H;
+  const uint8_t* __restrict__ raw = args.raw + img_off;
+  const long long n_pix = (long long)W * H;
+
+  if (threadIdx.x == 0) cta_last = -1;
+  {
+    constexpr int kChunks = kPrePitch / 16;
+    uint4* dst = reinterpret_cast<uint4*>(raw32);
+    for (int c = tid; c < kPreRows * kChunks; c += kPreThreads) {
+      const int r = c / kChunks, k = c - r * kChunks;
+      const long long idx = (long long)(y0 - 1 + r) * W + (x0 - 16 + 16 * k);      // linear memory, as the reference reads it
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (idx >= 0 && idx + 16 <= n_pix) v = __ldg(reinterpret_cast<const uint4*>(raw + idx));
+      dst[c] = v;
+    }
+  }
+  __syncthreads();
+  const uint8_t* raw8 = reinterpret_cast<const uint8_t*>(raw32);
+
+  // ---- smoothed pixels: thread = (quad column, band of rows), 3-row window of horizontal 3-sums ------------------
+  {
+    const int q = tid % (kPreW / 4), band = tid / (kPreW / 4);
+    const int gxq = x0 + 4 * q;
+    if (gxq < W) {
+      uint32_t colmask = 0xffffffffu;                      // clearBoundary: columns 0,1 and W-1
+      if (gxq == 0) colmask = 0xffff0000u;
+      if (gxq == W - 4) colmask &= 0x00ffffffu;
+      uint32_t ha[4], hb[4], hc[4];
+      auto load_h = [&](int r, uint32_t h[4]) {            // raw-tile row r = image row y0 - 1 + r
+        const uint32_t* row = raw32 + r * kPrePitchW + 4 + q;
+        const uint32_t wm1 = row[-1], w = row[0], wp1 = row[1];
+        h[0] = __dp4a(__funnelshift_r(wm1, w, 24), 0x00010101u, 0u);
+        h[1] = __dp4a(w, 0x00010101u, 0u);
+        h[2] = __dp4a(w, 0x01010100u, 0u);
+        h[3] = __dp4a(__funnelshift_r(w, wp1, 16), 0x00010101u, 0u);
+      };
+      const int j0 = band * kPreSegRows;
+      load_h(j0, ha);
+      load_h(j0 + 1, hb);
+#pragma unroll 4
+      for (int j = j0; j < j0 + kPreSegRows; j++) {
+        load_h(j + 2, hc);
+        uint32_t v = ninth(ha[0] + hb[0] + hc[0]) | (ninth(ha[1] + hb[1] + hc[1]) << 8) |
+                     (ninth(ha[2] + hb[2] + hc[2]) << 16) | (ninth(ha[3] + hb[3] + hc[3]) << 24);   // sums <= 2295: exact / 9
+        const int gy = y0 + j;
+        if (gy < 1 || gy > H - 3) v = 0u; else v &= colmask;      // clearBoundary: row 0, rows H-2, H-1
+        if (gy < H) {
+          *reinterpret_cast<uint32_t*>(args.smooth_x + img_off + (size_t)gy * W + gxq) = v;
+          if (kDebugOut && args.smooth_out)
+            *reinterpret_cast<uint32_t*>(args.smooth_out + img_off + (size_t)gy * W + gxq) = v;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) { ha[k] = hb[k]; hb[k] = hc[k]; }
+      }
+    }
+  }
+
+  // ---- Sobel predicate per pixel -> candidate bit masks per 16-pixel segment, per-row candidate counts -------------
+  {
+    const int segs_per_row = W / 16;
+    for (int sr = tid; sr < kPreH * (kPreW / 16); sr += kPreThreads) {
+      const int ry = sr / (kPreW / 16), sg = sr - ry * (kPreW / 16);
+      const int gy = y0 + ry, gxs = x0 + 16 * sg;
+      const bool valid = gy < H && gxs < W;
+      uint32_t m = 0;
+      // written outputs: linear positions W+1 .. (H-1)*W (filter.hpp:171-185): rows 1..H-2 except (1,0), plus (H-1,0)
+      if (valid && gy >= 1 && (gy <= H - 2 || (gy == H - 1 && gxs == 0))) {
+        const uint8_t* r0 = raw8 + (ry + 0) * kPrePitch + 16 + 16 * sg;    // image rows gy-1, gy, gy+1 at column gxs
+        const uint8_t* r1 = r0 + kPrePitch;
+        const uint8_t* r2 = r1 + kPrePitch;
+        const int npx = (gy == H - 1) ? 1 : 16;
+#pragma unroll 4
+        for (int j = 0; j < npx; j++) {
+          const int p11 = r0[j - 1], p12 = r0[j], p13 = r0[j + 1];
+          const int p21 = r1[j - 1], p23 = r1[j + 1];
+          const int p31 = r2[j - 1], p32 = r2[j], p33 = r2[j + 1];
+          const int sx = div9_toward_zero(p11 + p31 + 2 * p21 - p13 - 2 * p23 - p33);
+          const int sy = div9_toward_zero(p11 + p13 + 2 * p12 - p31 - 2 * p32 - p33);
+          if (sx * sx + sy * sy > args.thr2) m |= 1u << j;
+        }
+        if (gy == 1 && gxs == 0) m &= ~1u;                                 // (1,0) is never written
+      }
+      if (kDebugOut && args.grad_out && valid) {
+        uint32_t wv[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          uint32_t nib = (m >> (4 * k)) & 15u;
+          wv[k] = ((nib & 1u) * 0xffu) | ((nib & 2u) * (0xff00u >> 1)) | ((nib & 4u) * (0xff0000u >> 2)) |
+                  ((nib & 8u) * (0xff000000u >> 3));
+        }
+        *reinterpret_cast<uint4*>(args.grad_out + img_off + (size_t)gy * W + gxs) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+      }
+      const uint32_t bm = valid ? border_mask(m, gy, gxs, W, H) : 0u;
+      if (valid) args.cand[((size_t)img * H + gy) * segs_per_row + (gxs >> 4)] = (uint16_t)bm;
+      int cnt = __popc(bm);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, 8);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+      if ((tid & 15) == 0 && cnt > 0) {
+        atomicAdd(args.rowcnt + (size_t)img * H + gy, cnt);
+        atomicMax(&cta_last, gy);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0 && cta_last >= 0 && cta_last > *reinterpret_cast<volatile int32_t*>(args.lastrow + img))
+    atomicMax(args.lastrow + img, cta_last);
+}
+
 cudaError_t launch_smooth_sobel(const PreprocessArgs& args, int n_img, bool debug_out, cudaStream_t stream) {
   dim3 grid((args.W + kPreW - 1) / kPreW, (args.H + kPreH - 1) / kPreH, n_img);
+  if (args.naive) {
+    if (debug_out) smooth_sobel_naive_kernel<true><<<grid, kPreThreads, 0, stream>>>(args);
+    else smooth_sobel_naive_kernel<false><<<grid, kPreThreads, 0, stream>>>(args);
+    return cudaGetLastError();
+  }
   if (debug_out) smooth_sobel_kernel<true><<<grid, kPreThreads, 0, stream>>>(args);
   else smooth_sobel_kernel<false><<<grid, kPreThreads, 0, stream>>>(args);
   return cudaGetLastError();
@@ -207,13 +342,14 @@ cudaError_t launch_smooth_sobel(const PreprocessArgs& args, int n_img, bool debu
 // biased smooth image and the candidate masks kernel A2 consumes.  One thread per 16-pixel segment.
 __global__ void __launch_bounds__(256)
 prep_from_smooth_kernel(const uint8_t* __restrict__ smooth, const uint8_t* __restrict__ flags, uint8_t* __restrict__ smooth_x,
-                        uint16_t* __restrict__ cand, int32_t* __restrict__ rowcnt, int32_t* __restrict__ lastrow, int W, int H) {
+                        uint16_t* __restrict__ cand, int32_t* __restrict__ rowcnt, int32_t* __restrict__ lastrow, int W, int H,
+                        uint32_t bias) {
   const int segs_per_row = W / 16;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= segs_per_row * H) return;
   const int gy = i / segs_per_row, gxs = 16 * (i - gy * segs_per_row);
   uint4 v = __ldg(reinterpret_cast<const uint4*>(smooth + (size_t)gy * W + gxs));
-  v.x ^= 0x80808080u; v.y ^= 0x80808080u; v.z ^= 0x80808080u; v.w ^= 0x80808080u;
+  v.x ^= bias; v.y ^= bias; v.z ^= bias; v.w ^= bias;       // 0x80808080, or 0 in the naive result mode
   *reinterpret_cast<uint4*>(smooth_x + (size_t)gy * W + gxs) = v;
   const uint4 f = __ldg(reinterpret_cast<const uint4*>(flags + (size_t)gy * W + gxs));
   const uint32_t wv[4] = {f.x, f.y, f.z, f.w};
@@ -229,9 +365,10 @@ prep_from_smooth_kernel(const uint8_t* __restrict__ smooth, const uint8_t* __res
 }
 
 cudaError_t launch_prep_from_smooth(const uint8_t* smooth, const uint8_t* flags, uint8_t* smooth_x, uint16_t* cand, int32_t* rowcnt,
-                                    int32_t* lastrow, int W, int H, cudaStream_t stream) {
+                                    int32_t* lastrow, int W, int H, int naive, cudaStream_t stream) {
   const int n = (W / 16) * H;
-  prep_from_smooth_kernel<<<(n + 255) / 256, 256, 0, stream>>>(smooth, flags, smooth_x, cand, rowcnt, lastrow, W, H);
+  prep_from_smooth_kernel<<<(n + 255) / 256, 256, 0, stream>>>(smooth, flags, smooth_x, cand, rowcnt, lastrow, W, H,
+                                                               naive ? 0u : 0x80808080u);
   return cudaGetLastError();
 }
 

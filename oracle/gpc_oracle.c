@@ -184,6 +184,72 @@ void gpco_hash(const uint8_t* smooth, int w, int h, const gpco_forest* f,
 }
 
 /* ------------------------------------------------------------------------------------------
+ * The reference's SSE=OFF build (samples/CMakeLists.txt:13-17 option SSE): box, sobel, gpcFilter and
+ * gpcFilterTau forward to their *Naive versions (filter.hpp:295-296, :406-407, :550-551, :622-623),
+ * which produce different images, candidates and states than the SSE code.  All three walk the image
+ * as one linear array: "left" and "right" neighbours of the first / last column are the bytes of the
+ * adjacent rows, and the last two outputs read two bytes past the image (taken as 0 here; both land
+ * in rows / columns that are cleared or never become candidates).
+ * ---------------------------------------------------------------------------------------- */
+static inline int lin(const uint8_t* in, long long n, long long i) { return (i < 0 || i >= n) ? 0 : in[i]; }
+
+/* boxNaive (filter.hpp:207-231) + clearBoundary: plain sum of the 3x3 neighbourhood / 9 */
+void gpco_box_naive(const uint8_t* in, uint8_t* smooth, int w, int h) {
+  long long n = (long long)w * h;
+  memset(smooth, 0, (size_t)n);
+  for (long long o = w + 1; o <= (long long)(h - 1) * w; o++) {          /* (height-2)*width outputs from blurred+width+1 */
+    int sum = 0;
+    for (int dy = -1; dy <= 1; dy++)
+      for (int dx = -1; dx <= 1; dx++) sum += lin(in, n, o + (long long)dy * w + dx);
+    smooth[o] = (uint8_t)(sum / 9);
+  }
+  for (int y = 0; y < h; y++) {                                            /* clearBoundary, buffer.hpp:638-652 */
+    smooth[(size_t)y * w + 0] = 0;
+    if (w > 1) smooth[(size_t)y * w + 1] = 0;
+    smooth[(size_t)y * w + w - 1] = 0;
+  }
+  for (int x = 0; x < w; x++) {
+    smooth[x] = 0;
+    if (h >= 2) smooth[(size_t)(h - 2) * w + x] = 0;
+    if (h >= 1) smooth[(size_t)(h - 1) * w + x] = 0;
+  }
+}
+
+/* sobelNaive (filter.hpp:157-187): signed Sobel responses, C division (towards zero), int compare.
+ * Positions the reference never writes (row 0, (1,0), row h-1 from column 1) are 0 here. */
+void gpco_sobel_naive(const uint8_t* in, uint8_t* grad, int w, int h, int thr) {
+  long long n = (long long)w * h;
+  int thr2 = (thr & 255) * (thr & 255);
+  memset(grad, 0, (size_t)n);
+  for (long long o = w + 1; o <= (long long)(h - 1) * w; o++) {
+    int p11 = lin(in, n, o - w - 1), p12 = lin(in, n, o - w), p13 = lin(in, n, o - w + 1);
+    int p21 = lin(in, n, o - 1), p23 = lin(in, n, o + 1);
+    int p31 = lin(in, n, o + w - 1), p32 = lin(in, n, o + w), p33 = lin(in, n, o + w + 1);
+    int sx = (p11 + p31 + 2 * p21 - p13 - 2 * p23 - p33) / 9;            /* :176 */
+    int sy = (p11 + p13 + 2 * p12 - p31 - 2 * p32 - p33) / 9;            /* :177 */
+    grad[o] = (sx * sx + sy * sy > thr2) ? 255 : 0;                        /* :179-181 */
+  }
+}
+
+/* gpcFilterNaive / gpcFilterTauNaive (filter.hpp:245-262, :275-293): every candidate is hashed (no row
+ * range), the first test ends up in the highest bit, the tau comparison is plain int arithmetic */
+void gpco_hash_naive(const uint8_t* smooth, int w, int h, const gpco_forest* f,
+                     const int32_t* mask, int n, uint32_t* states) {
+  (void)h;
+  for (int i = 0; i < n; i++) {
+    int k = mask[i];
+    uint32_t st = 0;
+    for (int t = 0; t < f->n_tests && t < 32; t++) {
+      int a = smooth[k + f->ix[t] + f->iy[t] * w];
+      int b = smooth[k + f->jx[t] + f->jy[t] * w];
+      st <<= 1;
+      if (f->type == 1 ? (a > b - f->tau[t]) : (a > b)) st++;
+    }
+    states[i] = st;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
  * Row M: Forest::findCorrespondences (inference.hpp:227-254)
  * ---------------------------------------------------------------------------------------- */
 typedef struct { uint64_t key; int32_t idx; } kv_t;
@@ -409,18 +475,19 @@ int gpco_read_forest(const char* path, gpco_forest* f) {
 
 /* sparsematch.cpp:46-51 */
 static int pair_impl(const uint8_t* L, const uint8_t* R, int w, int h, const gpco_forest* f,
-                     const gpco_settings* s, gpco_support* supp, int* n_cand_l, int* n_cand_r, int use_hashtable) {
+                     const gpco_settings* s, gpco_support* supp, int* n_cand_l, int* n_cand_r, int use_hashtable, int naive) {
   size_t P = (size_t)w * h;
   uint8_t* sm[2]; uint8_t* gr[2]; int32_t* mk[2]; uint32_t* st[2]; int n[2];
   const uint8_t* img[2] = { L, R };
   for (int k = 0; k < 2; k++) {
     sm[k] = (uint8_t*)malloc(P); gr[k] = (uint8_t*)malloc(P);
     mk[k] = (int32_t*)malloc(P * 4 + 4);
-    gpco_box(img[k], sm[k], w, h);
-    gpco_sobel(img[k], gr[k], w, h, s->gradient_threshold);
+    if (naive) { gpco_box_naive(img[k], sm[k], w, h); gpco_sobel_naive(img[k], gr[k], w, h, s->gradient_threshold); }
+    else { gpco_box(img[k], sm[k], w, h); gpco_sobel(img[k], gr[k], w, h, s->gradient_threshold); }
     n[k] = gpco_candidates(gr[k], w, h, mk[k]);
     st[k] = (uint32_t*)malloc((size_t)(n[k] > 0 ? n[k] : 1) * 4);
-    gpco_hash(sm[k], w, h, f, mk[k], n[k], st[k]);
+    if (naive) gpco_hash_naive(sm[k], w, h, f, mk[k], n[k], st[k]);
+    else gpco_hash(sm[k], w, h, f, mk[k], n[k], st[k]);
   }
   int ns = use_hashtable ? gpco_match_hashtable(mk[0], st[0], n[0], mk[1], st[1], n[1], w, s, NULL, NULL, supp)
                          : gpco_match(mk[0], st[0], n[0], mk[1], st[1], n[1], w, s, NULL, NULL, supp);
@@ -432,10 +499,16 @@ static int pair_impl(const uint8_t* L, const uint8_t* R, int w, int h, const gpc
 
 int gpco_pair(const uint8_t* L, const uint8_t* R, int w, int h, const gpco_forest* f,
               const gpco_settings* s, gpco_support* supp, int* n_cand_l, int* n_cand_r) {
-  return pair_impl(L, R, w, h, f, s, supp, n_cand_l, n_cand_r, 0);
+  return pair_impl(L, R, w, h, f, s, supp, n_cand_l, n_cand_r, 0, 0);
 }
 
 int gpco_pair_hashtable(const uint8_t* L, const uint8_t* R, int w, int h, const gpco_forest* f,
                         const gpco_settings* s, gpco_support* supp, int* n_cand_l, int* n_cand_r) {
-  return pair_impl(L, R, w, h, f, s, supp, n_cand_l, n_cand_r, 1);
+  return pair_impl(L, R, w, h, f, s, supp, n_cand_l, n_cand_r, 1, 0);
+}
+
+/* the whole pair in the reference's SSE=OFF result mode (use_hashtable as in InferenceSettings) */
+int gpco_pair_naive(const uint8_t* L, const uint8_t* R, int w, int h, const gpco_forest* f,
+                    const gpco_settings* s, int use_hashtable, gpco_support* supp, int* n_cand_l, int* n_cand_r) {
+  return pair_impl(L, R, w, h, f, s, supp, n_cand_l, n_cand_r, use_hashtable, 1);
 }

@@ -86,6 +86,14 @@ int gpco_read_forest(const char* path, gpco_forest* f);
 int gpco_pair(const uint8_t* L, const uint8_t* R, int w, int h, const gpco_forest* f,
               const gpco_settings* s, gpco_support* supp, int* n_cand_l, int* n_cand_r);
 
+/* The reference's SSE=OFF build: boxNaive (filter.hpp:207-231) + clearBoundary, sobelNaive (:157-187),
+ * gpcFilterNaive / gpcFilterTauNaive (:245-262, :275-293); candidates and matching are shared with the SSE build. */
+void gpco_box_naive(const uint8_t* in, uint8_t* smooth, int w, int h);
+void gpco_sobel_naive(const uint8_t* in, uint8_t* grad, int w, int h, int thr);
+void gpco_hash_naive(const uint8_t* smooth, int w, int h, const gpco_forest* f,
+                     const int32_t* mask, int n, uint32_t* states);
+int gpco_pair_naive(const uint8_t* L, const uint8_t* R, int w, int h, const gpco_forest* f,
+                    const gpco_settings* s, int use_hashtable, gpco_support* supp, int* n_cand_l, int* n_cand_r);
 /* gpco_pair with InferenceSettings::useHashtable(true) */
 int gpco_pair_hashtable(const uint8_t* L, const uint8_t* R, int w, int h, const gpco_forest* f,
                         const gpco_settings* s, gpco_support* supp, int* n_cand_l, int* n_cand_r);

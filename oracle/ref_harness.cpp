@@ -44,8 +44,12 @@ Settings make_settings(int thr, int disp_high, int vt, int epipolar, int num_thr
 }
 
 void zero_unwritten_row(Forest::PreprocessedImage& p) {
+#ifdef _INTRINSICS_SSE
   int h = (int)p.smooth.rows(), w = (int)p.smooth.cols();
   if (h >= 3 && (h % 2) == 0) std::memset(p.smooth.data() + (size_t)(h - 3) * w, 0, (size_t)w);
+#else
+  (void)p;   // the SSE=OFF build (boxNaive, filter.hpp:207-231) writes every row that clearBoundary leaves
+#endif
 }
 
 double ms_between(gpc::inference::time_point a, gpc::inference::time_point b) {
@@ -57,6 +61,15 @@ double ms_between(gpc::inference::time_point a, gpc::inference::time_point b) {
 extern "C" {
 
 struct ref_support { int32_t x, y; float d; };
+
+// 1: compiled with -D_INTRINSICS_SSE (the reference's default build), 0: the SSE=OFF build (*Naive functions)
+int ref_is_sse_build() {
+#ifdef _INTRINSICS_SSE
+  return 1;
+#else
+  return 0;
+#endif
+}
 
 int ref_sizeof_descriptor() { return (int)sizeof(ndb::Descriptor); }
 int ref_sizeof_support() { return (int)sizeof(ndb::Support); }

@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "libgpc_oracle.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libgpc_ref.so")
+REF_NAIVE_SO = os.path.join(ORACLE_DIR, "_ref", "libgpc_ref_naive.so")      # the reference's SSE=OFF build
 FOREST_TAU = os.path.join(ROOT, "forests", "defaultTauForest.txt")
 FOREST_ZERO = os.path.join(ROOT, "forests", "defaultZeroForest.txt")
 
@@ -205,20 +206,44 @@ class Oracle:
         st = self.hash(sm, forest, mk)
         return sm, gr, mk, st
 
+    # ---- the reference's SSE=OFF build (the *Naive functions of filter.hpp) ---------------------
+    def stages_naive(self, img, forest, thr):
+        h, w = img.shape
+        img = np.ascontiguousarray(img)
+        sm = np.empty((h, w), np.uint8)
+        gr = np.empty((h, w), np.uint8)
+        self.lib.gpco_box_naive(_p(img), _p(sm), C.c_int(w), C.c_int(h))
+        self.lib.gpco_sobel_naive(_p(img), _p(gr), C.c_int(w), C.c_int(h), C.c_int(thr))
+        mk = self.candidates(gr)
+        st = np.empty(max(len(mk), 1), np.uint32)
+        self.lib.gpco_hash_naive(_p(sm), C.c_int(w), C.c_int(h), C.byref(forest), _p(mk), C.c_int(len(mk)), _p(st))
+        return sm, gr, mk, st[:len(mk)].copy()
+
+    def pair_naive(self, Lm, Rm, forest, s, use_hashtable=False):
+        h, w = Lm.shape
+        supp = np.empty(max((w - 26) * (h - 26), 1), SUPPORT_DTYPE)
+        ncl, ncr = C.c_int(0), C.c_int(0)
+        n = self.lib.gpco_pair_naive(_p(np.ascontiguousarray(Lm)), _p(np.ascontiguousarray(Rm)), C.c_int(w), C.c_int(h),
+                                     C.byref(forest), C.byref(s), C.c_int(int(use_hashtable)), _p(supp), C.byref(ncl), C.byref(ncr))
+        return supp[:n].copy(), ncl.value, ncr.value
+
 
 class Reference:
     """The compiled, unmodified reference (None-like if the prebuilt library is absent)."""
 
     @staticmethod
-    def available():
-        if not os.path.exists(REF_SO) and os.path.isdir("/root/reference/lib/gpc"):
-            build_oracle()
-        return os.path.exists(REF_SO)
+    def available(naive=False):
+        so = REF_NAIVE_SO if naive else REF_SO
+        if not os.path.exists(so) and os.path.isdir("/root/reference/lib/gpc"):
+            build_oracle(force=True)
+        return os.path.exists(so)
 
-    def __init__(self):
-        if not self.available():
-            raise RuntimeError("oracle/_ref/libgpc_ref.so not built (needs /root/reference)")
-        self.lib = C.CDLL(REF_SO)
+    def __init__(self, naive=False):
+        """naive=True: the reference compiled without -D_INTRINSICS_SSE (its SSE=OFF result mode)."""
+        if not self.available(naive):
+            raise RuntimeError("oracle/_ref reference build missing (needs /root/reference)")
+        self.lib = C.CDLL(REF_NAIVE_SO if naive else REF_SO)
+        assert self.lib.ref_is_sse_build() == (0 if naive else 1)
         L = self.lib
         for name in ("ref_read_forest", "ref_preprocess", "ref_hash", "ref_find_correspondences", "ref_pair",
                      "ref_sizeof_descriptor", "ref_sizeof_support", "ref_sizeof_correspondence"):

@@ -73,11 +73,13 @@ def test_png_codec_roundtrip():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("forest,epipolar,vt,dh,thr,w,h", [("tau", 1, 0, 128, 5, 1024, 436), ("zero", 1, 0, 128, 5, 640, 200),
-                                                          ("tau", 0, 1, 128, 10, 512, 160), ("deep", 1, 0, 64, 5, 500, 130)])
-def test_cpp_api_vs_oracle(oracle, forest, epipolar, vt, dh, thr, w, h):
+@pytest.mark.parametrize("forest,epipolar,vt,dh,thr,w,h,naive", [("tau", 1, 0, 128, 5, 1024, 436, 0), ("zero", 1, 0, 128, 5, 640, 200, 0),
+                                                                ("tau", 0, 1, 128, 10, 512, 160, 0), ("deep", 1, 0, 64, 5, 500, 130, 0),
+                                                                ("tau", 1, 0, 128, 5, 640, 200, 1), ("zero", 0, 1, 128, 10, 500, 130, 1)])
+def test_cpp_api_vs_oracle(oracle, forest, epipolar, vt, dh, thr, w, h, naive):
     """preprocessImage / rectifiedMatch / stereoMatch / evalFastMaskOnSubsetSSE / findCorrespondences through
-    the C++ headers, on PNG inputs (width 500 exercises the 16-pixel padding), against the oracle."""
+    the C++ headers, on PNG inputs (width 500 exercises the 16-pixel padding), against the oracle.  naive: the same
+    program compiled with -DGPC_B200_NAIVE_RESULTS against the oracle's SSE=OFF restatement."""
     from opengpc_b200.synth import synth_pair
     _build()
     wa = (w + 15) // 16 * 16
@@ -90,7 +92,7 @@ def test_cpp_api_vs_oracle(oracle, forest, epipolar, vt, dh, thr, w, h):
     with tempfile.TemporaryDirectory() as d:
         pl, pr, pout = (os.path.join(d, n) for n in ("l.png", "r.png", "out.bin"))
         _write_png(pl, L); _write_png(pr, R)
-        r = subprocess.run([API_TEST, FORESTS[forest], pl, pr, pout, str(epipolar), str(vt), str(dh), str(thr)],
+        r = subprocess.run([API_TEST + ("_naive" if naive else ""), FORESTS[forest], pl, pr, pout, str(epipolar), str(vt), str(dh), str(thr)],
                            capture_output=True, text=True)
         assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
         if forest == "deep":
@@ -106,16 +108,21 @@ def test_cpp_api_vs_oracle(oracle, forest, epipolar, vt, dh, thr, w, h):
     supp2 = v[p:p + 3 * nS2].reshape(-1, 3); p += 3 * nS2
     states = v[p:p + nD].view(np.uint32); p += nD
     supp_ht = v[p:p + 3 * nH].reshape(-1, 3)
-    _, _, omkL, ostL = oracle.stages(Lp, of, thr)
-    _, _, omkR, _ = oracle.stages(Rp, of, thr)
+    stages = oracle.stages_naive if naive else oracle.stages
+    _, _, omkL, ostL = stages(Lp, of, thr)
+    _, _, omkR, _ = stages(Rp, of, thr)
     assert np.array_equal(maskL, omkL) and np.array_equal(maskR, omkR)
     assert np.array_equal(states, ostL)
-    ref, _, _ = oracle.pair(Lp, Rp, of, s)
+    if naive:
+        ref, _, _ = oracle.pair_naive(Lp, Rp, of, s)
+        ht, _, _ = oracle.pair_naive(Lp, Rp, of, s, use_hashtable=True)
+    else:
+        ref, _, _ = oracle.pair(Lp, Rp, of, s)
+        ht = oracle.pair_hashtable(Lp, Rp, of, s)
+        assert np.array_equal(corr, oracle.correspondences(Lp, Rp, of, s))
     want = np.stack([ref["x"], ref["y"], ref["d"].astype(np.int32)], 1)
     assert np.array_equal(supp, want)
     assert np.array_equal(supp2, want), "hand-built PreprocessedImage path differs"
-    assert np.array_equal(corr, oracle.correspondences(Lp, Rp, of, s))
-    ht = oracle.pair_hashtable(Lp, Rp, of, s)
     assert np.array_equal(supp_ht, np.stack([ht["x"], ht["y"], ht["d"].astype(np.int32)], 1)), "useHashtable(true) differs"
 
 
