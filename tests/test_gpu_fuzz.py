@@ -1,6 +1,6 @@
 """Randomised parity campaign (pytest -m gpu): random shapes, textures, thresholds, forests and settings
 against the oracle, every case through the whole path in both matching modes, every third also through the
-hashtable matcher.  GPC_FUZZ_CASES scales it up."""
+hashtable matcher and every fourth in the result mode of the reference's SSE=OFF build.  GPC_FUZZ_CASES scales it up."""
 import os
 
 import numpy as np
@@ -33,7 +33,9 @@ def test_fuzz_vs_oracle(oracle):
     import opengpc_b200 as g
     n_cases = int(os.environ.get("GPC_FUZZ_CASES", "60"))
     rng = np.random.default_rng(int(os.environ.get("GPC_FUZZ_SEED", "2026")))
-    with g.Context(device=0, max_w=1408, max_h=160, max_batch=1) as ctx:
+    with g.Context(device=0, max_w=1408, max_h=160, max_batch=1) as ctx, \
+            g.Context(device=0, max_w=1408, max_h=160, max_batch=1) as nctx:
+        nctx.set_result_mode(True)                                  # the reference's SSE=OFF build
         for it in range(n_cases):
             w = 16 * int(rng.integers(1, 89))
             h = int(rng.integers(20, 161))
@@ -67,3 +69,9 @@ def test_fuzz_vs_oracle(oracle):
                 ref_h = oracle.pair_hashtable(L, R, of, osettings(thr, dh, vt, epi))
                 supp_h, _, _ = ctx.match_pair(L, R, g.make_settings(thr=thr, disp_high=dh, vt=vt, epipolar=epi, use_hashtable=True))
                 assert np.array_equal(supp_h, ref_h), info + ("hashtable", len(supp_h), len(ref_h))
+            if it % 4 == 1 and nt <= 31:                            # the same case in the naive result mode
+                nctx.set_forest(g.make_forest(tests, taus))
+                ref_n, ocl_n, ocr_n = oracle.pair_naive(L, R, of, osettings(thr, dh, vt, epi))
+                supp_n, ncl_n, ncr_n = nctx.match_pair(L, R, g.make_settings(thr=thr, disp_high=dh, vt=vt, epipolar=epi))
+                assert (ncl_n, ncr_n) == (ocl_n, ocr_n), info + ("naive",)
+                assert np.array_equal(supp_n, ref_n), info + ("naive", len(supp_n), len(ref_n))
