@@ -30,6 +30,17 @@ def test_library_exports_every_declared_symbol():
     assert set(capi.SYMBOLS) <= set(names)
 
 
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/gpc_b200.h compiles as C99 (plain pointers and sizes, no C++ or torch
+    types), and the ctypes binding knows every symbol it declares."""
+    import subprocess
+    from opengpc_b200 import capi
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-x", "c",
+                        os.path.join(ROOT, "include", "gpc_b200.h")], capture_output=True, text=True)
+    assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+    assert sorted(capi.SYMBOLS) == _declared_symbols()
+
+
 def test_no_cpu_fallback():
     """Without a device gpc_create must fail with GPC_E_CUDA; nothing computes on the CPU."""
     import torch
