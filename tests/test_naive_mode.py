@@ -180,3 +180,25 @@ def test_result_mode_switching(g, oracle):
         with pytest.raises(g.GpcError) as e:
             c.set_result_mode(True)
         assert e.value.status == capi.GPC_E_UNSUPPORTED
+
+
+@pytest.mark.gpu
+def test_naive_pyramid_and_resident_images(g, nctx, oracle):
+    """The other entry points run the same pipeline: multi-level matching and resident images in the naive mode."""
+    from opengpc_b200.synth import downsample2x, synth_pair
+    of = oracle.read_forest(FORESTS["tau"])
+    nctx.set_forest(FORESTS["tau"])
+    L, R = synth_pair(1024, 436, 11)
+    supp, offs, ncand = nctx.match_pyramid(L, R, 3, g.sparsematch_settings())
+    dh, Ll, Rl = 128, L, R
+    for l in range(3):
+        ref, ocl, ocr = oracle.pair_naive(Ll, Rl, of, osettings(5, dh, 0, True))
+        assert (ncand[l, 0], ncand[l, 1]) == (ocl, ocr) and np.array_equal(supp[offs[l]:offs[l + 1]], ref), l
+        Ll, Rl, dh = downsample2x(Ll), downsample2x(Rl), dh // 2
+    il, ir = nctx.upload(L), nctx.upload(R)
+    sm, gr, mk = il.preprocess(5)
+    osm, ogr, omk, _ = oracle.stages_naive(L, of, 5)
+    assert np.array_equal(sm, osm) and np.array_equal(gr, ogr) and np.array_equal(mk, omk)
+    got = nctx.match_images(il, ir, g.make_settings(thr=5, disp_high=128, vt=1, epipolar=False))[0]
+    assert np.array_equal(got, oracle.pair_naive(L, R, of, osettings(5, 128, 1, False))[0])
+    il.release(); ir.release()
