@@ -11,6 +11,7 @@ from oraclelib import ROOT, settings as osettings
 
 API_TEST = os.path.join(ROOT, "tests", "cpp", "api_test")
 SPARSEMATCH = os.path.join(ROOT, "samples", "sparsematch")
+C_EXAMPLE = os.path.join(ROOT, "samples", "c_api_example")
 
 
 def _build():
@@ -29,7 +30,7 @@ def test_cpp_host_builds():
     """sparsematch, api_test and the PNG codec compile against the drop-in headers; the reference's
     own samples/sparsematch.cpp compiles UNCHANGED against them where the tree is present."""
     _build()
-    assert os.path.exists(API_TEST) and os.path.exists(SPARSEMATCH)
+    assert os.path.exists(API_TEST) and os.path.exists(SPARSEMATCH) and os.path.exists(C_EXAMPLE)
     ref_src = "/root/reference/samples/sparsematch.cpp"
     if os.path.exists(ref_src):
         with tempfile.TemporaryDirectory() as d:
@@ -139,3 +140,23 @@ def test_sparsematch_cli(oracle):
         assert "#candidatesL:377030, #candidatesR:378097" in r.stdout and "num matches:40839" in r.stdout, r.stdout
         from PIL import Image
         assert np.array(Image.open(po)).shape == (436, 1024, 3)
+
+
+@pytest.mark.gpu
+def test_c_api_from_plain_c(oracle):
+    """samples/c_api_example.c (C99, no C++ on the caller's side): the SURVEY 8c golden values of the Sintel-sized
+    synthetic pair, and the SSE=OFF result mode against the oracle."""
+    from oraclelib import digest
+    from opengpc_b200.synth import synth_pair
+    _build()
+    L, R = synth_pair(1024, 436, 1234)
+    with tempfile.TemporaryDirectory() as d:
+        pl, pr = os.path.join(d, "l.raw"), os.path.join(d, "r.raw")
+        L.tofile(pl); R.tofile(pr)
+        r = subprocess.run([C_EXAMPLE, FORESTS["tau"], "1024", "436", pl, pr], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "#candidatesL:377030, #candidatesR:378097, num matches:40839, digest:fb3f3b2728785637" in r.stdout, r.stdout
+        r = subprocess.run([C_EXAMPLE, FORESTS["zero"], "1024", "436", pl, pr, "naive"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        ref, ncl, ncr = oracle.pair_naive(L, R, oracle.read_forest(FORESTS["zero"]), osettings())
+        assert f"#candidatesL:{ncl}, #candidatesR:{ncr}, num matches:{len(ref)}, digest:{digest(ref):016x}" in r.stdout, r.stdout
