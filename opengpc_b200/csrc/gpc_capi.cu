@@ -32,7 +32,7 @@ cudaError_t launch_emit_supports(const uint32_t* stage, const int32_t* rowmatch,
                                  cudaStream_t);
 cudaError_t launch_mask_list(const uint32_t* hash, const int32_t* rowcnt, int32_t* rowoff, int W, int H, int32_t* mask,
                              int cap, cudaStream_t);
-size_t global_workspace_bytes(long long max_records, int n_pairs, int H);
+size_t global_workspace_bytes(long long max_records, int n_pairs, int H, int W);
 cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int W, int H, int n_pairs, int epipolar, int key_bits,
                                 int disp_high, int vertical_tolerance, int mode, void* ws, long long max_records, void* out,
                                 long long out_stride, long long cap, int32_t* n_out, int32_t* n_cand, cudaStream_t stream,
@@ -278,10 +278,10 @@ int ensure_global_ws(gpc_ctx* c, size_t bytes) {
 // Counts to d_n_out[i], candidate counts to d_n_cand[2i..].
 size_t sort_workspace_bytes(int w, int h, int n, int* chunk_out) {
   const long long records = 2ll * std::max(w - 2 * gpc::kRadius, 0) * std::max(h - 2 * gpc::kRadius, 0) + 2;
-  const size_t per_pair = gpc::global_workspace_bytes(records, 1, h);
+  const size_t per_pair = gpc::global_workspace_bytes(records, 1, h, w);
   const int chunk = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)1 << 30) / per_pair));
   if (chunk_out) *chunk_out = chunk;
-  return gpc::global_workspace_bytes(records, std::min(chunk, std::max(n, 1)), h);
+  return gpc::global_workspace_bytes(records, std::min(chunk, std::max(n, 1)), h, w);
 }
 
 int run_match_sort(gpc_ctx* c, const uint32_t* hash, int p0, int n, int w, int h, const gpc_settings* s, int mode, void* d_out,
@@ -293,7 +293,7 @@ int run_match_sort(gpc_ctx* c, const uint32_t* hash, int p0, int n, int w, int h
   sort_workspace_bytes(w, h, n, &chunk);
   for (int q0 = 0; q0 < n; q0 += chunk) {
     const int m = std::min(chunk, n - q0);
-    int rc = ensure_global_ws(c, gpc::global_workspace_bytes(records, m, h)); if (rc) return rc;
+    int rc = ensure_global_ws(c, gpc::global_workspace_bytes(records, m, h, w)); if (rc) return rc;
     int launches = 0;
     GPC_CUDA(c, gpc::launch_match_global(hash + (size_t)(2 * (p0 + q0)) * P, c->d_rows + (size_t)(2 * (p0 + q0)) * h, w, h, m,
                                          s->epipolar_mode ? 1 : 0, 31, s->disp_high, s->vertical_tolerance, mode, c->d_gws, records,
@@ -976,7 +976,7 @@ int gpc_find_correspondences(gpc_ctx* c, const uint64_t* src_keys, int n_src, co
   if ((long long)n_src + n_tar >= 0x7fffffffll) return fail(c, GPC_E_DIMS, "too many descriptors");
   GPC_CUDA(c, cudaSetDevice(c->device));
   const long long n = (long long)n_src + n_tar;
-  int rc = ensure_global_ws(c, gpc::global_workspace_bytes(n + 2, 1, 0)); if (rc) return rc;
+  int rc = ensure_global_ws(c, gpc::global_workspace_bytes(n + 2, 1, 0, 0)); if (rc) return rc;
   uint64_t kmax = 0;
   for (int i = 0; i < n_src; i++) kmax = std::max(kmax, src_keys[i]);
   for (int i = 0; i < n_tar; i++) kmax = std::max(kmax, tar_keys[i]);
@@ -1014,7 +1014,7 @@ int gpc_hashmatch(gpc_ctx* c, const uint64_t* src_keys, int n_src, const uint64_
   if ((long long)n_src + n_tar >= 0x7fffffffll) return fail(c, GPC_E_DIMS, "too many descriptors");
   GPC_CUDA(c, cudaSetDevice(c->device));
   const long long n = (long long)n_src + n_tar;
-  int rc = ensure_global_ws(c, gpc::global_workspace_bytes(n + 2, 1, 0)); if (rc) return rc;
+  int rc = ensure_global_ws(c, gpc::global_workspace_bytes(n + 2, 1, 0, 0)); if (rc) return rc;
   const long long need = std::min<long long>(n_src, n_tar);
   uint8_t* d_tmp = nullptr;                                    // keys, then the output pairs
   GPC_CUDA(c, cudaMalloc(&d_tmp, (size_t)n * 8 + (size_t)std::max<long long>(need, 1) * 2 * sizeof(int32_t)));

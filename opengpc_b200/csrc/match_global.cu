@@ -21,9 +21,18 @@
 // order (all left, then all right, each in raster order), and one thread replays the bucket: the first 10
 // records in stable ascending key order, walked by the reference's pairing rules.
 //
+// Pre-filter (hash-image input, sort-path semantics): a record can only take part in a match, or spoil one, if
+// its key also occurs on the OTHER side.  Each side's keys are marked in a bit table (2^22 bits per side and pair,
+// indexed by a hash of the key), and only records whose bit is set in the other side's table are gathered and
+// sorted -- a superset of every run that holds both sides, complete for each such key, in the same raster order,
+// so the sorted runs the rules above look at are unchanged while ~85 % of the records never enter the sort.
+// The largest right key is taken over ALL right records (per-row maxima, then a reduction), not from the
+// filtered array.  The hashtable matcher does not use the filter: its buckets depend on every record.
+//
 // Every kernel carries a pair dimension (blockIdx.y): a chunk of independent pairs is sorted by the
 // same launches, each pair in its own slice of the workspace.
 #include <algorithm>
+#include <cstdlib>
 
 #include "gpc_device.cuh"
 
@@ -38,6 +47,8 @@ constexpr int kDigits = 256;
 constexpr uint32_t kSideBit = 0x80000000u;
 constexpr uint32_t kHtBuckets = 214673u;    // inference.hpp:212
 constexpr int kHtDepth = 10;                // hashmatch.hpp:95: a bucket keeps the first 10 elements offered to it
+constexpr int kBloomLog2 = 22;              // pre-filter: bits per side and pair (512 KB; a chunk of pairs stays L2 resident)
+constexpr int kBloomWords = (1 << kBloomLog2) / 32;
 
 // Workspace of a chunk of pairs (device pointers; slice `pair` starts at pair * stride of each array).
 template <typename KeyT>
@@ -50,6 +61,11 @@ struct SortWs {
   int32_t* n_side;               // [n_pairs][2] left / right record counts
   unsigned long long* tmax;      // [n_pairs] largest right key + 1 (0: no right record)
   int32_t* rowoff;               // [n_pairs][2][H] candidate offsets (hash-image input only)
+  int32_t* rowcnt_f;             // [n_pairs][2][H] records per row that pass the pre-filter
+  unsigned long long* rowmax;    // [n_pairs][H] largest right key + 1 of the row (0: none)
+  uint32_t* bloom;               // [n_pairs][2][kBloomWords] key bit tables of the two sides
+  uint32_t* keep;                // [n_pairs][2][H][keep_words] pre-filter result, one bit per pixel
+  int keep_words;                // ceil(W / 32)
   long long rec_stride;
   int nb_max;
 };
@@ -89,10 +105,90 @@ global_rowoff_kernel(const int32_t* __restrict__ rowcnt, int H, int32_t* __restr
   if (tid == 0) n_side_all[2 * pair + side] = carry;
 }
 
+// ---- pre-filter ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bloom_hash(unsigned long long key) {
+  const uint32_t h = (uint32_t)key * 0x9E3779B1u ^ (uint32_t)(key >> 32) * 0x85EBCA6Bu;
+  return h >> (32 - kBloomLog2);
+}
+
+// One warp per (side, row): mark the row's keys in the side's bit table; per-row maximum of the right keys.
+__global__ void __launch_bounds__(128)
+bloom_build_kernel(const uint32_t* __restrict__ hash, int W, int H, int epipolar, const SortWs<uint32_t> ws) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, pair = blockIdx.y;
+  if (warp >= 2 * H) return;
+  const int side = warp / H, y = warp - side * H;
+  const uint32_t* row = hash + ((size_t)(2 * pair + side) * H + y) * W;
+  uint32_t* table = ws.bloom + ((size_t)2 * pair + side) * kBloomWords;
+  unsigned long long kmax = 0;
+  for (int x0 = 0; x0 < W; x0 += 128) {
+    uint32_t v4[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { const int x = x0 + 32 * q + lane; v4[q] = (x < W) ? row[x] : 0u; }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (v4[q] >> 31) {
+        unsigned long long k = v4[q] & 0x7fffffffu;
+        if (epipolar) k |= (unsigned long long)y << 32;
+        const uint32_t b = bloom_hash(k), bit = 1u << (b & 31);
+        // test first: repeated keys (flat images) must not pile atomics on one word
+        if (!(*reinterpret_cast<volatile uint32_t*>(table + (b >> 5)) & bit)) atomicOr(table + (b >> 5), bit);
+        kmax = max(kmax, k + 1ull);
+      }
+    }
+  }
+  if (side == 1) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, d));
+    if (lane == 0) ws.rowmax[(size_t)pair * H + y] = kmax;
+  }
+}
+
+// tmax[pair] = largest right key + 1 over all rows (0: no right record)
+__global__ void __launch_bounds__(32)
+rowmax_reduce_kernel(const SortWs<uint32_t> ws, int H) {
+  const int pair = blockIdx.x, lane = threadIdx.x;
+  unsigned long long m = 0;
+  for (int y = lane; y < H; y += 32) m = max(m, ws.rowmax[(size_t)pair * H + y]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if (lane == 0) ws.tmax[pair] = m;
+}
+
+// One warp per (side, row): keep[...] = candidates whose key is marked in the OTHER side's table; rowcnt_f = their count.
+__global__ void __launch_bounds__(128)
+bloom_filter_kernel(const uint32_t* __restrict__ hash, int W, int H, int epipolar, const SortWs<uint32_t> ws) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, pair = blockIdx.y;
+  if (warp >= 2 * H) return;
+  const int side = warp / H, y = warp - side * H;
+  const uint32_t* row = hash + ((size_t)(2 * pair + side) * H + y) * W;
+  const uint32_t* other = ws.bloom + ((size_t)2 * pair + (side ^ 1)) * kBloomWords;
+  uint32_t* keep = ws.keep + (((size_t)2 * pair + side) * H + y) * ws.keep_words;
+  int count = 0;
+  for (int x0 = 0; x0 < W; x0 += 128) {
+    uint32_t v4[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { const int x = x0 + 32 * q + lane; v4[q] = (x < W) ? row[x] : 0u; }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      bool c = false;
+      if (v4[q] >> 31) {
+        unsigned long long k = v4[q] & 0x7fffffffu;
+        if (epipolar) k |= (unsigned long long)y << 32;
+        const uint32_t b = bloom_hash(k);
+        c = (__ldg(other + (b >> 5)) >> (b & 31)) & 1u;
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, c);
+      if (x0 + 32 * q < W && lane == 0) keep[(x0 >> 5) + q] = m;
+      count += __popc(m);
+    }
+  }
+  if (lane == 0) ws.rowcnt_f[((size_t)2 * pair + side) * H + y] = count;
+}
+
 // One warp per (side, row): candidates in raster order.
 template <typename KeyT>
 __global__ void __launch_bounds__(128)
-global_gather_kernel(const uint32_t* __restrict__ hash, int W, int H, int epipolar, int hashtable, const SortWs<KeyT> ws) {
+global_gather_kernel(const uint32_t* __restrict__ hash, int W, int H, int epipolar, int hashtable, int filtered, const SortWs<KeyT> ws) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, pair = blockIdx.y;
   if (warp >= 2 * H) return;
   const int side = warp / H, y = warp - side * H;
@@ -101,6 +197,7 @@ global_gather_kernel(const uint32_t* __restrict__ hash, int W, int H, int epipol
   KeyT* keys = ws.keys[0] + (size_t)pair * ws.rec_stride;
   uint32_t* vals = ws.vals[0] + (size_t)pair * ws.rec_stride;
   int off = ws.rowoff[((size_t)2 * pair + side) * H + y] + (side ? n_side[0] : 0);
+  const uint32_t* keepw = filtered ? ws.keep + (((size_t)2 * pair + side) * H + y) * ws.keep_words : nullptr;
   for (int x0 = 0; x0 < W; x0 += 128) {                  // four 32-pixel groups per trip, their loads issued together
     uint32_t v4[4];
 #pragma unroll
@@ -109,8 +206,8 @@ global_gather_kernel(const uint32_t* __restrict__ hash, int W, int H, int epipol
     for (int q = 0; q < 4; q++) {
       const int x = x0 + 32 * q + lane;
       const uint32_t v = v4[q];
-      const bool c = (v >> 31) != 0u;
-      const uint32_t b = __ballot_sync(0xffffffffu, c);
+      const uint32_t b = filtered ? ((x0 + 32 * q < W) ? keepw[(x0 >> 5) + q] : 0u) : __ballot_sync(0xffffffffu, (v >> 31) != 0u);
+      const bool c = (b >> lane) & 1u;
       if (c) {
         const int p = off + __popc(b & ((1u << lane) - 1u));
         unsigned long long k = v & 0x7fffffffu;
@@ -156,18 +253,17 @@ __device__ __forceinline__ void load_keys16(const unsigned long long* p, unsigne
 // ---- LSD radix sort, 8-bit digits; a block owns a tile of kTile keys, visited in kRounds rounds of 1024
 // consecutive keys (round-major order = input order, which keeps the sort stable) ------------------------
 template <typename KeyT>
-__global__ void __launch_bounds__(kSortThreads)
-radix_hist_kernel(const SortWs<KeyT> ws, int cur, int shift) {
+__device__ __forceinline__ void radix_hist_kernel_tile(const SortWs<KeyT> ws, int cur, int shift, const int tile) {
   __shared__ uint32_t tot[kDigits];
   const int pair = blockIdx.y;
   const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
   const int nb = (n + kTile - 1) / kTile;
-  if ((int)blockIdx.x >= nb) return;
+  if (tile >= nb) return;
   const KeyT* keys = (cur ? ws.keys[1] : ws.keys[0]) + (size_t)pair * ws.rec_stride;
   const int tid = threadIdx.x;
   if (tid < kDigits) tot[tid] = 0u;
   // the histogram does not care about order: each thread takes kRounds consecutive keys with 16-byte loads
-  const int i0 = blockIdx.x * kTile + kRounds * tid;
+  const int i0 = tile * kTile + kRounds * tid;
   KeyT k[kRounds];
   const bool full = i0 + kRounds <= n && (reinterpret_cast<uintptr_t>(keys + i0) & 15u) == 0u;
   if (full) {
@@ -190,7 +286,19 @@ radix_hist_kernel(const SortWs<KeyT> ws, int cur, int shift) {
     else if (active) atomicAdd(&tot[d], 1u);
   }
   __syncthreads();
-  if (tid < kDigits) ws.blockhist[((size_t)pair * kDigits + tid) * ws.nb_max + blockIdx.x] = tot[tid];
+  if (tid < kDigits) ws.blockhist[((size_t)pair * kDigits + tid) * ws.nb_max + tile] = tot[tid];
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortThreads)
+radix_hist_kernel(const SortWs<KeyT> ws, int cur, int shift) {
+  // a block walks the tiles tile = blockIdx.x, blockIdx.x + gridDim.x, ... of its pair
+  for (int tile = blockIdx.x;; tile += gridDim.x) {
+    const int n = ws.n_side[2 * blockIdx.y] + ws.n_side[2 * blockIdx.y + 1];
+    if (tile * kTile >= n) return;
+    radix_hist_kernel_tile<KeyT>(ws, cur, shift, tile);
+    __syncthreads();
+  }
 }
 
 // per-digit exclusive scan over the nb active blocks (one warp per digit, coalesced 32-wide
@@ -227,8 +335,7 @@ template <typename KeyT>
 __host__ __device__ constexpr int scatter_smem_bytes() { return scatter_region_bytes<KeyT>() + (kSortWarps / 8 + 3) * kDigits * 4; }
 
 template <typename KeyT>
-__global__ void __launch_bounds__(kSortThreads, 2)
-radix_scatter_kernel(const SortWs<KeyT> ws, int cur, int shift) {
+__device__ __forceinline__ void radix_scatter_kernel_tile(const SortWs<KeyT> ws, int cur, int shift, const int tile) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int kGroups = kSortWarps / 8;                // warps are prefix-summed in groups of eight
   static_assert(kGroups * kDigits == kSortThreads, "one thread per (digit, group of warps)");
@@ -242,14 +349,14 @@ radix_scatter_kernel(const SortWs<KeyT> ws, int cur, int shift) {
   const int pair = blockIdx.y;
   const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
   const int nb = (n + kTile - 1) / kTile;
-  if ((int)blockIdx.x >= nb) return;
+  if (tile >= nb) return;
   const KeyT* keys_in = (cur ? ws.keys[1] : ws.keys[0]) + (size_t)pair * ws.rec_stride;
   const uint32_t* vals_in = (cur ? ws.vals[1] : ws.vals[0]) + (size_t)pair * ws.rec_stride;
   KeyT* keys_out = (cur ? ws.keys[0] : ws.keys[1]) + (size_t)pair * ws.rec_stride;
   uint32_t* vals_out = (cur ? ws.vals[0] : ws.vals[1]) + (size_t)pair * ws.rec_stride;
   const uint32_t* digit_tot = ws.digit_tot + (size_t)pair * kDigits;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int tile0 = blockIdx.x * kTile;
+  const int tile0 = tile * kTile;
   const int w0 = tile0 + wid * (32 * kRounds) + lane;    // the thread's record of round r is w0 + 32 r
   // all of the thread's records first, so that every load is in flight at once
   KeyT k[kRounds];
@@ -275,7 +382,7 @@ radix_scatter_kernel(const SortWs<KeyT> ws, int cur, int shift) {
     uint32_t run = incl - sum;
 #pragma unroll
     for (int q = 0; q < 8; q++) {
-      dbase[8 * lane + q] = run + ws.blockhist[((size_t)pair * kDigits + 8 * lane + q) * ws.nb_max + blockIdx.x];
+      dbase[8 * lane + q] = run + ws.blockhist[((size_t)pair * kDigits + 8 * lane + q) * ws.nb_max + tile];
       run += c[q];
     }
   }
@@ -350,6 +457,18 @@ radix_scatter_kernel(const SortWs<KeyT> ws, int cur, int shift) {
       keys_out[pos] = key;
       vals_out[pos] = svals[j];
     }
+  }
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortThreads, 2)
+radix_scatter_kernel(const SortWs<KeyT> ws, int cur, int shift) {
+  // a block walks the tiles tile = blockIdx.x, blockIdx.x + gridDim.x, ... of its pair
+  for (int tile = blockIdx.x;; tile += gridDim.x) {
+    const int n = ws.n_side[2 * blockIdx.y] + ws.n_side[2 * blockIdx.y + 1];
+    if (tile * kTile >= n) return;
+    radix_scatter_kernel_tile<KeyT>(ws, cur, shift, tile);
+    __syncthreads();
   }
 }
 
@@ -434,23 +553,34 @@ __device__ __forceinline__ uint32_t window_matches(const KeyT* __restrict__ keys
 }
 
 template <typename KeyT>
-__global__ void __launch_bounds__(kSortThreads)
-global_count_kernel(const SortWs<KeyT> ws, int cur, const GlobalEmitArgs a) {
+__device__ __forceinline__ void global_count_kernel_tile(const SortWs<KeyT> ws, int cur, const GlobalEmitArgs a, const int tile) {
   __shared__ int cnt;
   const int pair = blockIdx.y;
   const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
   const int nb = (n + kTile - 1) / kTile;
-  if ((int)blockIdx.x >= nb) return;
+  if (tile >= nb) return;
   if (threadIdx.x == 0) cnt = 0;
   __syncthreads();
   uint32_t V[kRounds + 1];
   const uint32_t bits = window_matches((cur ? ws.keys[1] : ws.keys[0]) + (size_t)pair * ws.rec_stride,
                                        (cur ? ws.vals[1] : ws.vals[0]) + (size_t)pair * ws.rec_stride,
-                                       blockIdx.x * kTile + kRounds * threadIdx.x, n, ws.tmax[pair], a, V);
+                                       tile * kTile + kRounds * threadIdx.x, n, ws.tmax[pair], a, V);
   const int mine = __reduce_add_sync(0xffffffffu, __popc(bits));
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&cnt, mine);
   __syncthreads();
-  if (threadIdx.x == 0) ws.blockcount[(size_t)pair * (ws.nb_max + 1) + blockIdx.x] = cnt;
+  if (threadIdx.x == 0) ws.blockcount[(size_t)pair * (ws.nb_max + 1) + tile] = cnt;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortThreads)
+global_count_kernel(const SortWs<KeyT> ws, int cur, const GlobalEmitArgs a) {
+  // a block walks the tiles tile = blockIdx.x, blockIdx.x + gridDim.x, ... of its pair
+  for (int tile = blockIdx.x;; tile += gridDim.x) {
+    const int n = ws.n_side[2 * blockIdx.y] + ws.n_side[2 * blockIdx.y + 1];
+    if (tile * kTile >= n) return;
+    global_count_kernel_tile<KeyT>(ws, cur, a, tile);
+    __syncthreads();
+  }
 }
 
 // exclusive scan of a pair's block counts (one warp per pair), total -> n_out[pair]
@@ -485,18 +615,17 @@ __global__ void global_pairbase_kernel(const int32_t* __restrict__ n_out, int n_
 }
 
 template <typename KeyT>
-__global__ void __launch_bounds__(kSortThreads)
-global_emit_kernel(const SortWs<KeyT> ws, int cur, const GlobalEmitArgs a) {
+__device__ __forceinline__ void global_emit_kernel_tile(const SortWs<KeyT> ws, int cur, const GlobalEmitArgs a, const int tile) {
   __shared__ int warp_base[kSortWarps];
   const int pair = blockIdx.y;
   const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
   const int nb = (n + kTile - 1) / kTile;
-  if ((int)blockIdx.x >= nb) return;
+  if (tile >= nb) return;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   uint32_t V[kRounds + 1];
   const uint32_t bits = window_matches((cur ? ws.keys[1] : ws.keys[0]) + (size_t)pair * ws.rec_stride,
                                        (cur ? ws.vals[1] : ws.vals[0]) + (size_t)pair * ws.rec_stride,
-                                       blockIdx.x * kTile + kRounds * tid, n, ws.tmax[pair], a, V);
+                                       tile * kTile + kRounds * tid, n, ws.tmax[pair], a, V);
   // thread order = record order: exclusive scan of the per-thread match counts
   const int c = __popc(bits);
   int incl = c;
@@ -512,7 +641,7 @@ global_emit_kernel(const SortWs<KeyT> ws, int cur, const GlobalEmitArgs a) {
     if (lane < kSortWarps) warp_base[lane] = wi - v;
   }
   __syncthreads();
-  long long k = (long long)ws.blockcount[(size_t)pair * (ws.nb_max + 1) + blockIdx.x] + warp_base[wid] + (incl - c);
+  long long k = (long long)ws.blockcount[(size_t)pair * (ws.nb_max + 1) + tile] + warp_base[wid] + (incl - c);
 #pragma unroll
   for (int j = 0; j < kRounds; j++) {
     if (!((bits >> j) & 1u)) continue;
@@ -534,6 +663,18 @@ global_emit_kernel(const SortWs<KeyT> ws, int cur, const GlobalEmitArgs a) {
         o[0] = xl; o[1] = yl; o[2] = xr; o[3] = yr;
       }
     }
+  }
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortThreads)
+global_emit_kernel(const SortWs<KeyT> ws, int cur, const GlobalEmitArgs a) {
+  // a block walks the tiles tile = blockIdx.x, blockIdx.x + gridDim.x, ... of its pair
+  for (int tile = blockIdx.x;; tile += gridDim.x) {
+    const int n = ws.n_side[2 * blockIdx.y] + ws.n_side[2 * blockIdx.y + 1];
+    if (tile * kTile >= n) return;
+    global_emit_kernel_tile<KeyT>(ws, cur, a, tile);
+    __syncthreads();
   }
 }
 
@@ -573,8 +714,7 @@ __device__ __forceinline__ bool passes_filter(const GlobalEmitArgs& a, uint32_t 
 
 // The 64-bit key of every bucket-sorted record, gathered once (one thread per record) into the idle half of the
 // ping-pong key buffer, so that the bucket replay below reads consecutive memory.
-__global__ void __launch_bounds__(kSortThreads)
-ht_keys_kernel(const SortWs<uint32_t> ws, int cur, const HtArgs h) {
+__device__ __forceinline__ void ht_keys_kernel_tile(const SortWs<uint32_t> ws, int cur, const HtArgs h, const int tile) {
   const int pair = blockIdx.y;
   const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
   const uint32_t* vals = (cur ? ws.vals[1] : ws.vals[0]) + (size_t)pair * ws.rec_stride;
@@ -582,7 +722,7 @@ ht_keys_kernel(const SortWs<uint32_t> ws, int cur, const HtArgs h) {
   const uint32_t* img = h.keys64 ? nullptr : h.hash + (size_t)(2 * pair) * h.H * h.W;
 #pragma unroll
   for (int r = 0; r < kRounds; r++) {
-    const int i = blockIdx.x * kTile + r * kSortThreads + threadIdx.x;
+    const int i = tile * kTile + r * kSortThreads + threadIdx.x;
     if (i >= n) continue;
     const uint32_t v = vals[i], pix = v & ~kSideBit;
     unsigned long long k;
@@ -593,6 +733,16 @@ ht_keys_kernel(const SortWs<uint32_t> ws, int cur, const HtArgs h) {
       if (h.epipolar) k |= (unsigned long long)(pix / (uint32_t)h.W) << 32;
     }
     skey[i] = k;
+  }
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+ht_keys_kernel(const SortWs<uint32_t> ws, int cur, const HtArgs h) {
+  for (int tile = blockIdx.x;; tile += gridDim.x) {
+    const int n = ws.n_side[2 * blockIdx.y] + ws.n_side[2 * blockIdx.y + 1];
+    if (tile * kTile >= n) return;
+    ht_keys_kernel_tile(ws, cur, h, tile);
+    __syncthreads();
   }
 }
 
@@ -641,13 +791,12 @@ __device__ int ht_bucket(const uint32_t* __restrict__ keys, const uint32_t* __re
 }
 
 // Matches per record (non-zero only where a bucket opens) into the idle half of the value buffer, and per tile.
-__global__ void __launch_bounds__(kSortThreads)
-ht_count_kernel(const SortWs<uint32_t> ws, int cur, const GlobalEmitArgs a) {
+__device__ __forceinline__ void ht_count_kernel_tile(const SortWs<uint32_t> ws, int cur, const GlobalEmitArgs a, const int tile) {
   __shared__ int cnt;
   const int pair = blockIdx.y;
   const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
   const int nb = (n + kTile - 1) / kTile;
-  if ((int)blockIdx.x >= nb) return;
+  if (tile >= nb) return;
   if (threadIdx.x == 0) cnt = 0;
   __syncthreads();
   const uint32_t* keys = (cur ? ws.keys[1] : ws.keys[0]) + (size_t)pair * ws.rec_stride;
@@ -657,7 +806,7 @@ ht_count_kernel(const SortWs<uint32_t> ws, int cur, const GlobalEmitArgs a) {
   int mine = 0;
 #pragma unroll 1
   for (int r = 0; r < kRounds; r++) {                    // round-major: neighbouring lanes replay neighbouring buckets
-    const int i = blockIdx.x * kTile + r * kSortThreads + threadIdx.x;
+    const int i = tile * kTile + r * kSortThreads + threadIdx.x;
     const int c = ht_bucket<false>(keys, vals, skey, i, n, pair, a, 0);
     if (i < n) found[i] = (uint8_t)c;
     mine += c;
@@ -665,22 +814,31 @@ ht_count_kernel(const SortWs<uint32_t> ws, int cur, const GlobalEmitArgs a) {
   mine = __reduce_add_sync(0xffffffffu, mine);
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&cnt, mine);
   __syncthreads();
-  if (threadIdx.x == 0) ws.blockcount[(size_t)pair * (ws.nb_max + 1) + blockIdx.x] = cnt;
+  if (threadIdx.x == 0) ws.blockcount[(size_t)pair * (ws.nb_max + 1) + tile] = cnt;
 }
 
 __global__ void __launch_bounds__(kSortThreads)
-ht_emit_kernel(const SortWs<uint32_t> ws, int cur, const GlobalEmitArgs a) {
+ht_count_kernel(const SortWs<uint32_t> ws, int cur, const GlobalEmitArgs a) {
+  for (int tile = blockIdx.x;; tile += gridDim.x) {
+    const int n = ws.n_side[2 * blockIdx.y] + ws.n_side[2 * blockIdx.y + 1];
+    if (tile * kTile >= n) return;
+    ht_count_kernel_tile(ws, cur, a, tile);
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void ht_emit_kernel_tile(const SortWs<uint32_t> ws, int cur, const GlobalEmitArgs a, const int tile) {
   __shared__ int warp_base[kSortWarps];
   const int pair = blockIdx.y;
   const int n = ws.n_side[2 * pair] + ws.n_side[2 * pair + 1];
   const int nb = (n + kTile - 1) / kTile;
-  if ((int)blockIdx.x >= nb) return;
+  if (tile >= nb) return;
   const uint32_t* keys = (cur ? ws.keys[1] : ws.keys[0]) + (size_t)pair * ws.rec_stride;
   const uint32_t* vals = (cur ? ws.vals[1] : ws.vals[0]) + (size_t)pair * ws.rec_stride;
   const unsigned long long* skey = reinterpret_cast<const unsigned long long*>(cur ? ws.keys[0] : ws.keys[1]) + (size_t)pair * ws.rec_stride;
   const uint8_t* found = reinterpret_cast<const uint8_t*>((cur ? ws.vals[0] : ws.vals[1]) + (size_t)pair * ws.rec_stride);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int i0 = blockIdx.x * kTile + kRounds * tid;     // thread order = record order = bucket order
+  const int i0 = tile * kTile + kRounds * tid;     // thread order = record order = bucket order
   int cr[kRounds], c = 0;
 #pragma unroll
   for (int r = 0; r < kRounds; r++) { cr[r] = (i0 + r < n) ? found[i0 + r] : 0; c += cr[r]; }
@@ -697,25 +855,43 @@ ht_emit_kernel(const SortWs<uint32_t> ws, int cur, const GlobalEmitArgs a) {
     if (lane < kSortWarps) warp_base[lane] = wi - v;
   }
   __syncthreads();
-  long long slot = (long long)ws.blockcount[(size_t)pair * (ws.nb_max + 1) + blockIdx.x] + warp_base[wid] + (incl - c);
+  long long slot = (long long)ws.blockcount[(size_t)pair * (ws.nb_max + 1) + tile] + warp_base[wid] + (incl - c);
 #pragma unroll 1
   for (int r = 0; r < kRounds; r++)
     if (cr[r]) slot += ht_bucket<true>(keys, vals, skey, i0 + r, n, pair, a, slot);      // only buckets that hold a match
 }
 
+__global__ void __launch_bounds__(kSortThreads)
+ht_emit_kernel(const SortWs<uint32_t> ws, int cur, const GlobalEmitArgs a) {
+  for (int tile = blockIdx.x;; tile += gridDim.x) {
+    const int n = ws.n_side[2 * blockIdx.y] + ws.n_side[2 * blockIdx.y + 1];
+    if (tile * kTile >= n) return;
+    ht_emit_kernel_tile(ws, cur, a, tile);
+    __syncthreads();
+  }
+}
+
 // ---- host-side launch sequences -----------------------------------------------------------------------
 static size_t pad256(size_t b) { return (b + 255) / 256 * 256; }
 
-// bytes of workspace for n_pairs pairs of up to max_records records each, H rows (0 for explicit keys)
-size_t global_workspace_bytes(long long max_records, int n_pairs, int H) {
+// Blocks per pair of the tile kernels: the number of tiles is only known on the device (and small after the
+// pre-filter), so a block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; enough blocks to fill the GPU
+// for several waves when few pairs share a launch (the hashtable replay is latency bound and wants them), no more
+// than that when many do.
+static int tile_grid_x(int nb_capacity, int n_pairs) { return std::max(1, std::min(nb_capacity, std::max(48, 2400 / std::max(n_pairs, 1)))); }
+
+// bytes of workspace for n_pairs pairs of up to max_records records each, images of W x H (0 x 0 for explicit keys)
+size_t global_workspace_bytes(long long max_records, int n_pairs, int H, int W) {
   const size_t nb = (size_t)((max_records + kTile - 1) / kTile + 1);
-  const size_t np = (size_t)n_pairs;
-  return pad256(np * 8) + pad256(np * 2 * 4) + 2 * pad256(np * (size_t)max_records * 8) + 2 * pad256(np * (size_t)max_records * 4) +
-         pad256(np * kDigits * nb * 4) + pad256(np * kDigits * 4) + pad256(np * (nb + 1) * 4) + pad256(np * 2 * (size_t)std::max(H, 1) * 4) + 256;
+  const size_t np = (size_t)n_pairs, rows = (size_t)std::max(H, 1), kw = (size_t)(W + 31) / 32;
+  size_t b = pad256(np * 8) + pad256(np * 2 * 4) + 2 * pad256(np * (size_t)max_records * 8) + 2 * pad256(np * (size_t)max_records * 4) +
+             pad256(np * kDigits * nb * 4) + pad256(np * kDigits * 4) + pad256(np * (nb + 1) * 4) + pad256(np * 2 * rows * 4) + 256;
+  if (W > 0) b += pad256(np * 2 * rows * 4) + pad256(np * rows * 8) + pad256(np * 2 * (size_t)kBloomWords * 4) + pad256(np * 2 * rows * kw * 4);
+  return b;
 }
 
 template <typename KeyT>
-static SortWs<KeyT> carve(void* ws, long long max_records, int n_pairs, int H) {
+static SortWs<KeyT> carve(void* ws, long long max_records, int n_pairs, int H, int W = 0) {
   SortWs<KeyT> w;
   uint8_t* p = reinterpret_cast<uint8_t*>(ws);
   auto take = [&p](size_t bytes) { uint8_t* r = p; p += pad256(bytes); return r; };
@@ -732,6 +908,15 @@ static SortWs<KeyT> carve(void* ws, long long max_records, int n_pairs, int H) {
   w.digit_tot = reinterpret_cast<uint32_t*>(take(np * kDigits * 4));
   w.blockcount = reinterpret_cast<int32_t*>(take(np * ((size_t)w.nb_max + 1) * 4));
   w.rowoff = reinterpret_cast<int32_t*>(take(np * 2 * (size_t)std::max(H, 1) * 4));
+  w.rowcnt_f = nullptr; w.rowmax = nullptr; w.bloom = nullptr; w.keep = nullptr;
+  w.keep_words = (W + 31) / 32;
+  if (W > 0) {                                           // pre-filter buffers (hash-image input)
+    const size_t rows = (size_t)std::max(H, 1);
+    w.rowcnt_f = reinterpret_cast<int32_t*>(take(np * 2 * rows * 4));
+    w.rowmax = reinterpret_cast<unsigned long long*>(take(np * rows * 8));
+    w.bloom = reinterpret_cast<uint32_t*>(take(np * 2 * (size_t)kBloomWords * 4));
+    w.keep = reinterpret_cast<uint32_t*>(take(np * 2 * rows * (size_t)w.keep_words * 4));
+  }
   return w;
 }
 
@@ -739,7 +924,7 @@ template <typename KeyT>
 static cudaError_t sort_passes(SortWs<KeyT>& w, long long max_records, int n_pairs, int key_bits, cudaStream_t stream, int* launches,
                                int* cur_out) {
   const int nb = (int)((max_records + kTile - 1) / kTile);
-  const dim3 grid(nb, n_pairs);
+  const dim3 grid(tile_grid_x(nb, n_pairs), n_pairs);
   {                                                       // per device and per call: cheap next to the sort itself
     cudaError_t e = cudaFuncSetAttribute(radix_scatter_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_smem_bytes<KeyT>());
     if (e != cudaSuccess) return e;
@@ -758,16 +943,16 @@ static cudaError_t sort_passes(SortWs<KeyT>& w, long long max_records, int n_pai
 
 template <typename KeyT>
 static cudaError_t sort_and_emit(SortWs<KeyT>& w, long long max_records, int n_pairs, int key_bits, const GlobalEmitArgs& ea,
-                                 cudaStream_t stream, int* launches, int first_chunk = 1) {
+                                 cudaStream_t stream, int* launches, int first_chunk = 1, bool tmax_known = false) {
   const int nb = (int)((max_records + kTile - 1) / kTile);
   if (nb <= 0 || n_pairs <= 0) return cudaSuccess;
-  const dim3 grid(nb, n_pairs);
+  const dim3 grid(tile_grid_x(nb, n_pairs), n_pairs);
   int cur = 0;
   {
     cudaError_t e = sort_passes(w, max_records, n_pairs, key_bits, stream, launches, &cur);
     if (e != cudaSuccess) return e;
   }
-  global_tmax_kernel<KeyT><<<n_pairs, 32, 0, stream>>>(w, cur);
+  if (!tmax_known) global_tmax_kernel<KeyT><<<n_pairs, 32, 0, stream>>>(w, cur);      // else: taken over all right records
   global_count_kernel<KeyT><<<grid, kSortThreads, 0, stream>>>(w, cur, ea);
   global_blockscan_kernel<KeyT><<<n_pairs, 32, 0, stream>>>(w, ea);
   if (ea.pair_base) { global_pairbase_kernel<<<1, 32, 0, stream>>>(ea.n_out, n_pairs, const_cast<long long*>(ea.pair_base), first_chunk); *launches += 1; }
@@ -779,7 +964,7 @@ static cudaError_t sort_and_emit(SortWs<KeyT>& w, long long max_records, int n_p
 // Hash images of n_pairs pairs ([2 * n_pairs][H][W], rowcnt [2 * n_pairs][H]) -> ordered supports (mode 0)
 // or correspondences (mode 1); pair p writes at out + p * out_stride records (pair_base == nullptr) or packed
 // from out + pair_base[p] (pair_base filled here; first_chunk = 0 continues the prefix of an earlier call), count to
-// n_out[p], candidate counts to n_cand[2p], n_cand[2p+1] (optional).  ws from global_workspace_bytes(max_records, n_pairs, H).
+// n_out[p], candidate counts to n_cand[2p], n_cand[2p+1] (optional).  ws from global_workspace_bytes(max_records, n_pairs, H, W).
 cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int W, int H, int n_pairs, int epipolar, int key_bits,
                                 int disp_high, int vertical_tolerance, int mode, void* ws, long long max_records, void* out,
                                 long long out_stride, long long cap, int32_t* n_out, int32_t* n_cand, cudaStream_t stream,
@@ -790,16 +975,16 @@ cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int
   const dim3 gather_grid((2 * H * 32 + 127) / 128, n_pairs);
   cudaError_t e;
   if (hashtable) {                                       // inference.hpp:204-225: sort by bucket, then replay the buckets
-    SortWs<uint32_t> w = carve<uint32_t>(ws, max_records, n_pairs, H);
+    SortWs<uint32_t> w = carve<uint32_t>(ws, max_records, n_pairs, H, W);
     global_rowoff_kernel<<<dim3(2, n_pairs), 1024, 0, stream>>>(rowcnt, H, w.rowoff, w.n_side);
-    global_gather_kernel<uint32_t><<<gather_grid, 128, 0, stream>>>(hash, W, H, epipolar, 1, w);
+    global_gather_kernel<uint32_t><<<gather_grid, 128, 0, stream>>>(hash, W, H, epipolar, 1, 0, w);
     *launches += 2;
     const int nb = (int)((max_records + kTile - 1) / kTile);
     if (nb <= 0 || n_pairs <= 0) return cudaGetLastError();
     int cur = 0;
     if ((e = sort_passes(w, max_records, n_pairs, 18, stream, launches, &cur)) != cudaSuccess) return e;   // 214673 < 2^18
     HtArgs h{hash, nullptr, W, H, epipolar, 0};
-    const dim3 grid(nb, n_pairs);
+    const dim3 grid(tile_grid_x(nb, n_pairs), n_pairs);
     ht_keys_kernel<<<grid, kSortThreads, 0, stream>>>(w, cur, h);
     ht_count_kernel<<<grid, kSortThreads, 0, stream>>>(w, cur, ea);
     global_blockscan_kernel<uint32_t><<<n_pairs, 32, 0, stream>>>(w, ea);
@@ -810,22 +995,37 @@ cudaError_t launch_match_global(const uint32_t* hash, const int32_t* rowcnt, int
     if (e == cudaSuccess && n_cand) e = cudaMemcpyAsync(n_cand, w.n_side, (size_t)n_pairs * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
     return e;
   }
+  // sort-path semantics: pre-filter, gather the surviving records, sort, scan
+  static const bool prefilter = !(std::getenv("GPC_GLOBAL_PREFILTER") && std::atoi(std::getenv("GPC_GLOBAL_PREFILTER")) == 0);
+  SortWs<uint32_t> w32 = carve<uint32_t>(ws, max_records, n_pairs, H, W);
+  const int32_t* counts = rowcnt;
+  if (prefilter) {
+    if ((e = cudaMemsetAsync(w32.bloom, 0, (size_t)n_pairs * 2 * kBloomWords * sizeof(uint32_t), stream)) != cudaSuccess) return e;
+    if (n_cand) {                                        // the reported candidate counts are the unfiltered ones
+      global_rowoff_kernel<<<dim3(2, n_pairs), 1024, 0, stream>>>(rowcnt, H, w32.rowoff, n_cand);
+      *launches += 1;
+    }
+    bloom_build_kernel<<<gather_grid, 128, 0, stream>>>(hash, W, H, epipolar, w32);
+    rowmax_reduce_kernel<<<n_pairs, 32, 0, stream>>>(w32, H);
+    bloom_filter_kernel<<<gather_grid, 128, 0, stream>>>(hash, W, H, epipolar, w32);
+    *launches += 3;
+    counts = w32.rowcnt_f;
+  }
   if (epipolar) {
-    SortWs<unsigned long long> w = carve<unsigned long long>(ws, max_records, n_pairs, H);
-    global_rowoff_kernel<<<dim3(2, n_pairs), 1024, 0, stream>>>(rowcnt, H, w.rowoff, w.n_side);
-    global_gather_kernel<unsigned long long><<<gather_grid, 128, 0, stream>>>(hash, W, H, 1, 0, w);
+    SortWs<unsigned long long> w = carve<unsigned long long>(ws, max_records, n_pairs, H, W);
+    global_rowoff_kernel<<<dim3(2, n_pairs), 1024, 0, stream>>>(counts, H, w.rowoff, w.n_side);
+    global_gather_kernel<unsigned long long><<<gather_grid, 128, 0, stream>>>(hash, W, H, 1, 0, prefilter ? 1 : 0, w);
     *launches += 2;
     int hb = 1; while ((1 << hb) < H) hb++;
-    e = sort_and_emit(w, max_records, n_pairs, 32 + hb, ea, stream, launches, first_chunk);
-    if (e == cudaSuccess && n_cand) e = cudaMemcpyAsync(n_cand, w.n_side, (size_t)n_pairs * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
+    e = sort_and_emit(w, max_records, n_pairs, 32 + hb, ea, stream, launches, first_chunk, prefilter);
+    if (e == cudaSuccess && n_cand && !prefilter) e = cudaMemcpyAsync(n_cand, w.n_side, (size_t)n_pairs * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
     return e;
   }
-  SortWs<uint32_t> w = carve<uint32_t>(ws, max_records, n_pairs, H);
-  global_rowoff_kernel<<<dim3(2, n_pairs), 1024, 0, stream>>>(rowcnt, H, w.rowoff, w.n_side);
-  global_gather_kernel<uint32_t><<<gather_grid, 128, 0, stream>>>(hash, W, H, 0, 0, w);
+  global_rowoff_kernel<<<dim3(2, n_pairs), 1024, 0, stream>>>(counts, H, w32.rowoff, w32.n_side);
+  global_gather_kernel<uint32_t><<<gather_grid, 128, 0, stream>>>(hash, W, H, 0, 0, prefilter ? 1 : 0, w32);
   *launches += 2;
-  e = sort_and_emit(w, max_records, n_pairs, key_bits, ea, stream, launches, first_chunk);
-  if (e == cudaSuccess && n_cand) e = cudaMemcpyAsync(n_cand, w.n_side, (size_t)n_pairs * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
+  e = sort_and_emit(w32, max_records, n_pairs, key_bits, ea, stream, launches, first_chunk, prefilter);
+  if (e == cudaSuccess && n_cand && !prefilter) e = cudaMemcpyAsync(n_cand, w32.n_side, (size_t)n_pairs * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
   return e;
 }
 
