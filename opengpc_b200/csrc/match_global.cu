@@ -47,7 +47,10 @@ constexpr int kDigits = 256;
 constexpr uint32_t kSideBit = 0x80000000u;
 constexpr uint32_t kHtBuckets = 214673u;    // inference.hpp:212
 constexpr int kHtDepth = 10;                // hashmatch.hpp:95: a bucket keeps the first 10 elements offered to it
-constexpr int kBloomLog2 = 22;              // pre-filter: bits per side and pair (512 KB; a chunk of pairs stays L2 resident)
+#ifndef GPC_BLOOM_LOG2
+#define GPC_BLOOM_LOG2 22
+#endif
+constexpr int kBloomLog2 = GPC_BLOOM_LOG2;  // pre-filter: bits per side and pair (2^22: 512 KB; a chunk of pairs stays L2 resident)
 constexpr int kBloomWords = (1 << kBloomLog2) / 32;
 
 // Workspace of a chunk of pairs (device pointers; slice `pair` starts at pair * stride of each array).
