@@ -152,3 +152,24 @@ def test_hashmatch_explicit_keys(g, ctx, oracle, ht_golden):
             pool = rng.integers(0, 2 ** 20, size=5000, dtype=np.uint64)
         src, tar = rng.choice(pool, ns), rng.choice(pool, nt)
         assert np.array_equal(ctx.hashmatch(src, tar), oracle.hashmatch(src, tar)), case
+
+
+@pytest.mark.gpu
+def test_hashtable_many_pairs_per_launch(g, oracle):
+    """20 Sintel-sized pairs in one chunk: more tiles per pair (185) than blocks per pair (120), so every sort /
+    replay kernel walks several tiles per block, and the packed output spans the pairs of the chunk."""
+    from opengpc_b200.synth import synth_batch
+    n = 20
+    imgs = np.tile(synth_batch(1024, 436, 4, seed0=900), (n // 4, 1, 1, 1))
+    imgs[7] = synth_batch(1024, 436, 1, seed0=77)[0]
+    of = oracle.read_forest(FORESTS["tau"])
+    s = g.make_settings(thr=5, disp_high=128, vt=0, epipolar=True, use_hashtable=True)
+    with g.Context(device=0, max_w=1024, max_h=436, max_batch=n) as c:
+        c.set_forest(FORESTS["tau"])
+        supp, offs, _ = c.match_batch(imgs, s)
+    refs = {}
+    for p in range(n):
+        key = 7 if p == 7 else p % 4
+        if key not in refs:
+            refs[key] = oracle.pair_hashtable(imgs[p, 0], imgs[p, 1], of, osettings())
+        assert np.array_equal(supp[offs[p]:offs[p + 1]], refs[key]), p
