@@ -85,6 +85,97 @@ def workload_name(args, w, h):
             f"synthetic {w}x{h} stereo pairs" + (" (low-texture variant)" if args.sparse else ""))
 
 
+def config_dict(args, w, h):
+    """The SAME dict in both arms (the driver compares them): what is computed, not how much of it an arm samples."""
+    P = w * h
+    return {"workload": workload_name(args, w, h), "shape": f"{w}x{h}", "forest": os.path.basename(FORESTS[args.forest]),
+            "settings": "gradientThreshold 5, verticalTolerance 0, dispHigh 128, epipolarMode, sort matcher (sparsematch.cpp:29-34)",
+            "pairs_per_step_per_gpu": args.batch, "distinct_pairs": min(args.distinct, args.batch),
+            "sharding": "pairs round-robin over the GPUs, no collective",
+            "l2": f"inputs larger than L2: {2 * args.batch * P / 1e6:.0f} MB raw + {8 * args.batch * P / 1e6:.0f} MB hash per step vs 126 MB L2"}
+
+
+def support_digest(supp):
+    """FNV-1a-64 variant over an ordered support list [n, 3] int32 (x, y, d as float bits) -- SURVEY.md appendix C.
+    Plain Python on purpose: the product arm of bench.py never touches oracle/."""
+    supp = np.ascontiguousarray(supp).reshape(-1, 3)
+    d = supp[:, 2].copy().view(np.float32).astype(np.int64)
+    vals = np.stack([supp[:, 0].astype(np.int64), supp[:, 1].astype(np.int64), d], axis=1).reshape(-1) & 0xFFFFFFFF
+    hsh = 1469598103934665603
+    for v in vals.tolist():
+        hsh = ((hsh ^ v) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return "%016x" % hsh
+
+
+def golden_records(args, w, h):
+    """Reference-generated count + digest per seed for this workload (tests/golden/bench_pairs.json), or None."""
+    p = os.path.join(ROOT, "tests", "golden", "bench_pairs.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        g = json.load(f)
+    key = f"{w}x{h}/{args.forest}" + ("/sparse" if args.sparse else "")
+    recs = g["cases"].get(key)
+    return {r["seed"]: r for r in recs} if recs else None
+
+
+def verify_batch(args, w, h, B, rank, d_out, d_n, d_nc, torch):
+    """Checks the batch the timed region just produced: every pair's counts against its seed's golden record, the
+    ordered support list of the first distinct pairs by digest, and every tiled copy bit-identical to its original."""
+    gold = golden_records(args, w, h)
+    distinct = min(args.distinct, B)
+    n = d_n.cpu().numpy().astype(np.int64)
+    nc = d_nc.cpu().numpy().astype(np.int64)
+    seed_of = lambda j: 1234 + ((j - rank) % B) % distinct        # images were rolled by `rank` along the batch axis
+    checked = 0
+    first = {}
+    for j in range(B):
+        sd = seed_of(j)
+        if sd not in first:
+            first[sd] = j
+            if gold and sd in gold:
+                rec = gold[sd]
+                got = d_out[j, :int(n[j])].cpu().numpy()
+                assert (int(nc[j, 0]), int(nc[j, 1]), int(n[j])) == (rec["n_cand_l"], rec["n_cand_r"], rec["n_supports"]), \
+                    f"pair {j} (seed {sd}): counts {nc[j].tolist()} {int(n[j])} != golden {rec}"
+                dg = support_digest(got)
+                assert dg == rec["digest"], f"pair {j} (seed {sd}): digest {dg} != golden {rec['digest']}"
+                checked += 1
+        else:
+            k = first[sd]
+            assert int(n[j]) == int(n[k]) and (nc[j] == nc[k]).all(), f"pair {j} differs from pair {k} (same seed)"
+            assert bool(torch.equal(d_out[j, :int(n[j])], d_out[k, :int(n[k])])), f"pair {j} differs from pair {k} (same seed)"
+    return {"pairs_in_batch": B, "digest_checked_pairs": checked, "copies_identical": B - len(first),
+            "against": "tests/golden/bench_pairs.json (count + FNV digest of the unmodified reference, scripts/make_golden_bench.py)"
+                       if checked else "no golden record for this workload: copies compared with their originals only"}
+
+
+def copy_ceiling(torch, h_img, d_img, h_out, d_flat, n_out_bytes, dist, reps=3):
+    """The box's bare copy ceiling for this step's traffic: pinned H2D of the images and D2H of the supports on two
+    streams at once (all ranks at the same time), no kernels.  Returns seconds per step (max over ranks)."""
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+    n_el = n_out_bytes // 4
+    def once():
+        with torch.cuda.stream(s_up):
+            d_img.copy_(h_img, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            h_out.view(-1)[:n_el].copy_(d_flat[:n_el], non_blocking=True)
+    once()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize()
+    sec = (time.perf_counter() - t0) / reps
+    if dist is not None:
+        t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    return sec
+
+
 def ncu_traffic(kernel, n_pixels):
     """DRAM bytes per launch from the committed ncu capture (profiles/traffic.json: bytes per pixel)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -176,14 +267,14 @@ def make_images(w, h, batch, distinct, sparse=False):
     return np.ascontiguousarray(np.tile(base, (reps, 1, 1, 1))[:batch])
 
 
-def cpu_reference_run(images, forest_path, threads, iters):
+def cpu_reference_run(images, forest_path, threads, iters, disp_high=128):
     """Times the compiled, unmodified reference (oracle/_ref) or, if absent, the C port."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oraclelib import Oracle, Reference, settings
     n_pairs, _, h, w = images.shape
     if Reference.available():
         ref = Reference()
-        sec, tot = ref.time_pairs(images, forest_path, threads=threads, iters=iters)
+        sec, tot = ref.time_pairs(images, forest_path, threads=threads, iters=iters, disp_high=disp_high)
         return threads * iters / sec, "reference", tot
     o = Oracle()   # scalar port, single thread
     f = o.read_forest(forest_path)
@@ -191,7 +282,7 @@ def cpu_reference_run(images, forest_path, threads, iters):
     tot = 0
     n = max(1, iters)
     for i in range(n):
-        s, _, _ = o.pair(images[i % n_pairs, 0], images[i % n_pairs, 1], f, settings())
+        s, _, _ = o.pair(images[i % n_pairs, 0], images[i % n_pairs, 1], f, settings(disp_high=disp_high))
         tot += len(s)
     return n / (time.perf_counter() - t0), "port", tot
 
@@ -218,7 +309,7 @@ def run_reference_arm(args, w, h):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "mpix_per_s": value * 2 * w * h / 1e6,
-            "config": {"workload": workload_name(args, w, h), "pairs_per_step": threads},
+            "config": config_dict(args, w, h),
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": kind,
                              "sample": f"{threads} pairs per step ({threads} host threads x 1 pair), "
                                        f"t0..t2 window of sparsematch.cpp:45-52"},
@@ -256,6 +347,18 @@ def run_pyramid(args, g, ctx, images, w, h, world, rank, dist, torch):
     sec = time.perf_counter() - t0
     offs = h_off.numpy().copy()
     supp = h_out[:int(offs[-1])]
+    # check the levels the timed steps produced against the reference-generated fixture (tests/golden/pyramid.json)
+    verified = {"levels_checked": 0}
+    gp = os.path.join(ROOT, "tests", "golden", "pyramid.json")
+    if os.path.exists(gp) and args.forest == "tau" and not args.sparse and (world == 1 or rank == 0):
+        with open(gp) as f:
+            for case in json.load(f)["cases"]:
+                if (case["w"], case["h"], case["seed"], case["forest"]) == (w, h, 1234, "tau"):
+                    for lv in case["levels"][:levels]:
+                        got = supp[int(offs[lv["level"]]):int(offs[lv["level"] + 1])].numpy()
+                        assert len(got) == lv["n_supports"] and support_digest(got) == lv["digest"], f"pyramid level {lv['level']} differs from the golden record"
+                        verified["levels_checked"] += 1
+                    verified["against"] = "tests/golden/pyramid.json (the unmodified reference run per level)"
     from opengpc_b200.shard import reduce_timing
     ms, launches = reduce_timing(sec * 1e3, ctx.launches - l0, dist, "cuda")
     clocks = sampler.stop()
@@ -266,11 +369,25 @@ def run_pyramid(args, g, ctx, images, w, h, world, rank, dist, torch):
     line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "mpix_per_s": value * pix / 1e6,
-            "config": {"workload": workload_name(args, w, h), "levels": levels, "supports_per_level": np.diff(offs).tolist(),
-                       "note": "host-buffer API only: value == e2e (upload + per-level download inside the timed region)"},
-            "clocks": clocks, "gpu_launches": launches,
+            "config": config_dict(args, w, h), "levels": levels, "supports_per_level": np.diff(offs).tolist(),
+            "note": "host-buffer API only: value == e2e (upload + per-level download inside the timed region)",
+            "verified": verified, "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 2 * w * h, "d2h_bytes_per_step": int(len(supp)) * 12,
                     "api": "gpc_match_pyramid"}}
+    if not args.no_cpu_baseline and world == 1:
+        # the reference has no pyramid: its sparsematch window per level on the identically down-sampled images,
+        # every host core running one pair of that level
+        from opengpc_b200.synth import downsample2x
+        cores = os.cpu_count() or 1
+        lv_imgs, sec_per_pair, kind = images[:1], 0.0, "reference"
+        for l in range(levels):
+            rate, kind, _ = cpu_reference_run(lv_imgs, FORESTS[args.forest], cores, 1, disp_high=128 >> l)
+            sec_per_pair += 1.0 / rate
+            lv_imgs = np.ascontiguousarray(np.stack([np.stack([downsample2x(lv_imgs[0, 0]), downsample2x(lv_imgs[0, 1])])]))
+        threads = cores if kind == "reference" else 1
+        line["cpu_baseline"] = {"value": 1.0 / sec_per_pair, "unit": "pairs/s", "cores": threads, "kind": kind,
+                                "sample": f"{levels} levels x {threads} pairs ({threads} host threads x 1 pair per level), "
+                                          f"sparsematch.cpp:45-52 window per level"}
     print(json.dumps(line), flush=True)
 
 
@@ -354,6 +471,7 @@ def main():
     ms_total, launches = reduce_timing(ms_total, launches, dist, "cuda")     # max over ranks, sum over ranks
     ms_per_step = ms_total / args.steps
     value = world * B / (ms_per_step / 1e3)
+    verified = verify_batch(args, w, h, B, rank if world > 1 else 0, d_out, d_n, d_nc, torch)   # the batch the timed steps produced
 
     # ---- end to end through the C ABI with host buffers -----------------------------------------
     e2e = None
@@ -379,7 +497,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             sec = float(t.item())
         assert int(h_off[B]) == tot_sup
+        offs = h_off.numpy()
+        assert (np.diff(offs) == n_sup).all(), "end-to-end support counts differ from the device-resident run"
+        j0 = 0
+        assert support_digest(h_out[int(offs[j0]):int(offs[j0 + 1])].numpy()) == support_digest(d_out[j0, :int(n_sup[j0])].cpu().numpy())
         clocks = sampler.stop()
+        ceil_sec = copy_ceiling(torch, h_img, d_img, h_out, d_out.view(-1), tot_sup * 12, dist)
         # single-pair latency through the same API (SURVEY.md 8d asks for it beside the batched throughput)
         lat = []
         for _ in range(12):
@@ -390,7 +513,11 @@ def main():
         e2e = {"value": world * B * args.steps / sec, "unit": "pairs/s",
                "h2d_bytes_per_step": int(2 * B * P), "d2h_bytes_per_step": int(tot_sup * 12 + (B + 1) * 8),
                "single_pair_latency_ms": single_pair_ms,
+               "copy_ceiling_pairs_per_s": world * B / ceil_sec,
+               "copy_ceiling_gbs": world * (2 * B * P + tot_sup * 12) / ceil_sec / 1e9,
+               "copy_ceiling_note": "bare pinned H2D of the images + D2H of the supports on two streams, all ranks at once, no kernels",
                "api": "gpc_match_batch (pinned host buffers; upload, kernels and download pipelined over 3 streams)"}
+        e2e["frac_of_ceiling"] = e2e["value"] / e2e["copy_ceiling_pairs_per_s"]
 
     if args.no_e2e:
         clocks = sampler.stop()
@@ -459,21 +586,22 @@ def main():
     achieved = alg_bytes[dominant] / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
     path_bytes = (10.0 * P + 12.0 * mean_sup)                     # B_alg per pair
     traffic, traffic_src = ncu_traffic(dominant, (2 * B if dominant in ("smooth_sobel", "hash_tiles") else B) * P)
-    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+    path_gbs = path_bytes * value / world / 1e9                   # B_alg x pairs/s of one GPU
+    kernel_frac = {k: (alg_bytes[k] / (v / 1e3) / 1e9 / peak if v > 0 else None) for k, v in per_kernel_ms.items()}
+    all_traffic = {k: ncu_traffic(k, (2 * B if k in ("smooth_sobel", "hash_tiles") else B) * P)[0] for k in per_kernel_ms}
+    roofline = {"bound": "hbm", "achieved": path_gbs, "peak": peak, "unit": "GB/s", "frac": path_gbs / peak,
+                "definition": "whole path: (10*W*H + 12*Ns) bytes per pair x pairs/s per GPU / measured HBM peak (SURVEY.md 8d)",
+                "path_bytes_per_pair": path_bytes, "peak_source": peak_src,
+                "kernel": dominant, "kernel_achieved": achieved, "kernel_frac": achieved / peak,
                 "algorithmic_bytes_per_launch": alg_bytes[dominant],
-                "kernel_ms_per_step": per_kernel_ms,
-                "path_bytes_per_pair": path_bytes,
-                "path_frac": path_bytes * value / world / 1e9 / peak}
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel_ms_per_step": per_kernel_ms, "kernel_fracs": kernel_frac, "kernel_traffic": all_traffic}
 
     line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "mpix_per_s": value * 2 * P / 1e6,
-            "config": {"workload": workload_name(args, w, h), "pairs_per_step_per_gpu": B,
-                       "distinct_pairs": min(args.distinct, B), "sharding": f"pairs round-robin over {world} GPU(s), no collective",
-                       "supports_per_pair": mean_sup, "host": numa_note,
-                       "l2": f"inputs larger than L2: {2 * B * P / 1e6:.0f} MB raw + {8 * B * P / 1e6:.0f} MB hash per step vs 126 MB L2"},
+            "config": config_dict(args, w, h), "supports_per_pair": mean_sup, "host": numa_note, "verified": verified,
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
     if e2e:
         line["e2e"] = e2e

@@ -22,7 +22,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <iostream>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -113,6 +115,7 @@ inline std::string png_decode(const std::string& filename, PngImage* out) {
     if (pos + 12 + (size_t)len > file.size()) break;
     const uint8_t* type = &file[pos + 4];
     const uint8_t* data = &file[pos + 8];
+    if ((uint32_t)crc32(0L, type, (uInt)(len + 4)) != be32(data + len)) return "ERR: Error during read_image";   // libpng rejects a bad CRC too
     if (!std::memcmp(type, "IHDR", 4) && len >= 13) {
       out->width = (int)be32(data); out->height = (int)be32(data + 4);
       out->bit_depth = data[8]; out->color_type = data[9]; interlace = data[12];
@@ -125,6 +128,8 @@ inline std::string png_decode(const std::string& filename, PngImage* out) {
     pos += 12 + (size_t)len;
   }
   if (!have_ihdr) return "ERR: Error during init_io";
+  if (out->width <= 0 || out->height <= 0 || out->width > (1 << 16) || out->height > (1 << 16))
+    return "ERR: Error during read_image";                // IHDR sizes are unsigned 31-bit: no negative / absurd allocations
   switch (out->color_type) {
     case 0: out->channels = 1; break;
     case 2: out->channels = 3; break;
@@ -210,30 +215,37 @@ class Buffer {
   Buffer(const int r, const int c) : width(c), height(r), rows_(r), cols_(detail::align16(c)), v_((size_t)rows_ * cols_) {}
   Buffer(const int r, const int c, T color) : width(c), height(r), rows_(r), cols_(detail::align16(c)), v_((size_t)rows_ * cols_, color) {}
 
-  T* data() { return v_.data(); }
-  const T* data() const { return v_.data(); }
+  // B200 addition: the pixels may be produced on first access (Forest::preprocessImage leaves smooth / grad on the
+  // device until somebody reads them).  `fill` receives data(); dimensions are known from the start.
+  void setLazyFill(std::function<void(T*)> fill) { lazy_ = std::make_shared<std::function<void(T*)>>(std::move(fill)); }
+  bool isLazy() const { return (bool)lazy_; }
+
+  T* data() { materialize(); return v_.data(); }
+  const T* data() const { materialize(); return v_.data(); }
   int rows() const { return rows_; }
   int cols() const { return cols_; }
   long size() const { return (long)v_.size(); }
-  T& operator()(int r, int c) { return v_[(size_t)r * cols_ + c]; }
-  const T& operator()(int r, int c) const { return v_[(size_t)r * cols_ + c]; }
+  T& operator()(int r, int c) { materialize(); return v_[(size_t)r * cols_ + c]; }
+  const T& operator()(int r, int c) const { materialize(); return v_[(size_t)r * cols_ + c]; }
 
   // Eigen-style resize: contents unspecified afterwards (here: zero)
-  void resize(int r, int c) { rows_ = r; cols_ = c; v_.assign((size_t)r * c, T()); }
+  void resize(int r, int c) { lazy_.reset(); rows_ = r; cols_ = c; v_.assign((size_t)r * c, T()); }
   void conservativeResize(int r, int c) {
+    materialize();
     std::vector<T> nv((size_t)r * c, T());
     for (int y = 0; y < std::min(r, rows_); y++)
       for (int x = 0; x < std::min(c, cols_); x++) nv[(size_t)y * c + x] = v_[(size_t)y * cols_ + x];
     v_.swap(nv); rows_ = r; cols_ = c;
   }
 
-  void setPixel(int x, int y, T color) { v_[(size_t)cols_ * y + x] = color; }
-  T getPixel(int x, int y) const { return v_[(size_t)cols_ * y + x]; }
-  void set(T color) { std::fill(v_.begin(), v_.end(), color); }
+  void setPixel(int x, int y, T color) { materialize(); v_[(size_t)cols_ * y + x] = color; }
+  T getPixel(int x, int y) const { materialize(); return v_[(size_t)cols_ * y + x]; }
+  void set(T color) { lazy_.reset(); std::fill(v_.begin(), v_.end(), color); }
   Dimension getDimension() { return Dimension(cols_, rows_); }
 
   // buffer.hpp:630-654
   void clearBoundary() {
+    materialize();
     const int h = height, w = width, wa = cols_;
     for (int x = 0; x < 2; x++) for (int y = 0; y < h; y++) v_[(size_t)y * wa + x] = T();
     for (int x = 0; x < w; x++) v_[x] = T();
@@ -257,6 +269,7 @@ class Buffer {
     detail::PngImage img;
     const std::string err = detail::png_decode(filename, &img);
     if (!err.empty()) { std::cout << err << std::endl; return 1; }
+    lazy_.reset();
     width = img.width; height = img.height;
     rows_ = height; cols_ = detail::align16(width);
     v_.assign((size_t)rows_ * cols_, T());
@@ -303,11 +316,21 @@ class Buffer {
     std::cout << "ERR: writePNGRGB needs a Buffer<RGBColor>" << std::endl;
   }
 
+  void materialize() const {
+    if (!lazy_) return;
+    std::shared_ptr<std::function<void(T*)>> f;
+    f.swap(lazy_);                                  // cleared first: the fill may touch this buffer
+    (*f)(v_.data());
+  }
+
   int rows_ = 0, cols_ = 0;
-  std::vector<T> v_;
+  mutable std::vector<T> v_;
+  mutable std::shared_ptr<std::function<void(T*)>> lazy_;
 };
 
-// buffer.hpp:949-1014: supports drawn over the gray image with the KITTI disparity colour map.
+// buffer.hpp:949-1014: supports drawn over the gray image with the KITTI disparity colour map.  The eight-entry table
+// and the interpolation below ARE Geiger's KITTI stereo devkit colour map as the reference uses it: a restatement kept
+// value for value because disparity.png has to come out pixel-identical to the reference's (host-side visualisation only).
 inline Buffer<RGBColor> getDisparityVisualization(Buffer<uint8_t>& srcImg, std::vector<Support>& support) {
   const float min_disparity = 0.f, max_disparity = 128.f;
   Buffer<RGBColor> vis = srcImg.convertToRGB();

@@ -42,6 +42,7 @@
 #include <functional>
 #include <iostream>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -104,28 +105,40 @@ inline gpc_settings to_c(const InferenceSettings& s) {
   return c;
 }
 
-// One resident context per (process, device); grown when a larger image arrives.
-struct Runtime {
+// A resident context and its lock.  The reference's Forest methods are stateless and may be called from several
+// threads; here they share one device context per process, so every call into it holds `mu`.
+struct Context {
   gpc_ctx* ctx = nullptr;
   int max_w = 0, max_h = 0, device = 0;
-  ~Runtime() { if (ctx) gpc_destroy(ctx); }
-  gpc_ctx* get(int w, int h) {
-    if (ctx && w <= max_w && h <= max_h) return ctx;
-    if (ctx) { gpc_destroy(ctx); ctx = nullptr; }
+  std::recursive_mutex mu;      // recursive: a lazily fetched smooth / grad buffer may be touched inside a locked call
+  ~Context() { if (ctx) gpc_destroy(ctx); }
+};
+
+// One current context per process; when a larger image arrives a NEW context is created and becomes current.  The old
+// one lives on for as long as PreprocessedImages made with it do (they hold a reference), so their resident images stay
+// valid and rectifiedMatch on two images of the same context keeps working.
+struct Runtime {
+  std::mutex mu;
+  std::shared_ptr<Context> cur;
+  std::shared_ptr<Context> get(int w, int h) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cur && w <= cur->max_w && h <= cur->max_h) return cur;
+    auto nc = std::make_shared<Context>();
     const char* dev = std::getenv("GPC_DEVICE");
-    device = dev ? std::atoi(dev) : 0;
-    max_w = std::max(w, max_w); max_h = std::max(h, max_h);
-    const int rc = gpc_create(&ctx, device, max_w, max_h, 1);
+    nc->device = dev ? std::atoi(dev) : 0;
+    nc->max_w = std::max(w, cur ? cur->max_w : 0); nc->max_h = std::max(h, cur ? cur->max_h : 0);
+    const int rc = gpc_create(&nc->ctx, nc->device, nc->max_w, nc->max_h, 1);
     if (rc != GPC_OK) throw GpcError(rc, std::string("gpc_create: ") + gpc_last_error(nullptr));
 #ifdef GPC_B200_NAIVE_RESULTS
-    gpc_set_result_mode(ctx, GPC_RESULTS_NAIVE);   // the reference's SSE=OFF build (filter.hpp *Naive functions)
+    gpc_set_result_mode(nc->ctx, GPC_RESULTS_NAIVE);   // the reference's SSE=OFF build (filter.hpp *Naive functions)
 #endif
-    return ctx;
+    cur = nc;
+    return cur;
   }
 };
 
-inline std::shared_ptr<Runtime>& runtime() {
-  static std::shared_ptr<Runtime> rt = std::make_shared<Runtime>();
+inline Runtime& runtime() {
+  static Runtime rt;
   return rt;
 }
 
@@ -133,12 +146,14 @@ inline void check(gpc_ctx* c, int rc, const char* where) {
   if (rc != GPC_OK) throw GpcError(rc, std::string(where) + ": " + gpc_last_error(c));
 }
 
-// Raw image resident on the device; keeps the runtime (and so the context) alive.
+// Raw image resident on the device; keeps its context alive.
 struct ResidentImage {
-  std::shared_ptr<Runtime> rt;
-  gpc_ctx* ctx = nullptr;     // the context the image was uploaded to
+  std::shared_ptr<Context> cx;
   gpc_image* image = nullptr;
-  ~ResidentImage() { if (image) gpc_image_release(image); }
+  int thr = 0;                // gradient threshold of the preprocessImage call that made it
+  ~ResidentImage() {
+    if (image) { std::lock_guard<std::recursive_mutex> lk(cx->mu); gpc_image_release(image); }
+  }
 };
 
 }  // namespace detail
@@ -195,20 +210,42 @@ class Forest {
 
   // inference.hpp:302-333: box blur, Sobel mask, candidate indices -- here one fused CUDA kernel;
   // the raw image stays resident on the device for rectifiedMatch.
+  // One pass: upload, kernel A1 (and A2 when a forest is already set on the context); the outputs stay cached on the
+  // device for rectifiedMatch.  `mask` is filled eagerly (sparsematch.cpp:54-55 reads mask.size()); `smooth` and `grad`
+  // are fetched from the device on first access (Buffer::setLazyFill).
   PreprocessedImage preprocessImage(ndb::Buffer<uint8_t>& img, InferenceSettings settings) {
     const int w = img.cols(), h = img.rows();
     assert(w % 16 == 0 && "width must be multiple of 16!");
-    auto rt = detail::runtime();
-    gpc_ctx* c = rt->get(w, h);
+    auto cx = detail::runtime().get(w, h);
+    gpc_ctx* c = cx->ctx;
     auto res = std::make_shared<detail::ResidentImage>();
-    res->rt = rt; res->ctx = c;
-    detail::check(c, gpc_image_upload(c, img.data(), w, h, w, &res->image), "gpc_image_upload");
-    ndb::Buffer<uint8_t> smooth(h, w), grad(h, w);
-    std::vector<int> mask((size_t)w * h);
+    res->cx = cx; res->thr = settings.gradientThreshold_;
+    std::vector<int> mask((size_t)(w - 26 > 0 ? w - 26 : 0) * (size_t)(h - 26 > 0 ? h - 26 : 0) + 1);
     int n = 0;
-    detail::check(c, gpc_image_preprocess(c, res->image, settings.gradientThreshold_, smooth.data(), grad.data(),
-                                          mask.data(), (int)mask.size(), &n), "gpc_image_preprocess");
+    {
+      std::lock_guard<std::recursive_mutex> lk(cx->mu);
+      detail::check(c, gpc_image_upload(c, img.data(), w, h, w, &res->image), "gpc_image_upload");
+      detail::check(c, gpc_image_preprocess(c, res->image, settings.gradientThreshold_, nullptr, nullptr,
+                                            mask.data(), (int)mask.size(), &n), "gpc_image_preprocess");
+    }
     mask.resize((size_t)n);
+    ndb::Buffer<uint8_t> smooth(h, w), grad(h, w);
+    // both images come from one kernel run: whichever is touched first fetches the pair into a shared block
+    struct Pair { std::vector<uint8_t> s, g; bool done = false; std::mutex mu; };
+    auto pr = std::make_shared<Pair>();
+    const size_t P = (size_t)w * h;
+    auto fetch = [res, pr, P](uint8_t* dst, bool want_smooth) {
+      std::lock_guard<std::recursive_mutex> lk2(res->cx->mu);      // context lock first, always in this order
+      std::lock_guard<std::mutex> lk(pr->mu);
+      if (!pr->done) {
+        pr->s.resize(P); pr->g.resize(P);
+        detail::check(res->cx->ctx, gpc_image_fetch(res->cx->ctx, res->image, res->thr, pr->s.data(), pr->g.data()), "gpc_image_fetch");
+        pr->done = true;
+      }
+      std::memcpy(dst, want_smooth ? pr->s.data() : pr->g.data(), P);
+    };
+    smooth.setLazyFill([fetch](uint8_t* d) { fetch(d, true); });
+    grad.setLazyFill([fetch](uint8_t* d) { fetch(d, false); });
     PreprocessedImage out(smooth, grad, mask);
     out.resident = res;
     return out;
@@ -220,17 +257,18 @@ class Forest {
     std::vector<ndb::Support> supp;
     if (resident_pair(simg, timg)) {
       check_dims(simg, timg, forestmask);
-      gpc_ctx* c = simg.resident->ctx;
+      std::lock_guard<std::recursive_mutex> lk(simg.resident->cx->mu);
+      gpc_ctx* c = simg.resident->cx->ctx;
       upload_forest(c, forestmask);
-      const gpc_settings cs = detail::to_c(settings);
-      const int cap = std::max(1, (int)std::min(simg.mask.size(), timg.mask.size()));
-      supp.resize((size_t)cap);
+      gpc_settings cs = detail::to_c(settings);
+      cs.gradient_threshold = simg.resident->thr;          // the candidates are preprocessImage's (inference.hpp:375-393 never re-thresholds)
       int n = 0;
       static_assert(sizeof(ndb::Support) == sizeof(gpc_support), "Support layout");
-      detail::check(c, gpc_match_images(c, simg.resident->image, timg.resident->image, &cs,
-                                        reinterpret_cast<gpc_support*>(supp.data()), cap, &n, nullptr, nullptr),
-                    "gpc_match_images");
+      // count first, then fetch exactly that many records (a worst-case vector would cost more than the matcher)
+      const int rc = gpc_match_images(c, simg.resident->image, timg.resident->image, &cs, nullptr, 0, &n, nullptr, nullptr);
+      if (rc != GPC_E_CAPACITY) detail::check(c, rc, "gpc_match_images");
       supp.resize((size_t)n);
+      detail::check(c, gpc_fetch_supports(c, reinterpret_cast<gpc_support*>(supp.data()), n), "gpc_fetch_supports");
       return supp;
     }
     std::vector<ndb::Correspondence> corr = stereoMatch(simg, timg, forestmask, settings);
@@ -251,9 +289,11 @@ class Forest {
   std::vector<ndb::Correspondence> depthPriorFast(PreprocessedImage& src, PreprocessedImage& tar, FilterMask& fastmask,
                                                   InferenceSettings& settings) {
     if (resident_pair(src, tar)) {
-      gpc_ctx* c = src.resident->ctx;
+      std::lock_guard<std::recursive_mutex> lk(src.resident->cx->mu);
+      gpc_ctx* c = src.resident->cx->ctx;
       upload_forest(c, fastmask);
-      const gpc_settings cs = detail::to_c(settings);
+      gpc_settings cs = detail::to_c(settings);
+      cs.gradient_threshold = src.resident->thr;
       const int cap = std::max(1, (int)std::min(src.mask.size(), tar.mask.size()));
       std::vector<gpc_correspondence> raw((size_t)cap);
       int n = 0;
@@ -283,7 +323,9 @@ class Forest {
                                                        InferenceSettings& settings) {
     (void)grad; (void)settings;
     const int w = img.cols(), h = img.rows();
-    gpc_ctx* c = detail::runtime()->get(w, h);
+    auto cx = detail::runtime().get(w, h);
+    std::lock_guard<std::recursive_mutex> lk(cx->mu);
+    gpc_ctx* c = cx->ctx;
     upload_forest(c, fastmask);
     std::vector<uint32_t> states(idx.size());
     std::vector<int32_t> idx32(idx.begin(), idx.end());
@@ -299,8 +341,9 @@ class Forest {
                                                        std::vector<ndb::Descriptor>& tarStates) {
     std::vector<ndb::Correspondence> corr;
     if (srcStates.empty() || tarStates.empty()) return corr;
-    auto rt = detail::runtime();
-    gpc_ctx* c = rt->get(std::max(rt->max_w, 16), std::max(rt->max_h, 1));
+    auto cx = detail::runtime().get(16, 1);
+    std::lock_guard<std::recursive_mutex> lk(cx->mu);
+    gpc_ctx* c = cx->ctx;
     std::vector<uint64_t> ks(srcStates.size()), kt(tarStates.size());
     for (size_t i = 0; i < ks.size(); i++) ks[i] = srcStates[i].state;
     for (size_t i = 0; i < kt.size(); i++) kt[i] = tarStates[i].state;
@@ -317,8 +360,9 @@ class Forest {
   std::vector<ndb::Correspondence> hashMatch(std::vector<ndb::Descriptor>& srcStates, std::vector<ndb::Descriptor>& tarStates) {
     std::vector<ndb::Correspondence> corr;
     if (srcStates.empty() || tarStates.empty()) return corr;
-    auto rt = detail::runtime();
-    gpc_ctx* c = rt->get(std::max(rt->max_w, 16), std::max(rt->max_h, 1));
+    auto cx = detail::runtime().get(16, 1);
+    std::lock_guard<std::recursive_mutex> lk(cx->mu);
+    gpc_ctx* c = cx->ctx;
     std::vector<uint64_t> ks(srcStates.size()), kt(tarStates.size());
     for (size_t i = 0; i < ks.size(); i++) ks[i] = srcStates[i].state;
     for (size_t i = 0; i < kt.size(); i++) kt[i] = tarStates[i].state;
@@ -332,9 +376,10 @@ class Forest {
   }
 
  private:
+  // both images resident on the SAME context (it need not be the current one: a PreprocessedImage keeps its own alive)
   static bool resident_pair(const PreprocessedImage& a, const PreprocessedImage& b) {
-    return a.resident && b.resident && a.resident->image && b.resident->image && a.resident->ctx == b.resident->ctx &&
-           a.resident->rt->ctx == a.resident->ctx;
+    return a.resident && b.resident && a.resident->image && b.resident->image && a.resident->cx == b.resident->cx &&
+           a.resident->thr == b.resident->thr;
   }
 
   static void check_dims(const PreprocessedImage& simg, const PreprocessedImage& timg, const FilterMask& fm) {

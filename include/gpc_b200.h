@@ -141,16 +141,25 @@ int gpc_hash_smooth(gpc_ctx* ctx, const uint8_t* smooth, int w, int h, const int
 typedef struct gpc_image gpc_image;
 int gpc_image_upload(gpc_ctx* ctx, const uint8_t* img, int w, int h, int stride, gpc_image** out);
 void gpc_image_release(gpc_image* image);
-int gpc_image_preprocess(gpc_ctx* ctx, const gpc_image* image, int gradient_threshold, uint8_t* smooth,
+/* smooth, grad, mask and n_mask are optional (NULL: not computed / not copied).  The image keeps what the kernels
+ * produced on the device -- the smoothed image and candidates for this threshold and, if the context has a forest,
+ * the hash image -- so that gpc_match_images / gpc_correspond_images with the same threshold and forest run the
+ * matcher only (a changed threshold, result mode or forest is detected and recomputed). */
+int gpc_image_preprocess(gpc_ctx* ctx, gpc_image* image, int gradient_threshold, uint8_t* smooth,
                          uint8_t* grad, int32_t* mask, int mask_cap, int* n_mask);
-int gpc_match_images(gpc_ctx* ctx, const gpc_image* left, const gpc_image* right, const gpc_settings* s,
+/* preprocessImage's smoothed / gradient images of a resident image, on demand (either may be NULL) */
+int gpc_image_fetch(gpc_ctx* ctx, const gpc_image* image, int gradient_threshold, uint8_t* smooth, uint8_t* grad);
+int gpc_match_images(gpc_ctx* ctx, gpc_image* left, gpc_image* right, const gpc_settings* s,
                      gpc_support* out, int cap, int* n_out, int* n_cand_l, int* n_cand_r);
+/* The first n supports of the most recent gpc_match_pair / gpc_match_images result, which stays on the device: a
+ * caller that cannot bound the count calls the matcher with cap = 0 (GPC_E_CAPACITY, *n_out = count) and then this. */
+int gpc_fetch_supports(gpc_ctx* ctx, gpc_support* out, int n);
 
 /* == ndb::Correspondence (buffer.hpp:94-97): source point, target point */
 typedef struct { int32_t xs, ys, xt, yt; } gpc_correspondence;
 /* Forest::stereoMatch / depthPriorFast (inference.hpp:344-361, :184-226): every unique-unique
  * correspondence before rectifiedMatch's filter, ascending key order (both matching modes). */
-int gpc_correspond_images(gpc_ctx* ctx, const gpc_image* left, const gpc_image* right, const gpc_settings* s,
+int gpc_correspond_images(gpc_ctx* ctx, gpc_image* left, gpc_image* right, const gpc_settings* s,
                           gpc_correspondence* out, int cap, int* n_out);
 /* Forest::findCorrespondences (inference.hpp:227-254) on explicit 64-bit keys (Descriptor::state):
  * out_pairs[2i], out_pairs[2i+1] = indices into src_keys / tar_keys of match i, ascending src key;
@@ -178,11 +187,13 @@ int gpc_hashmatch(gpc_ctx* ctx, const uint64_t* src_keys, int n_src, const uint6
 #define GPC_RESULTS_NAIVE 1
 int gpc_set_result_mode(gpc_ctx* ctx, int mode);
 
-/* Matcher selection.  AUTO: epipolar mode uses the per-row shared-memory matcher, global mode the
- * device-wide radix sort + segmented scan.  SORT forces the radix-sort matcher for both (same
- * results; used to cross-check the two implementations). */
+/* Matcher selection.  AUTO: epipolar mode uses the per-row shared-memory matchers (a fast kernel for
+ * ordinary rows, a general one for the rows it hands over), global mode the device-wide radix sort +
+ * segmented scan.  SORT forces the radix-sort matcher for both, ROWS_GENERAL sends every row of epipolar
+ * mode through the general row kernel (same results; used to cross-check the implementations). */
 #define GPC_MATCHER_AUTO 0
 #define GPC_MATCHER_SORT 1
+#define GPC_MATCHER_ROWS_GENERAL 2
 int gpc_set_matcher(gpc_ctx* ctx, int matcher);
 
 /* After gpc_set_forest the hashing kernel is rebuilt with the forest baked into its code (NVRTC,
@@ -192,6 +203,8 @@ const char* gpc_jit_status(const gpc_ctx* ctx);
 
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t gpc_launch_count(const gpc_ctx* ctx);
+/* process-unique serial of a context (never reused, unlike its address) */
+int64_t gpc_context_id(const gpc_ctx* ctx);
 
 /* Per-kernel device times, measured with CUDA events on the launching stream around each
  * kernel of the whole-path entry points (bench.py's roofline figures).  Slots:

@@ -16,14 +16,14 @@ GPC_OK, GPC_E_ARG, GPC_E_WIDTH16, GPC_E_DIMS, GPC_E_CUDA, GPC_E_CAPACITY, GPC_E_
 
 SUPPORT_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("d", "<f4")])   # == ndb::Support, 12 bytes
 CORR_DTYPE = np.dtype([("xs", "<i4"), ("ys", "<i4"), ("xt", "<i4"), ("yt", "<i4")])   # == ndb::Correspondence
-MATCHER_AUTO, MATCHER_SORT = 0, 1
+MATCHER_AUTO, MATCHER_SORT, MATCHER_ROWS_GENERAL = 0, 1, 2
 
 # every symbol include/gpc_b200.h declares (checked by tests/test_capi_cpu.py)
 SYMBOLS = ["gpc_create", "gpc_destroy", "gpc_last_error", "gpc_status_string", "gpc_set_stream", "gpc_synchronize",
            "gpc_read_forest", "gpc_set_forest", "gpc_match_pair", "gpc_match_batch", "gpc_match_batch_device",
            "gpc_preprocess", "gpc_hash", "gpc_match_hash_images", "gpc_launch_count", "gpc_enable_kernel_timing",
            "gpc_kernel_times", "gpc_hash_smooth", "gpc_image_upload", "gpc_image_release", "gpc_image_preprocess",
-           "gpc_match_images", "gpc_correspond_images", "gpc_find_correspondences", "gpc_hashmatch", "gpc_set_result_mode", "gpc_set_matcher", "gpc_match_pyramid", "gpc_jit_status"]
+           "gpc_match_images", "gpc_correspond_images", "gpc_find_correspondences", "gpc_hashmatch", "gpc_set_result_mode", "gpc_set_matcher", "gpc_match_pyramid", "gpc_jit_status", "gpc_context_id", "gpc_image_fetch", "gpc_fetch_supports"]
 KERNEL_NAMES = ["smooth_sobel", "hash_tiles", "match_rows", "scans", "emit_supports"]
 
 
@@ -335,14 +335,23 @@ class ResidentImage:
     def __init__(self, ctx, handle, w, h):
         self.ctx, self.handle, self.w, self.h = ctx, handle, w, h
 
-    def preprocess(self, thr):
-        smooth = np.empty((self.h, self.w), np.uint8)
-        grad = np.empty((self.h, self.w), np.uint8)
+    def preprocess(self, thr, images=True):
+        """preprocessImage on the resident image.  images=False: candidate list only (smooth / grad stay on the
+        device until `fetch`); either way the image keeps the kernels' outputs for match_images."""
+        smooth = np.empty((self.h, self.w), np.uint8) if images else None
+        grad = np.empty((self.h, self.w), np.uint8) if images else None
         mask = np.empty(self.h * self.w, np.int32)
         n = C.c_int(0)
         self.ctx._check(self.ctx.lib.gpc_image_preprocess(self.ctx._h, self.handle, int(thr), _ptr(smooth), _ptr(grad),
                                                           _ptr(mask), C.c_int(self.h * self.w), C.byref(n)))
         return smooth, grad, mask[:n.value].copy()
+
+    def fetch(self, thr):
+        """(smooth, grad) of preprocessImage, computed on demand (gpc_image_fetch)."""
+        smooth = np.empty((self.h, self.w), np.uint8)
+        grad = np.empty((self.h, self.w), np.uint8)
+        self.ctx._check(self.ctx.lib.gpc_image_fetch(self.ctx._h, self.handle, int(thr), _ptr(smooth), _ptr(grad)))
+        return smooth, grad
 
     def release(self):
         if self.handle is not None and self.handle.value:

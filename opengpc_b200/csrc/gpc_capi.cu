@@ -10,6 +10,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -21,8 +23,10 @@ cudaError_t configure_hash_tiles();
 int make_smooth_tensor_map(void* out_map, const uint8_t* base, int W, int H, int n_img);
 cudaError_t launch_hash_tiles(const void* tensor_map, const HashArgs&, const ForestDev&, int n_img, cudaStream_t);
 size_t match_smem_bytes(int wcap, int table_log2);
+size_t match_fast_smem_bytes(int nib_log2, int slot_log2, int pow2cap);
 cudaError_t configure_match_rows(int max_smem);
-cudaError_t launch_match_rows(const MatchArgs&, int n_pairs, cudaStream_t);
+cudaError_t configure_match_global();
+cudaError_t launch_match_rows(const MatchArgs&, int n_pairs, int general, int sm_count, cudaStream_t);
 int match_rows_threads(int W);
 cudaError_t launch_row_scan(const int32_t* rowmatch, const int32_t* rowcnt, int H, int n_pairs, int32_t* rowoff,
                             int32_t* totals, int32_t* n_cand, cudaStream_t);
@@ -52,12 +56,17 @@ cudaError_t jit_launch_hash_tiles(JitKernel* k, const void* tensor_map, const Ha
 
 static thread_local std::string g_create_error;
 
+// live contexts by serial: gpc_image_release gives an image's block back to its context if that still exists
+static std::mutex g_registry_mu;
+static std::map<long long, gpc_ctx*> g_registry;
+
 struct gpc_ctx {
   long long id = 0;
   int device = 0;
   int max_w = 0, max_h = 0, max_batch = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   bool has_forest = false;
+  long long forest_serial = 0;     // bumped whenever forest_dev is re-baked (resident images key their hash cache on it)
   gpc_forest forest_host{};
   int result_mode = GPC_RESULTS_SSE;   // gpc_set_result_mode
   gpc::ForestDev forest_dev{};
@@ -81,6 +90,8 @@ struct gpc_ctx {
   std::vector<cudaEvent_t> ev_chunk;
   int chunk_pairs = 16;
   int32_t* d_rowmatch = nullptr;   // [B][H]
+  uint32_t* d_fb = nullptr;        // [B][2 * max_h + 2] row lists of the fast row matcher (one per slot, at p0 * stride)
+  int sm_count = 148;
   int32_t* d_rowoff = nullptr;     // [B][H+1]
   int32_t* d_totals = nullptr;     // [B]
   int32_t* d_ncand = nullptr;      // [B][2]
@@ -96,6 +107,8 @@ struct gpc_ctx {
   void* d_gws = nullptr;           // radix-sort matcher workspace (lazily allocated, grown on demand)
   size_t gws_bytes = 0;
   int matcher = GPC_MATCHER_AUTO;
+  // device blocks of released resident images, reused by gpc_image_upload (cudaMalloc / cudaFree cost more than the kernels)
+  std::vector<std::pair<size_t, uint8_t*>> image_pool;
   int64_t launches = 0;
   int match_smem_max = 0;
   // optional per-kernel timing (CUDA events on the launching stream), see gpc_kernel_times
@@ -110,9 +123,20 @@ struct gpc_ctx {
 // A raw image resident on a context's device (Forest::PreprocessedImage's device side).
 struct gpc_image {
   long long ctx_id = 0;       // serial of the owning context (a context pointer may be reused)
+  gpc_ctx* owner = nullptr;   // only dereferenced after ctx_id was found in the registry of live contexts
   int device = 0;
-  uint8_t* d_raw = nullptr;   // [h][w], tightly packed
+  uint8_t* d_raw = nullptr;   // [h][w], tightly packed; start of the image's single device block
+  size_t block_bytes = 0;
   int w = 0, h = 0;
+  // outputs of gpc_image_preprocess kept for gpc_match_images / gpc_correspond_images, in the same block after the
+  // raw image: biased smoothed image [h][w] | candidate masks u16 [h][w/16] | rowcnt i32 [h] + lastrow i32 | hash u32 [h][w]
+  uint8_t* d_cache = nullptr;
+  int cache_thr = -1, cache_mode = -1;     // gradient threshold / result mode the cache was computed with (-1: none)
+  long long hash_serial = 0;               // forest serial the cached hash image belongs to (0: none)
+  size_t off_cand() const { return ((size_t)w * h + 255) / 256 * 256; }
+  size_t off_rows() const { return off_cand() + ((size_t)h * (w / 16) * 2 + 255) / 256 * 256; }
+  size_t off_hash() const { return off_rows() + ((size_t)(h + 1) * 4 + 255) / 256 * 256; }
+  size_t cache_bytes() const { return off_hash() + (size_t)w * h * 4; }
 };
 
 namespace {
@@ -221,14 +245,18 @@ int mark_on(gpc_ctx* c, const Slot& sl) { return (sl.stream == c->stream) ? mark
 
 // Kernels A1 + A2 over n_img resident images of the slot; clears and fills rowcnt / lastrow.
 // d_flags != nullptr: d_images holds SMOOTHED images and d_flags the pixels to hash (gpc_hash_smooth).
+// skip_a1: the slot's smooth / cand / rowcnt / lastrow buffers already hold kernel A1's output (resident images).
 int run_preprocess(gpc_ctx* c, const Slot& sl, const uint8_t* d_images, int n_img, int w, int h, int thr,
-                   const gpc::ForestDev& forest, uint8_t* d_smooth_out, uint8_t* d_grad_out, const uint8_t* d_flags = nullptr) {
+                   const gpc::ForestDev& forest, uint8_t* d_smooth_out, uint8_t* d_grad_out, const uint8_t* d_flags = nullptr,
+                   bool skip_a1 = false) {
   const size_t P = (size_t)w * h;
   const int img0 = 2 * sl.p0;
   int32_t* rowcnt = c->d_rows + (size_t)img0 * h;
   int32_t* lastrow = c->d_lastrow + img0;
-  GPC_CUDA(c, cudaMemsetAsync(rowcnt, 0, (size_t)n_img * h * sizeof(int32_t), sl.stream));
-  GPC_CUDA(c, cudaMemsetAsync(lastrow, 0xff, (size_t)n_img * sizeof(int32_t), sl.stream));   // -1
+  if (!skip_a1) {
+    GPC_CUDA(c, cudaMemsetAsync(rowcnt, 0, (size_t)n_img * h * sizeof(int32_t), sl.stream));
+    GPC_CUDA(c, cudaMemsetAsync(lastrow, 0xff, (size_t)n_img * sizeof(int32_t), sl.stream));   // -1
+  }
   if (c->tmap_w != w || c->tmap_h != h) {
     const int n_cap = (int)std::min<size_t>(2 * (size_t)c->max_batch * ((size_t)c->max_w * c->max_h / P), 1u << 30);
     if (gpc::make_smooth_tensor_map(c->tmap, c->d_smooth, w, h, n_cap) != 0)
@@ -238,7 +266,8 @@ int run_preprocess(gpc_ctx* c, const Slot& sl, const uint8_t* d_images, int n_im
   uint8_t* smooth_x = c->d_smooth + (size_t)img0 * P;
   uint16_t* cand = c->d_cand + (size_t)img0 * h * (w / 16);
   int rc = mark_on(c, sl); if (rc) return rc;                                      // event 0
-  if (d_flags) {
+  if (skip_a1) {
+  } else if (d_flags) {
     if (n_img != 1) return fail(c, GPC_E_ARG, "internal: the smooth seam handles one image");
     GPC_CUDA(c, gpc::launch_prep_from_smooth(d_images, d_flags, smooth_x, cand, rowcnt, lastrow, w, h, forest.naive, sl.stream));
   } else {
@@ -258,7 +287,7 @@ int run_preprocess(gpc_ctx* c, const Slot& sl, const uint8_t* d_images, int n_im
     GPC_CUDA(c, gpc::jit_launch_hash_tiles(c->jit, c->tmap, ha, forest, n_img, sl.stream));
   else
     GPC_CUDA(c, gpc::launch_hash_tiles(c->tmap, ha, forest, n_img, sl.stream));
-  c->launches += 2;
+  c->launches += skip_a1 ? 1 : 2;
   return mark_on(c, sl);                                                           // event 2
 }
 
@@ -340,13 +369,31 @@ int run_match(gpc_ctx* c, const Slot& sl, int n_pairs, int w, int h, const gpc_s
          m.table_log2 > std::max(ceil_log2(4 * gpc::match_rows_threads(w)), m.x_bits + 1))
     m.table_log2--;                                  // wide rows: fewer, longer buckets keep >= 3 CTAs per SM
   m.key_bits = 31;   // hash images may come from the caller (gpc_match_hash_images): assume full 31-bit states
-  if ((int)gpc::match_smem_bytes(m.wcap, m.table_log2) > c->match_smem_max)
+  // fast matcher: ~32 four-bit buckets and ~4 slots per candidate of a side.  Constraints: remainder + x of a slot
+  // entry fit one word (slot_log2 >= x_bits), buckets refine slots (slot_log2 <= nib_log2 + 3), the byte offset of a
+  // word fits 16 bits (nib_log2 <= 14), and the ordering pass (8 bytes per match) reuses both tables.
+  static const int nib_env = std::getenv("GPC_B_NIB_LOG2") ? std::atoi(std::getenv("GPC_B_NIB_LOG2")) : 0;
+  static const int slot_env = std::getenv("GPC_B_SLOT_LOG2") ? std::atoi(std::getenv("GPC_B_SLOT_LOG2")) : 0;
+  const int tbl_min = std::max(ceil_log2(4 * gpc::match_rows_threads(w)), m.x_bits);     // the zero fill writes 16 bytes per thread and round
+  m.nib_log2 = std::min(14, std::max(ceil_log2(4 * m.wcap), tbl_min));
+  m.slot_log2 = std::max(m.nib_log2 - 1, tbl_min);       // measured: 2 slots per candidate beat 4 (one more CTA per SM)
+  while ((int)gpc::match_fast_smem_bytes(m.nib_log2, m.slot_log2, m.pow2cap) > 80 * 1024 && (1 << (m.nib_log2 - 1)) >= m.pow2cap &&
+         m.nib_log2 - 1 >= tbl_min) {
+    m.nib_log2--; m.slot_log2 = std::max(m.slot_log2 - 1, tbl_min);   // wide rows: keep several CTAs per SM
+  }
+  if (nib_env > 0) m.nib_log2 = std::min(14, std::max(nib_env, tbl_min));
+  if (slot_env > 0) m.slot_log2 = std::min(m.nib_log2 + 3, std::max(slot_env, tbl_min));
+  while ((1 << m.nib_log2) + (1 << m.slot_log2) < 2 * m.pow2cap) { if (m.nib_log2 < 14) m.nib_log2++; else m.slot_log2++; }
+  m.fb_list = c->d_fb + (size_t)sl.p0 * (2 * (size_t)c->max_h + 2);
+  const bool general = (c->matcher == GPC_MATCHER_ROWS_GENERAL);
+  if ((int)gpc::match_smem_bytes(m.wcap, m.table_log2) > c->match_smem_max ||
+      (int)gpc::match_fast_smem_bytes(m.nib_log2, m.slot_log2, m.pow2cap) > c->match_smem_max)
     return fail(c, GPC_E_DIMS, "image too wide for the row matcher's shared memory");
   if (h - 2 * gpc::kRadius <= 0) GPC_CUDA(c, cudaMemsetAsync(rowmatch, 0, (size_t)n_pairs * h * sizeof(int32_t), sl.stream));
-  GPC_CUDA(c, gpc::launch_match_rows(m, n_pairs, sl.stream));
+  GPC_CUDA(c, gpc::launch_match_rows(m, n_pairs, general ? 1 : 0, c->sm_count, sl.stream));
   int rc = mark_on(c, sl); if (rc) return rc;                                      // event 3
   GPC_CUDA(c, gpc::launch_row_scan(rowmatch, rowcnt, h, n_pairs, rowoff, d_n_out, d_n_cand, sl.stream));
-  c->launches += 2;
+  c->launches += general ? 2 : 3;
   const long long* pair_base = nullptr;
   if (packed) {
     GPC_CUDA(c, gpc::launch_pair_scan(d_n_out, n_pairs, c->d_pair_base + 2 * sl.p0, sl.stream));
@@ -416,6 +463,7 @@ int gpc_create(gpc_ctx** out, int device, int max_w, int max_h, int max_batch) {
   TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   c->match_smem_max = smem_optin - 1024;
   TRY(gpc::configure_match_rows(c->match_smem_max));
+  TRY(gpc::configure_match_global());
   const size_t P = (size_t)max_w * max_h, B = (size_t)max_batch;
   TRY(cudaMalloc(&c->d_raw, 2 * B * P));
   TRY(cudaMalloc(&c->d_smooth, 2 * B * P));
@@ -428,6 +476,9 @@ int gpc_create(gpc_ctx** out, int device, int max_w, int max_h, int max_batch) {
   TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   if (const char* e = std::getenv("GPC_CHUNK_PAIRS")) c->chunk_pairs = std::max(1, std::atoi(e));
   TRY(cudaMalloc(&c->d_rowmatch, B * max_h * sizeof(int32_t)));
+  TRY(cudaMalloc(&c->d_fb, B * (2 * (size_t)max_h + 2) * sizeof(uint32_t)));
+  TRY(cudaMemsetAsync(c->d_fb, 0, B * (2 * (size_t)max_h + 2) * sizeof(uint32_t), c->stream));
+  TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
   TRY(cudaMalloc(&c->d_rowoff, B * (max_h + 1) * sizeof(int32_t)));
   TRY(cudaMalloc(&c->d_totals, B * sizeof(int32_t)));
   TRY(cudaMalloc(&c->d_ncand, 2 * B * sizeof(int32_t)));
@@ -440,14 +491,17 @@ int gpc_create(gpc_ctx** out, int device, int max_w, int max_h, int max_batch) {
   TRY(cudaMemsetAsync(c->d_rowmatch, 0, B * max_h * sizeof(int32_t), c->stream));
   TRY(cudaStreamSynchronize(c->stream));
 #undef TRY
+  { std::lock_guard<std::mutex> lk(g_registry_mu); g_registry[c->id] = c; }
   *out = c;
   return GPC_OK;
 }
 
 void gpc_destroy(gpc_ctx* c) {
   if (!c) return;
+  { std::lock_guard<std::mutex> lk(g_registry_mu); g_registry.erase(c->id); }
   cudaSetDevice(c->device);
-  cudaFree(c->d_raw); cudaFree(c->d_smooth); cudaFree(c->d_cand); cudaFree(c->d_hash); cudaFree(c->d_stage); cudaFree(c->d_rows); cudaFree(c->d_lastrow); cudaFree(c->d_rowmatch);
+  for (auto& b : c->image_pool) cudaFree(b.second);
+  cudaFree(c->d_raw); cudaFree(c->d_smooth); cudaFree(c->d_cand); cudaFree(c->d_hash); cudaFree(c->d_stage); cudaFree(c->d_rows); cudaFree(c->d_lastrow); cudaFree(c->d_rowmatch); cudaFree(c->d_fb);
   for (int l = 0; l < gpc_ctx::kLanes; l++) if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (cudaEvent_t e : c->ev_chunk) cudaEventDestroy(e);
@@ -475,6 +529,8 @@ int gpc_synchronize(gpc_ctx* c) {
 }
 
 int64_t gpc_launch_count(const gpc_ctx* c) { return c ? c->launches : 0; }
+
+int64_t gpc_context_id(const gpc_ctx* c) { return c ? (int64_t)c->id : 0; }
 
 const char* gpc_jit_status(const gpc_ctx* c) { return c ? c->jit_note.c_str() : ""; }
 
@@ -558,6 +614,7 @@ int gpc_set_forest(gpc_ctx* c, const gpc_forest* f) {
   c->forest_host = *f;
   bake_forest(*f, &c->forest_dev, c->result_mode);
   c->has_forest = true;
+  c->forest_serial++;
   if (c->result_mode == GPC_RESULTS_NAIVE) { c->jit_note = "generic: naive result mode"; return GPC_OK; }
   std::string why;
   c->jit = gpc::jit_build_hash_tiles(c->forest_dev, &why);
@@ -574,11 +631,17 @@ int gpc_set_result_mode(gpc_ctx* c, int mode) {
   if (mode == c->result_mode) return GPC_OK;
   if (mode == GPC_RESULTS_NAIVE && c->has_forest && c->forest_host.n_tests > 31)
     return fail(c, GPC_E_UNSUPPORTED, "GPC_RESULTS_NAIVE supports forests of at most 31 tests (bit 31 of a hash word is the candidate flag)");
+  const int old_mode = c->result_mode;
   c->result_mode = mode;
   if (!c->has_forest) return GPC_OK;
   const gpc_forest f = c->forest_host;
   c->has_forest = false;                              // defeat the "unchanged forest" shortcut
-  return gpc_set_forest(c, &f);
+  const int rc = gpc_set_forest(c, &f);
+  if (rc != GPC_OK && !c->has_forest) {               // nothing was re-baked: the context keeps its mode and forest
+    c->result_mode = old_mode;
+    c->has_forest = true;
+  }
+  return rc;
 }
 
 int gpc_match_batch_device(gpc_ctx* c, const uint8_t* d_images, int n_pairs, int w, int h, const gpc_settings* s,
@@ -602,6 +665,11 @@ static int match_batch_pipelined(gpc_ctx* c, const uint8_t* images, int n_pairs,
   const size_t P = (size_t)w * h;
   const int CH = c->chunk_pairs;
   const long long per_pair = c->out_cap / c->max_batch;
+  // whatever the exit path, no copy from `images` or into `out` may still be queued when the caller gets control back
+  struct LaneGuard {
+    gpc_ctx* c;
+    ~LaneGuard() { for (int l = 0; l < gpc_ctx::kLanes; l++) cudaStreamSynchronize(c->lane_stream[l]); }
+  } lane_guard{c};
   // chunk sizes ramp up at the start and down at the end (CH/4, CH/2, CH, ..., CH, CH/2, CH/4): the
   // first upload and the last kernels + download are the only parts of the pipeline nothing overlaps
   std::vector<int> sizes;
@@ -735,7 +803,7 @@ int gpc_match_pair(gpc_ctx* c, const uint8_t* left, const uint8_t* right, int w,
 }
 
 static int preprocess_device(gpc_ctx* c, const uint8_t* d_img, int w, int h, int thr, uint8_t* smooth, uint8_t* grad,
-                             int32_t* mask, int mask_cap, int* n_mask);
+                             int32_t* mask, int mask_cap, int* n_mask, gpc_image* im);
 
 int gpc_preprocess(gpc_ctx* c, const uint8_t* img, int w, int h, int thr, uint8_t* smooth, uint8_t* grad,
                    int32_t* mask, int mask_cap, int* n_mask) {
@@ -744,7 +812,7 @@ int gpc_preprocess(gpc_ctx* c, const uint8_t* img, int w, int h, int thr, uint8_
   if (thr < 0 || thr > 255) return fail(c, GPC_E_ARG, "gradientThreshold needs to be within 0...255");
   GPC_CUDA(c, cudaSetDevice(c->device));
   GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, img, (size_t)w * h, cudaMemcpyHostToDevice, c->stream));
-  return preprocess_device(c, c->d_raw, w, h, thr, smooth, grad, mask, mask_cap, n_mask);
+  return preprocess_device(c, c->d_raw, w, h, thr, smooth, grad, mask, mask_cap, n_mask, nullptr);
 }
 
 int gpc_hash(gpc_ctx* c, const uint8_t* img, int w, int h, int thr, uint32_t* states, int32_t* mask, int cap, int* n,
@@ -784,22 +852,31 @@ int gpc_match_hash_images(gpc_ctx* c, const uint32_t* hash_l, const uint32_t* ha
   rc = check_settings(c, s); if (rc) return rc;
   GPC_CUDA(c, cudaSetDevice(c->device));
   const size_t P = (size_t)w * h;
-  // rowcnt / lastrow are derived on the host here (kernel A normally provides them)
+  // rowcnt / lastrow are derived on the host here (kernel A normally provides them).  A candidate is by definition an
+  // interior pixel (border lambda, inference.hpp:318-330) and every matcher sizes its tables for the interior, so the
+  // flag of a word outside 13 <= x < w-13, 13 <= y < h-13 is cleared on the staged copy.
   std::vector<int32_t> rows((size_t)2 * h + 2, 0);
   rows[(size_t)2 * h] = rows[(size_t)2 * h + 1] = -1;
   const uint32_t* src[2] = {hash_l, hash_r};
+  std::vector<uint32_t> staged(2 * P);
+  const int R = gpc::kRadius;
   for (int k = 0; k < 2; k++)
     for (int y = 0; y < h; y++) {
       int cnt = 0;
-      for (int x = 0; x < w; x++) cnt += (int)(src[k][(size_t)y * w + x] >> 31);
+      const bool row_in = (y >= R && y < h - R);
+      for (int x = 0; x < w; x++) {
+        uint32_t v = src[k][(size_t)y * w + x];
+        if (!row_in || x < R || x >= w - R) v &= 0x7fffffffu;
+        staged[(size_t)k * P + (size_t)y * w + x] = v;
+        cnt += (int)(v >> 31);
+      }
       rows[(size_t)k * h + y] = cnt;
       if (cnt) rows[(size_t)2 * h + k] = y;
     }
-  GPC_CUDA(c, cudaMemcpyAsync(c->d_hash, hash_l, P * 4, cudaMemcpyHostToDevice, c->stream));
-  GPC_CUDA(c, cudaMemcpyAsync(c->d_hash + P, hash_r, P * 4, cudaMemcpyHostToDevice, c->stream));
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_hash, staged.data(), 2 * P * 4, cudaMemcpyHostToDevice, c->stream));
   GPC_CUDA(c, cudaMemcpyAsync(c->d_rows, rows.data(), (size_t)2 * h * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   GPC_CUDA(c, cudaMemcpyAsync(c->d_lastrow, rows.data() + (size_t)2 * h, 2 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-  GPC_CUDA(c, cudaStreamSynchronize(c->stream));   // `rows` is pageable and about to go out of scope
+  GPC_CUDA(c, cudaStreamSynchronize(c->stream));   // `rows` and `staged` are pageable and about to go out of scope
   rc = run_match(c, Slot{0, c->stream}, 1, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
   if (rc) return rc;
   GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_totals, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -818,8 +895,18 @@ int gpc_image_upload(gpc_ctx* c, const uint8_t* img, int w, int h, int stride, g
   int rc = check_dims(c, w, h, 1); if (rc) return rc;
   GPC_CUDA(c, cudaSetDevice(c->device));
   gpc_image* im = new gpc_image();
-  im->ctx_id = c->id; im->device = c->device; im->w = w; im->h = h;
-  cudaError_t e = cudaMalloc(&im->d_raw, (size_t)w * h);
+  im->ctx_id = c->id; im->owner = c; im->device = c->device; im->w = w; im->h = h;
+  const size_t raw_bytes = ((size_t)w * h + 255) / 256 * 256;
+  im->block_bytes = raw_bytes + im->cache_bytes();
+  cudaError_t e = cudaSuccess;
+  for (size_t i = 0; i < c->image_pool.size(); i++)
+    if (c->image_pool[i].first == im->block_bytes) {
+      im->d_raw = c->image_pool[i].second;
+      c->image_pool.erase(c->image_pool.begin() + (long)i);
+      break;
+    }
+  if (!im->d_raw) e = cudaMalloc(&im->d_raw, im->block_bytes);
+  im->d_cache = im->d_raw ? im->d_raw + raw_bytes : nullptr;
   if (e == cudaSuccess) e = cudaMemcpy2DAsync(im->d_raw, w, img, stride, w, h, cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // the caller's buffer may be pageable / short-lived
   if (e != cudaSuccess) {
@@ -833,46 +920,135 @@ int gpc_image_upload(gpc_ctx* c, const uint8_t* img, int w, int h, int stride, g
 
 void gpc_image_release(gpc_image* im) {
   if (!im) return;
-  cudaSetDevice(im->device);
-  cudaFree(im->d_raw);
+  bool pooled = false;
+  {
+    std::lock_guard<std::mutex> lk(g_registry_mu);
+    auto it = g_registry.find(im->ctx_id);
+    if (it != g_registry.end() && it->second == im->owner && im->owner->image_pool.size() < 8) {
+      // later work of the context is stream-ordered after anything that read this block
+      im->owner->image_pool.emplace_back(im->block_bytes, im->d_raw);
+      pooled = true;
+    }
+  }
+  if (!pooled) { cudaSetDevice(im->device); cudaFree(im->d_raw); }
   delete im;
 }
 
+// Copies between the slot-0 buffers of the context and an image's cache (device to device, on the context's stream).
+// slot_img: 0 = left, 1 = right position of the pair in slot 0.
+static int cache_copy(gpc_ctx* c, gpc_image* im, int slot_img, bool to_cache, bool a1, bool hash) {
+  const int w = im->w, h = im->h;
+  const size_t P = (size_t)w * h, CW = (size_t)h * (w / 16);
+  auto cp = [&](void* slot_ptr, size_t off, size_t bytes) {
+    return to_cache ? cudaMemcpyAsync(im->d_cache + off, slot_ptr, bytes, cudaMemcpyDeviceToDevice, c->stream)
+                    : cudaMemcpyAsync(slot_ptr, im->d_cache + off, bytes, cudaMemcpyDeviceToDevice, c->stream);
+  };
+  if (a1) {
+    GPC_CUDA(c, cp(c->d_smooth + (size_t)slot_img * P, 0, P));
+    GPC_CUDA(c, cp(c->d_cand + (size_t)slot_img * CW, im->off_cand(), CW * 2));
+    GPC_CUDA(c, cp(c->d_rows + (size_t)slot_img * h, im->off_rows(), (size_t)h * 4));
+    GPC_CUDA(c, cp(c->d_lastrow + slot_img, im->off_rows() + (size_t)h * 4, 4));
+  }
+  if (hash) GPC_CUDA(c, cp(c->d_hash + (size_t)slot_img * P, im->off_hash(), P * 4));
+  return GPC_OK;
+}
+
+// im != nullptr: the image's cache receives kernel A1's output (and the hash image if the context has a forest), so
+// that gpc_match_images / gpc_correspond_images need not run the kernels again.
 static int preprocess_device(gpc_ctx* c, const uint8_t* d_img, int w, int h, int thr, uint8_t* smooth, uint8_t* grad,
-                             int32_t* mask, int mask_cap, int* n_mask) {
-  int rc = ensure_debug_buffers(c); if (rc) return rc;
+                             int32_t* mask, int mask_cap, int* n_mask, gpc_image* im) {
+  int rc = GPC_OK;
+  const bool dbg = smooth || grad;
+  if (dbg || mask || n_mask) { rc = ensure_debug_buffers(c); if (rc) return rc; }
   const size_t P = (size_t)w * h;
   gpc::ForestDev none{};                           // no tests: hash image carries the candidate flag only
   none.naive = (c->result_mode == GPC_RESULTS_NAIVE) ? gpc::kResultsNaive : gpc::kResultsSse;
-  uint8_t* d_smooth = c->d_dbg8;
-  uint8_t* d_grad = c->d_dbg8 + (size_t)c->max_w * c->max_h;
-  rc = run_preprocess(c, Slot{0, c->stream}, d_img, 1, w, h, thr, none, d_smooth, d_grad);
+  uint8_t* d_smooth = dbg ? c->d_dbg8 : nullptr;
+  uint8_t* d_grad = dbg ? c->d_dbg8 + (size_t)c->max_w * c->max_h : nullptr;
+  const bool with_forest = im && c->has_forest;
+  rc = run_preprocess(c, Slot{0, c->stream}, d_img, 1, w, h, thr, with_forest ? c->forest_dev : none, d_smooth, d_grad);
   if (rc) return rc;
-  GPC_CUDA(c, gpc::launch_mask_list(c->d_hash, c->d_rows, c->d_rowoff, w, h, c->d_mask, (int)std::min<size_t>(P, 0x7fffffff), c->stream));
-  c->launches += 2;
-  GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_rowoff + h, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (im) {
+    rc = cache_copy(c, im, 0, true, true, with_forest); if (rc) return rc;
+    im->cache_thr = thr; im->cache_mode = c->result_mode;
+    im->hash_serial = with_forest ? c->forest_serial : 0;
+  }
+  if (mask || n_mask) {
+    GPC_CUDA(c, gpc::launch_mask_list(c->d_hash, c->d_rows, c->d_rowoff, w, h, c->d_mask, (int)std::min<size_t>(P, 0x7fffffff), c->stream));
+    c->launches += 2;
+    GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_rowoff + h, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  }
   if (smooth) GPC_CUDA(c, cudaMemcpyAsync(smooth, d_smooth, P, cudaMemcpyDeviceToHost, c->stream));
   if (grad) GPC_CUDA(c, cudaMemcpyAsync(grad, d_grad, P, cudaMemcpyDeviceToHost, c->stream));
   GPC_CUDA(c, cudaStreamSynchronize(c->stream));
-  const int n = c->h_counts[0];
-  if (n_mask) *n_mask = n;
-  if (mask) {
-    if (n > mask_cap) return fail(c, GPC_E_CAPACITY, "mask buffer too small: need " + std::to_string(n));
-    GPC_CUDA(c, cudaMemcpy(mask, c->d_mask, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (mask || n_mask) {
+    const int n = c->h_counts[0];
+    if (n_mask) *n_mask = n;
+    if (mask) {
+      if (n > mask_cap) return fail(c, GPC_E_CAPACITY, "mask buffer too small: need " + std::to_string(n));
+      GPC_CUDA(c, cudaMemcpy(mask, c->d_mask, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
   }
   return GPC_OK;
 }
 
-int gpc_image_preprocess(gpc_ctx* c, const gpc_image* im, int thr, uint8_t* smooth, uint8_t* grad, int32_t* mask,
+int gpc_image_preprocess(gpc_ctx* c, gpc_image* im, int thr, uint8_t* smooth, uint8_t* grad, int32_t* mask,
                          int mask_cap, int* n_mask) {
   if (!c || !im || im->ctx_id != c->id) return fail(c, GPC_E_ARG, "image does not belong to this context");
   int rc = check_dims(c, im->w, im->h, 1); if (rc) return rc;
   if (thr < 0 || thr > 255) return fail(c, GPC_E_ARG, "gradientThreshold needs to be within 0...255");
   GPC_CUDA(c, cudaSetDevice(c->device));
-  return preprocess_device(c, im->d_raw, im->w, im->h, thr, smooth, grad, mask, mask_cap, n_mask);
+  return preprocess_device(c, im->d_raw, im->w, im->h, thr, smooth, grad, mask, mask_cap, n_mask, im);
 }
 
-int gpc_match_images(gpc_ctx* c, const gpc_image* l, const gpc_image* r, const gpc_settings* s, gpc_support* out, int cap,
+// The smoothed and gradient images of preprocessImage for a resident image (the C++ API fills
+// PreprocessedImage::smooth / grad from here on first access; the kernels run again with their debug outputs on).
+int gpc_image_fetch(gpc_ctx* c, const gpc_image* im, int thr, uint8_t* smooth, uint8_t* grad) {
+  if (!c || !im || im->ctx_id != c->id) return fail(c, GPC_E_ARG, "image does not belong to this context");
+  if (!smooth && !grad) return GPC_OK;
+  int rc = check_dims(c, im->w, im->h, 1); if (rc) return rc;
+  if (thr < 0 || thr > 255) return fail(c, GPC_E_ARG, "gradientThreshold needs to be within 0...255");
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  return preprocess_device(c, im->d_raw, im->w, im->h, thr, smooth, grad, nullptr, 0, nullptr, nullptr);
+}
+
+// Brings the hash images of two resident images into slot 0 of the context (left = image 0, right = image 1) with as
+// little work as their caches allow: hash images computed with the current forest are copied; kernel A1's cached output
+// needs kernel A2 only (the result is cached); anything else goes through both kernels from the raw image.
+static int resident_pair_hashes(gpc_ctx* c, gpc_image* l, gpc_image* r, const gpc_settings* s) {
+  const int w = l->w, h = l->h;
+  const size_t P = (size_t)w * h;
+  gpc_image* im[2] = {l, r};
+  bool a1_ok = true, hash_ok = true;
+  for (int k = 0; k < 2; k++) {
+    const bool a1 = im[k]->cache_thr >= 0 && im[k]->cache_thr == s->gradient_threshold && im[k]->cache_mode == c->result_mode;
+    a1_ok = a1_ok && a1;
+    hash_ok = hash_ok && a1 && im[k]->hash_serial == c->forest_serial;
+  }
+  if (hash_ok) {
+    for (int k = 0; k < 2; k++) {
+      GPC_CUDA(c, cudaMemcpyAsync(c->d_rows + (size_t)k * h, im[k]->d_cache + im[k]->off_rows(), (size_t)h * 4, cudaMemcpyDeviceToDevice, c->stream));
+      GPC_CUDA(c, cudaMemcpyAsync(c->d_lastrow + k, im[k]->d_cache + im[k]->off_rows() + (size_t)h * 4, 4, cudaMemcpyDeviceToDevice, c->stream));
+      GPC_CUDA(c, cudaMemcpyAsync(c->d_hash + (size_t)k * P, im[k]->d_cache + im[k]->off_hash(), P * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return GPC_OK;
+  }
+  if (a1_ok) {
+    for (int k = 0; k < 2; k++) { int rc = cache_copy(c, im[k], k, false, true, false); if (rc) return rc; }
+    int rc = run_preprocess(c, Slot{0, c->stream}, c->d_raw, 2, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr, nullptr, true);
+    if (rc) return rc;
+    for (int k = 0; k < 2; k++) {
+      rc = cache_copy(c, im[k], k, true, false, true); if (rc) return rc;
+      im[k]->hash_serial = c->forest_serial;
+    }
+    return GPC_OK;
+  }
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, l->d_raw, P, cudaMemcpyDeviceToDevice, c->stream));
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_raw + P, r->d_raw, P, cudaMemcpyDeviceToDevice, c->stream));
+  return run_preprocess(c, Slot{0, c->stream}, c->d_raw, 2, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
+}
+
+int gpc_match_images(gpc_ctx* c, gpc_image* l, gpc_image* r, const gpc_settings* s, gpc_support* out, int cap,
                      int* n_out, int* n_cand_l, int* n_cand_r) {
   if (!c || !l || !r || !n_out || cap < 0 || (cap > 0 && !out)) return fail(c, GPC_E_ARG, "null argument");
   if (l->ctx_id != c->id || r->ctx_id != c->id) return fail(c, GPC_E_ARG, "image does not belong to this context");
@@ -882,10 +1058,7 @@ int gpc_match_images(gpc_ctx* c, const gpc_image* l, const gpc_image* r, const g
   rc = check_settings(c, s); if (rc) return rc;
   if (!c->has_forest) return fail(c, GPC_E_FOREST, "no forest set");
   GPC_CUDA(c, cudaSetDevice(c->device));
-  const size_t P = (size_t)w * h;
-  GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, l->d_raw, P, cudaMemcpyDeviceToDevice, c->stream));
-  GPC_CUDA(c, cudaMemcpyAsync(c->d_raw + P, r->d_raw, P, cudaMemcpyDeviceToDevice, c->stream));
-  rc = run_preprocess(c, Slot{0, c->stream}, c->d_raw, 2, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
+  rc = resident_pair_hashes(c, l, r, s);
   if (rc) return rc;
   rc = run_match(c, Slot{0, c->stream}, 1, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
   if (rc) return rc;
@@ -929,16 +1102,30 @@ int gpc_hash_smooth(gpc_ctx* c, const uint8_t* smooth, int w, int h, const int32
   return GPC_OK;
 }
 
+// The first n supports of the context's most recent single-pair result (gpc_match_pair / gpc_match_images), still on
+// the device: lets a caller that cannot bound the count ask for it first (cap = 0 -> GPC_E_CAPACITY with *n_out set).
+int gpc_fetch_supports(gpc_ctx* c, gpc_support* out, int n) {
+  if (!c || n < 0 || (n > 0 && !out)) return fail(c, GPC_E_ARG, "null argument");
+  if (n > c->out_cap) return fail(c, GPC_E_ARG, "more supports requested than the context holds");
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  if (n > 0) {
+    GPC_CUDA(c, cudaMemcpyAsync(out, c->d_out, (size_t)n * sizeof(gpc_support), cudaMemcpyDeviceToHost, c->stream));
+    GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return GPC_OK;
+}
+
 int gpc_set_matcher(gpc_ctx* c, int matcher) {
   if (!c) return GPC_E_ARG;
-  if (matcher != GPC_MATCHER_AUTO && matcher != GPC_MATCHER_SORT) return fail(c, GPC_E_ARG, "unknown matcher");
+  if (matcher != GPC_MATCHER_AUTO && matcher != GPC_MATCHER_SORT && matcher != GPC_MATCHER_ROWS_GENERAL)
+    return fail(c, GPC_E_ARG, "unknown matcher");
   c->matcher = matcher;
   return GPC_OK;
 }
 
 // Forest::stereoMatch (inference.hpp:344-361): every unique-unique correspondence, before the
 // rectifiedMatch filter, in ascending key order.  Always runs the radix-sort matcher.
-int gpc_correspond_images(gpc_ctx* c, const gpc_image* l, const gpc_image* r, const gpc_settings* s,
+int gpc_correspond_images(gpc_ctx* c, gpc_image* l, gpc_image* r, const gpc_settings* s,
                           gpc_correspondence* out, int cap, int* n_out) {
   if (!c || !l || !r || !n_out || cap < 0 || (cap > 0 && !out)) return fail(c, GPC_E_ARG, "null argument");
   if (l->ctx_id != c->id || r->ctx_id != c->id) return fail(c, GPC_E_ARG, "image does not belong to this context");
@@ -948,10 +1135,7 @@ int gpc_correspond_images(gpc_ctx* c, const gpc_image* l, const gpc_image* r, co
   rc = check_settings(c, s); if (rc) return rc;
   if (!c->has_forest) return fail(c, GPC_E_FOREST, "no forest set");
   GPC_CUDA(c, cudaSetDevice(c->device));
-  const size_t P = (size_t)w * h;
-  GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, l->d_raw, P, cudaMemcpyDeviceToDevice, c->stream));
-  GPC_CUDA(c, cudaMemcpyAsync(c->d_raw + P, r->d_raw, P, cudaMemcpyDeviceToDevice, c->stream));
-  rc = run_preprocess(c, Slot{0, c->stream}, c->d_raw, 2, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
+  rc = resident_pair_hashes(c, l, r, s);
   if (rc) return rc;
   // a correspondence is 16 bytes, a support 12: d_out holds out_cap * 12 / 16 correspondences
   const long long dcap = c->out_cap * 12 / 16;

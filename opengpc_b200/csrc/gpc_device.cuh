@@ -108,6 +108,10 @@ struct MatchArgs {
   int32_t wcap;            // per-side candidate capacity used to carve shared memory
   int32_t pow2cap;         // wcap rounded up to a power of two
   int32_t key_bits;        // number of significant state bits (forest dependent)
+  // fast row matcher (match_rows_fast_kernel)
+  int32_t nib_log2;        // log2 of the words of the 4-bit bucket table (8 buckets per word)
+  int32_t slot_log2;       // log2 of the slot table; x_bits <= slot_log2 <= nib_log2
+  uint32_t* fb_list;       // rows handed to the general kernel: [0] count, [1] CTAs done, then (pair, row) words
 };
 
 }  // namespace gpc

@@ -62,7 +62,8 @@ struct SortWs {
   uint32_t* digit_tot;           // [n_pairs][kDigits]
   int32_t* blockcount;           // [n_pairs][nb_max + 1]
   int32_t* n_side;               // [n_pairs][2] left / right record counts
-  unsigned long long* tmax;      // [n_pairs] largest right key + 1 (0: no right record)
+  unsigned long long* tmax;      // [n_pairs] largest right key
+  uint32_t* tmax_has;            // [n_pairs] 1 if there is a right record (a key of 2^64 - 1 is legal, so no sentinel value)
   int32_t* rowoff;               // [n_pairs][2][H] candidate offsets (hash-image input only)
   int32_t* rowcnt_f;             // [n_pairs][2][H] records per row that pass the pre-filter
   unsigned long long* rowmax;    // [n_pairs][H] largest right key + 1 of the row (0: none)
@@ -146,7 +147,7 @@ bloom_build_kernel(const uint32_t* __restrict__ hash, int W, int H, int epipolar
   }
 }
 
-// tmax[pair] = largest right key + 1 over all rows (0: no right record)
+// tmax[pair] = largest right key over all rows, tmax_has[pair] = there is a right record
 __global__ void __launch_bounds__(32)
 rowmax_reduce_kernel(const SortWs<uint32_t> ws, int H) {
   const int pair = blockIdx.x, lane = threadIdx.x;
@@ -154,7 +155,7 @@ rowmax_reduce_kernel(const SortWs<uint32_t> ws, int H) {
   for (int y = lane; y < H; y += 32) m = max(m, ws.rowmax[(size_t)pair * H + y]);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-  if (lane == 0) ws.tmax[pair] = m;
+  if (lane == 0) { ws.tmax[pair] = m ? m - 1ull : 0ull; ws.tmax_has[pair] = m ? 1u : 0u; }
 }
 
 // One warp per (side, row): keep[...] = candidates whose key is marked in the OTHER side's table; rowcnt_f = their count.
@@ -475,8 +476,8 @@ radix_scatter_kernel(const SortWs<KeyT> ws, int cur, int shift) {
   }
 }
 
-// tmax[pair] = 1 + the largest key carried by a right record = the key of the last right record of the
-// sorted array (0: no right record).  One warp per pair, scanning backwards; it normally stops at once.
+// tmax[pair] = the largest key carried by a right record = the key of the last right record of the
+// sorted array; tmax_has[pair] = 0 if there is no right record.  One warp per pair, scanning backwards; it normally stops at once.
 template <typename KeyT>
 __global__ void __launch_bounds__(32)
 global_tmax_kernel(const SortWs<KeyT> ws, int cur) {
@@ -489,11 +490,11 @@ global_tmax_kernel(const SortWs<KeyT> ws, int cur) {
     const bool right = i >= 0 && (vals[i] & kSideBit) != 0u;
     const uint32_t b = __ballot_sync(0xffffffffu, right);
     if (b) {
-      if (lane == __ffs(b) - 1) ws.tmax[pair] = (unsigned long long)keys[i] + 1ull;
+      if (lane == __ffs(b) - 1) { ws.tmax[pair] = (unsigned long long)keys[i]; ws.tmax_has[pair] = 1u; }
       return;
     }
   }
-  if (lane == 0) ws.tmax[pair] = 0ull;
+  if (lane == 0) { ws.tmax[pair] = 0ull; ws.tmax_has[pair] = 0u; }
 }
 
 // ---- segmented scan over the sorted records ---------------------------------------------------------
@@ -512,7 +513,7 @@ struct GlobalEmitArgs {
 // its partner's.  The window (one record before, three after) is loaded with 16-byte loads where it can be.
 template <typename KeyT>
 __device__ __forceinline__ uint32_t window_matches(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, int i0, int n,
-                                                   unsigned long long tmax1, const GlobalEmitArgs& a, uint32_t (&V)[kRounds + 1]) {
+                                                   unsigned long long tmax, bool has_tmax, const GlobalEmitArgs& a, uint32_t (&V)[kRounds + 1]) {
   if (i0 >= n) return 0u;
   KeyT K[kRounds + 4];                                   // K[j] = key of record i0 - 1 + j
   const bool full = i0 + kRounds <= n && (reinterpret_cast<uintptr_t>(keys + i0) & 15u) == 0u &&
@@ -540,7 +541,7 @@ __device__ __forceinline__ uint32_t window_matches(const KeyT* __restrict__ keys
     bool m = i < n && !(V[j] & kSideBit);                                  // a left record ...
     m = m && !(i > 0 && K[j] == k);                                        // ... the first of its run ...
     m = m && i + 1 < n && K[j + 2] == k && (V[j + 1] & kSideBit);          // ... followed by a right record
-    const bool is_tail = (tmax1 != 0ull) && ((unsigned long long)k == tmax1 - 1ull);
+    const bool is_tail = has_tmax && ((unsigned long long)k == tmax);
     const bool k2 = i + 2 < n && K[j + 3] == k, k3 = i + 3 < n && K[j + 4] == k;
     m = m && (is_tail ? (k2 && !k3) : !k2);              // tail key: exactly {L, R, R}; elsewhere exactly {L, R}
     if (m && a.mode == 0) {
@@ -567,7 +568,7 @@ __device__ __forceinline__ void global_count_kernel_tile(const SortWs<KeyT> ws, 
   uint32_t V[kRounds + 1];
   const uint32_t bits = window_matches((cur ? ws.keys[1] : ws.keys[0]) + (size_t)pair * ws.rec_stride,
                                        (cur ? ws.vals[1] : ws.vals[0]) + (size_t)pair * ws.rec_stride,
-                                       tile * kTile + kRounds * threadIdx.x, n, ws.tmax[pair], a, V);
+                                       tile * kTile + kRounds * threadIdx.x, n, ws.tmax[pair], ws.tmax_has[pair] != 0u, a, V);
   const int mine = __reduce_add_sync(0xffffffffu, __popc(bits));
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&cnt, mine);
   __syncthreads();
@@ -628,7 +629,7 @@ __device__ __forceinline__ void global_emit_kernel_tile(const SortWs<KeyT> ws, i
   uint32_t V[kRounds + 1];
   const uint32_t bits = window_matches((cur ? ws.keys[1] : ws.keys[0]) + (size_t)pair * ws.rec_stride,
                                        (cur ? ws.vals[1] : ws.vals[0]) + (size_t)pair * ws.rec_stride,
-                                       tile * kTile + kRounds * tid, n, ws.tmax[pair], a, V);
+                                       tile * kTile + kRounds * tid, n, ws.tmax[pair], ws.tmax_has[pair] != 0u, a, V);
   // thread order = record order: exclusive scan of the per-thread match counts
   const int c = __popc(bits);
   int incl = c;
@@ -887,7 +888,7 @@ static int tile_grid_x(int nb_capacity, int n_pairs) { return std::max(1, std::m
 size_t global_workspace_bytes(long long max_records, int n_pairs, int H, int W) {
   const size_t nb = (size_t)((max_records + kTile - 1) / kTile + 1);
   const size_t np = (size_t)n_pairs, rows = (size_t)std::max(H, 1), kw = (size_t)(W + 31) / 32;
-  size_t b = pad256(np * 8) + pad256(np * 2 * 4) + 2 * pad256(np * (size_t)max_records * 8) + 2 * pad256(np * (size_t)max_records * 4) +
+  size_t b = pad256(np * 8) + pad256(np * 4) + pad256(np * 2 * 4) + 2 * pad256(np * (size_t)max_records * 8) + 2 * pad256(np * (size_t)max_records * 4) +
              pad256(np * kDigits * nb * 4) + pad256(np * kDigits * 4) + pad256(np * (nb + 1) * 4) + pad256(np * 2 * rows * 4) + 256;
   if (W > 0) b += pad256(np * 2 * rows * 4) + pad256(np * rows * 8) + pad256(np * 2 * (size_t)kBloomWords * 4) + pad256(np * 2 * rows * kw * 4);
   return b;
@@ -902,6 +903,7 @@ static SortWs<KeyT> carve(void* ws, long long max_records, int n_pairs, int H, i
   w.nb_max = (int)((max_records + kTile - 1) / kTile + 1);
   w.rec_stride = max_records;
   w.tmax = reinterpret_cast<unsigned long long*>(take(np * 8));
+  w.tmax_has = reinterpret_cast<uint32_t*>(take(np * 4));
   w.n_side = reinterpret_cast<int32_t*>(take(np * 2 * 4));
   w.keys[0] = reinterpret_cast<KeyT*>(take(np * (size_t)max_records * 8));        // sized for 64-bit keys either way
   w.keys[1] = reinterpret_cast<KeyT*>(take(np * (size_t)max_records * 8));
@@ -923,15 +925,19 @@ static SortWs<KeyT> carve(void* ws, long long max_records, int n_pairs, int H, i
   return w;
 }
 
+// The scatter kernel's dynamic shared memory: set once per device, when a context is created.
+cudaError_t configure_match_global() {
+  cudaError_t e = cudaFuncSetAttribute(radix_scatter_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_smem_bytes<uint32_t>());
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(radix_scatter_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_smem_bytes<unsigned long long>());
+  return e;
+}
+
 template <typename KeyT>
 static cudaError_t sort_passes(SortWs<KeyT>& w, long long max_records, int n_pairs, int key_bits, cudaStream_t stream, int* launches,
                                int* cur_out) {
   const int nb = (int)((max_records + kTile - 1) / kTile);
   const dim3 grid(tile_grid_x(nb, n_pairs), n_pairs);
-  {                                                       // per device and per call: cheap next to the sort itself
-    cudaError_t e = cudaFuncSetAttribute(radix_scatter_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_smem_bytes<KeyT>());
-    if (e != cudaSuccess) return e;
-  }
   int cur = 0;
   for (int shift = 0; shift < key_bits; shift += 8) {
     radix_hist_kernel<KeyT><<<grid, kSortThreads, 0, stream>>>(w, cur, shift);

@@ -22,40 +22,48 @@ constexpr int kBucketLimit = 64;              // above this the in-bucket rank p
 
 constexpr uint32_t kHashMul = 0x9E3779B1u;    // odd: state -> state * kHashMul is a bijection mod 2^32
 
-// Shared-memory atomics in this kernel always consume their return value.  Fire-and-forget
-// shared atomics (ATOMS with an RZ destination, addressed through a uniform register into the
-// dynamic shared window) were observed on B200 / nvcc 12.9 to land late or at a wrong address
-// (lost flag bits, corrupted neighbours, occasional illegal-address faults; reproduced with
-// scripts/micro/match_harness.cu) -- the value-returning form does not show it.
 __device__ __forceinline__ uint32_t atomic_inc_ret(uint32_t* p) { return atomicAdd(p, 1u); }
 
-// shared memory: out[pow2cap] u64 | cnt[nb] u32 | entry[2*wcap] u32 | bcnt/bstart/bfill
+// Bounds checks of every computed shared-memory index, compiled in with -DGPC_DEBUG_CHECKS (the checked build the
+// GPU tests and the fuzz campaign are also run with, see profiles/r02_checked_build.md; compute-sanitizer is not
+// available on the GPU pool).  A failed check traps, which the host sees as a CUDA error.
+#ifdef GPC_DEBUG_CHECKS
+#define GPC_CHECK(cond) do { if (!(cond)) __trap(); } while (0)
+#else
+#define GPC_CHECK(cond) do { } while (0)
+#endif
+
+constexpr int kOvCap = 128;                   // fast matcher: capacity of each side's overflow list
+
+// shared memory of the general matcher: out[pow2cap] u64 | cnt[nb] u32 | entry[2*wcap] u32 | bcnt, bstart
 size_t match_smem_bytes(int wcap, int table_log2) {
   size_t nb = (size_t)1 << table_log2;
   size_t pow2 = 1; while ((int)pow2 < wcap) pow2 <<= 1;
   size_t body = ((size_t)2 * wcap * 4 + 15) / 16 * 16;
   if (body < pow2 * 8) body = pow2 * 8;                       // out2 (ordering pass) reuses the entry array
-  return pow2 * 8 + nb * 4 + body + 3 * kBuckets * 4 + 64;
+  return pow2 * 8 + nb * 4 + body + 2 * kBuckets * 4 + 64;
+}
+
+// shared memory of the fast matcher: nib[2^nib_log2] u32 | slot[2^slot_log2] u32 | live list 2 x [pow2cap] u32 |
+// 4 overflow arrays | bcnt, bstart  (the ordering pass reuses nib + slot, which are dead by then)
+size_t match_fast_smem_bytes(int nib_log2, int slot_log2, int pow2cap) {
+  return ((size_t)4 << nib_log2) + ((size_t)4 << slot_log2) + (size_t)pow2cap * 8 + 4 * kOvCap * 4 + 2 * kBuckets * 4;
 }
 
 // Orders the m matches of a row (records key << 32 | xl << 16 | xr in out[]) by state -- the keys are
 // unique -- and writes xl << 16 | xr to the row's slice of `stage`.  Counting pass on the top 8 state bits,
-// then an exact rank inside each (tiny) bucket; bitonic network for skewed states.
+// then an exact rank inside each (tiny) bucket; bitonic network for skewed states.  bcnt[] must be zero.
 template <int kThreadsB>
 __device__ __forceinline__ void order_and_stage(const MatchArgs& args, unsigned long long* out, unsigned long long* out2,
-                                                uint32_t* bcnt, uint32_t* bstart, uint32_t* bfill, uint32_t* big_bucket,
+                                                uint32_t* bcnt, uint32_t* bstart, uint32_t* big_bucket,
                                                 int m, int pair, int y) {
   const int tid = threadIdx.x, lane = tid & 31;
-  // ---- order the matches by state (unique keys) and stage them ------------------------------------------
   uint32_t* stage = args.stage + ((size_t)pair * args.H + y) * args.W;
   if (m > 1) {
-    // counting pass on the top 8 state bits, then an exact rank inside each (tiny) bucket
     const int shift = args.key_bits > 8 ? args.key_bits - 8 : 0;
-    uint32_t seen = 0;
-    for (int i = tid; i < m; i += kThreadsB) seen |= atomic_inc_ret(&bcnt[(uint32_t)(out[i] >> 32) >> shift]);
-    if (seen == 0xffffffffu) __trap();
+    for (int i = tid; i < m; i += kThreadsB) atomicAdd(&bcnt[(uint32_t)(out[i] >> 32) >> shift], 1u);
     __syncthreads();
-    if (tid < 32) {                                   // exclusive scan of 256 counters: 8 per lane
+    if (tid < 32) {                                   // inclusive scan of 256 counters, 8 per lane: bstart = END of the bucket
       uint32_t c[8], sum = 0, mx = 0;
 #pragma unroll
       for (int k = 0; k < 8; k++) { c[k] = bcnt[8 * tid + k]; sum += c[k]; mx = max(mx, c[k]); }
@@ -70,16 +78,16 @@ __device__ __forceinline__ void order_and_stage(const MatchArgs& args, unsigned 
     }
     __syncthreads();
     if (!*big_bucket) {
-      for (int i = tid; i < m; i += kThreadsB) {      // scatter into bucket segments (arbitrary order inside)
-        const unsigned long long rec = out[i];
+      for (int i = tid; i < m; i += kThreadsB) {      // scatter into bucket segments (arbitrary order inside); the
+        const unsigned long long rec = out[i];        // cursor bstart[b] ends at the bucket's end
         const uint32_t b = (uint32_t)(rec >> 32) >> shift;
-        out2[bstart[b] + atomic_inc_ret(&bfill[b])] = rec;
+        out2[atomic_inc_ret(&bstart[b])] = rec;
       }
       __syncthreads();
       for (int i = tid; i < m; i += kThreadsB) {      // rank inside the bucket, write to the final position
         const unsigned long long rec = out2[i];
         const uint32_t b = (uint32_t)(rec >> 32) >> shift;
-        const uint32_t s0 = bstart[b], n = bcnt[b];
+        const uint32_t n = bcnt[b], s0 = bstart[b] - n;
         uint32_t rank = 0;
         for (uint32_t j = 0; j < n; j++) rank += (out2[s0 + j] < rec) ? 1u : 0u;
         stage[s0 + rank] = (uint32_t)(rec & 0xffffffffull);
@@ -107,24 +115,25 @@ __device__ __forceinline__ void order_and_stage(const MatchArgs& args, unsigned 
   }
 }
 
-// One CTA per (row, pair).  Every thread keeps its 4*KQ left and right pixels of the row in
-// registers.  h = state * odd constant (a bijection on 32-bit words): the top log2(nb) bits pick
-// the bucket, so inside a bucket two states are equal iff the remaining low bits of h are.  An
-// entry therefore fits one word: remainder | side | x  (needs nb >= 2 * W, see launch).
+// ------------------------------------------------------------------------------------------------
+// General row matcher (any multiplicities, tail rules).  Every thread keeps its 4*KQ left and right
+// pixels of the row in registers.  h = state * odd constant (a bijection on 32-bit words): the top
+// log2(nb) bits pick the bucket, so inside a bucket two states are equal iff the remaining low bits
+// of h are.  An entry therefore fits one word: remainder | side | x  (needs nb >= 2 * W, see launch).
 //   count   : one atomicAdd per candidate on its bucket counter; the returned rank is kept
 //   scan    : exclusive prefix of the counters -> word = start | count << 16 (bank-conflict free:
 //             thread t owns buckets t, t+256, ...; the order of buckets in the entry array is free)
 //   scatter : entry stored at start[bucket] + rank
 //   resolve : every left candidate reads its bucket (<= 4 entries in one unrolled step, longer
 //             buckets in a loop) counting equal states per side; unique on both sides = match
+// Since round 2 it serves the rows the fast matcher hands over (the row holding the globally last right
+// key, rows with many duplicated states) and GPC_MATCHER_ROWS_GENERAL.
+// ------------------------------------------------------------------------------------------------
 template <int KQ, int kThreadsB>
-__global__ void __launch_bounds__(kThreadsB)
-match_rows_kernel(const MatchArgs args) {
-  extern __shared__ __align__(16) uint8_t smem[];
+__device__ __forceinline__ void general_row(const MatchArgs& args, uint8_t* smem, const int pair, const int y) {
   const int W = args.W, H = args.H, log2nb = args.table_log2, xb = args.x_bits;
   const int nb = 1 << log2nb;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int y = kRadius + blockIdx.x, pair = blockIdx.y;
   const int pow2cap = args.pow2cap;
 
   unsigned long long* out = reinterpret_cast<unsigned long long*>(smem);           // [pow2cap] emitted matches
@@ -133,9 +142,8 @@ match_rows_kernel(const MatchArgs args) {
   unsigned long long* out2 = reinterpret_cast<unsigned long long*>(entry);          // ordering pass, reuses entry
   size_t body = ((size_t)2 * args.wcap * 4 + 15) / 16 * 16;
   if (body < (size_t)pow2cap * 8) body = (size_t)pow2cap * 8;
-  uint32_t* bcnt = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(entry) + body);   // [kBuckets] x3
+  uint32_t* bcnt = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(entry) + body);   // [kBuckets] x2
   uint32_t* bstart = bcnt + kBuckets;
-  uint32_t* bfill = bstart + kBuckets;
   __shared__ int n_out, have_s[2];
   __shared__ uint32_t kmax_s, big_bucket, warp_tot[kThreadsB / 32];
   __shared__ int cmax_r, cmax_l, xmin_s;
@@ -144,7 +152,7 @@ match_rows_kernel(const MatchArgs args) {
   {
     uint4* z = reinterpret_cast<uint4*>(cnt);
     for (int i = tid; i < nb / 4; i += kThreadsB) z[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < 3 * kBuckets; i += kThreadsB) bcnt[i] = 0u;
+    for (int i = tid; i < kBuckets; i += kThreadsB) bcnt[i] = 0u;
   }
 
   // ---- this thread's pixels of the left and right hash rows ---------------------------------------
@@ -219,6 +227,7 @@ match_rows_kernel(const MatchArgs args) {
           const uint32_t h = (v[sd][e] & 0x7fffffffu) * kHashMul;
           const uint32_t r = (e & 1) ? (rank[sd][e >> 1] >> 16) : (rank[sd][e >> 1] & 0xffffu);
           const uint32_t x = 4u * (uint32_t)(tid + (e >> 2) * kThreadsB) + (uint32_t)(e & 3);
+          GPC_CHECK((cnt[h >> rs] & 0xffffu) + r < 2u * (uint32_t)args.wcap);
           entry[(cnt[h >> rs] & 0xffffu) + r] = ((h << log2nb) >> es) | ((uint32_t)sd << xb) | x;
         }
       }
@@ -229,7 +238,7 @@ match_rows_kernel(const MatchArgs args) {
 #pragma unroll
       for (int e = 0; e < 4 * KQ; e++) if (v[1][e] >> 31) km = max(km, v[1][e] & 0x7fffffffu);
       km = __reduce_max_sync(0xffffffffu, km);
-      if (lane == 0 && atomicMax(&kmax_s, km) == 0xffffffffu) __trap();
+      if (lane == 0) atomicMax(&kmax_s, km);
       __syncthreads();
       km = kmax_s;
       int cr = 0, cl = 0, xm = 0x7fffffff;
@@ -241,9 +250,7 @@ match_rows_kernel(const MatchArgs args) {
       cr = __reduce_add_sync(0xffffffffu, cr);
       cl = __reduce_add_sync(0xffffffffu, cl);
       xm = __reduce_min_sync(0xffffffffu, xm);
-      if (lane == 0) {
-        if (atomicAdd(&cmax_r, cr) < 0 || atomicAdd(&cmax_l, cl) < 0 || atomicMin(&xmin_s, xm) < 0) __trap();
-      }
+      if (lane == 0) { atomicAdd(&cmax_r, cr); atomicAdd(&cmax_l, cl); atomicMin(&xmin_s, xm); }
     }
     __syncthreads();
     // ---- resolve + emit: a left state that is unique in its bucket on both sides is a match ---------
@@ -304,13 +311,365 @@ match_rows_kernel(const MatchArgs args) {
       base = __shfl_sync(0xffffffffu, base, 31) + incl - mine_n;
 #pragma unroll
       for (int e = 0; e < 4 * KQ; e++)
-        if ((okmask >> e) & 1u) out[base++] = rec[e];
+        if ((okmask >> e) & 1u) { GPC_CHECK(base < pow2cap); out[base++] = rec[e]; }
     }
     __syncthreads();
     m = n_out;
   }
 
-  order_and_stage<kThreadsB>(args, out, out2, bcnt, bstart, bfill, &big_bucket, m, pair, y);
+  order_and_stage<kThreadsB>(args, out, out2, bcnt, bstart, &big_bucket, m, pair, y);
+  if (tid == 0) args.rowmatch[(size_t)pair * H + y] = m;
+}
+
+// list == nullptr: one CTA per (row, pair) of the grid.  Otherwise the CTAs walk the row list the fast
+// matcher left: list[0] = number of rows, list[1] = CTAs done, list[2 + 2i] = pair, list[3 + 2i] = row;
+// the last CTA to finish clears the two counters for the next launch.
+template <int KQ, int kThreadsB>
+__global__ void __launch_bounds__(kThreadsB)
+match_rows_general_kernel(const MatchArgs args, uint32_t* list) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  if (list == nullptr) {
+    general_row<KQ, kThreadsB>(args, smem, blockIdx.y, kRadius + blockIdx.x);
+    return;
+  }
+  const uint32_t n = *reinterpret_cast<volatile uint32_t*>(list);
+  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    general_row<KQ, kThreadsB>(args, smem, (int)list[2 + 2 * i], (int)list[3 + 2 * i]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&list[1], 1u) == gridDim.x - 1) { list[0] = 0u; list[1] = 0u; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast row matcher (round 2).  A match is a state that occurs exactly once in the left row and exactly
+// once in the right row (inference.hpp:227-254 in epipolar mode); about nine candidates in ten have no
+// partner at all, so the kernel finds that out as cheaply as possible and continues with short lists:
+//   right    : 4 bits per bucket -- "a left", "a second left", "a right", "a second right" -- eight
+//              buckets per word, ~32 buckets per candidate.  h = v * odd constant (a bijection; the
+//              candidate flag stays in v, every candidate carries it); the top bits select the bucket.
+//              Every right candidate ORs its bit in (a second atomicOr for the few that find it set).
+//   left     : every left candidate ORs its bit in; the value the atomic returns already holds the final
+//              right bits, so a candidate whose bucket has no right candidate is dropped on the spot
+//              (~85 %); the others go to the "live" list (v, x).
+//   pair     : a right candidate re-reads its nibble; in a bucket with exactly one left and one right it
+//              claims slot[h >> ..] with atomicCAS (remainder | x in one word).  Buckets with both sides
+//              and a duplicate go to the overflow lists; so does the loser of a slot (the slot table is
+//              coarser than the buckets).
+//   resolve  : one thread per live left entry: in a pair bucket it reads the slot -- same remainder = same
+//              state = match; a stranger's entry = its partner lost the slot -> overflow list.
+//   overflow : every left overflow entry counts equal states in both lists (tens of entries; complete per
+//              state, because equal states share a bucket and a bucket is listed as a whole).
+// A match is recorded in place in its live-list entry (x | xr << 13 | flag).  The row holding the globally
+// last right key (tail rules) and rows whose overflow lists do not fit are appended to a row list for the
+// general kernel.  Matches are ordered by state as before (counting pass + rank inside the bucket).
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kClassLut = (1u << 10) | (2u << 14) | (2u << 26) | (2u << 30);   // nibble -> 1 pair bucket, 2 overflow
+constexpr uint32_t kMatchFlag = 0x80000000u;
+#ifndef GPC_B_MINB
+#define GPC_B_MINB 6                          // resident 256-thread CTAs per SM the register budget allows
+#endif
+#ifndef GPC_B_OVLANES
+#define GPC_B_OVLANES 1
+#endif
+constexpr int kOvLanes = GPC_B_OVLANES;       // lanes sharing one left overflow entry (1: 16-byte reads)
+
+__device__ __forceinline__ uint32_t atom_add_shared(uint32_t* p, uint32_t v) {
+  // plain atom: ptxas wraps a uniform-address atomicAdd whose result is used into a 20-instruction warp scan
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+  return old;
+}
+
+template <int KQ, int kThreadsB>
+__global__ void __launch_bounds__(kThreadsB, (KQ == 1 && kThreadsB <= 512) ? (GPC_B_MINB * 256) / kThreadsB : 1)
+match_rows_fast_kernel(const MatchArgs args) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  static_assert(kOvCap <= kThreadsB && kOvCap % 4 == 0, "one thread per left overflow entry, 16-byte reads");
+  const int W = args.W, H = args.H, xb = args.x_bits, nwl = args.nib_log2, nsl = args.slot_log2;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int y = kRadius + blockIdx.x, pair = blockIdx.y;
+
+  uint32_t* nib = reinterpret_cast<uint32_t*>(smem);                                // [1 << nwl]
+  uint32_t* slot = nib + ((size_t)1 << nwl);                                        // [1 << nsl]
+  uint32_t* live_v = slot + ((size_t)1 << nsl);                                     // [pow2cap] live left candidates: v
+  uint32_t* live_x = live_v + args.pow2cap;                                         // [pow2cap] x, later | xr << 13 | kMatchFlag
+  uint32_t* ovl_s = live_x + args.pow2cap;                                          // overflow lists: left state, live index
+  uint32_t* ovl_i = ovl_s + kOvCap;
+  uint32_t* ovr_s = ovl_i + kOvCap;                                                 // right state, x
+  uint32_t* ovr_x = ovr_s + kOvCap;
+  uint32_t* bcnt = ovr_x + kOvCap;                                                  // [kBuckets] x2
+  uint32_t* bstart = bcnt + kBuckets;
+  unsigned long long* out2 = reinterpret_cast<unsigned long long*>(nib);            // ordering pass: the tables are dead by then
+  __shared__ uint32_t n_live, n_ovl, n_ovr, n_out, big_bucket, warp_tot[kThreadsB / 32];
+
+  // ---- this thread's pixels of the left and right hash rows (issued first: the zero fill hides their latency)
+  const size_t row0 = ((size_t)(2 * pair) * H + y) * W;
+  const uint4* row_l = reinterpret_cast<const uint4*>(args.hash + row0);
+  const uint4* row_r = reinterpret_cast<const uint4*>(args.hash + row0 + (size_t)H * W);
+  const int nquads = W / 4;
+  uint32_t v[2][4 * KQ];                       // [side][element]
+#pragma unroll
+  for (int k = 0; k < KQ; k++) {
+    const int q = tid + k * kThreadsB;
+    uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+    if (q < nquads) { a = __ldg(row_l + q); b = __ldg(row_r + q); }
+    v[0][4 * k] = a.x; v[0][4 * k + 1] = a.y; v[0][4 * k + 2] = a.z; v[0][4 * k + 3] = a.w;
+    v[1][4 * k] = b.x; v[1][4 * k + 1] = b.y; v[1][4 * k + 2] = b.z; v[1][4 * k + 3] = b.w;
+  }
+  if (tid == 0) { n_live = 0; n_ovl = 0; n_ovr = 0; n_out = 0; big_bucket = 0; }
+  {
+    uint4* z = reinterpret_cast<uint4*>(nib) + tid;
+    const int rounds = ((1 << nwl) + (1 << nsl)) / (4 * kThreadsB);            // tables are multiples of 4 * kThreadsB words
+    for (int i = 0; i < rounds; i++) z[i * kThreadsB] = make_uint4(0, 0, 0, 0);
+    if (tid < kBuckets / 4) reinterpret_cast<uint4*>(bcnt)[tid] = make_uint4(0, 0, 0, 0);
+    if (tid < kOvCap / 4) { reinterpret_cast<uint4*>(ovl_s)[tid] = make_uint4(0, 0, 0, 0); reinterpret_cast<uint4*>(ovr_s)[tid] = make_uint4(0, 0, 0, 0); }
+  }
+  uint32_t any_l = 0, any_r = 0;
+#pragma unroll
+  for (int e = 0; e < 4 * KQ; e++) { any_l |= v[0][e]; any_r |= v[1][e]; }
+  const int have_l = __syncthreads_or((int)(any_l >> 31));       // also orders the zero fill before the atomics
+  const int have_r = __syncthreads_or((int)(any_r >> 31));
+  if (!(have_l && have_r)) {
+    if (tid == 0) args.rowmatch[(size_t)pair * H + y] = 0;
+    return;
+  }
+  if (args.lastrow[2 * pair + 1] == y) {       // tail rules of inference.hpp:243-249: the general kernel's job
+    if (tid == 0) {
+      const uint32_t i = atomicAdd(&args.fb_list[0], 1u);
+      args.fb_list[2 + 2 * i] = (uint32_t)pair; args.fb_list[3 + 2 * i] = (uint32_t)y;
+    }
+    return;
+  }
+
+  // Everything below is branch-free per pixel (a non-candidate ORs 0 into some word and is never live): the
+  // pixels of a side keep independent chains in flight.
+  const int bs = 29 - nwl;                     // bucket = h >> bs: word = bucket >> 3, nibble = bucket & 7
+  const int s_addr = bs + 1, s_sh = bs - 2;    // byte offset of the word = (h >> s_addr) & ~3, bit offset of the nibble = (h >> s_sh) & 28
+  uint8_t* const nib8 = reinterpret_cast<uint8_t*>(nib);
+  // ---- right candidates: count ------------------------------------------------------------------------
+  uint32_t pk[4 * KQ];                         // byte offset of the word | bit offset of the nibble << 16
+  {
+    uint32_t bit[4 * KQ], old[4 * KQ];
+#pragma unroll
+    for (int e = 0; e < 4 * KQ; e++) {
+      const uint32_t h = v[1][e] * kHashMul;
+      const uint32_t off = (h >> s_addr) & ~3u, sh = (h >> s_sh) & 28u;
+      pk[e] = off | (sh << 16);
+      bit[e] = (v[1][e] >> 31) << (sh | 2u);
+      GPC_CHECK(off < (4u << nwl) && (sh | 2u) < 32u);
+      old[e] = atomicOr(reinterpret_cast<uint32_t*>(nib8 + off), bit[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4 * KQ; e++)
+      if (old[e] & bit[e]) atomicOr(reinterpret_cast<uint32_t*>(nib8 + (pk[e] & 0xffffu)), bit[e] << 1);
+  }
+  __syncthreads();
+  // ---- left candidates: count; the returned word holds the final right bits -----------------------------
+  {
+    uint32_t bit[4 * KQ], old[4 * KQ], livem = 0;
+#pragma unroll
+    for (int e = 0; e < 4 * KQ; e++) {
+      const uint32_t h = v[0][e] * kHashMul;
+      const uint32_t off = (h >> s_addr) & ~3u, sh = (h >> s_sh) & 28u;
+      bit[e] = (v[0][e] >> 31) << sh;
+      old[e] = atomicOr(reinterpret_cast<uint32_t*>(nib8 + off), bit[e]);
+      if (old[e] & bit[e]) atomicOr(reinterpret_cast<uint32_t*>(nib8 + off), bit[e] << 1);
+    }
+#pragma unroll
+    for (int e = 0; e < 4 * KQ; e++) livem |= ((old[e] & (bit[e] << 2)) ? 1u : 0u) << e;      // a right candidate in my bucket
+    if (livem) {
+      uint32_t p = atom_add_shared(&n_live, (uint32_t)__popc(livem));
+      do {
+        const int e = __ffs((int)livem) - 1;
+        livem &= livem - 1u;
+        uint32_t val = v[0][0];
+#pragma unroll
+        for (int k = 1; k < 4 * KQ; k++) val = (e == k) ? v[0][k] : val;
+        GPC_CHECK(p < (uint32_t)args.pow2cap);
+        live_v[p] = val;
+        live_x[p] = 4u * (uint32_t)(tid + (e >> 2) * kThreadsB) + (uint32_t)(e & 3);
+        p++;
+      } while (livem);
+    }
+  }
+  __syncthreads();
+  // ---- right candidates of pair buckets claim their slot -----------------------------------------------
+  const int ss = 32 - nsl;                     // slot = h >> ss, entry = (h << nsl) >> (nsl - xb) | x
+  const int s_slot = ss - 2;                   // byte offset of the slot = (h >> s_slot) & ~3
+  uint8_t* const slot8 = reinterpret_cast<uint8_t*>(slot);
+  {
+    uint32_t ovm = 0;
+#pragma unroll
+    for (int e = 0; e < 4 * KQ; e++) {
+      const uint32_t t = *reinterpret_cast<const uint32_t*>(nib8 + (pk[e] & 0xffffu)) >> (pk[e] >> 16);
+      uint32_t c = (v[1][e] >> 31) ? ((kClassLut >> ((t & 15u) << 1)) & 3u) : 0u;
+      const uint32_t h = v[1][e] * kHashMul;
+      const uint32_t x = 4u * (uint32_t)(tid + (e >> 2) * kThreadsB) + (uint32_t)(e & 3);
+      uint32_t prev = 0;
+      GPC_CHECK(((h >> s_slot) & ~3u) < (4u << nsl) && (c != 1u || x != 0u));
+      if (c == 1u) prev = atomicCAS(reinterpret_cast<uint32_t*>(slot8 + ((h >> s_slot) & ~3u)), 0u, ((h << nsl) >> (nsl - xb)) | x);
+      c = prev ? 2u : c;                       // slot taken by another pair bucket: overflow
+      ovm |= (c >> 1) << e;
+    }
+    if (ovm) {
+      uint32_t p = atom_add_shared(&n_ovr, (uint32_t)__popc(ovm));
+      do {
+        const int e = __ffs((int)ovm) - 1;
+        ovm &= ovm - 1u;
+        uint32_t val = v[1][0];
+#pragma unroll
+        for (int k = 1; k < 4 * KQ; k++) val = (e == k) ? v[1][k] : val;
+        if (p < (uint32_t)kOvCap) { ovr_s[p] = val; ovr_x[p] = 4u * (uint32_t)(tid + (e >> 2) * kThreadsB) + (uint32_t)(e & 3); }
+        p++;
+      } while (ovm);
+    }
+  }
+  __syncthreads();
+  // ---- live left candidates: pair buckets read their slot -------------------------------------------------
+  const uint32_t XL = 1u << xb;
+  const int same_bucket_shift = xb + 29 - nwl;       // entry bits above this: the bucket bits the slot index lacks
+  const uint32_t nlive = n_live;
+  const int oshift = args.key_bits > 8 ? args.key_bits - 8 : 0;
+  for (uint32_t i = tid; i < nlive; i += kThreadsB) {
+    const uint32_t lv = live_v[i], xl = live_x[i];
+    const uint32_t h = lv * kHashMul;
+    const uint32_t nibble = (*reinterpret_cast<const uint32_t*>(nib8 + ((h >> s_addr) & ~3u)) >> ((h >> s_sh) & 28u)) & 15u;
+    const uint32_t t = *reinterpret_cast<const uint32_t*>(slot8 + ((h >> s_slot) & ~3u)) ^ ((h << nsl) >> (nsl - xb));
+    const int dx = (int)xl - (int)t;
+    // pair bucket, t < XL: same state, t = x of the right candidate.  Otherwise bits above same_bucket_shift tell
+    // a stranger's entry (my partner lost the slot: overflow lists) from the bucket's own right candidate.
+    const bool pairb = (nibble == 5u);
+    if (pairb && t < XL && dx <= args.disp_high && -dx <= args.disp_high && 0 <= args.vertical_tolerance) {
+      live_x[i] = xl | (t << 13) | kMatchFlag;
+      atomicAdd(&n_out, 1u);
+      atomicAdd(&bcnt[(lv & 0x7fffffffu) >> oshift], 1u);       // counting pass of the ordering below
+    } else if (nibble != 5u || (t >> same_bucket_shift) != 0u) {     // duplicates in the bucket, or a stranger in the slot
+      const uint32_t p = atom_add_shared(&n_ovl, 1u);
+      if (p < (uint32_t)kOvCap) { ovl_s[p] = lv; ovl_i[p] = i; }
+    }
+  }
+  __syncthreads();
+  // ---- overflow entries: exact counts over both lists, kOvLanes lanes per left entry ------------------------
+  const uint32_t nl = n_ovl, nr = n_ovr;
+  if (nl > (uint32_t)kOvCap || nr > (uint32_t)kOvCap) {          // too many duplicated states: general kernel
+    if (tid == 0) {
+      const uint32_t i = atomicAdd(&args.fb_list[0], 1u);
+      args.fb_list[2 + 2 * i] = (uint32_t)pair; args.fb_list[3 + 2 * i] = (uint32_t)y;
+    }
+    return;
+  }
+  if (kOvLanes == 1) {
+  if ((uint32_t)tid < nl && nr > 0u) {             // (kOvCap <= kThreadsB; entries past a list's end are 0 = equal to nothing)
+      const uint32_t s = ovl_s[tid];
+      uint32_t cl = 0, cr = 0, jr = 0;
+      for (uint32_t j = 0; j < nl; j += 4) {
+        const uint4 q = *reinterpret_cast<const uint4*>(ovl_s + j);
+        cl += (q.x == s ? 1u : 0u) + (q.y == s ? 1u : 0u) + (q.z == s ? 1u : 0u) + (q.w == s ? 1u : 0u);
+      }
+      for (uint32_t j = 0; j < nr; j += 4) {
+        const uint4 q = *reinterpret_cast<const uint4*>(ovr_s + j);
+        const bool e0 = q.x == s, e1 = q.y == s, e2 = q.z == s, e3 = q.w == s;
+        cr += (e0 ? 1u : 0u) + (e1 ? 1u : 0u) + (e2 ? 1u : 0u) + (e3 ? 1u : 0u);
+        jr = e0 ? j : e1 ? j + 1 : e2 ? j + 2 : e3 ? j + 3 : jr;
+      }
+      if (cl == 1u && cr == 1u) {
+        const uint32_t li = ovl_i[tid], xl = live_x[li], x2 = ovr_x[jr];
+        const int dx = (int)xl - (int)x2;
+        if (dx <= args.disp_high && -dx <= args.disp_high && 0 <= args.vertical_tolerance) {
+          live_x[li] = xl | (x2 << 13) | kMatchFlag;
+          atomicAdd(&n_out, 1u);
+          atomicAdd(&bcnt[(s & 0x7fffffffu) >> oshift], 1u);
+        }
+      }
+    }
+  } else if (nl > 0u && nr > 0u) {
+    for (uint32_t i0 = 0; i0 < nl; i0 += kThreadsB / kOvLanes) {
+      if (i0 + (uint32_t)(tid & ~31) / kOvLanes >= nl) break;        // whole warps leave (shuffles below)
+      const uint32_t i = i0 + (uint32_t)tid / kOvLanes, part = (uint32_t)tid % kOvLanes;
+      const uint32_t s = (i < nl) ? ovl_s[i] : 0u;                 // 0: no candidate flag, equals nothing
+      uint32_t cl = 0, cr = 0, x2 = 0;
+      for (uint32_t j = part; j < nl; j += kOvLanes) cl += (ovl_s[j] == s) ? 1u : 0u;
+      for (uint32_t j = part; j < nr; j += kOvLanes) { const bool eq = (ovr_s[j] == s); cr += eq ? 1u : 0u; x2 += eq ? ovr_x[j] : 0u; }
+#pragma unroll
+      for (int d = 1; d < kOvLanes; d <<= 1) {
+        cl += __shfl_xor_sync(0xffffffffu, cl, d); cr += __shfl_xor_sync(0xffffffffu, cr, d); x2 += __shfl_xor_sync(0xffffffffu, x2, d);
+      }
+      if (part == 0u && i < nl && cl == 1u && cr == 1u) {
+        const uint32_t li = ovl_i[i], xl = live_x[li];
+        const int dx = (int)xl - (int)x2;
+        if (dx <= args.disp_high && -dx <= args.disp_high && 0 <= args.vertical_tolerance) {
+          live_x[li] = xl | (x2 << 13) | kMatchFlag;
+          atomicAdd(&n_out, 1u);
+          atomicAdd(&bcnt[(s & 0x7fffffffu) >> oshift], 1u);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- order the matches by state (unique keys) and stage them: counting pass on the top 8 state bits,
+  // then an exact rank inside each (tiny) bucket; bitonic network for skewed states ----------------------------
+  const int m = (int)n_out;
+  uint32_t* stage = args.stage + ((size_t)pair * H + y) * W;
+  if (m > 0) {
+    const int shift = oshift;
+    {                                                 // exclusive scan of the 256 counters: one per thread of the first 8 warps
+      uint32_t c = 0;
+      if (tid < kBuckets) c = bcnt[tid];
+      uint32_t incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+      if (lane == 31) warp_tot[wid] = incl;
+      if (c > (uint32_t)kBucketLimit) big_bucket = 1u;              // benign same-value race
+      __syncthreads();
+      uint32_t base = incl - c;
+#pragma unroll
+      for (int w = 0; w < kBuckets / 32; w++) if (w < wid) base += warp_tot[w];
+      if (tid < kBuckets) bstart[tid] = base;
+    }
+    __syncthreads();
+    // scatter into bucket segments (arbitrary order inside); the cursor bstart[b] ends at the bucket's end
+    for (uint32_t i = tid; i < nlive; i += kThreadsB) {
+      const uint32_t lx = live_x[i];
+      if (lx & kMatchFlag) {
+        const uint32_t key = live_v[i] & 0x7fffffffu;
+        const uint32_t xl = lx & 0x1fffu, xr = (lx >> 13) & 0x1fffu;
+        const uint32_t pos = atomicAdd(&bstart[key >> shift], 1u);
+        GPC_CHECK(pos < (uint32_t)m && (key >> shift) < (uint32_t)kBuckets);
+        out2[pos] = ((unsigned long long)key << 32) | (unsigned long long)((xl << 16) | xr);
+      }
+    }
+    __syncthreads();
+    if (!big_bucket) {
+      for (int i = tid; i < m; i += kThreadsB) {      // rank inside the bucket, write to the final position
+        const unsigned long long rec = out2[i];
+        const uint32_t b = (uint32_t)(rec >> 32) >> shift;
+        const uint32_t n = bcnt[b], s0 = bstart[b] - n;
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < n; j++) rank += (out2[s0 + j] < rec) ? 1u : 0u;
+        stage[s0 + rank] = (uint32_t)(rec & 0xffffffffull);
+      }
+    } else {                                          // skewed states: bitonic network over all matches
+      int p2 = 1; while (p2 < m) p2 <<= 1;
+      for (int i = m + tid; i < p2; i += kThreadsB) out2[i] = ~0ull;
+      __syncthreads();
+      for (int k = 2; k <= p2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = tid; i < p2; i += kThreadsB) {
+            const int l = i ^ j;
+            if (l > i) {
+              const unsigned long long a = out2[i], b2 = out2[l];
+              const bool up = ((i & k) == 0);
+              if ((a > b2) == up) { out2[i] = b2; out2[l] = a; }
+            }
+          }
+          __syncthreads();
+        }
+      for (int i = tid; i < m; i += kThreadsB) stage[i] = (uint32_t)(out2[i] & 0xffffffffull);
+    }
+  }
   if (tid == 0) args.rowmatch[(size_t)pair * H + y] = m;
 }
 
@@ -319,7 +678,9 @@ match_rows_kernel(const MatchArgs args) {
 // each has to bring more warps); beyond 4096 pixels KQ grows.
 template <int KQ, int T>
 static cudaError_t configure_one(int max_smem) {
-  return cudaFuncSetAttribute(match_rows_kernel<KQ, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaError_t e = cudaFuncSetAttribute(match_rows_general_kernel<KQ, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(match_rows_fast_kernel<KQ, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  return e;
 }
 
 cudaError_t configure_match_rows(int max_smem) {
@@ -335,17 +696,31 @@ int match_rows_threads(int W) {
   return quads <= 256 ? 256 : quads <= 512 ? 512 : 1024;
 }
 
-cudaError_t launch_match_rows(const MatchArgs& args, int n_pairs, cudaStream_t stream) {
+// general != 0: every row through the general kernel (GPC_MATCHER_ROWS_GENERAL).  Otherwise the fast kernel
+// over all rows, then the general kernel over the row list it left (args.fb_list, sized for every row).
+cudaError_t launch_match_rows(const MatchArgs& args, int n_pairs, int general, int sm_count, cudaStream_t stream) {
   int rows = args.H - 2 * kRadius;
   if (rows <= 0 || n_pairs <= 0) return cudaSuccess;
   const int quads = args.W / 4;
+  if (quads > 2048) return cudaErrorInvalidValue;
   dim3 grid(rows, n_pairs);
-  size_t smem = match_smem_bytes(args.wcap, args.table_log2);
-  if (quads <= 256) match_rows_kernel<1, 256><<<grid, 256, smem, stream>>>(args);
-  else if (quads <= 512) match_rows_kernel<1, 512><<<grid, 512, smem, stream>>>(args);
-  else if (quads <= 1024) match_rows_kernel<1, 1024><<<grid, 1024, smem, stream>>>(args);
-  else if (quads <= 2048) match_rows_kernel<2, 1024><<<grid, 1024, smem, stream>>>(args);
-  else return cudaErrorInvalidValue;
+  const size_t smem_g = match_smem_bytes(args.wcap, args.table_log2);
+  const size_t smem_f = match_fast_smem_bytes(args.nib_log2, args.slot_log2, args.pow2cap);
+  const long long all_rows = (long long)rows * n_pairs;
+  const int list_grid = (int)(all_rows < 4ll * sm_count ? all_rows : 4ll * sm_count);
+#define GPC_LAUNCH_ROWS(KQ, T)                                                                                  \
+  do {                                                                                                          \
+    if (general) match_rows_general_kernel<KQ, T><<<grid, T, smem_g, stream>>>(args, nullptr);                  \
+    else {                                                                                                      \
+      match_rows_fast_kernel<KQ, T><<<grid, T, smem_f, stream>>>(args);                                         \
+      match_rows_general_kernel<KQ, T><<<list_grid, T, smem_g, stream>>>(args, args.fb_list);                   \
+    }                                                                                                           \
+  } while (0)
+  if (quads <= 256) GPC_LAUNCH_ROWS(1, 256);
+  else if (quads <= 512) GPC_LAUNCH_ROWS(1, 512);
+  else if (quads <= 1024) GPC_LAUNCH_ROWS(1, 1024);
+  else GPC_LAUNCH_ROWS(2, 1024);
+#undef GPC_LAUNCH_ROWS
   return cudaGetLastError();
 }
 

@@ -24,6 +24,11 @@ __global__ void k(uint32_t* out, int iters) {
     if (MODE == 5) acc += __match_any_sync(0xffffffffu, key & 1023u);
     if (MODE == 6) acc += atomicMin(&tab32[slot], key);
     if (MODE == 7) acc += atomicExch(&tab32[slot], key);
+    if (MODE == 8) acc += atomicOr(&tab32[slot], 1u << (key & 31));
+    if (MODE == 9) { atomicOr(&tab32[slot], 1u << (key & 31)); }
+    if (MODE == 10) { uint32_t b = 1u << (2 * (key & 15)); uint32_t o = atomicOr(&tab32[slot], b); if (o & b) acc += atomicOr(&tab32[slot], b << 1); if ((it & 63) == 63) tab32[slot] = 0; }
+    if (MODE == 11) { acc += tab32[slot]; }                          // LDS only
+    if (MODE == 12) { if (key & 0x30000) acc += atomicAdd(&tab32[slot], 1u); }   // 75 % of the lanes active
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
@@ -56,6 +61,11 @@ int main() {
   run<5>("match_any", d, iters);
   run<6>("atomicMin u32", d, iters);
   run<7>("atomicExch u32", d, iters);
+  run<8>("atomicOr u32 (return)", d, iters);
+  run<9>("atomicOr u32 (no return)", d, iters);
+  run<10>("atomicOr 2-level nibble", d, iters);
+  run<11>("LDS random", d, iters);
+  run<12>("atomicAdd 75% lanes", d, iters);
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }

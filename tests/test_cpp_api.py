@@ -17,7 +17,7 @@ C_EXAMPLE = os.path.join(ROOT, "samples", "c_api_example")
 def _build():
     from opengpc_b200.build import build_native
     build_native()
-    r = subprocess.run(["make", "-C", os.path.join(ROOT, "samples")], capture_output=True, text=True)
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "samples")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
 
 
@@ -36,7 +36,7 @@ def test_cpp_host_builds():
         with tempfile.TemporaryDirectory() as d:
             r = subprocess.run(["g++", "-std=c++11", "-w", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "sm"), ref_src,
                                 "-L" + os.path.join(ROOT, "opengpc_b200"), "-lgpc_b200", "-lz", "-lpthread"],
-                               capture_output=True, text=True)
+                               capture_output=True, text=True, timeout=300)
             assert r.returncode == 0, r.stderr
 
 
@@ -48,7 +48,7 @@ def test_png_codec_roundtrip():
     with tempfile.TemporaryDirectory() as d:
         exe = os.path.join(d, "png_test")
         r = subprocess.run(["g++", "-std=c++11", "-O1", "-I", os.path.join(ROOT, "include"), "-o", exe,
-                            os.path.join(ROOT, "tests", "cpp", "png_test.cpp"), "-lz"], capture_output=True, text=True)
+                            os.path.join(ROOT, "tests", "cpp", "png_test.cpp"), "-lz"], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr
         gray = rng.integers(0, 256, (37, 50), dtype=np.uint8)
         rgb = rng.integers(0, 256, (20, 33, 3), dtype=np.uint8)
@@ -61,7 +61,7 @@ def test_png_codec_roundtrip():
                 Image.fromarray(src).save(pin)        # mode I;16
             else:
                 Image.fromarray(src).save(pin)
-            r = subprocess.run([exe, pin, pout, praw], capture_output=True, text=True)
+            r = subprocess.run([exe, pin, pout, praw], capture_output=True, text=True, timeout=300)
             assert r.returncode == 0, (name, r.returncode, r.stdout)
             raw = np.fromfile(praw, np.uint8)
             w, h, cols = np.frombuffer(raw[:12].tobytes(), np.int32)
@@ -94,7 +94,7 @@ def test_cpp_api_vs_oracle(oracle, forest, epipolar, vt, dh, thr, w, h, naive):
         pl, pr, pout = (os.path.join(d, n) for n in ("l.png", "r.png", "out.bin"))
         _write_png(pl, L); _write_png(pr, R)
         r = subprocess.run([API_TEST + ("_naive" if naive else ""), FORESTS[forest], pl, pr, pout, str(epipolar), str(vt), str(dh), str(thr)],
-                           capture_output=True, text=True)
+                           capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
         if forest == "deep":
             assert r.stdout.count("Note: A maximum of 32 fern features") == 160
@@ -128,6 +128,28 @@ def test_cpp_api_vs_oracle(oracle, forest, epipolar, vt, dh, thr, w, h, naive):
 
 
 @pytest.mark.gpu
+def test_cpp_api_threads_and_regrowth(oracle):
+    """tests/cpp/thread_test.cpp: four host threads through the shared, locked device context give the
+    single-threaded result; images preprocessed before a larger image forced a new context still match;
+    lazily fetched smooth / grad images feed the hand-built path; the counts equal the oracle's."""
+    from opengpc_b200.synth import synth_pair
+    _build()
+    exe = os.path.join(ROOT, "tests", "cpp", "thread_test")
+    L, R = synth_pair(640, 200, 99)
+    l, r = synth_pair(256, 96, 98)
+    of = oracle.read_forest(FORESTS["tau"])
+    want_big = len(oracle.pair(L, R, of, osettings())[0])
+    want_small = len(oracle.pair(l, r, of, osettings())[0])
+    with tempfile.TemporaryDirectory() as d:
+        paths = [os.path.join(d, n) for n in ("L.png", "R.png", "l.png", "r.png")]
+        for pth, im in zip(paths, (L, R, l, r)):
+            _write_png(pth, im)
+        res = subprocess.run([exe, FORESTS["tau"]] + paths + ["4", "6"], capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, (res.returncode, res.stdout[-1500:], res.stderr[-1500:])
+        assert f"ok {want_big} {want_small}" in res.stdout, res.stdout[-500:]
+
+
+@pytest.mark.gpu
 def test_sparsematch_cli(oracle):
     from opengpc_b200.synth import synth_pair
     _build()
@@ -135,7 +157,7 @@ def test_sparsematch_cli(oracle):
     with tempfile.TemporaryDirectory() as d:
         pl, pr, po = (os.path.join(d, n) for n in ("l.png", "r.png", "disp.png"))
         _write_png(pl, L); _write_png(pr, R)
-        r = subprocess.run([SPARSEMATCH, FORESTS["tau"], pl, pr, po, "3"], capture_output=True, text=True)
+        r = subprocess.run([SPARSEMATCH, FORESTS["tau"], pl, pr, po, "3"], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stdout + r.stderr
         assert "#candidatesL:377030, #candidatesR:378097" in r.stdout and "num matches:40839" in r.stdout, r.stdout
         from PIL import Image
@@ -153,10 +175,10 @@ def test_c_api_from_plain_c(oracle):
     with tempfile.TemporaryDirectory() as d:
         pl, pr = os.path.join(d, "l.raw"), os.path.join(d, "r.raw")
         L.tofile(pl); R.tofile(pr)
-        r = subprocess.run([C_EXAMPLE, FORESTS["tau"], "1024", "436", pl, pr], capture_output=True, text=True)
+        r = subprocess.run([C_EXAMPLE, FORESTS["tau"], "1024", "436", pl, pr], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stdout + r.stderr
         assert "#candidatesL:377030, #candidatesR:378097, num matches:40839, digest:fb3f3b2728785637" in r.stdout, r.stdout
-        r = subprocess.run([C_EXAMPLE, FORESTS["zero"], "1024", "436", pl, pr, "naive"], capture_output=True, text=True)
+        r = subprocess.run([C_EXAMPLE, FORESTS["zero"], "1024", "436", pl, pr, "naive"], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stdout + r.stderr
         ref, ncl, ncr = oracle.pair_naive(L, R, oracle.read_forest(FORESTS["zero"]), osettings())
         assert f"#candidatesL:{ncl}, #candidatesR:{ncr}, num matches:{len(ref)}, digest:{digest(ref):016x}" in r.stdout, r.stdout

@@ -65,6 +65,13 @@ def test_fuzz_vs_oracle(oracle):
             info = (it, w, h, nt, tkind, thr, dh, epi, vt, mode)
             assert (ncl, ncr) == (ocl, ocr), info
             assert np.array_equal(supp, ref), info + (len(supp), len(ref))
+            if epi and it % 2 == 0:                                 # every row through the general row kernel
+                ctx.set_matcher(g.MATCHER_ROWS_GENERAL)
+                try:
+                    supp_g, _, _ = ctx.match_pair(L, R, g.make_settings(thr=thr, disp_high=dh, vt=vt, epipolar=epi))
+                finally:
+                    ctx.set_matcher(g.MATCHER_AUTO)
+                assert np.array_equal(supp_g, ref), info + ("general rows", len(supp_g), len(ref))
             if it % 3 == 0:                                         # the same case through useHashtable(true)
                 ref_h = oracle.pair_hashtable(L, R, of, osettings(thr, dh, vt, epi))
                 supp_h, _, _ = ctx.match_pair(L, R, g.make_settings(thr=thr, disp_high=dh, vt=vt, epipolar=epi, use_hashtable=True))

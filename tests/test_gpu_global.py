@@ -79,16 +79,52 @@ def test_sort_matcher_equals_row_matcher(g, ctx, oracle):
         ctx.set_forest(FORESTS[forest])
         ctx.set_matcher(g.MATCHER_AUTO)
         a, oa, na = ctx.match_batch(imgs, s)
-        ctx.set_matcher(g.MATCHER_SORT)
-        try:
-            b, ob, nb = ctx.match_batch(imgs, s)
-        finally:
-            ctx.set_matcher(g.MATCHER_AUTO)
-        assert np.array_equal(oa, ob) and np.array_equal(na, nb)
-        assert np.array_equal(a, b), forest
+        for other in (g.MATCHER_SORT, g.MATCHER_ROWS_GENERAL):      # radix sort; every row through the general row kernel
+            ctx.set_matcher(other)
+            try:
+                b, ob, nb = ctx.match_batch(imgs, s)
+            finally:
+                ctx.set_matcher(g.MATCHER_AUTO)
+            assert np.array_equal(oa, ob) and np.array_equal(na, nb)
+            assert np.array_equal(a, b), (forest, other)
     of = oracle.read_forest(FORESTS["zero"])
     ref, _, _ = oracle.pair(imgs[2, 0], imgs[2, 1], of, osettings())
     assert np.array_equal(b[ob[2]:ob[3]], ref)
+
+
+def test_find_correspondences_largest_key(g, ctx, oracle):
+    """A right key of 2^64 - 1 is legal (explicit 64-bit keys): the tail rules of inference.hpp:243-249 still apply to it."""
+    top = (1 << 64) - 1
+    for src, tar in (([1, top], [1, top]), ([top], [5, top, top]), ([3, top], [3, top, top, top]), ([top, 7], [7, top - 1, top])):
+        want = oracle.find_correspondences(np.array(src, np.uint64), np.array(tar, np.uint64))
+        got = ctx.find_correspondences(src, tar)
+        assert got.tolist() == want.tolist(), (src, tar, got.tolist(), want.tolist())
+
+
+def test_match_hash_images_ignores_border_flags(g, ctx, oracle):
+    """Candidate flags outside the 13-pixel interior (which the reference's border lambda never produces,
+    inference.hpp:318-330) are cleared on the staged copy: same result as without them, in every matcher."""
+    from opengpc_b200.synth import synth_pair
+    L, R = synth_pair(256, 64, 77)
+    ctx.set_forest(FORESTS["tau"])
+    hl, hr = ctx.hash(L, 5, want_image=True)[2], ctx.hash(R, 5, want_image=True)[2]
+    s = g.sparsematch_settings()
+    base = ctx.match_hash_images(hl, hr, s)
+    dl, dr = hl.copy(), hr.copy()
+    rng = np.random.default_rng(3)
+    for img in (dl, dr):
+        img[:13, :] = rng.integers(0, 1 << 31, (13, 256), dtype=np.uint32) | 0x80000000
+        img[-13:, :] = 0x80000001
+        img[:, :13] |= 0x80000000
+        img[:, -13:] = rng.integers(0, 1 << 31, (64, 13), dtype=np.uint32) | 0x80000000
+    for matcher in (g.MATCHER_AUTO, g.MATCHER_ROWS_GENERAL, g.MATCHER_SORT):
+        ctx.set_matcher(matcher)
+        try:
+            assert np.array_equal(ctx.match_hash_images(dl, dr, s), base), matcher
+            assert np.array_equal(ctx.match_hash_images(dl, dr, g.make_settings(thr=5, disp_high=128, vt=1, epipolar=False)),
+                                  ctx.match_hash_images(hl, hr, g.make_settings(thr=5, disp_high=128, vt=1, epipolar=False))), matcher
+        finally:
+            ctx.set_matcher(g.MATCHER_AUTO)
 
 
 def test_find_correspondences_kats_and_random(g, ctx, golden, oracle):
@@ -152,6 +188,38 @@ def test_resident_images(g, ctx, oracle):
         want = oracle.correspondences(L, R, of, osettings(5, 128, vt, epi))
         got = np.stack([corr["xs"], corr["ys"], corr["xt"], corr["yt"]], 1)
         assert np.array_equal(got, want), (epi, len(got), len(want))
+    il.release(); ir.release()
+    # the cache of a resident image: every combination of cached / stale state gives the oracle's result, and the
+    # cached paths launch fewer kernels (matcher only: no A1, no A2)
+    ref5, _, _ = oracle.pair(L, R, of, osettings(5, 128, 0, True))
+    ref9, _, _ = oracle.pair(L, R, of, osettings(9, 128, 0, True))
+    of0 = oracle.read_forest(FORESTS["zero"])
+    ref5z, _, _ = oracle.pair(L, R, of0, osettings(5, 128, 0, True))
+    s5, s9 = g.make_settings(thr=5, disp_high=128, vt=0, epipolar=True), g.make_settings(thr=9, disp_high=128, vt=0, epipolar=True)
+    il, ir = ctx.upload(L), ctx.upload(R)
+    n0 = ctx.launches
+    assert np.array_equal(ctx.match_images(il, ir, s5)[0], ref5)                # nothing cached: both kernels
+    cold = ctx.launches - n0
+    _, _, mk = il.preprocess(5, images=False)
+    ir.preprocess(5, images=False)
+    assert np.array_equal(mk, omk)
+    n0 = ctx.launches
+    assert np.array_equal(ctx.match_images(il, ir, s5)[0], ref5)                # hash images cached: matcher only
+    warm = ctx.launches - n0
+    assert warm == cold - 2, (cold, warm)
+    assert np.array_equal(ctx.match_images(il, ir, s9)[0], ref9)                # other threshold: recomputed from the raw image
+    assert np.array_equal(ctx.match_images(il, ir, s5)[0], ref5)
+    ctx.set_forest(FORESTS["zero"])                                             # other forest: kernel A2 only, then cached again
+    n0 = ctx.launches
+    assert np.array_equal(ctx.match_images(il, ir, s5)[0], ref5z)
+    assert ctx.launches - n0 == cold - 1
+    n0 = ctx.launches
+    assert np.array_equal(ctx.match_images(il, ir, s5)[0], ref5z)
+    assert ctx.launches - n0 == warm
+    ctx.set_forest(FORESTS["tau"])
+    sm2, gr2 = il.fetch(5)
+    assert np.array_equal(sm2, osm) and np.array_equal(gr2, ogr)
+    assert np.array_equal(ctx.match_images(il, ir, s5)[0], ref5)
     il.release(); ir.release()
     with g.Context(device=0, max_w=768, max_h=200, max_batch=1) as other:
         io = other.upload(L)
