@@ -201,6 +201,28 @@ int gpc_set_matcher(gpc_ctx* ctx, int matcher);
  * precompiled kernel is in use (NVRTC absent, build failure, GPC_JIT=0).  Results are identical. */
 const char* gpc_jit_status(const gpc_ctx* ctx);
 
+/* ---- gpc_pool: one resident context + one host thread per GPU (multi-GPU driver) ----------
+ * The reference has no multi-device path; stereo pairs are independent units, so a batch is cut into chunks that are
+ * dealt round-robin to the devices.  Every device pipelines its chunks (upload / kernels / download) and the supports
+ * land in pair order directly in the caller's buffer -- no device-to-device traffic, no collective, no second host copy.
+ * gpc_pool_match_batch has gpc_match_batch's arguments and result.  `devices` may name a device more than once (several
+ * contexts on one GPU).  max_batch_per_device bounds the pairs one device receives per call (ceil(n_pairs / n) + a
+ * chunk).  A pool is driven from one host thread at a time. */
+typedef struct gpc_pool gpc_pool;
+int gpc_pool_create(gpc_pool** out, const int* devices, int n_devices, int max_w, int max_h, int max_batch_per_device);
+void gpc_pool_destroy(gpc_pool* pool);
+int gpc_pool_size(const gpc_pool* pool);
+gpc_ctx* gpc_pool_context(gpc_pool* pool, int i);            /* the i-th device's context (settings such as gpc_set_matcher) */
+const char* gpc_pool_last_error(const gpc_pool* pool);
+int64_t gpc_pool_launch_count(const gpc_pool* pool);
+int gpc_pool_set_forest(gpc_pool* pool, const gpc_forest* forest);
+int gpc_pool_set_result_mode(gpc_pool* pool, int mode);
+int gpc_pool_match_batch(gpc_pool* pool, const uint8_t* images, int n_pairs, int w, int h, const gpc_settings* s,
+                         gpc_support* out, int64_t cap, int64_t* offsets, int32_t* n_cand);
+/* page-locked host memory usable by every device (cudaHostAllocPortable) for `images` / `out`; NULL on failure */
+void* gpc_host_alloc(size_t bytes);
+void gpc_host_free(void* p);
+
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t gpc_launch_count(const gpc_ctx* ctx);
 /* process-unique serial of a context (never reused, unlike its address) */

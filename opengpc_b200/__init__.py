@@ -5,8 +5,8 @@ Layout: csrc/ (hand-written CUDA kernels + the C ABI of include/gpc_b200.h), cap
 binding used by tests and bench.py), synth.py (synthetic stereo pairs), build.py (nvcc build).
 The drop-in C++ API mirroring gpc::inference::Forest is in include/gpc/.
 """
-from .capi import (CORR_DTYPE, MATCHER_AUTO, MATCHER_ROWS_GENERAL, MATCHER_SORT, Context, GpcError, GpcForest, GpcSettings, SUPPORT_DTYPE, load_library, make_forest, make_settings,
+from .capi import (CORR_DTYPE, MATCHER_AUTO, MATCHER_ROWS_GENERAL, MATCHER_SORT, Context, GpcError, Pool, GpcForest, GpcSettings, SUPPORT_DTYPE, load_library, make_forest, make_settings,
                    read_forest, sparsematch_settings)
 
-__all__ = ["CORR_DTYPE", "MATCHER_AUTO", "MATCHER_ROWS_GENERAL", "MATCHER_SORT", "Context", "GpcError", "GpcForest", "GpcSettings", "SUPPORT_DTYPE", "load_library", "make_forest",
+__all__ = ["CORR_DTYPE", "MATCHER_AUTO", "MATCHER_ROWS_GENERAL", "MATCHER_SORT", "Context", "GpcError", "Pool", "GpcForest", "GpcSettings", "SUPPORT_DTYPE", "load_library", "make_forest",
            "make_settings", "read_forest", "sparsematch_settings"]

@@ -23,7 +23,9 @@ SYMBOLS = ["gpc_create", "gpc_destroy", "gpc_last_error", "gpc_status_string", "
            "gpc_read_forest", "gpc_set_forest", "gpc_match_pair", "gpc_match_batch", "gpc_match_batch_device",
            "gpc_preprocess", "gpc_hash", "gpc_match_hash_images", "gpc_launch_count", "gpc_enable_kernel_timing",
            "gpc_kernel_times", "gpc_hash_smooth", "gpc_image_upload", "gpc_image_release", "gpc_image_preprocess",
-           "gpc_match_images", "gpc_correspond_images", "gpc_find_correspondences", "gpc_hashmatch", "gpc_set_result_mode", "gpc_set_matcher", "gpc_match_pyramid", "gpc_jit_status", "gpc_context_id", "gpc_image_fetch", "gpc_fetch_supports"]
+           "gpc_match_images", "gpc_correspond_images", "gpc_find_correspondences", "gpc_hashmatch", "gpc_set_result_mode", "gpc_set_matcher", "gpc_match_pyramid", "gpc_jit_status", "gpc_context_id", "gpc_image_fetch", "gpc_fetch_supports",
+           "gpc_pool_create", "gpc_pool_destroy", "gpc_pool_size", "gpc_pool_context", "gpc_pool_last_error", "gpc_pool_launch_count",
+           "gpc_pool_set_forest", "gpc_pool_set_result_mode", "gpc_pool_match_batch", "gpc_host_alloc", "gpc_host_free"]
 KERNEL_NAMES = ["smooth_sobel", "hash_tiles", "match_rows", "scans", "emit_supports"]
 
 
@@ -68,6 +70,20 @@ def load_library():
     lib.gpc_destroy.argtypes = [C.c_void_p]
     lib.gpc_image_release.restype = None
     lib.gpc_image_release.argtypes = [C.c_void_p]
+    lib.gpc_pool_destroy.restype = None
+    lib.gpc_pool_destroy.argtypes = [C.c_void_p]
+    lib.gpc_pool_last_error.restype = C.c_char_p
+    lib.gpc_pool_last_error.argtypes = [C.c_void_p]
+    lib.gpc_pool_launch_count.restype = C.c_int64
+    lib.gpc_pool_launch_count.argtypes = [C.c_void_p]
+    lib.gpc_pool_context.restype = C.c_void_p
+    lib.gpc_pool_context.argtypes = [C.c_void_p, C.c_int]
+    lib.gpc_host_alloc.restype = C.c_void_p
+    lib.gpc_host_alloc.argtypes = [C.c_size_t]
+    lib.gpc_host_free.restype = None
+    lib.gpc_host_free.argtypes = [C.c_void_p]
+    lib.gpc_context_id.restype = C.c_int64
+    lib.gpc_context_id.argtypes = [C.c_void_p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int:
@@ -327,6 +343,70 @@ class Context:
         self._check(self.lib.gpc_correspond_images(self._h, left.handle, right.handle, C.byref(settings), _ptr(out),
                                                    C.c_int(cap), C.byref(n)))
         return out[:n.value].copy()
+
+
+class Pool:
+    """gpc_pool: one resident context and host thread per listed device; match_batch has Context.match_batch's result."""
+
+    def __init__(self, devices, max_w=1024, max_h=436, max_batch_per_device=1):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        rc = self.lib.gpc_pool_create(C.byref(self._h), devs, len(devices), int(max_w), int(max_h), int(max_batch_per_device))
+        if rc != GPC_OK:
+            raise GpcError(rc, self.lib.gpc_last_error(None).decode())
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.gpc_pool_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != GPC_OK:
+            raise GpcError(rc, self.lib.gpc_pool_last_error(self._h).decode())
+
+    @property
+    def launches(self):
+        return int(self.lib.gpc_pool_launch_count(self._h))
+
+    def set_forest(self, forest):
+        if isinstance(forest, (str, bytes, os.PathLike)):
+            forest = read_forest(forest)
+        self._check(self.lib.gpc_pool_set_forest(self._h, C.byref(forest)))
+
+    def set_result_mode(self, naive):
+        self._check(self.lib.gpc_pool_set_result_mode(self._h, 1 if naive else 0))
+
+    def set_matcher(self, matcher):
+        for i in range(len(self.devices)):
+            rc = self.lib.gpc_set_matcher(C.c_void_p(self.lib.gpc_pool_context(self._h, i)), int(matcher))
+            if rc != GPC_OK:
+                raise GpcError(rc, "gpc_set_matcher")
+
+    def match_batch_raw(self, images_ptr, n_pairs, w, h, settings, out_ptr, cap, offsets_ptr, n_cand_ptr=None):
+        self._check(self.lib.gpc_pool_match_batch(self._h, C.c_void_p(images_ptr), n_pairs, w, h, C.byref(settings),
+                                                  C.c_void_p(out_ptr), C.c_int64(cap), C.c_void_p(offsets_ptr),
+                                                  C.c_void_p(n_cand_ptr or 0)))
+
+    def match_batch(self, images, settings, cap=None):
+        """images uint8 [n_pairs, 2, h, w] -> (supports, offsets[n_pairs+1], n_cand[n_pairs,2])."""
+        images = np.ascontiguousarray(images, np.uint8)
+        n_pairs, _, h, w = images.shape
+        cap = max(n_pairs * (w - 26) * (h - 26), 1) if cap is None else cap
+        out = np.empty(max(cap, 1), SUPPORT_DTYPE)
+        offsets = np.zeros(n_pairs + 1, np.int64)
+        n_cand = np.zeros((n_pairs, 2), np.int32)
+        self.match_batch_raw(images.ctypes.data, n_pairs, w, h, settings, out.ctypes.data, cap, offsets.ctypes.data, n_cand.ctypes.data)
+        return out[:offsets[-1]].copy(), offsets, n_cand
 
 
 class ResidentImage:

@@ -10,8 +10,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -656,37 +659,80 @@ int gpc_match_batch_device(gpc_ctx* c, const uint8_t* d_images, int n_pairs, int
   return run_match(c, Slot{0, c->stream}, n_pairs, w, h, s, d_out, cap_per_pair, false, d_n_out, d_n_cand);
 }
 
-// Pipelined body of gpc_match_batch (row matcher): the batch is cut into chunks of pairs, each on its
-// own slice of the resident buffers; one stream uploads all chunks back to back, a second runs the
-// kernels chunk after chunk, a third downloads each chunk's supports as soon as its count is known --
-// upload, kernels and download overlap (PCIe is full duplex).
-static int match_batch_pipelined(gpc_ctx* c, const uint8_t* images, int n_pairs, int w, int h, const gpc_settings* s,
-                                 gpc_support* out, int64_t cap, int64_t* offsets, int32_t* n_cand) {
+// ---- chunked, pipelined batches ---------------------------------------------------------------------------------
+// A batch is cut into chunks of pairs.  Chunk k's supports start where the supports of chunks 0 .. k-1 end, so a
+// download can only be aimed once every earlier chunk has reported its count.  ChunkBoard is that bookkeeping; with one
+// context it is trivial, with a pool (one context and host thread per GPU, chunks dealt round-robin) it is the only
+// thing the workers share: a host-side decoupled look-back.  Nothing is copied twice -- every chunk's supports go from
+// its device straight to their final place in the caller's buffer.
+struct ChunkBoard {
+  std::vector<int> first;                 // [n_chunks + 1] first pair of each chunk
+  std::vector<long long> total;           // [n_chunks] supports of the chunk, valid once known[k]
+  std::vector<char> known;
+  std::mutex mu;
+  std::condition_variable cv;
+  bool failed = false;                    // a worker gave up: nobody waits any longer
+
+  // chunk sizes ramp up at the start and down at the end (CH/4, CH/2, CH, ..., CH, CH/2, CH/4): the first upload and
+  // the last kernels + download are the only parts of the pipeline nothing overlaps
+  void plan(int n_pairs, int CH) {
+    std::vector<int> sizes, ramp;
+    for (int v = std::max(1, CH / 4); v < CH; v *= 2) ramp.push_back(v);
+    int ramp_sum = 0;
+    for (int v : ramp) ramp_sum += v;
+    int rest = n_pairs;
+    const bool ramped = n_pairs >= 2 * ramp_sum + CH;
+    if (ramped) { sizes = ramp; rest -= 2 * ramp_sum; }
+    for (; rest > 0; rest -= CH) sizes.push_back(std::min(CH, rest));
+    if (ramped) sizes.insert(sizes.end(), ramp.rbegin(), ramp.rend());
+    first.assign(sizes.size() + 1, 0);
+    for (size_t k = 0; k < sizes.size(); k++) first[k + 1] = first[k] + sizes[k];
+    total.assign(sizes.size(), 0);
+    known.assign(sizes.size(), 0);
+  }
+  int n_chunks() const { return (int)total.size(); }
+  void publish(int k, long long t) {
+    { std::lock_guard<std::mutex> lk(mu); total[(size_t)k] = t; known[(size_t)k] = 1; }
+    cv.notify_all();
+  }
+  void fail_all() {
+    { std::lock_guard<std::mutex> lk(mu); failed = true; }
+    cv.notify_all();
+  }
+  // supports of chunks 0 .. k-1; false if another worker failed
+  bool base_of(int k, long long* base) {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] {
+      if (failed) return true;
+      for (int j = 0; j < k; j++) if (!known[(size_t)j]) return false;
+      return true;
+    });
+    if (failed) return false;
+    long long b = 0;
+    for (int j = 0; j < k; j++) b += total[(size_t)j];
+    *base = b;
+    return true;
+  }
+};
+
+// The chunks `mine` (ascending) of the board on context c: one stream uploads them back to back, a second runs the
+// kernels chunk after chunk, a third downloads each chunk's supports as soon as its place is known -- upload, kernels
+// and download overlap (PCIe is full duplex).  The chunks occupy consecutive slices of the context's resident buffers.
+// *need (optional) receives the supports of the whole batch seen by this worker's last chunk base + its own total.
+static int run_chunks(gpc_ctx* c, ChunkBoard& board, const std::vector<int>& mine, const uint8_t* images, int w, int h,
+                      const gpc_settings* s, gpc_support* out, int64_t cap, int64_t* offsets, int32_t* n_cand, bool* overflow_out) {
   const size_t P = (size_t)w * h;
-  const int CH = c->chunk_pairs;
   const long long per_pair = c->out_cap / c->max_batch;
   // whatever the exit path, no copy from `images` or into `out` may still be queued when the caller gets control back
   struct LaneGuard {
     gpc_ctx* c;
     ~LaneGuard() { for (int l = 0; l < gpc_ctx::kLanes; l++) cudaStreamSynchronize(c->lane_stream[l]); }
   } lane_guard{c};
-  // chunk sizes ramp up at the start and down at the end (CH/4, CH/2, CH, ..., CH, CH/2, CH/4): the
-  // first upload and the last kernels + download are the only parts of the pipeline nothing overlaps
-  std::vector<int> sizes;
-  {
-    std::vector<int> ramp;
-    for (int v = std::max(1, CH / 4); v < CH; v *= 2) ramp.push_back(v);
-    int ramp_sum = 0;
-    for (int v : ramp) ramp_sum += v;
-    int rest = n_pairs;
-    if (n_pairs >= 2 * ramp_sum + CH) { sizes = ramp; rest -= 2 * ramp_sum; }
-    for (; rest > 0; rest -= CH) sizes.push_back(std::min(CH, rest));
-    if (n_pairs >= 2 * ramp_sum + CH) sizes.insert(sizes.end(), ramp.rbegin(), ramp.rend());
-  }
-  const int nch = (int)sizes.size();
-  std::vector<int> first(nch + 1, 0);
-  for (int k = 0; k < nch; k++) first[k + 1] = first[k] + sizes[k];
-  while ((int)c->ev_chunk.size() < 2 * nch) {
+  const int nm = (int)mine.size();
+  std::vector<int> local0((size_t)nm + 1, 0);                       // first local pair slot of each of my chunks
+  for (int i = 0; i < nm; i++) local0[(size_t)i + 1] = local0[(size_t)i] + (board.first[(size_t)mine[(size_t)i] + 1] - board.first[(size_t)mine[(size_t)i]]);
+  if (local0[(size_t)nm] > c->max_batch) return fail(c, GPC_E_DIMS, "image or batch exceeds the context's capacity");
+  while ((int)c->ev_chunk.size() < 2 * nm) {
     cudaEvent_t e;
     GPC_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->ev_chunk.push_back(e);
@@ -695,16 +741,16 @@ static int match_batch_pipelined(gpc_ctx* c, const uint8_t* images, int n_pairs,
   cudaStream_t s_up = c->lane_stream[0], s_run = c->lane_stream[1], s_down = c->lane_stream[2];
   GPC_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));               // order after earlier work of the context
   for (int l = 0; l < gpc_ctx::kLanes; l++) GPC_CUDA(c, cudaStreamWaitEvent(c->lane_stream[l], c->ev_fork, 0));
-  for (int k = 0; k < nch; k++) {
-    const int p0 = first[k], n = sizes[k];
-    GPC_CUDA(c, cudaMemcpyAsync(c->d_raw + (size_t)(2 * p0) * P, images + (size_t)(2 * p0) * P, 2 * (size_t)n * P,
+  for (int i = 0; i < nm; i++) {
+    const int g0 = board.first[(size_t)mine[(size_t)i]], n = local0[(size_t)i + 1] - local0[(size_t)i], p0 = local0[(size_t)i];
+    GPC_CUDA(c, cudaMemcpyAsync(c->d_raw + (size_t)(2 * p0) * P, images + (size_t)(2 * g0) * P, 2 * (size_t)n * P,
                                 cudaMemcpyHostToDevice, s_up));
-    GPC_CUDA(c, cudaEventRecord(c->ev_chunk[2 * k], s_up));
+    GPC_CUDA(c, cudaEventRecord(c->ev_chunk[2 * (size_t)i], s_up));
   }
-  for (int k = 0; k < nch; k++) {
-    const int p0 = first[k], n = sizes[k];
+  for (int i = 0; i < nm; i++) {
+    const int n = local0[(size_t)i + 1] - local0[(size_t)i], p0 = local0[(size_t)i];
     const Slot sl{p0, s_run};
-    GPC_CUDA(c, cudaStreamWaitEvent(s_run, c->ev_chunk[2 * k], 0));
+    GPC_CUDA(c, cudaStreamWaitEvent(s_run, c->ev_chunk[2 * (size_t)i], 0));
     int rc = run_preprocess(c, sl, c->d_raw + (size_t)(2 * p0) * P, 2 * n, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
     if (rc) return rc;
     rc = run_match(c, sl, n, w, h, s, c->d_out + (size_t)p0 * per_pair, (long long)n * per_pair, true, c->d_totals + p0,
@@ -715,26 +761,41 @@ static int match_batch_pipelined(gpc_ctx* c, const uint8_t* images, int n_pairs,
     if (n_cand)
       GPC_CUDA(c, cudaMemcpyAsync(c->h_counts + 2 * p0, c->d_ncand + 2 * p0, 2 * (size_t)n * sizeof(int32_t),
                                   cudaMemcpyDeviceToHost, s_run));
-    GPC_CUDA(c, cudaEventRecord(c->ev_chunk[2 * k + 1], s_run));
+    GPC_CUDA(c, cudaEventRecord(c->ev_chunk[2 * (size_t)i + 1], s_run));
   }
-  long long total = 0;
   bool overflow = false;
-  offsets[0] = 0;
-  for (int k = 0; k < nch; k++) {                                      // downloads follow the kernels chunk by chunk
-    const int p0 = first[k], n = sizes[k];
-    GPC_CUDA(c, cudaEventSynchronize(c->ev_chunk[2 * k + 1]));
+  for (int i = 0; i < nm; i++) {                                       // downloads follow the kernels chunk by chunk
+    const int k = mine[(size_t)i], g0 = board.first[(size_t)k], n = local0[(size_t)i + 1] - local0[(size_t)i], p0 = local0[(size_t)i];
+    GPC_CUDA(c, cudaEventSynchronize(c->ev_chunk[2 * (size_t)i + 1]));
     const long long* pb = c->h_pair_base + 2 * p0;
-    for (int i = 0; i < n; i++) offsets[p0 + i + 1] = total + pb[i + 1];
-    if (n_cand) std::memcpy(n_cand + 2 * p0, c->h_counts + 2 * p0, 2 * (size_t)n * sizeof(int32_t));
     const long long m = pb[n];
-    if (total + m > cap) overflow = true;
+    board.publish(k, m);
+    long long base = 0;
+    if (!board.base_of(k, &base)) return fail(c, GPC_E_CUDA, "another device of the pool failed");
+    for (int j = 0; j < n; j++) offsets[g0 + j + 1] = base + pb[j + 1];
+    if (n_cand) std::memcpy(n_cand + 2 * g0, c->h_counts + 2 * p0, 2 * (size_t)n * sizeof(int32_t));
+    if (base + m > cap) overflow = true;
     else if (m > 0)
-      GPC_CUDA(c, cudaMemcpyAsync(out + total, c->d_out + (size_t)p0 * per_pair, (size_t)m * sizeof(gpc_support),
+      GPC_CUDA(c, cudaMemcpyAsync(out + base, c->d_out + (size_t)p0 * per_pair, (size_t)m * sizeof(gpc_support),
                                   cudaMemcpyDeviceToHost, s_down));
-    total += m;
   }
   for (int l = 0; l < gpc_ctx::kLanes; l++) GPC_CUDA(c, cudaStreamSynchronize(c->lane_stream[l]));
-  if (overflow) return fail(c, GPC_E_CAPACITY, "support buffer too small: need " + std::to_string(total));
+  if (overflow_out) *overflow_out = overflow;
+  return GPC_OK;
+}
+
+// Pipelined body of gpc_match_batch: every chunk on this one context.
+static int match_batch_pipelined(gpc_ctx* c, const uint8_t* images, int n_pairs, int w, int h, const gpc_settings* s,
+                                 gpc_support* out, int64_t cap, int64_t* offsets, int32_t* n_cand) {
+  ChunkBoard board;
+  board.plan(n_pairs, c->chunk_pairs);
+  std::vector<int> mine((size_t)board.n_chunks());
+  for (int k = 0; k < board.n_chunks(); k++) mine[(size_t)k] = k;
+  offsets[0] = 0;
+  bool overflow = false;
+  const int rc = run_chunks(c, board, mine, images, w, h, s, out, cap, offsets, n_cand, &overflow);
+  if (rc) return rc;
+  if (overflow) return fail(c, GPC_E_CAPACITY, "support buffer too small: need " + std::to_string(offsets[n_pairs]));
   return GPC_OK;
 }
 
@@ -1277,5 +1338,172 @@ int gpc_match_pyramid(gpc_ctx* c, const uint8_t* left, const uint8_t* right, int
   if (overflow) return fail(c, GPC_E_CAPACITY, "support buffer too small: need " + std::to_string(total));
   return GPC_OK;
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// gpc_pool: the library-level multi-GPU driver.  One resident context and one host thread
+// per GPU; a batch is cut into chunks that are dealt round-robin to the devices, every device pipelines its chunks
+// (upload / kernels / download) and the supports land, in pair order, directly in the caller's buffer (ChunkBoard).
+// Pairs are independent units: there is no device-to-device traffic and no collective.
+// ------------------------------------------------------------------------------------------------------------------
+struct gpc_pool {
+  std::vector<gpc_ctx*> ctx;
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv_job, cv_done;
+  uint64_t job_serial = 0;
+  int pending = 0;
+  bool quit = false;
+  std::function<int(int)> job;          // worker index -> status
+  std::vector<int> rc;
+  std::string err;
+  int max_w = 0, max_h = 0, max_batch = 0;
+
+  void worker_loop(int g) {
+    uint64_t seen = 0;
+    for (;;) {
+      std::function<int(int)> fn;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_job.wait(lk, [&] { return quit || job_serial != seen; });
+        if (quit) return;
+        seen = job_serial;
+        fn = job;
+      }
+      const int r = fn(g);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        rc[(size_t)g] = r;
+        pending--;
+      }
+      cv_done.notify_all();
+    }
+  }
+  // runs fn(worker) on every worker thread and waits; returns the first non-zero status
+  int run(std::function<int(int)> fn) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      job = std::move(fn);
+      pending = (int)ctx.size();
+      job_serial++;
+    }
+    cv_job.notify_all();
+    std::unique_lock<std::mutex> lk(mu);
+    cv_done.wait(lk, [&] { return pending == 0; });
+    for (size_t g = 0; g < ctx.size(); g++)
+      if (rc[g] != GPC_OK) { err = "device " + std::to_string(ctx[g]->device) + ": " + ctx[g]->err; return rc[g]; }
+    return GPC_OK;
+  }
+};
+
+extern "C" {
+
+int gpc_pool_create(gpc_pool** out, const int* devices, int n_devices, int max_w, int max_h, int max_batch_per_device) {
+  if (!out) return fail(nullptr, GPC_E_ARG, "out is NULL");
+  *out = nullptr;
+  if (!devices || n_devices <= 0 || n_devices > 64) return fail(nullptr, GPC_E_ARG, "need 1..64 devices");
+  gpc_pool* p = new gpc_pool();
+  p->max_w = max_w; p->max_h = max_h; p->max_batch = max_batch_per_device;
+  for (int g = 0; g < n_devices; g++) {
+    gpc_ctx* c = nullptr;
+    const int rc = gpc_create(&c, devices[g], max_w, max_h, max_batch_per_device);
+    if (rc != GPC_OK) {
+      for (gpc_ctx* d : p->ctx) gpc_destroy(d);
+      delete p;
+      return rc;                                       // gpc_last_error(NULL) has the text
+    }
+    p->ctx.push_back(c);
+  }
+  p->rc.assign((size_t)n_devices, GPC_OK);
+  for (int g = 0; g < n_devices; g++) p->workers.emplace_back([p, g] { p->worker_loop(g); });
+  *out = p;
+  return GPC_OK;
+}
+
+void gpc_pool_destroy(gpc_pool* p) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(p->mu);
+    p->quit = true;
+  }
+  p->cv_job.notify_all();
+  for (std::thread& t : p->workers) t.join();
+  for (gpc_ctx* c : p->ctx) gpc_destroy(c);
+  delete p;
+}
+
+int gpc_pool_size(const gpc_pool* p) { return p ? (int)p->ctx.size() : 0; }
+gpc_ctx* gpc_pool_context(gpc_pool* p, int i) { return (p && i >= 0 && i < (int)p->ctx.size()) ? p->ctx[(size_t)i] : nullptr; }
+const char* gpc_pool_last_error(const gpc_pool* p) { return p ? p->err.c_str() : g_create_error.c_str(); }
+
+int64_t gpc_pool_launch_count(const gpc_pool* p) {
+  int64_t n = 0;
+  if (p) for (gpc_ctx* c : p->ctx) n += c->launches;
+  return n;
+}
+
+// every device bakes (and, with NVRTC, specialises) the forest on its own thread
+int gpc_pool_set_forest(gpc_pool* p, const gpc_forest* f) {
+  if (!p || !f) return GPC_E_ARG;
+  return p->run([p, f](int g) { return gpc_set_forest(p->ctx[(size_t)g], f); });
+}
+
+int gpc_pool_set_result_mode(gpc_pool* p, int mode) {
+  if (!p) return GPC_E_ARG;
+  return p->run([p, mode](int g) { return gpc_set_result_mode(p->ctx[(size_t)g], mode); });
+}
+
+// gpc_match_batch over all devices of the pool: same arguments, same result (pair order, packed supports).
+int gpc_pool_match_batch(gpc_pool* p, const uint8_t* images, int n_pairs, int w, int h, const gpc_settings* s,
+                         gpc_support* out, int64_t cap, int64_t* offsets, int32_t* n_cand) {
+  if (!p) return GPC_E_ARG;
+  auto bad = [p](int code, const char* msg) { p->err = msg; return code; };
+  if (!images || !offsets || cap < 0 || (cap > 0 && !out) || n_pairs <= 0) return bad(GPC_E_ARG, "null argument");
+  if (!s) return bad(GPC_E_ARG, "settings is NULL");
+  const int G = (int)p->ctx.size();
+  for (gpc_ctx* c : p->ctx) {
+    int rc = check_dims(c, w, h, 1); if (rc) { p->err = c->err; return rc; }
+    rc = check_settings(c, s); if (rc) { p->err = c->err; return rc; }
+    if (!c->has_forest) return bad(GPC_E_FOREST, "no forest set");
+  }
+  if (h <= 2 * gpc::kRadius) {                         // nothing can match: no kernels needed
+    for (int i = 0; i <= n_pairs; i++) offsets[i] = 0;
+    if (n_cand) std::memset(n_cand, 0, 2 * (size_t)n_pairs * sizeof(int32_t));
+    return GPC_OK;
+  }
+  ChunkBoard board;
+  const int CH = std::max(1, std::min(p->ctx[0]->chunk_pairs, std::max(2, n_pairs / (4 * G))));
+  board.plan(n_pairs, CH);
+  std::vector<std::vector<int>> mine((size_t)G);
+  for (int k = 0; k < board.n_chunks(); k++) mine[(size_t)(k % G)].push_back(k);
+  offsets[0] = 0;
+  std::vector<char> overflow((size_t)G, 0);
+  const int rc = p->run([&](int g) {
+    gpc_ctx* c = p->ctx[(size_t)g];
+    if (mine[(size_t)g].empty()) return (int)GPC_OK;
+    cudaError_t e = cudaSetDevice(c->device);
+    int r = GPC_OK;
+    if (e != cudaSuccess) r = fail(c, GPC_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    if (r == GPC_OK && use_sort_matcher(c, s)) r = ensure_global_ws(c, sort_workspace_bytes(w, h, CH, nullptr));
+    bool ov = false;
+    if (r == GPC_OK) r = run_chunks(c, board, mine[(size_t)g], images, w, h, s, out, cap, offsets, n_cand, &ov);
+    overflow[(size_t)g] = ov ? 1 : 0;
+    if (r != GPC_OK) board.fail_all();
+    return r;
+  });
+  if (rc) return rc;
+  for (char o : overflow)
+    if (o) return bad(GPC_E_CAPACITY, ("support buffer too small: need " + std::to_string(offsets[n_pairs])).c_str());
+  return GPC_OK;
+}
+
+// Page-locked host memory every device of the machine can DMA from / to (cudaHostAllocPortable): what `images`
+// and `out` of the batch calls should live in.  Plain malloc'ed memory works too, at a fraction of the speed.
+void* gpc_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  return cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess ? p : nullptr;
+}
+void gpc_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 }  // extern "C"
