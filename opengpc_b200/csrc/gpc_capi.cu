@@ -27,6 +27,8 @@ int make_smooth_tensor_map(void* out_map, const uint8_t* base, int W, int H, int
 cudaError_t launch_hash_tiles(const void* tensor_map, const HashArgs&, const ForestDev&, int n_img, cudaStream_t);
 size_t match_smem_bytes(int wcap, int table_log2);
 size_t match_fast_smem_bytes(int nib_log2, int slot_log2, int pow2cap);
+size_t order_rows_smem_bytes(int pow2cap);
+int match_ov_cap();
 cudaError_t configure_match_rows(int max_smem);
 cudaError_t configure_match_global();
 cudaError_t launch_match_rows(const MatchArgs&, int n_pairs, int general, int sm_count, cudaStream_t);
@@ -94,6 +96,10 @@ struct gpc_ctx {
   int chunk_pairs = 16;
   int32_t* d_rowmatch = nullptr;   // [B][H]
   uint32_t* d_fb = nullptr;        // [B][2 * max_h + 2] row lists of the fast row matcher (one per slot, at p0 * stride)
+  uint32_t* d_big = nullptr;       // same, rows for the block-wide ordering kernel
+  unsigned long long* d_mrec = nullptr;   // [B][H][W] unordered match records (fast row matcher -> tail kernel)
+  uint32_t* d_ovbuf = nullptr;     // [B][H][4][ov_cap] overflow lists of the rows
+  int32_t* d_rowhdr = nullptr;     // [B][H][4]
   int sm_count = 148;
   int32_t* d_rowoff = nullptr;     // [B][H+1]
   int32_t* d_totals = nullptr;     // [B]
@@ -345,8 +351,10 @@ bool use_sort_matcher(const gpc_ctx* c, const gpc_settings* s) {
 
 // Kernels B, scan, C over the slot's hash images.  packed: supports of the slot's pairs back to back
 // from d_out[0], prefix in d_pair_base + 2 * p0; else pair i at d_out + i * cap.
+// foreign_hash: the hash images came from the caller (gpc_match_hash_images), so nothing is known about which state
+// bits are in use.
 int run_match(gpc_ctx* c, const Slot& sl, int n_pairs, int w, int h, const gpc_settings* s, gpc_support* d_out,
-              long long cap, bool packed, int32_t* d_n_out, int32_t* d_n_cand) {
+              long long cap, bool packed, int32_t* d_n_out, int32_t* d_n_cand, bool foreign_hash = false) {
   const size_t P = (size_t)w * h;
   const uint32_t* hash = c->d_hash + (size_t)(2 * sl.p0) * P;
   if (use_sort_matcher(c, s)) {
@@ -371,7 +379,13 @@ int run_match(gpc_ctx* c, const Slot& sl, int n_pairs, int w, int h, const gpc_s
   while ((int)gpc::match_smem_bytes(m.wcap, m.table_log2) > 72 * 1024 &&
          m.table_log2 > std::max(ceil_log2(4 * gpc::match_rows_threads(w)), m.x_bits + 1))
     m.table_log2--;                                  // wide rows: fewer, longer buckets keep >= 3 CTAs per SM
-  m.key_bits = 31;   // hash images may come from the caller (gpc_match_hash_images): assume full 31-bit states
+  // significant state bits (only the balance of the ordering buckets depends on it): the kernels place test t < 8 in
+  // bit t and test t > 8 in bit t - 1 (test 8 is OR-ed into bit 0, filter.hpp:574-584); the naive mode uses bits 0 .. T-1
+  {
+    const int T = c->has_forest ? c->forest_host.n_tests : 0;
+    const int bits = (c->result_mode == GPC_RESULTS_NAIVE) ? T : (T <= 8 ? T : T - 1);
+    m.key_bits = (foreign_hash || !c->has_forest) ? 31 : std::max(1, std::min(31, bits));
+  }
   // fast matcher: ~32 four-bit buckets and ~4 slots per candidate of a side.  Constraints: remainder + x of a slot
   // entry fit one word (slot_log2 >= x_bits), buckets refine slots (slot_log2 <= nib_log2 + 3), the byte offset of a
   // word fits 16 bits (nib_log2 <= 14), and the ordering pass (8 bytes per match) reuses both tables.
@@ -387,16 +401,24 @@ int run_match(gpc_ctx* c, const Slot& sl, int n_pairs, int w, int h, const gpc_s
   if (nib_env > 0) m.nib_log2 = std::min(14, std::max(nib_env, tbl_min));
   if (slot_env > 0) m.slot_log2 = std::min(m.nib_log2 + 3, std::max(slot_env, tbl_min));
   while ((1 << m.nib_log2) + (1 << m.slot_log2) < 2 * m.pow2cap) { if (m.nib_log2 < 14) m.nib_log2++; else m.slot_log2++; }
-  m.fb_list = c->d_fb + (size_t)sl.p0 * (2 * (size_t)c->max_h + 2);
+  // row lists: 2 header words per pair slot at the front of each array, then 2 * max_h entry words per pair slot
+  m.fb_hdr = c->d_fb + 2 * (size_t)sl.p0;
+  m.fb_ent = c->d_fb + 2 * (size_t)c->max_batch + (size_t)sl.p0 * 2 * c->max_h;
+  m.big_hdr = c->d_big + 2 * (size_t)sl.p0;
+  m.big_ent = c->d_big + 2 * (size_t)c->max_batch + (size_t)sl.p0 * 2 * c->max_h;
+  m.mrec = c->d_mrec + (size_t)sl.p0 * P;
+  m.ovbuf = c->d_ovbuf + (size_t)sl.p0 * h * 4 * gpc::match_ov_cap();
+  m.rowhdr = c->d_rowhdr + (size_t)sl.p0 * h * 4;
   const bool general = (c->matcher == GPC_MATCHER_ROWS_GENERAL);
   if ((int)gpc::match_smem_bytes(m.wcap, m.table_log2) > c->match_smem_max ||
-      (int)gpc::match_fast_smem_bytes(m.nib_log2, m.slot_log2, m.pow2cap) > c->match_smem_max)
+      (int)gpc::match_fast_smem_bytes(m.nib_log2, m.slot_log2, m.pow2cap) > c->match_smem_max ||
+      (int)gpc::order_rows_smem_bytes(m.pow2cap) > c->match_smem_max)
     return fail(c, GPC_E_DIMS, "image too wide for the row matcher's shared memory");
   if (h - 2 * gpc::kRadius <= 0) GPC_CUDA(c, cudaMemsetAsync(rowmatch, 0, (size_t)n_pairs * h * sizeof(int32_t), sl.stream));
   GPC_CUDA(c, gpc::launch_match_rows(m, n_pairs, general ? 1 : 0, c->sm_count, sl.stream));
   int rc = mark_on(c, sl); if (rc) return rc;                                      // event 3
   GPC_CUDA(c, gpc::launch_row_scan(rowmatch, rowcnt, h, n_pairs, rowoff, d_n_out, d_n_cand, sl.stream));
-  c->launches += general ? 2 : 3;
+  c->launches += general ? 2 : 5;
   const long long* pair_base = nullptr;
   if (packed) {
     GPC_CUDA(c, gpc::launch_pair_scan(d_n_out, n_pairs, c->d_pair_base + 2 * sl.p0, sl.stream));
@@ -481,6 +503,11 @@ int gpc_create(gpc_ctx** out, int device, int max_w, int max_h, int max_batch) {
   TRY(cudaMalloc(&c->d_rowmatch, B * max_h * sizeof(int32_t)));
   TRY(cudaMalloc(&c->d_fb, B * (2 * (size_t)max_h + 2) * sizeof(uint32_t)));
   TRY(cudaMemsetAsync(c->d_fb, 0, B * (2 * (size_t)max_h + 2) * sizeof(uint32_t), c->stream));
+  TRY(cudaMalloc(&c->d_big, B * (2 * (size_t)max_h + 2) * sizeof(uint32_t)));
+  TRY(cudaMemsetAsync(c->d_big, 0, B * (2 * (size_t)max_h + 2) * sizeof(uint32_t), c->stream));
+  TRY(cudaMalloc(&c->d_mrec, B * P * sizeof(unsigned long long)));
+  TRY(cudaMalloc(&c->d_ovbuf, B * (size_t)max_h * 4 * gpc::match_ov_cap() * sizeof(uint32_t)));
+  TRY(cudaMalloc(&c->d_rowhdr, B * (size_t)max_h * 4 * sizeof(int32_t)));
   TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
   TRY(cudaMalloc(&c->d_rowoff, B * (max_h + 1) * sizeof(int32_t)));
   TRY(cudaMalloc(&c->d_totals, B * sizeof(int32_t)));
@@ -504,7 +531,7 @@ void gpc_destroy(gpc_ctx* c) {
   { std::lock_guard<std::mutex> lk(g_registry_mu); g_registry.erase(c->id); }
   cudaSetDevice(c->device);
   for (auto& b : c->image_pool) cudaFree(b.second);
-  cudaFree(c->d_raw); cudaFree(c->d_smooth); cudaFree(c->d_cand); cudaFree(c->d_hash); cudaFree(c->d_stage); cudaFree(c->d_rows); cudaFree(c->d_lastrow); cudaFree(c->d_rowmatch); cudaFree(c->d_fb);
+  cudaFree(c->d_raw); cudaFree(c->d_smooth); cudaFree(c->d_cand); cudaFree(c->d_hash); cudaFree(c->d_stage); cudaFree(c->d_rows); cudaFree(c->d_lastrow); cudaFree(c->d_rowmatch); cudaFree(c->d_fb); cudaFree(c->d_big); cudaFree(c->d_mrec); cudaFree(c->d_ovbuf); cudaFree(c->d_rowhdr);
   for (int l = 0; l < gpc_ctx::kLanes; l++) if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   for (cudaEvent_t e : c->ev_chunk) cudaEventDestroy(e);
@@ -938,7 +965,7 @@ int gpc_match_hash_images(gpc_ctx* c, const uint32_t* hash_l, const uint32_t* ha
   GPC_CUDA(c, cudaMemcpyAsync(c->d_rows, rows.data(), (size_t)2 * h * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   GPC_CUDA(c, cudaMemcpyAsync(c->d_lastrow, rows.data() + (size_t)2 * h, 2 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   GPC_CUDA(c, cudaStreamSynchronize(c->stream));   // `rows` and `staged` are pageable and about to go out of scope
-  rc = run_match(c, Slot{0, c->stream}, 1, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand);
+  rc = run_match(c, Slot{0, c->stream}, 1, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand, true);
   if (rc) return rc;
   GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_totals, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   GPC_CUDA(c, cudaStreamSynchronize(c->stream));

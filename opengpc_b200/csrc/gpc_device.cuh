@@ -111,7 +111,13 @@ struct MatchArgs {
   // fast row matcher (match_rows_fast_kernel)
   int32_t nib_log2;        // log2 of the words of the 4-bit bucket table (8 buckets per word)
   int32_t slot_log2;       // log2 of the slot table; x_bits <= slot_log2 <= nib_log2
-  uint32_t* fb_list;       // rows handed to the general kernel: [0] count, [1] CTAs done, then (pair, row) words
+  uint32_t* fb_hdr;        // rows handed to the general kernel: hdr[0] count, hdr[1] CTAs done; ent = (pair, row) words
+  uint32_t* fb_ent;
+  uint32_t* big_hdr;       // rows handed to the block-wide ordering kernel, same layout
+  uint32_t* big_ent;
+  unsigned long long* mrec;  // [n_pair][H][W] unordered match records of a row: key << 32 | xl << 16 | xr
+  uint32_t* ovbuf;         // [n_pair][H][4][kOvCap] overflow lists of a row: left v, left x, right v, right x
+  int32_t* rowhdr;         // [n_pair][H][4] matches, left overflow, right overflow, done (1: nothing left for the tail kernel)
 };
 
 }  // namespace gpc

@@ -44,11 +44,12 @@ size_t match_smem_bytes(int wcap, int table_log2) {
   return pow2 * 8 + nb * 4 + body + 2 * kBuckets * 4 + 64;
 }
 
-// shared memory of the fast matcher: nib[2^nib_log2] u32 | slot[2^slot_log2] u32 | live list 2 x [pow2cap] u32 |
-// 4 overflow arrays | bcnt, bstart  (the ordering pass reuses nib + slot, which are dead by then)
+// shared memory of the fast matcher: nib[2^nib_log2] u32 | slot[2^slot_log2] u32 | live list 2 x [pow2cap] u32
 size_t match_fast_smem_bytes(int nib_log2, int slot_log2, int pow2cap) {
-  return ((size_t)4 << nib_log2) + ((size_t)4 << slot_log2) + (size_t)pow2cap * 8 + 4 * kOvCap * 4 + 2 * kBuckets * 4;
+  return ((size_t)4 << nib_log2) + ((size_t)4 << slot_log2) + (size_t)pow2cap * 8;
 }
+size_t order_rows_smem_bytes(int pow2cap) { return (size_t)pow2cap * 16 + 2 * kBuckets * 4; }
+int match_ov_cap() { return kOvCap; }
 
 // Orders the m matches of a row (records key << 32 | xl << 16 | xr in out[]) by state -- the keys are
 // unique -- and writes xl << 16 | xr to the row's slice of `stage`.  Counting pass on the top 8 state bits,
@@ -321,25 +322,24 @@ __device__ __forceinline__ void general_row(const MatchArgs& args, uint8_t* smem
   if (tid == 0) args.rowmatch[(size_t)pair * H + y] = m;
 }
 
-// list == nullptr: one CTA per (row, pair) of the grid.  Otherwise the CTAs walk the row list the fast
-// matcher left: list[0] = number of rows, list[1] = CTAs done, list[2 + 2i] = pair, list[3 + 2i] = row;
-// the last CTA to finish clears the two counters for the next launch.
+// hdr == nullptr: one CTA per (row, pair) of the grid.  Otherwise the CTAs walk the row list the fast matcher left
+// (push_row below); the last CTA to finish clears the two counters for the next launch.
 template <int KQ, int kThreadsB>
 __global__ void __launch_bounds__(kThreadsB)
-match_rows_general_kernel(const MatchArgs args, uint32_t* list) {
+match_rows_general_kernel(const MatchArgs args, uint32_t* hdr, const uint32_t* ent) {
   extern __shared__ __align__(16) uint8_t smem[];
-  if (list == nullptr) {
+  if (hdr == nullptr) {
     general_row<KQ, kThreadsB>(args, smem, blockIdx.y, kRadius + blockIdx.x);
     return;
   }
-  const uint32_t n = *reinterpret_cast<volatile uint32_t*>(list);
+  const uint32_t n = *reinterpret_cast<volatile uint32_t*>(hdr);
   for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-    general_row<KQ, kThreadsB>(args, smem, (int)list[2 + 2 * i], (int)list[3 + 2 * i]);
+    general_row<KQ, kThreadsB>(args, smem, (int)ent[2 * i], (int)ent[2 * i + 1]);
     __syncthreads();
   }
   if (threadIdx.x == 0) {
     __threadfence();
-    if (atomicAdd(&list[1], 1u) == gridDim.x - 1) { list[0] = 0u; list[1] = 0u; }
+    if (atomicAdd(&hdr[1], 1u) == gridDim.x - 1) { hdr[0] = 0u; hdr[1] = 0u; }
   }
 }
 
@@ -360,21 +360,14 @@ match_rows_general_kernel(const MatchArgs args, uint32_t* list) {
 //              coarser than the buckets).
 //   resolve  : one thread per live left entry: in a pair bucket it reads the slot -- same remainder = same
 //              state = match; a stranger's entry = its partner lost the slot -> overflow list.
-//   overflow : every left overflow entry counts equal states in both lists (tens of entries; complete per
-//              state, because equal states share a bucket and a bucket is listed as a whole).
-// A match is recorded in place in its live-list entry (x | xr << 13 | flag).  The row holding the globally
-// last right key (tail rules) and rows whose overflow lists do not fit are appended to a row list for the
-// general kernel.  Matches are ordered by state as before (counting pass + rank inside the bucket).
+// Matches (unordered) and the overflow lists go to global memory; the warp-per-row tail kernel below resolves the
+// overflow entries and orders the matches.  The row holding the globally last right key (tail rules) and rows whose
+// overflow lists do not fit are appended to a row list for the general kernel.
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kClassLut = (1u << 10) | (2u << 14) | (2u << 26) | (2u << 30);   // nibble -> 1 pair bucket, 2 overflow
-constexpr uint32_t kMatchFlag = 0x80000000u;
 #ifndef GPC_B_MINB
 #define GPC_B_MINB 6                          // resident 256-thread CTAs per SM the register budget allows
 #endif
-#ifndef GPC_B_OVLANES
-#define GPC_B_OVLANES 1
-#endif
-constexpr int kOvLanes = GPC_B_OVLANES;       // lanes sharing one left overflow entry (1: 16-byte reads)
 
 __device__ __forceinline__ uint32_t atom_add_shared(uint32_t* p, uint32_t v) {
   // plain atom: ptxas wraps a uniform-address atomicAdd whose result is used into a 20-instruction warp scan
@@ -383,27 +376,35 @@ __device__ __forceinline__ uint32_t atom_add_shared(uint32_t* p, uint32_t v) {
   return old;
 }
 
+// Row lists (rows handed to the general kernel / the block-wide ordering kernel): hdr[0] = number of rows,
+// hdr[1] = CTAs of the consuming kernel that are done, ent[2i] = pair, ent[2i + 1] = row.  Headers and entries live in
+// separate arrays: the slices of the resident buffers that different launches work on overlap in arbitrary ways.
+__device__ __forceinline__ void push_row(uint32_t* hdr, uint32_t* ent, int pair, int y) {
+  const uint32_t i = atomicAdd(&hdr[0], 1u);
+  ent[2 * i] = (uint32_t)pair; ent[2 * i + 1] = (uint32_t)y;
+}
+
 template <int KQ, int kThreadsB>
 __global__ void __launch_bounds__(kThreadsB, (KQ == 1 && kThreadsB <= 512) ? (GPC_B_MINB * 256) / kThreadsB : 1)
 match_rows_fast_kernel(const MatchArgs args) {
   extern __shared__ __align__(16) uint8_t smem[];
-  static_assert(kOvCap <= kThreadsB && kOvCap % 4 == 0, "one thread per left overflow entry, 16-byte reads");
+  static_assert(kOvCap % 4 == 0, "16-byte reads of the overflow lists");
   const int W = args.W, H = args.H, xb = args.x_bits, nwl = args.nib_log2, nsl = args.slot_log2;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x;
   const int y = kRadius + blockIdx.x, pair = blockIdx.y;
 
   uint32_t* nib = reinterpret_cast<uint32_t*>(smem);                                // [1 << nwl]
   uint32_t* slot = nib + ((size_t)1 << nwl);                                        // [1 << nsl]
   uint32_t* live_v = slot + ((size_t)1 << nsl);                                     // [pow2cap] live left candidates: v
-  uint32_t* live_x = live_v + args.pow2cap;                                         // [pow2cap] x, later | xr << 13 | kMatchFlag
-  uint32_t* ovl_s = live_x + args.pow2cap;                                          // overflow lists: left state, live index
-  uint32_t* ovl_i = ovl_s + kOvCap;
-  uint32_t* ovr_s = ovl_i + kOvCap;                                                 // right state, x
+  uint32_t* live_x = live_v + args.pow2cap;                                         // [pow2cap] x
+  __shared__ uint32_t n_live, n_ovl, n_ovr, n_out;
+  const size_t grow = (size_t)pair * H + y;                                         // this row's records in global memory:
+  unsigned long long* mrec = args.mrec + grow * W;                                  //   matches, unordered (key << 32 | xl << 16 | xr)
+  uint32_t* ovl_s = args.ovbuf + grow * (4 * kOvCap);                               //   overflow lists: left v, x
+  uint32_t* ovl_x = ovl_s + kOvCap;
+  uint32_t* ovr_s = ovl_x + kOvCap;                                                 //   right v, x
   uint32_t* ovr_x = ovr_s + kOvCap;
-  uint32_t* bcnt = ovr_x + kOvCap;                                                  // [kBuckets] x2
-  uint32_t* bstart = bcnt + kBuckets;
-  unsigned long long* out2 = reinterpret_cast<unsigned long long*>(nib);            // ordering pass: the tables are dead by then
-  __shared__ uint32_t n_live, n_ovl, n_ovr, n_out, big_bucket, warp_tot[kThreadsB / 32];
+  int32_t* hdr = args.rowhdr + grow * 4;                                            //   {matches, left overflow, right overflow, done}
 
   // ---- this thread's pixels of the left and right hash rows (issued first: the zero fill hides their latency)
   const size_t row0 = ((size_t)(2 * pair) * H + y) * W;
@@ -419,13 +420,11 @@ match_rows_fast_kernel(const MatchArgs args) {
     v[0][4 * k] = a.x; v[0][4 * k + 1] = a.y; v[0][4 * k + 2] = a.z; v[0][4 * k + 3] = a.w;
     v[1][4 * k] = b.x; v[1][4 * k + 1] = b.y; v[1][4 * k + 2] = b.z; v[1][4 * k + 3] = b.w;
   }
-  if (tid == 0) { n_live = 0; n_ovl = 0; n_ovr = 0; n_out = 0; big_bucket = 0; }
+  if (tid == 0) { n_live = 0; n_ovl = 0; n_ovr = 0; n_out = 0; }
   {
     uint4* z = reinterpret_cast<uint4*>(nib) + tid;
     const int rounds = ((1 << nwl) + (1 << nsl)) / (4 * kThreadsB);            // tables are multiples of 4 * kThreadsB words
     for (int i = 0; i < rounds; i++) z[i * kThreadsB] = make_uint4(0, 0, 0, 0);
-    if (tid < kBuckets / 4) reinterpret_cast<uint4*>(bcnt)[tid] = make_uint4(0, 0, 0, 0);
-    if (tid < kOvCap / 4) { reinterpret_cast<uint4*>(ovl_s)[tid] = make_uint4(0, 0, 0, 0); reinterpret_cast<uint4*>(ovr_s)[tid] = make_uint4(0, 0, 0, 0); }
   }
   uint32_t any_l = 0, any_r = 0;
 #pragma unroll
@@ -433,13 +432,13 @@ match_rows_fast_kernel(const MatchArgs args) {
   const int have_l = __syncthreads_or((int)(any_l >> 31));       // also orders the zero fill before the atomics
   const int have_r = __syncthreads_or((int)(any_r >> 31));
   if (!(have_l && have_r)) {
-    if (tid == 0) args.rowmatch[(size_t)pair * H + y] = 0;
+    if (tid == 0) { args.rowmatch[grow] = 0; hdr[0] = 0; hdr[1] = 0; hdr[2] = 0; hdr[3] = 1; }
     return;
   }
   if (args.lastrow[2 * pair + 1] == y) {       // tail rules of inference.hpp:243-249: the general kernel's job
     if (tid == 0) {
-      const uint32_t i = atomicAdd(&args.fb_list[0], 1u);
-      args.fb_list[2 + 2 * i] = (uint32_t)pair; args.fb_list[3 + 2 * i] = (uint32_t)y;
+      push_row(args.fb_hdr, args.fb_ent, pair, y);
+      hdr[0] = 0; hdr[1] = 0; hdr[2] = 0; hdr[3] = 1;
     }
     return;
   }
@@ -532,7 +531,6 @@ match_rows_fast_kernel(const MatchArgs args) {
   const uint32_t XL = 1u << xb;
   const int same_bucket_shift = xb + 29 - nwl;       // entry bits above this: the bucket bits the slot index lacks
   const uint32_t nlive = n_live;
-  const int oshift = args.key_bits > 8 ? args.key_bits - 8 : 0;
   for (uint32_t i = tid; i < nlive; i += kThreadsB) {
     const uint32_t lv = live_v[i], xl = live_x[i];
     const uint32_t h = lv * kHashMul;
@@ -543,134 +541,210 @@ match_rows_fast_kernel(const MatchArgs args) {
     // a stranger's entry (my partner lost the slot: overflow lists) from the bucket's own right candidate.
     const bool pairb = (nibble == 5u);
     if (pairb && t < XL && dx <= args.disp_high && -dx <= args.disp_high && 0 <= args.vertical_tolerance) {
-      live_x[i] = xl | (t << 13) | kMatchFlag;
-      atomicAdd(&n_out, 1u);
-      atomicAdd(&bcnt[(lv & 0x7fffffffu) >> oshift], 1u);       // counting pass of the ordering below
+      const uint32_t p = atom_add_shared(&n_out, 1u);
+      GPC_CHECK(p < (uint32_t)W);
+      mrec[p] = ((unsigned long long)(lv & 0x7fffffffu) << 32) | (unsigned long long)((xl << 16) | t);
     } else if (nibble != 5u || (t >> same_bucket_shift) != 0u) {     // duplicates in the bucket, or a stranger in the slot
       const uint32_t p = atom_add_shared(&n_ovl, 1u);
-      if (p < (uint32_t)kOvCap) { ovl_s[p] = lv; ovl_i[p] = i; }
+      if (p < (uint32_t)kOvCap) { ovl_s[p] = lv; ovl_x[p] = xl; }
     }
   }
   __syncthreads();
-  // ---- overflow entries: exact counts over both lists, kOvLanes lanes per left entry ------------------------
-  const uint32_t nl = n_ovl, nr = n_ovr;
-  if (nl > (uint32_t)kOvCap || nr > (uint32_t)kOvCap) {          // too many duplicated states: general kernel
-    if (tid == 0) {
-      const uint32_t i = atomicAdd(&args.fb_list[0], 1u);
-      args.fb_list[2 + 2 * i] = (uint32_t)pair; args.fb_list[3 + 2 * i] = (uint32_t)y;
+  // ---- hand over: the tail kernel resolves the overflow lists and orders the matches -------------------------
+  if (tid == 0) {
+    const uint32_t nl = n_ovl, nr = n_ovr;
+    if (nl > (uint32_t)kOvCap || nr > (uint32_t)kOvCap) {        // too many duplicated states: general kernel
+      push_row(args.fb_hdr, args.fb_ent, pair, y);
+      hdr[0] = 0; hdr[1] = 0; hdr[2] = 0; hdr[3] = 1;
+    } else {
+      hdr[0] = (int32_t)n_out; hdr[1] = (int32_t)nl; hdr[2] = (int32_t)nr; hdr[3] = 0;
     }
-    return;
   }
-  if (kOvLanes == 1) {
-  if ((uint32_t)tid < nl && nr > 0u) {             // (kOvCap <= kThreadsB; entries past a list's end are 0 = equal to nothing)
-      const uint32_t s = ovl_s[tid];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tail of the fast matcher: ONE WARP per row (no block barriers, small footprint, many rows in flight per SM),
+// for the low-parallelism work the row CTA would otherwise hold its shared memory and seven idle warps for:
+//   overflow : every left overflow entry counts equal states in both lists (tens of entries; complete per state,
+//              because equal states share a bucket and a bucket is listed as a whole); unique on both sides and
+//              inside the disparity range = one more match record
+//   order    : the row's matches sorted by state (unique keys): counting pass on the top 8 state bits, exact rank
+//              inside each (tiny) bucket, written as xl << 16 | xr to `stage`; rowmatch[row] = their number
+// Rows with more than kTailCap matches, or a crowded bucket, go to a list for the block-wide ordering kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTailWarps = 8;                 // rows per CTA
+constexpr int kTailCap = 256;                 // matches a warp orders in its slice of shared memory
+
+
+__global__ void __launch_bounds__(32 * kTailWarps, 5)
+match_rows_tail_kernel(const MatchArgs args, int n_pairs) {
+  // per warp: 32 bucket counters / cursors (one bucket per lane: the top 5 state bits), keys and payloads of up to
+  // kTailCap records; the overflow states share the record arrays (they are consumed before the ordering starts)
+  __shared__ uint32_t sm_cnt[kTailWarps][32], sm_cur[kTailWarps][32], sm_m[kTailWarps];
+  __shared__ __align__(16) uint32_t sm_key[kTailWarps][kTailCap], sm_val[kTailWarps][kTailCap];
+  static_assert(kOvCap <= kTailCap, "overflow states fit the record arrays");
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int rows = args.H - 2 * kRadius;
+  const long long r = (long long)blockIdx.x * kTailWarps + wid;
+  if (r >= (long long)rows * n_pairs) return;
+  const int pair = (int)(r / rows), y = kRadius + (int)(r % rows);
+  const size_t grow = (size_t)pair * args.H + y;
+  const int4 hdr = *reinterpret_cast<const int4*>(args.rowhdr + grow * 4);
+  if (hdr.w != 0) return;                                   // empty row, or one the general kernel owns
+  unsigned long long* mrec = args.mrec + grow * args.W;
+  uint32_t m = (uint32_t)hdr.x;
+  const uint32_t nl = (uint32_t)hdr.y, nr = (uint32_t)hdr.z;
+  // the row's first kTailCap match records: issued now, consumed after the overflow step
+  unsigned long long rec[kTailCap / 32];
+#pragma unroll
+  for (int j = 0; j < kTailCap / 32; j++) {
+    const uint32_t i = (uint32_t)lane + 32u * j;
+    rec[j] = (i < m) ? mrec[i] : 0ull;
+  }
+  // ---- overflow entries ------------------------------------------------------------------------------------
+  uint32_t extra_key = 0, extra_val = 0;                    // a lane finds at most one match per round; rounds > 1 are rare
+  uint32_t lim = m;                                         // records held in rec[]
+  if (nl > 0u && nr > 0u) {
+    const uint32_t* ovl_s = args.ovbuf + grow * (4 * kOvCap);
+    const uint32_t* ovl_x = ovl_s + kOvCap;
+    const uint32_t* ovr_s = ovl_x + kOvCap;
+    const uint32_t* ovr_x = ovr_s + kOvCap;
+    uint32_t* ls = sm_key[wid];                             // left states, then (sm_val) right states
+    uint32_t* rs = sm_val[wid];
+    const uint32_t nl4 = (nl + 3u) & ~3u, nr4 = (nr + 3u) & ~3u;        // entries past a list's end: 0 = equal to nothing
+    for (uint32_t i = lane; i < nl4; i += 32) ls[i] = (i < nl) ? ovl_s[i] : 0u;
+    for (uint32_t i = lane; i < nr4; i += 32) rs[i] = (i < nr) ? ovr_s[i] : 0u;
+    if (lane == 0) sm_m[wid] = m;
+    __syncwarp();
+    for (uint32_t i = lane; i < nl; i += 32) {
+      const uint32_t s = ls[i];
       uint32_t cl = 0, cr = 0, jr = 0;
       for (uint32_t j = 0; j < nl; j += 4) {
-        const uint4 q = *reinterpret_cast<const uint4*>(ovl_s + j);
+        const uint4 q = *reinterpret_cast<const uint4*>(ls + j);
         cl += (q.x == s ? 1u : 0u) + (q.y == s ? 1u : 0u) + (q.z == s ? 1u : 0u) + (q.w == s ? 1u : 0u);
       }
-      for (uint32_t j = 0; j < nr; j += 4) {
-        const uint4 q = *reinterpret_cast<const uint4*>(ovr_s + j);
-        const bool e0 = q.x == s, e1 = q.y == s, e2 = q.z == s, e3 = q.w == s;
-        cr += (e0 ? 1u : 0u) + (e1 ? 1u : 0u) + (e2 ? 1u : 0u) + (e3 ? 1u : 0u);
-        jr = e0 ? j : e1 ? j + 1 : e2 ? j + 2 : e3 ? j + 3 : jr;
-      }
-      if (cl == 1u && cr == 1u) {
-        const uint32_t li = ovl_i[tid], xl = live_x[li], x2 = ovr_x[jr];
-        const int dx = (int)xl - (int)x2;
-        if (dx <= args.disp_high && -dx <= args.disp_high && 0 <= args.vertical_tolerance) {
-          live_x[li] = xl | (x2 << 13) | kMatchFlag;
-          atomicAdd(&n_out, 1u);
-          atomicAdd(&bcnt[(s & 0x7fffffffu) >> oshift], 1u);
+      if (cl == 1u) {                                       // most overflow entries are repeated left states: no match possible
+        for (uint32_t j = 0; j < nr; j += 4) {
+          const uint4 q = *reinterpret_cast<const uint4*>(rs + j);
+          const bool e0 = q.x == s, e1 = q.y == s, e2 = q.z == s, e3 = q.w == s;
+          cr += (e0 ? 1u : 0u) + (e1 ? 1u : 0u) + (e2 ? 1u : 0u) + (e3 ? 1u : 0u);
+          jr = e0 ? j : e1 ? j + 1 : e2 ? j + 2 : e3 ? j + 3 : jr;
         }
-      }
-    }
-  } else if (nl > 0u && nr > 0u) {
-    for (uint32_t i0 = 0; i0 < nl; i0 += kThreadsB / kOvLanes) {
-      if (i0 + (uint32_t)(tid & ~31) / kOvLanes >= nl) break;        // whole warps leave (shuffles below)
-      const uint32_t i = i0 + (uint32_t)tid / kOvLanes, part = (uint32_t)tid % kOvLanes;
-      const uint32_t s = (i < nl) ? ovl_s[i] : 0u;                 // 0: no candidate flag, equals nothing
-      uint32_t cl = 0, cr = 0, x2 = 0;
-      for (uint32_t j = part; j < nl; j += kOvLanes) cl += (ovl_s[j] == s) ? 1u : 0u;
-      for (uint32_t j = part; j < nr; j += kOvLanes) { const bool eq = (ovr_s[j] == s); cr += eq ? 1u : 0u; x2 += eq ? ovr_x[j] : 0u; }
-#pragma unroll
-      for (int d = 1; d < kOvLanes; d <<= 1) {
-        cl += __shfl_xor_sync(0xffffffffu, cl, d); cr += __shfl_xor_sync(0xffffffffu, cr, d); x2 += __shfl_xor_sync(0xffffffffu, x2, d);
-      }
-      if (part == 0u && i < nl && cl == 1u && cr == 1u) {
-        const uint32_t li = ovl_i[i], xl = live_x[li];
-        const int dx = (int)xl - (int)x2;
-        if (dx <= args.disp_high && -dx <= args.disp_high && 0 <= args.vertical_tolerance) {
-          live_x[li] = xl | (x2 << 13) | kMatchFlag;
-          atomicAdd(&n_out, 1u);
-          atomicAdd(&bcnt[(s & 0x7fffffffu) >> oshift], 1u);
-        }
-      }
-    }
-  }
-  __syncthreads();
-  // ---- order the matches by state (unique keys) and stage them: counting pass on the top 8 state bits,
-  // then an exact rank inside each (tiny) bucket; bitonic network for skewed states ----------------------------
-  const int m = (int)n_out;
-  uint32_t* stage = args.stage + ((size_t)pair * H + y) * W;
-  if (m > 0) {
-    const int shift = oshift;
-    {                                                 // exclusive scan of the 256 counters: one per thread of the first 8 warps
-      uint32_t c = 0;
-      if (tid < kBuckets) c = bcnt[tid];
-      uint32_t incl = c;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-      if (lane == 31) warp_tot[wid] = incl;
-      if (c > (uint32_t)kBucketLimit) big_bucket = 1u;              // benign same-value race
-      __syncthreads();
-      uint32_t base = incl - c;
-#pragma unroll
-      for (int w = 0; w < kBuckets / 32; w++) if (w < wid) base += warp_tot[w];
-      if (tid < kBuckets) bstart[tid] = base;
-    }
-    __syncthreads();
-    // scatter into bucket segments (arbitrary order inside); the cursor bstart[b] ends at the bucket's end
-    for (uint32_t i = tid; i < nlive; i += kThreadsB) {
-      const uint32_t lx = live_x[i];
-      if (lx & kMatchFlag) {
-        const uint32_t key = live_v[i] & 0x7fffffffu;
-        const uint32_t xl = lx & 0x1fffu, xr = (lx >> 13) & 0x1fffu;
-        const uint32_t pos = atomicAdd(&bstart[key >> shift], 1u);
-        GPC_CHECK(pos < (uint32_t)m && (key >> shift) < (uint32_t)kBuckets);
-        out2[pos] = ((unsigned long long)key << 32) | (unsigned long long)((xl << 16) | xr);
-      }
-    }
-    __syncthreads();
-    if (!big_bucket) {
-      for (int i = tid; i < m; i += kThreadsB) {      // rank inside the bucket, write to the final position
-        const unsigned long long rec = out2[i];
-        const uint32_t b = (uint32_t)(rec >> 32) >> shift;
-        const uint32_t n = bcnt[b], s0 = bstart[b] - n;
-        uint32_t rank = 0;
-        for (uint32_t j = 0; j < n; j++) rank += (out2[s0 + j] < rec) ? 1u : 0u;
-        stage[s0 + rank] = (uint32_t)(rec & 0xffffffffull);
-      }
-    } else {                                          // skewed states: bitonic network over all matches
-      int p2 = 1; while (p2 < m) p2 <<= 1;
-      for (int i = m + tid; i < p2; i += kThreadsB) out2[i] = ~0ull;
-      __syncthreads();
-      for (int k = 2; k <= p2; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int i = tid; i < p2; i += kThreadsB) {
-            const int l = i ^ j;
-            if (l > i) {
-              const unsigned long long a = out2[i], b2 = out2[l];
-              const bool up = ((i & k) == 0);
-              if ((a > b2) == up) { out2[i] = b2; out2[l] = a; }
-            }
+        if (cr == 1u) {
+          const uint32_t xl = ovl_x[i], x2 = ovr_x[jr];
+          const int dx = (int)xl - (int)x2;
+          if (dx <= args.disp_high && -dx <= args.disp_high && 0 <= args.vertical_tolerance) {
+            const uint32_t p = atom_add_shared(&sm_m[wid], 1u);
+            GPC_CHECK(p < (uint32_t)args.W);
+            mrec[p] = ((unsigned long long)(s & 0x7fffffffu) << 32) | (unsigned long long)((xl << 16) | x2);
+            if (p < (uint32_t)kTailCap && i < 32u) { extra_key = (s & 0x7fffffffu) | 0x80000000u; extra_val = (xl << 16) | x2; }
           }
-          __syncthreads();
         }
-      for (int i = tid; i < m; i += kThreadsB) stage[i] = (uint32_t)(out2[i] & 0xffffffffull);
+      }
+    }
+    __syncwarp();
+    const uint32_t m1 = m;
+    m = sm_m[wid];
+    __syncwarp();                                         // the arrays are reused below
+    // matches appended by this warp: lanes that found one in the first round still hold it; reload only in the
+    // rare other cases (several rounds) -- global writes of the warp are visible after __syncwarp
+    if (m != m1 && m <= (uint32_t)kTailCap && nl > 32u) {
+#pragma unroll
+      for (int j = 0; j < kTailCap / 32; j++) {
+        const uint32_t i = (uint32_t)lane + 32u * j;
+        rec[j] = (i < m) ? mrec[i] : 0ull;
+      }
+      extra_key = 0;
+      lim = m;
     }
   }
-  if (tid == 0) args.rowmatch[(size_t)pair * H + y] = m;
+  if (lane == 0) args.rowmatch[grow] = (int32_t)m;
+  if (m == 0u) return;
+  // ---- order by state and stage -------------------------------------------------------------------------
+  uint32_t* stage = args.stage + grow * args.W;
+  if (m > (uint32_t)kTailCap) {                           // a crowd: the block-wide ordering kernel
+    if (lane == 0) push_row(args.big_hdr, args.big_ent, pair, y);
+    return;
+  }
+  const int shift = args.key_bits > 5 ? args.key_bits - 5 : 0;        // bucket = top 5 state bits = the lane that owns it
+  uint32_t* cnt = sm_cnt[wid];
+  uint32_t* cur = sm_cur[wid];
+  uint32_t* bk = sm_key[wid];
+  uint32_t* bv = sm_val[wid];
+  cnt[lane] = 0u;
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < kTailCap / 32; j++) {
+    const uint32_t i = (uint32_t)lane + 32u * j;
+    if (i < lim) atomicAdd(&cnt[(uint32_t)(rec[j] >> 32) >> shift], 1u);
+  }
+  if (extra_key) atomicAdd(&cnt[(extra_key & 0x7fffffffu) >> shift], 1u);
+  __syncwarp();
+  {                                                       // exclusive scan of the 32 counters, one per lane
+    const uint32_t c = cnt[lane];
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    cur[lane] = incl - c;
+    if (__any_sync(0xffffffffu, c > 32u)) {               // skewed states: the block-wide kernel has finer buckets and a sorting network
+      if (lane == 0) push_row(args.big_hdr, args.big_ent, pair, y);
+      return;
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < kTailCap / 32; j++) {               // scatter into bucket segments; cur[b] ends at the bucket's end
+    const uint32_t i = (uint32_t)lane + 32u * j;
+    if (i < lim) {
+      const uint32_t key = (uint32_t)(rec[j] >> 32);
+      const uint32_t p = atomicAdd(&cur[key >> shift], 1u);
+      bk[p] = key; bv[p] = (uint32_t)rec[j];
+    }
+  }
+  if (extra_key) {
+    const uint32_t key = extra_key & 0x7fffffffu;
+    const uint32_t p = atomicAdd(&cur[key >> shift], 1u);
+    bk[p] = key; bv[p] = extra_val;
+  }
+  __syncwarp();
+  for (uint32_t i = lane; i < m; i += 32) {               // rank inside the bucket, write to the final position
+    const uint32_t key = bk[i];
+    const uint32_t b = key >> shift;
+    const uint32_t n = cnt[b], s0 = cur[b] - n;
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < n; j++) rank += (bk[s0 + j] < key) ? 1u : 0u;
+    stage[s0 + rank] = bv[i];
+  }
+}
+
+// Block-wide ordering of the rows the tail kernel listed (more than kTailCap matches, or skewed states).
+template <int kThreadsB>
+__global__ void __launch_bounds__(kThreadsB)
+order_rows_kernel(const MatchArgs args, uint32_t* hdr, const uint32_t* ent) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  unsigned long long* out = reinterpret_cast<unsigned long long*>(smem);           // [pow2cap] x2, then bcnt / bstart
+  unsigned long long* out2 = out + args.pow2cap;
+  uint32_t* bcnt = reinterpret_cast<uint32_t*>(out2 + args.pow2cap);
+  uint32_t* bstart = bcnt + kBuckets;
+  __shared__ uint32_t big_bucket;
+  const int tid = threadIdx.x;
+  const uint32_t n = *reinterpret_cast<volatile uint32_t*>(hdr);
+  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const int pair = (int)ent[2 * i], y = (int)ent[2 * i + 1];
+    const size_t grow = (size_t)pair * args.H + y;
+    const int m = args.rowmatch[grow];
+    const unsigned long long* mrec = args.mrec + grow * args.W;
+    for (int k = tid; k < m; k += kThreadsB) out[k] = mrec[k];
+    for (int k = tid; k < kBuckets; k += kThreadsB) bcnt[k] = 0u;
+    if (tid == 0) big_bucket = 0;
+    __syncthreads();
+    order_and_stage<kThreadsB>(args, out, out2, bcnt, bstart, &big_bucket, m, pair, y);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&hdr[1], 1u) == gridDim.x - 1) { hdr[0] = 0u; hdr[1] = 0u; }
+  }
 }
 
 // Launch shapes: every thread owns 4 * KQ pixels per side.  Rows up to 1024 pixels run 256 threads,
@@ -680,6 +754,7 @@ template <int KQ, int T>
 static cudaError_t configure_one(int max_smem) {
   cudaError_t e = cudaFuncSetAttribute(match_rows_general_kernel<KQ, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(match_rows_fast_kernel<KQ, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  if (e == cudaSuccess && KQ == 1) e = cudaFuncSetAttribute(order_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   return e;
 }
 
@@ -706,14 +781,18 @@ cudaError_t launch_match_rows(const MatchArgs& args, int n_pairs, int general, i
   dim3 grid(rows, n_pairs);
   const size_t smem_g = match_smem_bytes(args.wcap, args.table_log2);
   const size_t smem_f = match_fast_smem_bytes(args.nib_log2, args.slot_log2, args.pow2cap);
+  const size_t smem_o = order_rows_smem_bytes(args.pow2cap);
   const long long all_rows = (long long)rows * n_pairs;
   const int list_grid = (int)(all_rows < 4ll * sm_count ? all_rows : 4ll * sm_count);
+  const int tail_grid = (int)((all_rows + kTailWarps - 1) / kTailWarps);
 #define GPC_LAUNCH_ROWS(KQ, T)                                                                                  \
   do {                                                                                                          \
-    if (general) match_rows_general_kernel<KQ, T><<<grid, T, smem_g, stream>>>(args, nullptr);                  \
+    if (general) match_rows_general_kernel<KQ, T><<<grid, T, smem_g, stream>>>(args, nullptr, nullptr);                  \
     else {                                                                                                      \
       match_rows_fast_kernel<KQ, T><<<grid, T, smem_f, stream>>>(args);                                         \
-      match_rows_general_kernel<KQ, T><<<list_grid, T, smem_g, stream>>>(args, args.fb_list);                   \
+      match_rows_tail_kernel<<<tail_grid, 32 * kTailWarps, 0, stream>>>(args, n_pairs);                         \
+      order_rows_kernel<T><<<list_grid, T, smem_o, stream>>>(args, args.big_hdr, args.big_ent);                         \
+      match_rows_general_kernel<KQ, T><<<list_grid, T, smem_g, stream>>>(args, args.fb_hdr, args.fb_ent);                 \
     }                                                                                                           \
   } while (0)
   if (quads <= 256) GPC_LAUNCH_ROWS(1, 256);

@@ -16,5 +16,5 @@ SMALL="python bench.py --batch 32 --steps 1 --warmup 3 --no-cpu-baseline --no-e2
 $SMALL > gpurun_out/plain_${TAG}.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_${TAG}.log; exit 1; }
 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_${TAG}.csv $SMALL > gpurun_out/ncu_list_${TAG}.log 2>&1
 echo "ncu list rc=$?"
-ncu --set full --clock-control none --import-source on -k "regex:${KREGEX}" -s 6 -c 2 -f -o gpurun_out/prof_${TAG} $SMALL > gpurun_out/ncu_full_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:${KREGEX}" -s 1 -c 2 -f -o gpurun_out/prof_${TAG} $SMALL > gpurun_out/ncu_full_${TAG}.log 2>&1
 echo "ncu full rc=$?"

@@ -228,6 +228,31 @@ def test_resident_images(g, ctx, oracle):
         io.release()
 
 
+def test_row_lists_survive_mixed_slices(g, oracle):
+    """The row matcher's kernels pass rows to each other through lists that live in the context (rows for the general
+    kernel, rows for the block-wide ordering kernel).  A whole-batch launch followed by a chunked one on the same
+    context uses overlapping slices of those buffers: the dense pairs here (left == right: hundreds of matches per row)
+    fill the lists, and the chunked run must still see clean list headers."""
+    from opengpc_b200.synth import synth_batch
+    imgs = synth_batch(512, 96, 40, seed0=900)
+    imgs[::2, 1] = imgs[::2, 0]                                     # every other pair: identical images
+    s = g.sparsematch_settings()
+    of = oracle.read_forest(FORESTS["tau"])
+    refs = {p: oracle.pair(imgs[p, 0], imgs[p, 1], of, osettings())[0] for p in (0, 1, 38, 39)}
+    assert len(refs[0]) > 20 * len(refs[1])
+    with g.Context(device=0, max_w=512, max_h=96, max_batch=40) as c:
+        c.set_forest(FORESTS["tau"])
+        c.enable_kernel_timing(True)                                # timing on: one launch sequence over the whole batch
+        a, oa, _ = c.match_batch(imgs, s)
+        a = a.copy()
+        c.enable_kernel_timing(False)                               # timing off: chunks on slices of the same buffers
+        for rep in range(2):
+            b, ob, _ = c.match_batch(imgs, s)
+            assert np.array_equal(oa, ob) and np.array_equal(a, b), rep
+        for p, ref in refs.items():
+            assert np.array_equal(b[ob[p]:ob[p + 1]], ref), p
+
+
 @pytest.mark.parametrize("mode", ["rows", "global", "hashtable"])
 def test_pipelined_batch(g, oracle, monkeypatch, mode):
     """gpc_match_batch splits large batches into chunks that rotate over three streams (upload,
