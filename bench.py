@@ -64,6 +64,9 @@ def parse_args():
     ap.add_argument("--sparse", action="store_true", help="low-texture variant of the synthetic pairs (SURVEY.md 8d): ~25 %% of the candidates")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--extended", action="store_true",
+                    help="configs[4] with ALL tests of the deep forest (multi-word states, gpc_match_pair_wide) instead of the "
+                         "reference's first 32; parity unpinned (no reference result exists), end-to-end line only")
     ap.add_argument("--pool", action="store_true",
                     help="ONE process drives --gpus N devices through gpc_pool_match_batch (library-level multi-GPU driver); "
                          "prints an end-to-end line only")
@@ -449,11 +452,55 @@ def run_pool(args, w, h):
     lib.gpc_host_free(out_ptr)
 
 
+def run_extended(args, w, h):
+    """--extended: every test of the forest file (192 for the deep forest) through gpc_match_pair_wide, pair by pair,
+    host buffers (upload and download inside the timed region)."""
+    import opengpc_b200 as g
+    B = args.batch
+    images = make_images(w, h, B, args.distinct, args.sparse)
+    settings = g.sparsematch_settings()
+    tests = g.read_forest_tests(FORESTS[args.forest])
+    sampler = ClockSampler(0)
+    sampler.start()
+    with g.Context(device=0, max_w=w, max_h=h, max_batch=1) as ctx:
+        ctx.set_wide_forest(tests)
+        counts = []
+        for j in range(min(B, 3)):                                  # warm-up (also sizes the workspaces)
+            counts.append(len(ctx.match_pair_wide(images[j, 0], images[j, 1], settings)[0]))
+        l0 = ctx.launches
+        t0 = time.perf_counter()
+        n = 0
+        for _ in range(args.steps):
+            for j in range(B):
+                supp, _, _ = ctx.match_pair_wide(images[j, 0], images[j, 1], settings)
+                if j < len(counts):
+                    assert len(supp) == counts[j], "extended mode is not repeatable"
+                n += 1
+        sec = time.perf_counter() - t0
+        launches = ctx.launches - l0
+    clocks = sampler.stop()
+    value = n / sec
+    line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": 1, "steps": args.steps, "warmup": 3,
+            "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "mpix_per_s": value * 2 * w * h / 1e6, "config": config_dict(args, w, h),
+            "extended": {"tests": int(len(tests)), "state_words": (len(tests) + 31) // 32, "supports_first_pairs": counts,
+                         "parity": "unpinned: the reference keeps the first 32 tests (inference.hpp:426); checked against the "
+                                   "scalar restatement in tests/test_wide.py"},
+            "note": "pair by pair through gpc_match_pair_wide: value IS the end-to-end figure",
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 2 * B * w * h, "d2h_bytes_per_step": int(sum(counts)) * 12 * B // max(len(counts), 1),
+                    "api": "gpc_match_pair_wide"}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
     w, h = (int(v) for v in args.shape.lower().split("x"))
     if args.impl == "reference":
         run_reference_arm(args, w, h)
+        return
+    if args.extended:
+        run_extended(args, w, h)
         return
     if args.pool:
         run_pool(args, w, h)

@@ -201,6 +201,28 @@ int gpc_set_matcher(gpc_ctx* ctx, int matcher);
  * precompiled kernel is in use (NVRTC absent, build failure, GPC_JIT=0).  Results are identical. */
 const char* gpc_jit_status(const gpc_ctx* ctx);
 
+/* ---- forests of more than 32 tests ("extended mode") and 32-test forests in GPC_RESULTS_NAIVE --------------------
+ * The reference keeps the first 32 tests of a forest file and drops the rest (inference.hpp:426-432); config 5 of
+ * BASELINE.json asks for all tests of a 16 x 12 forest.  There is no reference result for that --
+ * PARITY UNPINNED: validated against this repository's scalar restatement (tests/test_wide.py) only.  Definition: the
+ * state of a candidate is the tuple of words (word k = tests 32k .. 32k+31 hashed as a forest of their own, so word 0
+ * is the reference's truncated state); two candidates match when the whole tuples are equal and unique on both sides;
+ * findCorrespondences' tail rules apply to the tuple order; supports come in ascending (y, tuple) order, the tuple
+ * compared from its last word down.
+ * In GPC_RESULTS_NAIVE the same machinery carries the T-bit state of gpcFilter[Tau]Naive (filter.hpp:245-293) in
+ * 31-bit words, which is what lets a 32-test forest through in that mode; there the reference defines the result
+ * (pinned against the SSE=OFF build, tests/golden/naive32.json).
+ * tests: n_tests rows of {ix, iy, jx, jy, tau}, file order, 1 <= n_tests <= GPC_MAX_WIDE_TESTS.  Set the result mode
+ * first: gpc_set_result_mode drops the wide forest. */
+#define GPC_MAX_WIDE_TESTS 256
+int gpc_read_forest_tests(const char* path, int32_t* tests, int cap, int* n_tests, int* n_ferns);
+int gpc_set_wide_forest(gpc_ctx* ctx, const int32_t* tests, int n_tests);
+int gpc_match_pair_wide(gpc_ctx* ctx, const uint8_t* left, const uint8_t* right, int w, int h, int stride,
+                        const gpc_settings* s, gpc_support* out, int cap, int* n_out, int* n_cand_l, int* n_cand_r);
+/* stage seam: words[k][y][x] = candidate flag | word k of the pixel's state (0 for non-candidates) */
+int gpc_hash_wide(gpc_ctx* ctx, const uint8_t* img, int w, int h, int gradient_threshold, uint32_t* words,
+                  int n_words_cap, int* n_words);
+
 /* ---- gpc_pool: one resident context + one host thread per GPU (multi-GPU driver) ----------
  * The reference has no multi-device path; stereo pairs are independent units, so a batch is cut into chunks that are
  * dealt round-robin to the devices.  Every device pipelines its chunks (upload / kernels / download) and the supports

@@ -6,7 +6,7 @@ binding used by tests and bench.py), synth.py (synthetic stereo pairs), build.py
 The drop-in C++ API mirroring gpc::inference::Forest is in include/gpc/.
 """
 from .capi import (CORR_DTYPE, MATCHER_AUTO, MATCHER_ROWS_GENERAL, MATCHER_SORT, Context, GpcError, Pool, GpcForest, GpcSettings, SUPPORT_DTYPE, load_library, make_forest, make_settings,
-                   read_forest, sparsematch_settings)
+                   read_forest, read_forest_tests, sparsematch_settings)
 
 __all__ = ["CORR_DTYPE", "MATCHER_AUTO", "MATCHER_ROWS_GENERAL", "MATCHER_SORT", "Context", "GpcError", "Pool", "GpcForest", "GpcSettings", "SUPPORT_DTYPE", "load_library", "make_forest",
-           "make_settings", "read_forest", "sparsematch_settings"]
+           "make_settings", "read_forest", "read_forest_tests", "sparsematch_settings"]

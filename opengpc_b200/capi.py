@@ -25,7 +25,8 @@ SYMBOLS = ["gpc_create", "gpc_destroy", "gpc_last_error", "gpc_status_string", "
            "gpc_kernel_times", "gpc_hash_smooth", "gpc_image_upload", "gpc_image_release", "gpc_image_preprocess",
            "gpc_match_images", "gpc_correspond_images", "gpc_find_correspondences", "gpc_hashmatch", "gpc_set_result_mode", "gpc_set_matcher", "gpc_match_pyramid", "gpc_jit_status", "gpc_context_id", "gpc_image_fetch", "gpc_fetch_supports",
            "gpc_pool_create", "gpc_pool_destroy", "gpc_pool_size", "gpc_pool_context", "gpc_pool_last_error", "gpc_pool_launch_count",
-           "gpc_pool_set_forest", "gpc_pool_set_result_mode", "gpc_pool_match_batch", "gpc_host_alloc", "gpc_host_free"]
+           "gpc_pool_set_forest", "gpc_pool_set_result_mode", "gpc_pool_match_batch", "gpc_host_alloc", "gpc_host_free",
+           "gpc_read_forest_tests", "gpc_set_wide_forest", "gpc_match_pair_wide", "gpc_hash_wide"]
 KERNEL_NAMES = ["smooth_sobel", "hash_tiles", "match_rows", "scans", "emit_supports"]
 
 
@@ -110,6 +111,18 @@ def read_forest(path):
     if rc != GPC_OK:
         raise GpcError(rc, lib.gpc_status_string(rc).decode())
     return f
+
+
+def read_forest_tests(path):
+    """Every test of a forest file, [n, 5] int32 rows of (ix, iy, jx, jy, tau): gpc_read_forest without the 32-test cap."""
+    lib = load_library()
+    n, nf = C.c_int(0), C.c_int(0)
+    rc = lib.gpc_read_forest_tests(os.fsencode(path), None, 0, C.byref(n), C.byref(nf))
+    if rc != GPC_OK:
+        raise GpcError(rc, lib.gpc_status_string(rc).decode())
+    tests = np.zeros((max(n.value, 1), 5), np.int32)
+    lib.gpc_read_forest_tests(os.fsencode(path), _ptr(tests), C.c_int(len(tests)), C.byref(n), C.byref(nf))
+    return tests[:n.value]
 
 
 def make_forest(tests, taus, type_=None):
@@ -319,6 +332,34 @@ class Context:
         self._check(self.lib.gpc_hashmatch(self._h, _ptr(src_keys), C.c_int(len(src_keys)), _ptr(tar_keys),
                                            C.c_int(len(tar_keys)), _ptr(out), C.c_int(cap), C.byref(n)))
         return out[:n.value].copy()
+
+    # ---- forests of more than 32 tests / 32-test forests in the naive result mode -------------------
+    def set_wide_forest(self, tests):
+        """tests: [n, 5] int32 rows of (ix, iy, jx, jy, tau) in file order, or a forest file path."""
+        if isinstance(tests, (str, bytes, os.PathLike)):
+            tests = read_forest_tests(tests)
+        tests = np.ascontiguousarray(tests, np.int32).reshape(-1, 5)
+        self._check(self.lib.gpc_set_wide_forest(self._h, _ptr(tests), C.c_int(len(tests))))
+
+    def match_pair_wide(self, left, right, settings, cap=None):
+        left = np.ascontiguousarray(left, np.uint8)
+        right = np.ascontiguousarray(right, np.uint8)
+        h, w = left.shape
+        cap = max((w - 26) * (h - 26), 1) if cap is None else cap
+        out = np.empty(max(cap, 1), SUPPORT_DTYPE)
+        n, ncl, ncr = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._check(self.lib.gpc_match_pair_wide(self._h, _ptr(left), _ptr(right), w, h, w, C.byref(settings), _ptr(out),
+                                                 C.c_int(cap), C.byref(n), C.byref(ncl), C.byref(ncr)))
+        return out[:n.value].copy(), ncl.value, ncr.value
+
+    def hash_wide(self, img, thr, max_words=8):
+        """uint32 [n_words, h, w]: candidate flag | state word per pixel under the wide forest."""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        words = np.zeros((max_words, h, w), np.uint32)
+        n = C.c_int(0)
+        self._check(self.lib.gpc_hash_wide(self._h, _ptr(img), w, h, int(thr), _ptr(words), C.c_int(max_words), C.byref(n)))
+        return words[:n.value].copy()
 
     # ---- resident images ----------------------------------------------------------------------
     def upload(self, img):

@@ -51,6 +51,9 @@ cudaError_t launch_hashmatch_keys(void* ws, long long max_records, const unsigne
 cudaError_t launch_match_keys(void* ws, long long max_records, int ns, int nt, int key_bits, int32_t* out_pairs, long long cap,
                               int32_t* n_out, cudaStream_t stream, int* launches);
 void* global_key_buffer(void* ws, long long max_records);
+size_t wide_workspace_bytes(long long max_records);
+cudaError_t launch_wide_rank(void* ws, long long max_records, const uint32_t* hi, const uint32_t* lo, long long n_pix, int key_bits,
+                             uint32_t* out, cudaStream_t stream, int* launches);
 cudaError_t launch_downsample2x(const uint8_t* src, uint8_t* dst, int sw, int sh, int n_img, cudaStream_t stream);
 struct JitKernel;
 JitKernel* jit_build_hash_tiles(const ForestDev& f, std::string* why);
@@ -115,6 +118,11 @@ struct gpc_ctx {
   uint8_t* d_pyr = nullptr;        // pyramid levels 1.. of one pair (lazily allocated)
   void* d_gws = nullptr;           // radix-sort matcher workspace (lazily allocated, grown on demand)
   size_t gws_bytes = 0;
+  // wide states (forests of more than 32 tests, gpc_set_wide_forest): one baked sub-forest per state word
+  std::vector<gpc::ForestDev> wide_words;
+  int wide_tests = 0;
+  uint32_t* d_wide = nullptr;      // hash planes [2 * words][2][H][W] (lazily allocated)
+  size_t wide_bytes = 0;
   int matcher = GPC_MATCHER_AUTO;
   // device blocks of released resident images, reused by gpc_image_upload (cudaMalloc / cudaFree cost more than the kernels)
   std::vector<std::pair<size_t, uint8_t*>> image_pool;
@@ -257,7 +265,7 @@ int mark_on(gpc_ctx* c, const Slot& sl) { return (sl.stream == c->stream) ? mark
 // skip_a1: the slot's smooth / cand / rowcnt / lastrow buffers already hold kernel A1's output (resident images).
 int run_preprocess(gpc_ctx* c, const Slot& sl, const uint8_t* d_images, int n_img, int w, int h, int thr,
                    const gpc::ForestDev& forest, uint8_t* d_smooth_out, uint8_t* d_grad_out, const uint8_t* d_flags = nullptr,
-                   bool skip_a1 = false) {
+                   bool skip_a1 = false, uint32_t* hash_base = nullptr) {
   const size_t P = (size_t)w * h;
   const int img0 = 2 * sl.p0;
   int32_t* rowcnt = c->d_rows + (size_t)img0 * h;
@@ -289,7 +297,7 @@ int run_preprocess(gpc_ctx* c, const Slot& sl, const uint8_t* d_images, int n_im
   }
   rc = mark_on(c, sl); if (rc) return rc;                                          // event 1
   gpc::HashArgs ha{};
-  ha.cand = c->d_cand; ha.hash = c->d_hash;
+  ha.cand = c->d_cand; ha.hash = hash_base ? hash_base : c->d_hash;    // hash_base: another [..][H][W] plane set (wide states)
   ha.W = w; ha.H = h; ha.img0 = img0;
   ha.hash_y_end = forest.naive ? h - gpc::kRadius : h - 15;                       // filter.hpp:601-604; the naive filters hash every candidate
   if (c->jit && &forest == &c->forest_dev)
@@ -537,7 +545,7 @@ void gpc_destroy(gpc_ctx* c) {
   for (cudaEvent_t e : c->ev_chunk) cudaEventDestroy(e);
   cudaFree(c->d_rowoff); cudaFree(c->d_totals); cudaFree(c->d_ncand); cudaFree(c->d_pair_base); cudaFree(c->d_out);
   gpc::jit_destroy(c->jit);
-  cudaFree(c->d_dbg8); cudaFree(c->d_mask); cudaFree(c->d_gws); cudaFree(c->d_pyr);
+  cudaFree(c->d_dbg8); cudaFree(c->d_mask); cudaFree(c->d_gws); cudaFree(c->d_pyr); cudaFree(c->d_wide);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->h_pair_base) cudaFreeHost(c->h_pair_base);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -663,6 +671,7 @@ int gpc_set_result_mode(gpc_ctx* c, int mode) {
     return fail(c, GPC_E_UNSUPPORTED, "GPC_RESULTS_NAIVE supports forests of at most 31 tests (bit 31 of a hash word is the candidate flag)");
   const int old_mode = c->result_mode;
   c->result_mode = mode;
+  c->wide_words.clear(); c->wide_tests = 0;       // the word layout depends on the mode
   if (!c->has_forest) return GPC_OK;
   const gpc_forest f = c->forest_host;
   c->has_forest = false;                              // defeat the "unchanged forest" shortcut
@@ -1363,6 +1372,171 @@ int gpc_match_pyramid(gpc_ctx* c, const uint8_t* left, const uint8_t* right, int
   }
   GPC_CUDA(c, cudaStreamSynchronize(c->stream));
   if (overflow) return fail(c, GPC_E_CAPACITY, "support buffer too small: need " + std::to_string(total));
+  return GPC_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Forests of more than 32 tests ("extended mode"; no reference semantics -- the reference keeps the
+// first 32 tests, inference.hpp:426) and 32-test forests in GPC_RESULTS_NAIVE (32 state bits + the candidate flag do not
+// fit one hash word).  The state of a candidate is a tuple of words:
+//   SSE results   : word k = tests 32k .. 32k+31 evaluated as a forest of their own (each word with the bit placement
+//                   of filter.hpp:574-584), so word 0 is exactly the reference's truncated 32-test state
+//   naive results : the T-bit state of gpcFilter[Tau]Naive (test t in bit T-1-t, filter.hpp:245-293) cut into 31-bit words
+// Kernel A2 runs once per word on kernel A1's output; the planes are folded pairwise into dense ranks (match_global.cu:
+// launch_wide_rank -- exact and order preserving) and the ordinary matchers run on the final rank plane.  Output order:
+// ascending (y,) then the state tuple compared from the LAST word down (for the naive mode: the numeric T-bit state).
+// ------------------------------------------------------------------------------------------------------------------
+static int run_wide_pair(gpc_ctx* c, int w, int h, const gpc_settings* s) {
+  const size_t P = (size_t)w * h;
+  const int K = (int)c->wide_words.size();
+  const size_t plane = 2 * P;                                        // one word of both images
+  const size_t need = (size_t)(2 * K + 1) * plane * sizeof(uint32_t);
+  if (need > c->wide_bytes) {
+    GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_wide); c->d_wide = nullptr; c->wide_bytes = 0;
+    GPC_CUDA(c, cudaMalloc(&c->d_wide, need));
+    c->wide_bytes = need;
+  }
+  const long long records = 2ll * std::max(w - 2 * gpc::kRadius, 0) * std::max(h - 2 * gpc::kRadius, 0) + 2;
+  int rc = ensure_global_ws(c, gpc::wide_workspace_bytes(records)); if (rc) return rc;
+  // kernel A1 once, kernel A2 once per word
+  for (int k = 0; k < K; k++) {
+    rc = run_preprocess(c, Slot{0, c->stream}, c->d_raw, 2, w, h, s->gradient_threshold, c->wide_words[(size_t)k], nullptr, nullptr, nullptr,
+                        k > 0, c->d_wide + (size_t)k * plane);
+    if (rc) return rc;
+  }
+  // fold the planes pairwise until one is left: (lo, hi) -> dense rank of the pair
+  std::vector<uint32_t*> cur((size_t)K);
+  for (int k = 0; k < K; k++) cur[(size_t)k] = c->d_wide + (size_t)k * plane;
+  int next_free = K;
+  while (cur.size() > 1) {
+    std::vector<uint32_t*> nxt;
+    for (size_t j = 0; j + 1 < cur.size(); j += 2) {
+      uint32_t* out = c->d_wide + (size_t)next_free * plane;
+      next_free = (next_free + 1 < 2 * K + 1) ? next_free + 1 : K;   // K + (K - 1) folds at most: never wraps onto a live plane
+      GPC_CUDA(c, cudaMemsetAsync(out, 0, plane * sizeof(uint32_t), c->stream));
+      int launches = 0;
+      GPC_CUDA(c, gpc::launch_wide_rank(c->d_gws, records, cur[j + 1], cur[j], (long long)plane, 64, out, c->stream, &launches));
+      c->launches += launches;
+      nxt.push_back(out);
+    }
+    if (cur.size() & 1) nxt.push_back(cur.back());
+    cur.swap(nxt);
+  }
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_hash, cur[0], plane * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+  return run_match(c, Slot{0, c->stream}, 1, w, h, s, c->d_out, c->out_cap, true, c->d_totals, c->d_ncand, true);
+}
+
+extern "C" {
+
+// tests: n_tests rows of {ix, iy, jx, jy, tau} in file order.  The result mode in force decides the word layout; calling
+// gpc_set_result_mode afterwards invalidates the wide forest (set it again).
+int gpc_set_wide_forest(gpc_ctx* c, const int32_t* tests, int n_tests) {
+  if (!c || !tests) return GPC_E_ARG;
+  if (n_tests < 1 || n_tests > GPC_MAX_WIDE_TESTS) return fail(c, GPC_E_FOREST, "a wide forest has 1 .. 256 tests");
+  int type = 0;
+  for (int t = 0; t < n_tests; t++) {
+    for (int k = 0; k < 4; k++)
+      if (tests[5 * t + k] < -GPC_PATCH_RADIUS || tests[5 * t + k] > GPC_PATCH_RADIUS)
+        return fail(c, GPC_E_FOREST, "test offset outside the 27x27 patch (|offset| <= 13)");
+    if (tests[5 * t + 4] != 0) type = 1;
+  }
+  const bool naive = (c->result_mode == GPC_RESULTS_NAIVE);
+  const int per = naive ? 31 : 32;
+  const int K = (n_tests + per - 1) / per;
+  c->wide_words.assign((size_t)K, gpc::ForestDev{});
+  for (int k = 0; k < K; k++) {
+    // SSE: tests 32k ..; naive: word k holds state bits 31k .. 31k+30 = tests T-31k-Tk .. T-31k-1, in file order
+    const int tk = std::min(per, n_tests - per * k);
+    const int t0 = naive ? n_tests - per * k - tk : per * k;
+    gpc_forest f;
+    std::memset(&f, 0, sizeof(f));
+    f.n_tests = tk; f.type = type;
+    for (int j = 0; j < tk; j++) {
+      const int32_t* src = tests + 5 * (size_t)(t0 + j);
+      f.ix[j] = src[0]; f.iy[j] = src[1]; f.jx[j] = src[2]; f.jy[j] = src[3]; f.tau[j] = src[4];
+    }
+    bake_forest(f, &c->wide_words[(size_t)k], c->result_mode);
+  }
+  c->wide_tests = n_tests;
+  return GPC_OK;
+}
+
+// gpc_match_pair with the wide forest: same arguments and result layout.
+int gpc_match_pair_wide(gpc_ctx* c, const uint8_t* left, const uint8_t* right, int w, int h, int stride, const gpc_settings* s,
+                        gpc_support* out, int cap, int* n_out, int* n_cand_l, int* n_cand_r) {
+  if (!c || !left || !right || !n_out || cap < 0 || (cap > 0 && !out)) return fail(c, GPC_E_ARG, "null argument");
+  if (stride < w) return fail(c, GPC_E_ARG, "stride smaller than width");
+  int rc = check_dims(c, w, h, 1); if (rc) return rc;
+  rc = check_settings(c, s); if (rc) return rc;
+  if (c->wide_words.empty()) return fail(c, GPC_E_FOREST, "no wide forest set");
+  if (s->use_hashtable) return fail(c, GPC_E_UNSUPPORTED, "the hashtable matcher is defined on single-word states only");
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  const size_t P = (size_t)w * h;
+  GPC_CUDA(c, cudaMemcpy2DAsync(c->d_raw, w, left, stride, w, h, cudaMemcpyHostToDevice, c->stream));
+  GPC_CUDA(c, cudaMemcpy2DAsync(c->d_raw + P, w, right, stride, w, h, cudaMemcpyHostToDevice, c->stream));
+  rc = run_wide_pair(c, w, h, s);
+  if (rc) return rc;
+  GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_totals, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA(c, cudaMemcpyAsync(c->h_counts + 1, c->d_ncand, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  *n_out = c->h_counts[0];
+  if (n_cand_l) *n_cand_l = c->h_counts[1];
+  if (n_cand_r) *n_cand_r = c->h_counts[2];
+  if (*n_out > cap) return fail(c, GPC_E_CAPACITY, "support buffer too small: need " + std::to_string(*n_out));
+  if (*n_out > 0) {
+    GPC_CUDA(c, cudaMemcpyAsync(out, c->d_out, (size_t)*n_out * sizeof(gpc_support), cudaMemcpyDeviceToHost, c->stream));
+    GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return GPC_OK;
+}
+
+// The hash words of one image under the wide forest (stage seam for parity tests): words[k * h * w + y * w + x] =
+// candidate flag | word k of the pixel's state, 0 for non-candidates.
+int gpc_hash_wide(gpc_ctx* c, const uint8_t* img, int w, int h, int thr, uint32_t* words, int n_words_cap, int* n_words) {
+  if (!c || !img || !words || !n_words) return fail(c, GPC_E_ARG, "null argument");
+  int rc = check_dims(c, w, h, 1); if (rc) return rc;
+  if (c->wide_words.empty()) return fail(c, GPC_E_FOREST, "no wide forest set");
+  if (thr < 0 || thr > 255) return fail(c, GPC_E_ARG, "gradientThreshold needs to be within 0...255");
+  const int K = (int)c->wide_words.size();
+  *n_words = K;
+  if (n_words_cap < K) return fail(c, GPC_E_CAPACITY, "word buffer too small: need " + std::to_string(K));
+  GPC_CUDA(c, cudaSetDevice(c->device));
+  const size_t P = (size_t)w * h;
+  GPC_CUDA(c, cudaMemcpyAsync(c->d_raw, img, P, cudaMemcpyHostToDevice, c->stream));
+  for (int k = 0; k < K; k++) {
+    rc = run_preprocess(c, Slot{0, c->stream}, c->d_raw, 1, w, h, thr, c->wide_words[(size_t)k], nullptr, nullptr, nullptr, k > 0);
+    if (rc) return rc;
+    GPC_CUDA(c, cudaMemcpyAsync(words + (size_t)k * P, c->d_hash, P * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  }
+  GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GPC_OK;
+}
+
+// The whole test list of a forest file (gpc_read_forest's parser without the 32-test cap): tests = rows of
+// {ix, iy, jx, jy, tau}; *n_tests receives the number of tests in the file even if it exceeds cap.
+int gpc_read_forest_tests(const char* path, int32_t* tests, int cap, int* n_tests, int* n_ferns) {
+  if (!path || !n_tests || cap < 0 || (cap > 0 && !tests)) return GPC_E_ARG;
+  std::ifstream ff(path);
+  if (ff.fail()) return GPC_E_IO;
+  int num_ferns = 0, n = 0;
+  ff >> num_ferns;
+  if (n_ferns) *n_ferns = num_ferns;
+  for (int i = 0; i < num_ferns && ff.good(); i++) {
+    int id = 0, nt = 0;
+    std::string scale;
+    ff >> id >> scale >> nt;
+    for (int j = 0; j < nt; j++) {
+      int lvl = 0, v[5] = {0, 0, 0, 0, 0};
+      ff >> lvl >> v[0] >> v[1] >> v[2] >> v[3] >> v[4];
+      if (ff.fail()) break;
+      if (n < cap) for (int k = 0; k < 5; k++) tests[5 * (size_t)n + k] = v[k];
+      n++;
+    }
+  }
+  *n_tests = n;
   return GPC_OK;
 }
 

@@ -1092,4 +1092,136 @@ void* global_key_buffer(void* ws, long long max_records) {
   return carve<unsigned long long>(ws, max_records, 1, 0).keys[0];
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Wide states (forests of more than 32 tests, gpc_capi.cu: run_wide_pair).  A candidate's state is a tuple of 32-bit
+// words, one hash plane per group of 32 tests.  Two planes are folded into one by replacing the word pair (hi, lo) of
+// every candidate of BOTH images of the pair by its dense rank among all pairs that occur: equal tuples get equal
+// ranks, and the rank order is the lexicographic order (hi, lo) -- an exact, order-preserving compression, so after
+// folding all planes the ordinary matchers run on a plain 31-bit "state" again.
+//   wide_gather : every candidate pixel appends key = hi << 32 | lo and its pixel id (image << 30.. see below)
+//   sort        : the 64-bit LSD radix sort above
+//   wide_rank   : run starts counted per tile, scanned, and rank | candidate flag scattered to the output planes
+// Pixel id = image * P + y * W + x (two images, P <= 2^30).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+wide_gather_kernel(const uint32_t* __restrict__ hi, const uint32_t* __restrict__ lo, long long n_pix, SortWs<unsigned long long> ws) {
+  // order inside the key array is irrelevant (it is sorted next): one warp-aggregated reservation per warp
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  uint32_t l = 0, h = 0;
+  if (i < n_pix) { l = lo[i]; h = hi ? hi[i] : 0u; }
+  const bool c = (l >> 31) != 0u;
+  const uint32_t b = __ballot_sync(0xffffffffu, c);
+  if (b == 0u) return;
+  int base = 0;
+  if (lane == __ffs(b) - 1) base = atomicAdd(&ws.n_side[0], __popc(b));
+  base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
+  if (c) {
+    const int p = base + __popc(b & ((1u << lane) - 1u));
+    ws.keys[0][p] = ((unsigned long long)(h & 0x7fffffffu) << 32) | (unsigned long long)(l & 0x7fffffffu);
+    ws.vals[0][p] = (uint32_t)i;
+  }
+}
+
+constexpr int kWidePer = kTile / 256;            // consecutive sorted keys per thread: one CTA of 256 threads per sort tile
+
+__global__ void __launch_bounds__(256)
+wide_count_kernel(const SortWs<unsigned long long> ws, int cur) {          // run starts per tile of kTile sorted keys
+  const int n = ws.n_side[0];
+  const unsigned long long* keys = cur ? ws.keys[1] : ws.keys[0];
+  const int i0 = blockIdx.x * kTile + threadIdx.x * kWidePer;
+  int c = 0;
+  for (int k = 0; k < kWidePer; k++) {
+    const int i = i0 + k;
+    c += (i < n && (i == 0 || keys[i] != keys[i - 1])) ? 1 : 0;
+  }
+  __shared__ int tot;
+  if (threadIdx.x == 0) tot = 0;
+  __syncthreads();
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&tot, c);
+  __syncthreads();
+  if (threadIdx.x == 0) ws.blockcount[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024)
+wide_scan_kernel(const SortWs<unsigned long long> ws, int n_tiles) {       // exclusive prefix of the tile counts, in place
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < n_tiles; i0 += 1024) {
+    const int i = i0 + tid;
+    const int v = (i < n_tiles) ? ws.blockcount[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const int w = warp_sums[lane];
+      int wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += t; }
+      warp_sums[lane] = wi - w;
+    }
+    __syncthreads();
+    const int base = carry + warp_sums[wid];
+    if (i < n_tiles) ws.blockcount[i] = base + incl - v;
+    __syncthreads();
+    if (tid == 1023) carry = base + incl;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+wide_rank_kernel(const SortWs<unsigned long long> ws, int cur, uint32_t* __restrict__ out) {
+  __shared__ int warp_sums[8];
+  const int n = ws.n_side[0];
+  const unsigned long long* keys = cur ? ws.keys[1] : ws.keys[0];
+  const uint32_t* vals = cur ? ws.vals[1] : ws.vals[0];
+  const int i0 = blockIdx.x * kTile + threadIdx.x * kWidePer, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int c = 0;
+  for (int k = 0; k < kWidePer; k++) {
+    const int i = i0 + k;
+    c += (i < n && (i == 0 || keys[i] != keys[i - 1])) ? 1 : 0;
+  }
+  int incl = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+  if (lane == 31) warp_sums[wid] = incl;
+  __syncthreads();
+  int run = ws.blockcount[blockIdx.x] + incl - c;                          // run starts before this thread's first key
+  for (int w = 0; w < wid; w++) run += warp_sums[w];
+  for (int k = 0; k < kWidePer; k++) {
+    const int i = i0 + k;
+    if (i >= n) break;
+    run += (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+    out[vals[i]] = kCandFlag | (uint32_t)(run - 1);                        // rank of the run this key belongs to
+  }
+}
+
+size_t wide_workspace_bytes(long long max_records) { return global_workspace_bytes(max_records, 1, 0, 0); }
+
+// out[pixel] = flag | dense rank of (hi[pixel], lo[pixel]) among the candidate pixels (flag = bit 31 of lo), 0 elsewhere
+// is the caller's job (out is expected to be zeroed).  hi == nullptr ranks lo alone.  key_bits: significant bits of the
+// 64-bit key hi << 32 | lo.
+cudaError_t launch_wide_rank(void* ws, long long max_records, const uint32_t* hi, const uint32_t* lo, long long n_pix, int key_bits,
+                             uint32_t* out, cudaStream_t stream, int* launches) {
+  SortWs<unsigned long long> w = carve<unsigned long long>(ws, max_records, 1, 0);
+  cudaError_t e = cudaMemsetAsync(w.n_side, 0, 2 * sizeof(int32_t), stream);
+  if (e != cudaSuccess) return e;
+  wide_gather_kernel<<<(unsigned)((n_pix + 255) / 256), 256, 0, stream>>>(hi, lo, n_pix, w);
+  int cur = 0;
+  e = sort_passes(w, max_records, 1, key_bits, stream, launches, &cur);
+  if (e != cudaSuccess) return e;
+  const int n_tiles = (int)((max_records + kTile - 1) / kTile);
+  wide_count_kernel<<<n_tiles, 256, 0, stream>>>(w, cur);
+  wide_scan_kernel<<<1, 1024, 0, stream>>>(w, n_tiles);
+  wide_rank_kernel<<<n_tiles, 256, 0, stream>>>(w, cur, out);
+  *launches += 4;
+  return cudaGetLastError();
+}
+
 }  // namespace gpc

@@ -852,17 +852,49 @@ cudaError_t launch_row_scan(const int32_t* rowmatch, const int32_t* rowcnt, int 
   return cudaGetLastError();
 }
 
-// Exclusive prefix of the per-pair totals (packed output mode); single CTA, n_pairs is small.
-__global__ void pair_scan_kernel(const int32_t* __restrict__ totals, int n_pairs, long long* __restrict__ pair_base) {
-  if (threadIdx.x == 0) {
-    long long acc = 0;
-    for (int p = 0; p < n_pairs; p++) { pair_base[p] = acc; acc += totals[p]; }
-    pair_base[n_pairs] = acc;
+// Exclusive prefix of n int32 values into long long out[0 .. n] (out[n] = total): one CTA of 1024 threads walks the
+// input in 1024-element steps (warp shuffles + one shared-memory hop), so batches of thousands of pairs and images
+// of thousands of rows cost a few microseconds instead of a serial loop.
+template <typename OutT>
+__device__ __forceinline__ void block_exclusive_scan(const int32_t* __restrict__ in, int n, OutT* __restrict__ out) {
+  __shared__ long long warp_sums[32];
+  __shared__ long long carry;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += 1024) {
+    const int i = i0 + tid;
+    const long long v = (i < n) ? (long long)in[i] : 0ll;
+    long long incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const long long w = warp_sums[lane];
+      long long wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += t; }
+      warp_sums[lane] = wi - w;
+    }
+    __syncthreads();
+    const long long base = carry + warp_sums[wid];
+    if (i < n) out[i] = (OutT)(base + incl - v);
+    __syncthreads();
+    if (tid == 1023) carry = base + incl;
+    __syncthreads();
   }
+  if (tid == 0) out[n] = (OutT)carry;
+}
+
+// Exclusive prefix of the per-pair totals (packed output mode).
+__global__ void __launch_bounds__(1024)
+pair_scan_kernel(const int32_t* __restrict__ totals, int n_pairs, long long* __restrict__ pair_base) {
+  block_exclusive_scan<long long>(totals, n_pairs, pair_base);
 }
 
 cudaError_t launch_pair_scan(const int32_t* totals, int n_pairs, long long* pair_base, cudaStream_t stream) {
-  pair_scan_kernel<<<1, 32, 0, stream>>>(totals, n_pairs, pair_base);
+  pair_scan_kernel<<<1, 1024, 0, stream>>>(totals, n_pairs, pair_base);
   return cudaGetLastError();
 }
 
@@ -919,12 +951,9 @@ cudaError_t launch_emit_supports(const uint32_t* stage, const int32_t* rowmatch,
 // Candidate index list (ndb::arr2ind + border lambda output, raster order) from the hash image.
 // One warp per row; debug / API-parity path only (PreprocessedImage::mask).
 // ------------------------------------------------------------------------------------------------
-__global__ void mask_scan_kernel(const int32_t* __restrict__ rowcnt, int H, int32_t* __restrict__ rowoff) {
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int y = 0; y < H; y++) { rowoff[y] = acc; acc += rowcnt[y]; }
-    rowoff[H] = acc;
-  }
+__global__ void __launch_bounds__(1024)
+mask_scan_kernel(const int32_t* __restrict__ rowcnt, int H, int32_t* __restrict__ rowoff) {
+  block_exclusive_scan<int32_t>(rowcnt, H, rowoff);
 }
 
 __global__ void __launch_bounds__(32)
@@ -947,7 +976,7 @@ mask_rows_kernel(const uint32_t* __restrict__ hash, const int32_t* __restrict__ 
 
 cudaError_t launch_mask_list(const uint32_t* hash, const int32_t* rowcnt, int32_t* rowoff, int W, int H, int32_t* mask,
                              int cap, cudaStream_t stream) {
-  mask_scan_kernel<<<1, 32, 0, stream>>>(rowcnt, H, rowoff);
+  mask_scan_kernel<<<1, 1024, 0, stream>>>(rowcnt, H, rowoff);
   mask_rows_kernel<<<H, 32, 0, stream>>>(hash, rowoff, W, H, mask, cap);
   return cudaGetLastError();
 }

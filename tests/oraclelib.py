@@ -320,3 +320,43 @@ class Reference:
                                       C.c_int(thr), C.c_int(disp_high), C.c_int(vt), C.c_int(int(epipolar)),
                                       C.c_int(threads), C.c_int(iters), C.byref(tot))
         return sec, tot.value
+
+
+# ---- wide states (forests of more than 32 tests; 32-test forests of the SSE=OFF build) ---------------------------
+def wide_words(o, img, tests, thr, naive):
+    """Scalar restatement of the word planes of include/gpc_b200.h's "extended mode": (mask, words[n_words][n_cand]).
+    SSE results: word k = tests 32k .. 32k+31 hashed as a forest of their own (gpco_hash).  Naive results: the T-bit
+    state of gpcFilter[Tau]Naive cut into 31-bit words (word k = state bits 31k .. 31k+30)."""
+    tests = np.asarray(tests, np.int32).reshape(-1, 5)
+    T = len(tests)
+    type_ = int(np.any(tests[:, 4] != 0))
+    per = 31 if naive else 32
+    K = (T + per - 1) // per
+    if naive:
+        sm, gr, mk, _ = o.stages_naive(img, o.make_forest([], [], type_=0), thr)
+    else:
+        sm, gr, mk, _ = o.stages(img, o.make_forest([], [], type_=0), thr)
+    h, w = img.shape
+    words = []
+    for k in range(K):
+        tk = min(per, T - per * k)
+        t0 = T - per * k - tk if naive else per * k
+        sub = tests[t0:t0 + tk]
+        f = o.make_forest([tuple(int(v) for v in r[:4]) for r in sub], [int(r[4]) for r in sub], type_=type_)
+        st = np.empty(max(len(mk), 1), np.uint32)
+        fn = o.lib.gpco_hash_naive if naive else o.lib.gpco_hash
+        fn(_p(np.ascontiguousarray(sm)), C.c_int(w), C.c_int(h), C.byref(f), _p(np.ascontiguousarray(mk, np.int32)), C.c_int(len(mk)), _p(st))
+        words.append(st[:len(mk)].copy())
+    return mk, np.stack(words) if words else np.zeros((0, len(mk)), np.uint32)
+
+
+def pair_wide(o, Lm, Rm, tests, s, naive=False):
+    """Supports of the extended mode: tuples compared from the last word down, dense ranks, then the ordinary
+    findCorrespondences + rectifiedMatch filter restatement (gpco_match) on the ranks."""
+    mkl, wl = wide_words(o, Lm, tests, s.gradient_threshold, naive)
+    mkr, wr = wide_words(o, Rm, tests, s.gradient_threshold, naive)
+    both = np.concatenate([wl, wr], axis=1)[::-1].T            # rows = candidates, columns = last word first
+    _, inv = np.unique(both, axis=0, return_inverse=True)       # lexicographic, dense
+    inv = inv.reshape(-1).astype(np.uint32)
+    h, w = Lm.shape
+    return o.match(mkl, inv[:len(mkl)], mkr, inv[len(mkl):], w, s), len(mkl), len(mkr)
