@@ -424,7 +424,13 @@ match_rows_fast_kernel(const MatchArgs args) {
   {
     uint4* z = reinterpret_cast<uint4*>(nib) + tid;
     const int rounds = ((1 << nwl) + (1 << nsl)) / (4 * kThreadsB);            // tables are multiples of 4 * kThreadsB words
-    for (int i = 0; i < rounds; i++) z[i * kThreadsB] = make_uint4(0, 0, 0, 0);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    if (rounds == 6) {                                                         // the usual sizing (16 + 8 bytes per candidate slot): straight-line stores
+#pragma unroll
+      for (int i = 0; i < 6; i++) z[i * kThreadsB] = zero;
+    } else {
+      for (int i = 0; i < rounds; i++, z += kThreadsB) *z = zero;
+    }
   }
   uint32_t any_l = 0, any_r = 0;
 #pragma unroll

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
-"""profiles/traffic.json from `ncu --set full` reports of the small bench (--batch 32: 64 images, 32 pairs):
-dram__bytes_read.sum + dram__bytes_write.sum per launch, divided by the launch's pixel count (kernel A: image pixels, kernel B: pixels of one image per pair).
-usage: python scripts/ncu_traffic.py <round tag> kernelA.ncu-rep kernelB.ncu-rep"""
+"""profiles/traffic.json from `ncu --set full` reports captured at the benchmarked batch (scripts/gpu_profile.sh):
+dram__bytes_read.sum + dram__bytes_write.sum per launch, divided by the launch's pixel count (kernels A1 / A2: pixels of all
+images of the step, matcher kernels: pixels of one image per pair).  bench.py multiplies back by the pixels of its step.
+The bench's "match_rows" bucket is the sum of the row matcher's kernels (fast + tail); "emit_supports" is kernel C.
+usage: python scripts/ncu_traffic.py <round tag> <pairs per step> report.ncu-rep [more reports]"""
 import csv
 import io
 import json
@@ -12,18 +14,25 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MULT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 PIX = 1024 * 436
-UNITS = {"smooth_sobel": 64 * PIX, "hash_tiles": 64 * PIX, "match_rows": 32 * PIX}      # image pixels / pair pixels (one side) per launch at --batch 32
-out = {"source": f"ncu --set full, {sys.argv[1]} (profiles/), small bench --batch 32", "dram_bytes_per_pixel": {}}
-for rep in sys.argv[2:]:
+B = int(sys.argv[2])
+BUCKET = {"smooth_sobel": ("smooth_sobel", 2 * B * PIX), "hash_tiles": ("hash_tiles", 2 * B * PIX), "match_rows_fast": ("match_rows", B * PIX),
+          "match_rows_tail": ("match_rows", B * PIX), "emit_supports": ("emit_supports", B * PIX)}
+out = {"source": f"ncu --set full, {sys.argv[1]} (profiles/), bench step of {B} pairs (the benchmarked batch)", "dram_bytes_per_pixel": {},
+       "per_kernel_dram_bytes_per_launch": {}}
+for rep in sys.argv[3:]:
     rows = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
+    seen = set()
     for r in rows[2:]:
         name = r[col["Kernel Name"]]
-        key = next((k for k in UNITS if k in name), None)
-        if key is None:
+        key = next((k for k in BUCKET if k in name), None)
+        if key is None or key in seen:
             continue
+        seen.add(key)
         tot = sum(float(r[col[m]].replace(",", "")) * MULT[units[col[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-        out["dram_bytes_per_pixel"][key] = tot / UNITS[key]
+        bucket, pix = BUCKET[key]
+        out["per_kernel_dram_bytes_per_launch"][key] = tot
+        out["dram_bytes_per_pixel"][bucket] = out["dram_bytes_per_pixel"].get(bucket, 0.0) + tot / pix
 json.dump(out, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 print(json.dumps(out, indent=1))
