@@ -33,7 +33,7 @@ __device__ __forceinline__ uint32_t atomic_inc_ret(uint32_t* p) { return atomicA
 #define GPC_CHECK(cond) do { } while (0)
 #endif
 
-constexpr int kOvCap = 128;                   // fast matcher: capacity of each side's overflow list
+constexpr int kOvCap = 256;                   // fast matcher: capacity of each side's overflow list
 
 // shared memory of the general matcher: out[pow2cap] u64 | cnt[nb] u32 | entry[2*wcap] u32 | bcnt, bstart
 size_t match_smem_bytes(int wcap, int table_log2) {
@@ -582,14 +582,21 @@ constexpr int kTailWarps = 8;                 // rows per CTA
 constexpr int kTailCap = 256;                 // matches a warp orders in its slice of shared memory
 
 
-__global__ void __launch_bounds__(32 * kTailWarps, 5)
+// per-warp shared memory: 256 group counters + 256 cursors (the ordering uses 32 of each), keys and payloads of up to
+// 2 * kOvCap overflow entries / kTailCap match records
+constexpr int kTailSlots = (2 * kOvCap > kTailCap) ? 2 * kOvCap : kTailCap;
+constexpr int kTailWords = 2 * kBuckets + 2 * kTailSlots;          // per warp
+size_t tail_smem_bytes() { return (size_t)kTailWarps * kTailWords * 4; }
+
+__global__ void __launch_bounds__(32 * kTailWarps, 4)
 match_rows_tail_kernel(const MatchArgs args, int n_pairs) {
-  // per warp: 32 bucket counters / cursors (one bucket per lane: the top 5 state bits), keys and payloads of up to
-  // kTailCap records; the overflow states share the record arrays (they are consumed before the ordering starts)
-  __shared__ uint32_t sm_cnt[kTailWarps][32], sm_cur[kTailWarps][32], sm_m[kTailWarps];
-  __shared__ __align__(16) uint32_t sm_key[kTailWarps][kTailCap], sm_val[kTailWarps][kTailCap];
-  static_assert(kOvCap <= kTailCap, "overflow states fit the record arrays");
+  extern __shared__ __align__(16) uint32_t tail_smem[];
+  __shared__ uint32_t sm_m[kTailWarps];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t* cnt = tail_smem + (size_t)wid * kTailWords;             // [kBuckets]
+  uint32_t* cur = cnt + kBuckets;                                    // [kBuckets]
+  uint32_t* bk = cur + kBuckets;                                     // [kTailSlots] keys
+  uint32_t* bv = bk + kTailSlots;                                    // [kTailSlots] payloads
   const int rows = args.H - 2 * kRadius;
   const long long r = (long long)blockIdx.x * kTailWarps + wid;
   if (r >= (long long)rows * n_pairs) return;
@@ -600,69 +607,71 @@ match_rows_tail_kernel(const MatchArgs args, int n_pairs) {
   unsigned long long* mrec = args.mrec + grow * args.W;
   uint32_t m = (uint32_t)hdr.x;
   const uint32_t nl = (uint32_t)hdr.y, nr = (uint32_t)hdr.z;
-  // the row's first kTailCap match records: issued now, consumed after the overflow step
-  unsigned long long rec[kTailCap / 32];
-#pragma unroll
-  for (int j = 0; j < kTailCap / 32; j++) {
-    const uint32_t i = (uint32_t)lane + 32u * j;
-    rec[j] = (i < m) ? mrec[i] : 0ull;
-  }
-  // ---- overflow entries ------------------------------------------------------------------------------------
-  uint32_t extra_key = 0, extra_val = 0;                    // a lane finds at most one match per round; rounds > 1 are rare
-  uint32_t lim = m;                                         // records held in rec[]
+  // ---- overflow entries: a hash-partitioned join (linear in their number) ------------------------------------
+  // group = 8 bits of a multiplicative hash of the state; both lists are counted, scanned and scattered into group
+  // segments (left entries carry bit 31 clear, right entries set), then every left entry walks its own group
   if (nl > 0u && nr > 0u) {
     const uint32_t* ovl_s = args.ovbuf + grow * (4 * kOvCap);
     const uint32_t* ovl_x = ovl_s + kOvCap;
     const uint32_t* ovr_s = ovl_x + kOvCap;
     const uint32_t* ovr_x = ovr_s + kOvCap;
-    uint32_t* ls = sm_key[wid];                             // left states, then (sm_val) right states
-    uint32_t* rs = sm_val[wid];
-    const uint32_t nl4 = (nl + 3u) & ~3u, nr4 = (nr + 3u) & ~3u;        // entries past a list's end: 0 = equal to nothing
-    for (uint32_t i = lane; i < nl4; i += 32) ls[i] = (i < nl) ? ovl_s[i] : 0u;
-    for (uint32_t i = lane; i < nr4; i += 32) rs[i] = (i < nr) ? ovr_s[i] : 0u;
+    const uint32_t n = nl + nr;
+#pragma unroll
+    for (int k = 0; k < kBuckets / 32 / 4; k++) reinterpret_cast<uint4*>(cnt)[lane + 32 * k] = make_uint4(0, 0, 0, 0);
     if (lane == 0) sm_m[wid] = m;
     __syncwarp();
-    for (uint32_t i = lane; i < nl; i += 32) {
-      const uint32_t s = ls[i];
-      uint32_t cl = 0, cr = 0, jr = 0;
-      for (uint32_t j = 0; j < nl; j += 4) {
-        const uint4 q = *reinterpret_cast<const uint4*>(ls + j);
-        cl += (q.x == s ? 1u : 0u) + (q.y == s ? 1u : 0u) + (q.z == s ? 1u : 0u) + (q.w == s ? 1u : 0u);
+    for (uint32_t i = lane; i < n; i += 32) {
+      const uint32_t v = (i < nl) ? ovl_s[i] : ovr_s[i - nl];
+      atomicAdd(&cnt[((v & 0x7fffffffu) * kHashMul) >> 24], 1u);
+    }
+    __syncwarp();
+    {                                                       // exclusive scan of the 256 counters, 8 per lane
+      const uint4 a = reinterpret_cast<const uint4*>(cnt)[2 * lane], b = reinterpret_cast<const uint4*>(cnt)[2 * lane + 1];
+      const uint32_t sum = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+      uint32_t incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+      uint32_t run = incl - sum;
+      uint4 o0, o1;
+      o0.x = run; run += a.x; o0.y = run; run += a.y; o0.z = run; run += a.z; o0.w = run; run += a.w;
+      o1.x = run; run += b.x; o1.y = run; run += b.y; o1.z = run; run += b.z; o1.w = run;
+      reinterpret_cast<uint4*>(cur)[2 * lane] = o0;
+      reinterpret_cast<uint4*>(cur)[2 * lane + 1] = o1;
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += 32) {               // scatter; cur[g] ends at the group's end
+      const bool left = i < nl;
+      const uint32_t v = (left ? ovl_s[i] : ovr_s[i - nl]) & 0x7fffffffu;
+      const uint32_t x = left ? ovl_x[i] : ovr_x[i - nl];
+      const uint32_t p = atomicAdd(&cur[(v * kHashMul) >> 24], 1u);
+      bk[p] = left ? v : (v | 0x80000000u);
+      bv[p] = x;
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += 32) {               // every left entry: equal states in its group, per side
+      const uint32_t key = bk[i];
+      if (key >> 31) continue;
+      const uint32_t g = (key * kHashMul) >> 24;
+      const uint32_t gn = cnt[g], g0 = cur[g] - gn;
+      uint32_t cl = 0, cr = 0, x2 = 0;
+      for (uint32_t j = 0; j < gn; j++) {
+        const uint32_t t = bk[g0 + j] ^ key;                // 0: same state, left; 0x80000000: same state, right
+        cl += (t == 0u) ? 1u : 0u;
+        if (t == 0x80000000u) { cr++; x2 = bv[g0 + j]; }
       }
-      if (cl == 1u) {                                       // most overflow entries are repeated left states: no match possible
-        for (uint32_t j = 0; j < nr; j += 4) {
-          const uint4 q = *reinterpret_cast<const uint4*>(rs + j);
-          const bool e0 = q.x == s, e1 = q.y == s, e2 = q.z == s, e3 = q.w == s;
-          cr += (e0 ? 1u : 0u) + (e1 ? 1u : 0u) + (e2 ? 1u : 0u) + (e3 ? 1u : 0u);
-          jr = e0 ? j : e1 ? j + 1 : e2 ? j + 2 : e3 ? j + 3 : jr;
-        }
-        if (cr == 1u) {
-          const uint32_t xl = ovl_x[i], x2 = ovr_x[jr];
-          const int dx = (int)xl - (int)x2;
-          if (dx <= args.disp_high && -dx <= args.disp_high && 0 <= args.vertical_tolerance) {
-            const uint32_t p = atom_add_shared(&sm_m[wid], 1u);
-            GPC_CHECK(p < (uint32_t)args.W);
-            mrec[p] = ((unsigned long long)(s & 0x7fffffffu) << 32) | (unsigned long long)((xl << 16) | x2);
-            if (p < (uint32_t)kTailCap && i < 32u) { extra_key = (s & 0x7fffffffu) | 0x80000000u; extra_val = (xl << 16) | x2; }
-          }
+      if (cl == 1u && cr == 1u) {
+        const uint32_t xl = bv[i];
+        const int dx = (int)xl - (int)x2;
+        if (dx <= args.disp_high && -dx <= args.disp_high && 0 <= args.vertical_tolerance) {
+          const uint32_t p = atom_add_shared(&sm_m[wid], 1u);
+          GPC_CHECK(p < (uint32_t)args.W);
+          mrec[p] = ((unsigned long long)key << 32) | (unsigned long long)((xl << 16) | x2);
         }
       }
     }
     __syncwarp();
-    const uint32_t m1 = m;
     m = sm_m[wid];
     __syncwarp();                                         // the arrays are reused below
-    // matches appended by this warp: lanes that found one in the first round still hold it; reload only in the
-    // rare other cases (several rounds) -- global writes of the warp are visible after __syncwarp
-    if (m != m1 && m <= (uint32_t)kTailCap && nl > 32u) {
-#pragma unroll
-      for (int j = 0; j < kTailCap / 32; j++) {
-        const uint32_t i = (uint32_t)lane + 32u * j;
-        rec[j] = (i < m) ? mrec[i] : 0ull;
-      }
-      extra_key = 0;
-      lim = m;
-    }
   }
   if (lane == 0) args.rowmatch[grow] = (int32_t)m;
   if (m == 0u) return;
@@ -673,18 +682,20 @@ match_rows_tail_kernel(const MatchArgs args, int n_pairs) {
     return;
   }
   const int shift = args.key_bits > 5 ? args.key_bits - 5 : 0;        // bucket = top 5 state bits = the lane that owns it
-  uint32_t* cnt = sm_cnt[wid];
-  uint32_t* cur = sm_cur[wid];
-  uint32_t* bk = sm_key[wid];
-  uint32_t* bv = sm_val[wid];
+  // the row's match records (the ones this warp appended are visible after the __syncwarp above)
+  unsigned long long rec[kTailCap / 32];
+#pragma unroll
+  for (int j = 0; j < kTailCap / 32; j++) {
+    const uint32_t i = (uint32_t)lane + 32u * j;
+    rec[j] = (i < m) ? mrec[i] : 0ull;
+  }
   cnt[lane] = 0u;
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < kTailCap / 32; j++) {
     const uint32_t i = (uint32_t)lane + 32u * j;
-    if (i < lim) atomicAdd(&cnt[(uint32_t)(rec[j] >> 32) >> shift], 1u);
+    if (i < m) atomicAdd(&cnt[(uint32_t)(rec[j] >> 32) >> shift], 1u);
   }
-  if (extra_key) atomicAdd(&cnt[(extra_key & 0x7fffffffu) >> shift], 1u);
   __syncwarp();
   {                                                       // exclusive scan of the 32 counters, one per lane
     const uint32_t c = cnt[lane];
@@ -701,16 +712,11 @@ match_rows_tail_kernel(const MatchArgs args, int n_pairs) {
 #pragma unroll
   for (int j = 0; j < kTailCap / 32; j++) {               // scatter into bucket segments; cur[b] ends at the bucket's end
     const uint32_t i = (uint32_t)lane + 32u * j;
-    if (i < lim) {
+    if (i < m) {
       const uint32_t key = (uint32_t)(rec[j] >> 32);
       const uint32_t p = atomicAdd(&cur[key >> shift], 1u);
       bk[p] = key; bv[p] = (uint32_t)rec[j];
     }
-  }
-  if (extra_key) {
-    const uint32_t key = extra_key & 0x7fffffffu;
-    const uint32_t p = atomicAdd(&cur[key >> shift], 1u);
-    bk[p] = key; bv[p] = extra_val;
   }
   __syncwarp();
   for (uint32_t i = lane; i < m; i += 32) {               // rank inside the bucket, write to the final position
@@ -765,7 +771,8 @@ static cudaError_t configure_one(int max_smem) {
 }
 
 cudaError_t configure_match_rows(int max_smem) {
-  cudaError_t e = configure_one<1, 256>(max_smem);
+  cudaError_t e = cudaFuncSetAttribute(match_rows_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem_bytes());
+  if (e == cudaSuccess) e = configure_one<1, 256>(max_smem);
   if (e == cudaSuccess) e = configure_one<1, 512>(max_smem);
   if (e == cudaSuccess) e = configure_one<1, 1024>(max_smem);
   if (e == cudaSuccess) e = configure_one<2, 1024>(max_smem);
@@ -796,7 +803,7 @@ cudaError_t launch_match_rows(const MatchArgs& args, int n_pairs, int general, i
     if (general) match_rows_general_kernel<KQ, T><<<grid, T, smem_g, stream>>>(args, nullptr, nullptr);                  \
     else {                                                                                                      \
       match_rows_fast_kernel<KQ, T><<<grid, T, smem_f, stream>>>(args);                                         \
-      match_rows_tail_kernel<<<tail_grid, 32 * kTailWarps, 0, stream>>>(args, n_pairs);                         \
+      match_rows_tail_kernel<<<tail_grid, 32 * kTailWarps, tail_smem_bytes(), stream>>>(args, n_pairs);         \
       order_rows_kernel<T><<<list_grid, T, smem_o, stream>>>(args, args.big_hdr, args.big_ent);                         \
       match_rows_general_kernel<KQ, T><<<list_grid, T, smem_g, stream>>>(args, args.fb_hdr, args.fb_ent);                 \
     }                                                                                                           \
