@@ -18,6 +18,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -25,6 +26,7 @@
 #include <functional>
 #include <iostream>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -214,22 +216,51 @@ class Buffer {
   Buffer() {}
   Buffer(const int r, const int c) : width(c), height(r), rows_(r), cols_(detail::align16(c)), v_((size_t)rows_ * cols_) {}
   Buffer(const int r, const int c, T color) : width(c), height(r), rows_(r), cols_(detail::align16(c)), v_((size_t)rows_ * cols_, color) {}
+  // copies of a buffer whose pixels have not been fetched yet stay lazy (each copy fetches into its own storage)
+  Buffer(const Buffer& o) { *this = o; }
+  Buffer(Buffer&& o) noexcept { *this = std::move(o); }
+  Buffer& operator=(const Buffer& o) {
+    if (this == &o) return *this;
+    width = o.width; height = o.height; rows_ = o.rows_; cols_ = o.cols_; lazy_ = o.lazy_;
+    const bool p = o.pending_.load(std::memory_order_acquire);
+    if (p) v_.clear(); else v_ = o.v_;
+    pending_.store(p, std::memory_order_release);
+    return *this;
+  }
+  Buffer& operator=(Buffer&& o) noexcept {
+    if (this == &o) return *this;
+    width = o.width; height = o.height; rows_ = o.rows_; cols_ = o.cols_; lazy_ = std::move(o.lazy_);
+    v_ = std::move(o.v_);
+    pending_.store(o.pending_.load(std::memory_order_acquire), std::memory_order_release);
+    return *this;
+  }
 
   // B200 addition: the pixels may be produced on first access (Forest::preprocessImage leaves smooth / grad on the
-  // device until somebody reads them).  `fill` receives data(); dimensions are known from the start.
-  void setLazyFill(std::function<void(T*)> fill) { lazy_ = std::make_shared<std::function<void(T*)>>(std::move(fill)); }
-  bool isLazy() const { return (bool)lazy_; }
+  // device until somebody reads them).  `fill` receives data(); dimensions are known from the start, the storage
+  // itself is allocated on first access too.
+  static Buffer lazy(const int r, const int c, std::function<void(T*)> fill) {
+    Buffer b;
+    b.width = c; b.height = r; b.rows_ = r; b.cols_ = detail::align16(c);
+    b.lazy_ = std::make_shared<std::function<void(T*)>>(std::move(fill));
+    b.pending_.store(true, std::memory_order_release);
+    return b;
+  }
+  void setLazyFill(std::function<void(T*)> fill) {
+    lazy_ = std::make_shared<std::function<void(T*)>>(std::move(fill));
+    pending_.store(true, std::memory_order_release);
+  }
+  bool isLazy() const { return pending_.load(std::memory_order_acquire); }
 
   T* data() { materialize(); return v_.data(); }
   const T* data() const { materialize(); return v_.data(); }
   int rows() const { return rows_; }
   int cols() const { return cols_; }
-  long size() const { return (long)v_.size(); }
+  long size() const { return (long)rows_ * cols_; }
   T& operator()(int r, int c) { materialize(); return v_[(size_t)r * cols_ + c]; }
   const T& operator()(int r, int c) const { materialize(); return v_[(size_t)r * cols_ + c]; }
 
   // Eigen-style resize: contents unspecified afterwards (here: zero)
-  void resize(int r, int c) { lazy_.reset(); rows_ = r; cols_ = c; v_.assign((size_t)r * c, T()); }
+  void resize(int r, int c) { drop_lazy(); rows_ = r; cols_ = c; v_.assign((size_t)r * c, T()); }
   void conservativeResize(int r, int c) {
     materialize();
     std::vector<T> nv((size_t)r * c, T());
@@ -240,7 +271,7 @@ class Buffer {
 
   void setPixel(int x, int y, T color) { materialize(); v_[(size_t)cols_ * y + x] = color; }
   T getPixel(int x, int y) const { materialize(); return v_[(size_t)cols_ * y + x]; }
-  void set(T color) { lazy_.reset(); std::fill(v_.begin(), v_.end(), color); }
+  void set(T color) { drop_lazy(); v_.assign((size_t)rows_ * cols_, color); }
   Dimension getDimension() { return Dimension(cols_, rows_); }
 
   // buffer.hpp:630-654
@@ -269,7 +300,7 @@ class Buffer {
     detail::PngImage img;
     const std::string err = detail::png_decode(filename, &img);
     if (!err.empty()) { std::cout << err << std::endl; return 1; }
-    lazy_.reset();
+    drop_lazy();
     width = img.width; height = img.height;
     rows_ = height; cols_ = detail::align16(width);
     v_.assign((size_t)rows_ * cols_, T());
@@ -316,16 +347,24 @@ class Buffer {
     std::cout << "ERR: writePNGRGB needs a Buffer<RGBColor>" << std::endl;
   }
 
+  // Reading a PreprocessedImage from several threads is safe in the reference (plain const reads), so the first access
+  // that fetches the pixels is made safe here: double-checked under one lock per element type.  The fill may take the
+  // device-context lock; nothing enters materialize() while holding that lock (inference.hpp touches lazy buffers first).
   void materialize() const {
-    if (!lazy_) return;
-    std::shared_ptr<std::function<void(T*)>> f;
-    f.swap(lazy_);                                  // cleared first: the fill may touch this buffer
-    (*f)(v_.data());
+    if (!pending_.load(std::memory_order_acquire)) return;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!pending_.load(std::memory_order_relaxed)) return;
+    if (v_.size() != (size_t)rows_ * cols_) v_.assign((size_t)rows_ * cols_, T());
+    if (lazy_) (*lazy_)(v_.data());
+    pending_.store(false, std::memory_order_release);
   }
+  void drop_lazy() { pending_.store(false, std::memory_order_release); lazy_.reset(); }
 
   int rows_ = 0, cols_ = 0;
   mutable std::vector<T> v_;
   mutable std::shared_ptr<std::function<void(T*)>> lazy_;
+  mutable std::atomic<bool> pending_{false};
 };
 
 // buffer.hpp:949-1014: supports drawn over the gray image with the KITTI disparity colour map.  The eight-entry table

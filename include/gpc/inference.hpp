@@ -181,6 +181,8 @@ class Forest {
     std::shared_ptr<detail::ResidentImage> resident;   // B200 addition: raw image kept on the device
     PreprocessedImage(ndb::Buffer<uint8_t>& smooth, ndb::Buffer<uint8_t>& grad, std::vector<int>& mask)
         : smooth(smooth), grad(grad), mask(mask) {}
+    PreprocessedImage(ndb::Buffer<uint8_t>&& smooth, ndb::Buffer<uint8_t>&& grad, std::vector<int>&& mask)   // B200 addition
+        : smooth(std::move(smooth)), grad(std::move(grad)), mask(std::move(mask)) {}
   };
 
   enum CorrMethod { sorting = 's', hashtable = 'h' };
@@ -220,16 +222,17 @@ class Forest {
     gpc_ctx* c = cx->ctx;
     auto res = std::make_shared<detail::ResidentImage>();
     res->cx = cx; res->thr = settings.gradientThreshold_;
-    std::vector<int> mask((size_t)(w - 26 > 0 ? w - 26 : 0) * (size_t)(h - 26 > 0 ? h - 26 : 0) + 1);
-    int n = 0;
+    std::vector<int> mask;
     {
       std::lock_guard<std::recursive_mutex> lk(cx->mu);
+      int n = 0;
       detail::check(c, gpc_image_upload(c, img.data(), w, h, w, &res->image), "gpc_image_upload");
-      detail::check(c, gpc_image_preprocess(c, res->image, settings.gradientThreshold_, nullptr, nullptr,
-                                            mask.data(), (int)mask.size(), &n), "gpc_image_preprocess");
+      detail::check(c, gpc_image_preprocess(c, res->image, settings.gradientThreshold_, nullptr, nullptr, nullptr, 0, &n),
+                    "gpc_image_preprocess");
+      const int32_t* view = gpc_mask_view(c, &n);            // the list sits in the context's pinned staging buffer:
+      static_assert(sizeof(int) == sizeof(int32_t), "mask element type");
+      if (view && n > 0) mask.assign(view, view + n);         // one copy, no zero fill
     }
-    mask.resize((size_t)n);
-    ndb::Buffer<uint8_t> smooth(h, w), grad(h, w);
     // both images come from one kernel run: whichever is touched first fetches the pair into a shared block
     struct Pair { std::vector<uint8_t> s, g; bool done = false; std::mutex mu; };
     auto pr = std::make_shared<Pair>();
@@ -244,9 +247,8 @@ class Forest {
       }
       std::memcpy(dst, want_smooth ? pr->s.data() : pr->g.data(), P);
     };
-    smooth.setLazyFill([fetch](uint8_t* d) { fetch(d, true); });
-    grad.setLazyFill([fetch](uint8_t* d) { fetch(d, false); });
-    PreprocessedImage out(smooth, grad, mask);
+    PreprocessedImage out(ndb::Buffer<uint8_t>::lazy(h, w, [fetch](uint8_t* d) { fetch(d, true); }),
+                          ndb::Buffer<uint8_t>::lazy(h, w, [fetch](uint8_t* d) { fetch(d, false); }), std::move(mask));
     out.resident = res;
     return out;
   }
@@ -323,13 +325,14 @@ class Forest {
                                                        InferenceSettings& settings) {
     (void)grad; (void)settings;
     const int w = img.cols(), h = img.rows();
+    const uint8_t* pixels = img.data();                     // a lazily fetched image materialises here, before the context lock
     auto cx = detail::runtime().get(w, h);
     std::lock_guard<std::recursive_mutex> lk(cx->mu);
     gpc_ctx* c = cx->ctx;
     upload_forest(c, fastmask);
     std::vector<uint32_t> states(idx.size());
     std::vector<int32_t> idx32(idx.begin(), idx.end());
-    detail::check(c, gpc_hash_smooth(c, img.data(), w, h, idx32.data(), (int)idx32.size(), states.data()), "gpc_hash_smooth");
+    detail::check(c, gpc_hash_smooth(c, pixels, w, h, idx32.data(), (int)idx32.size(), states.data()), "gpc_hash_smooth");
     std::vector<ndb::Descriptor> out(idx.size());
     for (size_t j = 0; j < idx.size(); j++)
       out[j] = ndb::Descriptor(ndb::Point(idx[j] % w, idx[j] / w), states[j]);

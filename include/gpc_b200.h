@@ -147,6 +147,9 @@ void gpc_image_release(gpc_image* image);
  * matcher only (a changed threshold, result mode or forest is detected and recomputed). */
 int gpc_image_preprocess(gpc_ctx* ctx, gpc_image* image, int gradient_threshold, uint8_t* smooth,
                          uint8_t* grad, int32_t* mask, int mask_cap, int* n_mask);
+/* the candidate list of the most recent gpc_image_preprocess / gpc_preprocess call of this context, in the context's
+ * page-locked staging buffer: n entries (as reported through n_mask); valid until the next call on the context */
+const int32_t* gpc_mask_view(gpc_ctx* ctx, int* n);
 /* preprocessImage's smoothed / gradient images of a resident image, on demand (either may be NULL) */
 int gpc_image_fetch(gpc_ctx* ctx, const gpc_image* image, int gradient_threshold, uint8_t* smooth, uint8_t* grad);
 int gpc_match_images(gpc_ctx* ctx, gpc_image* left, gpc_image* right, const gpc_settings* s,

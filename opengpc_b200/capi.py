@@ -23,7 +23,7 @@ SYMBOLS = ["gpc_create", "gpc_destroy", "gpc_last_error", "gpc_status_string", "
            "gpc_read_forest", "gpc_set_forest", "gpc_match_pair", "gpc_match_batch", "gpc_match_batch_device",
            "gpc_preprocess", "gpc_hash", "gpc_match_hash_images", "gpc_launch_count", "gpc_enable_kernel_timing",
            "gpc_kernel_times", "gpc_hash_smooth", "gpc_image_upload", "gpc_image_release", "gpc_image_preprocess",
-           "gpc_match_images", "gpc_correspond_images", "gpc_find_correspondences", "gpc_hashmatch", "gpc_set_result_mode", "gpc_set_matcher", "gpc_match_pyramid", "gpc_jit_status", "gpc_context_id", "gpc_image_fetch", "gpc_fetch_supports",
+           "gpc_match_images", "gpc_correspond_images", "gpc_find_correspondences", "gpc_hashmatch", "gpc_set_result_mode", "gpc_set_matcher", "gpc_match_pyramid", "gpc_jit_status", "gpc_context_id", "gpc_image_fetch", "gpc_fetch_supports", "gpc_mask_view",
            "gpc_pool_create", "gpc_pool_destroy", "gpc_pool_size", "gpc_pool_context", "gpc_pool_last_error", "gpc_pool_launch_count",
            "gpc_pool_set_forest", "gpc_pool_set_result_mode", "gpc_pool_match_batch", "gpc_host_alloc", "gpc_host_free",
            "gpc_read_forest_tests", "gpc_set_wide_forest", "gpc_match_pair_wide", "gpc_hash_wide"]
@@ -83,6 +83,8 @@ def load_library():
     lib.gpc_host_alloc.argtypes = [C.c_size_t]
     lib.gpc_host_free.restype = None
     lib.gpc_host_free.argtypes = [C.c_void_p]
+    lib.gpc_mask_view.restype = C.c_void_p
+    lib.gpc_mask_view.argtypes = [C.c_void_p, C.c_void_p]
     lib.gpc_context_id.restype = C.c_int64
     lib.gpc_context_id.argtypes = [C.c_void_p]
     for name in SYMBOLS:

@@ -124,6 +124,12 @@ struct gpc_ctx {
   uint32_t* d_wide = nullptr;      // hash planes [2 * words][2][H][W] (lazily allocated)
   size_t wide_bytes = 0;
   int matcher = GPC_MATCHER_AUTO;
+  // page-locked staging for the single-image entry points (uploads from / downloads to pageable caller memory are
+  // several times slower than a memcpy through this buffer); ev_stage marks the last asynchronous use
+  uint8_t* h_stage = nullptr;
+  size_t h_stage_bytes = 0;
+  cudaEvent_t ev_stage = nullptr;
+  int last_mask_n = 0;             // entries of the candidate list left in h_stage by gpc_image_preprocess (mask == NULL)
   // device blocks of released resident images, reused by gpc_image_upload (cudaMalloc / cudaFree cost more than the kernels)
   std::vector<std::pair<size_t, uint8_t*>> image_pool;
   int64_t launches = 0;
@@ -439,6 +445,20 @@ int run_match(gpc_ctx* c, const Slot& sl, int n_pairs, int w, int h, const gpc_s
   return mark_on(c, sl);                                                           // event 5
 }
 
+// Pinned staging of at least `bytes`; waits for the previous asynchronous use of the buffer.
+int ensure_host_stage(gpc_ctx* c, size_t bytes) {
+  if (!c->ev_stage) GPC_CUDA(c, cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
+  else GPC_CUDA(c, cudaEventSynchronize(c->ev_stage));
+  if (bytes > c->h_stage_bytes) {
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr; c->h_stage_bytes = 0;
+    const size_t want = std::max(bytes, (size_t)c->max_w * c->max_h * 4);
+    GPC_CUDA(c, cudaMallocHost(&c->h_stage, want));
+    c->h_stage_bytes = want;
+  }
+  return GPC_OK;
+}
+
 int ensure_debug_buffers(gpc_ctx* c) {
   size_t P = (size_t)c->max_w * c->max_h;
   if (!c->d_dbg8) GPC_CUDA(c, cudaMalloc(&c->d_dbg8, 2 * P));
@@ -546,6 +566,8 @@ void gpc_destroy(gpc_ctx* c) {
   cudaFree(c->d_rowoff); cudaFree(c->d_totals); cudaFree(c->d_ncand); cudaFree(c->d_pair_base); cudaFree(c->d_out);
   gpc::jit_destroy(c->jit);
   cudaFree(c->d_dbg8); cudaFree(c->d_mask); cudaFree(c->d_gws); cudaFree(c->d_pyr); cudaFree(c->d_wide);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->ev_stage) cudaEventDestroy(c->ev_stage);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->h_pair_base) cudaFreeHost(c->h_pair_base);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -1004,8 +1026,14 @@ int gpc_image_upload(gpc_ctx* c, const uint8_t* img, int w, int h, int stride, g
     }
   if (!im->d_raw) e = cudaMalloc(&im->d_raw, im->block_bytes);
   im->d_cache = im->d_raw ? im->d_raw + raw_bytes : nullptr;
-  if (e == cudaSuccess) e = cudaMemcpy2DAsync(im->d_raw, w, img, stride, w, h, cudaMemcpyHostToDevice, c->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // the caller's buffer may be pageable / short-lived
+  // the caller's buffer may be pageable and short-lived: copy it into pinned staging on the host (a memcpy), then one
+  // asynchronous DMA; nothing waits here -- the next user of the staging buffer waits for ev_stage
+  if (e == cudaSuccess && ensure_host_stage(c, (size_t)w * h) != GPC_OK) e = cudaErrorMemoryAllocation;
+  if (e == cudaSuccess) {
+    for (int y = 0; y < h; y++) std::memcpy(c->h_stage + (size_t)y * w, img + (size_t)y * stride, (size_t)w);
+    e = cudaMemcpyAsync(im->d_raw, c->h_stage, (size_t)w * h, cudaMemcpyHostToDevice, c->stream);
+  }
+  if (e == cudaSuccess) e = cudaEventRecord(c->ev_stage, c->stream);
   if (e != cudaSuccess) {
     cudaFree(im->d_raw);
     delete im;
@@ -1074,6 +1102,11 @@ static int preprocess_device(gpc_ctx* c, const uint8_t* d_img, int w, int h, int
     GPC_CUDA(c, gpc::launch_mask_list(c->d_hash, c->d_rows, c->d_rowoff, w, h, c->d_mask, (int)std::min<size_t>(P, 0x7fffffff), c->stream));
     c->launches += 2;
     GPC_CUDA(c, cudaMemcpyAsync(c->h_counts, c->d_rowoff + h, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    // the whole candidate capacity of the interior goes to pinned staging in the same stream (its length is not known
+    // on the host yet, the interior bounds it); the caller's copy, or gpc_mask_view, reads the first n entries
+    const size_t cap_bytes = (size_t)std::max(w - 2 * gpc::kRadius, 0) * (size_t)std::max(h - 2 * gpc::kRadius, 0) * sizeof(int32_t);
+    rc = ensure_host_stage(c, std::max<size_t>(cap_bytes, 4)); if (rc) return rc;
+    if (cap_bytes) GPC_CUDA(c, cudaMemcpyAsync(c->h_stage, c->d_mask, cap_bytes, cudaMemcpyDeviceToHost, c->stream));
   }
   if (smooth) GPC_CUDA(c, cudaMemcpyAsync(smooth, d_smooth, P, cudaMemcpyDeviceToHost, c->stream));
   if (grad) GPC_CUDA(c, cudaMemcpyAsync(grad, d_grad, P, cudaMemcpyDeviceToHost, c->stream));
@@ -1081,9 +1114,10 @@ static int preprocess_device(gpc_ctx* c, const uint8_t* d_img, int w, int h, int
   if (mask || n_mask) {
     const int n = c->h_counts[0];
     if (n_mask) *n_mask = n;
+    c->last_mask_n = n;
     if (mask) {
       if (n > mask_cap) return fail(c, GPC_E_CAPACITY, "mask buffer too small: need " + std::to_string(n));
-      GPC_CUDA(c, cudaMemcpy(mask, c->d_mask, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      std::memcpy(mask, c->h_stage, (size_t)n * sizeof(int32_t));
     }
   }
   return GPC_OK;
@@ -1199,15 +1233,26 @@ int gpc_hash_smooth(gpc_ctx* c, const uint8_t* smooth, int w, int h, const int32
   return GPC_OK;
 }
 
+// The candidate list the most recent gpc_image_preprocess / gpc_preprocess call left in the context's pinned staging
+// buffer (n entries as reported through n_mask); valid until the next call on the context.
+const int32_t* gpc_mask_view(gpc_ctx* c, int* n) {
+  if (!c || !c->h_stage) { if (n) *n = 0; return nullptr; }
+  if (n) *n = c->last_mask_n;
+  return reinterpret_cast<const int32_t*>(c->h_stage);
+}
+
 // The first n supports of the context's most recent single-pair result (gpc_match_pair / gpc_match_images), still on
 // the device: lets a caller that cannot bound the count ask for it first (cap = 0 -> GPC_E_CAPACITY with *n_out set).
 int gpc_fetch_supports(gpc_ctx* c, gpc_support* out, int n) {
   if (!c || n < 0 || (n > 0 && !out)) return fail(c, GPC_E_ARG, "null argument");
   if (n > c->out_cap) return fail(c, GPC_E_ARG, "more supports requested than the context holds");
   GPC_CUDA(c, cudaSetDevice(c->device));
-  if (n > 0) {
-    GPC_CUDA(c, cudaMemcpyAsync(out, c->d_out, (size_t)n * sizeof(gpc_support), cudaMemcpyDeviceToHost, c->stream));
+  if (n > 0) {                                                  // through pinned staging: `out` is usually pageable
+    int rc = ensure_host_stage(c, (size_t)n * sizeof(gpc_support)); if (rc) return rc;
+    GPC_CUDA(c, cudaMemcpyAsync(c->h_stage, c->d_out, (size_t)n * sizeof(gpc_support), cudaMemcpyDeviceToHost, c->stream));
     GPC_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::memcpy(out, c->h_stage, (size_t)n * sizeof(gpc_support));
+    c->last_mask_n = 0;
   }
   return GPC_OK;
 }
