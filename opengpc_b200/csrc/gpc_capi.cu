@@ -19,7 +19,9 @@
 #include <vector>
 
 namespace gpc {
-cudaError_t launch_smooth_sobel(const PreprocessArgs&, int n_img, bool debug_out, cudaStream_t);
+cudaError_t launch_smooth_sobel(const PreprocessArgs&, int n_img, bool debug_out, const void* raw_tmap, cudaStream_t);
+void smooth_sobel_tma_box(int* box_w, int* box_h);
+int make_u8_tensor_map(void* out_map, const uint8_t* base, int W, int H, int n_img, int box_w, int box_h);
 cudaError_t launch_prep_from_smooth(const uint8_t* smooth, const uint8_t* flags, uint8_t* smooth_x, uint16_t* cand, int32_t* rowcnt,
                                     int32_t* lastrow, int W, int H, int naive, cudaStream_t);
 cudaError_t configure_hash_tiles();
@@ -86,6 +88,12 @@ struct gpc_ctx {
   uint16_t* d_cand = nullptr;      // [2B][H][W/16] candidate masks
   alignas(64) unsigned char tmap[128];   // CUtensorMap over d_smooth for images of tmap_w x tmap_h
   int tmap_w = 0, tmap_h = 0;
+  // tensor maps over RAW images for kernel A1, keyed by (pointer, w, h, images): a few recent ones (the chunks of a
+  // pipelined batch alternate between slices of d_raw, callers of the device-resident entry bring their own buffers)
+  struct RawMap { alignas(64) unsigned char map[128]; const uint8_t* ptr = nullptr; int w = 0, h = 0, n = 0; };
+  RawMap raw_maps[8];
+  int raw_map_next = 0;
+  bool a1_tma = true;              // GPC_A1_TMA=0: always the staging-loop kernel
   uint32_t* d_hash = nullptr;      // [2B][H][W]
   uint32_t* d_stage = nullptr;     // [B][H][W]
   int32_t* d_rows = nullptr;       // rowcnt [2B][H]   (cleared per launch)
@@ -299,7 +307,22 @@ int run_preprocess(gpc_ctx* c, const Slot& sl, const uint8_t* d_images, int n_im
     a.smooth_out = d_smooth_out; a.grad_out = d_grad_out; a.W = w; a.H = h;
     a.naive = forest.naive;
     a.thr2 = forest.naive ? thr * thr : (int32_t)(int16_t)(thr * thr);             // filter.hpp:159 / :418
-    GPC_CUDA(c, gpc::launch_smooth_sobel(a, n_img, d_smooth_out || d_grad_out, sl.stream));
+    const void* raw_tmap = nullptr;
+    if (c->a1_tma && !forest.naive && (reinterpret_cast<uintptr_t>(d_images) & 15u) == 0) {
+      gpc_ctx::RawMap* hit = nullptr;
+      for (gpc_ctx::RawMap& m : c->raw_maps)
+        if (m.ptr == d_images && m.w == w && m.h == h && m.n == n_img) { hit = &m; break; }
+      if (!hit) {
+        hit = &c->raw_maps[c->raw_map_next];
+        c->raw_map_next = (c->raw_map_next + 1) % 8;
+        int bw = 0, bh = 0;
+        gpc::smooth_sobel_tma_box(&bw, &bh);
+        if (gpc::make_u8_tensor_map(hit->map, d_images, w, h, n_img, bw, bh) == 0) { hit->ptr = d_images; hit->w = w; hit->h = h; hit->n = n_img; }
+        else { hit->ptr = nullptr; hit = nullptr; }
+      }
+      if (hit) raw_tmap = hit->map;
+    }
+    GPC_CUDA(c, gpc::launch_smooth_sobel(a, n_img, d_smooth_out || d_grad_out, raw_tmap, sl.stream));
   }
   rc = mark_on(c, sl); if (rc) return rc;                                          // event 1
   gpc::HashArgs ha{};
@@ -528,6 +551,7 @@ int gpc_create(gpc_ctx** out, int device, int max_w, int max_h, int max_batch) {
   for (int l = 0; l < gpc_ctx::kLanes; l++) TRY(cudaStreamCreateWithFlags(&c->lane_stream[l], cudaStreamNonBlocking));
   TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   if (const char* e = std::getenv("GPC_CHUNK_PAIRS")) c->chunk_pairs = std::max(1, std::atoi(e));
+  if (const char* e = std::getenv("GPC_A1_TMA")) c->a1_tma = std::atoi(e) != 0;
   TRY(cudaMalloc(&c->d_rowmatch, B * max_h * sizeof(int32_t)));
   TRY(cudaMalloc(&c->d_fb, B * (2 * (size_t)max_h + 2) * sizeof(uint32_t)));
   TRY(cudaMemsetAsync(c->d_fb, 0, B * (2 * (size_t)max_h + 2) * sizeof(uint32_t), c->stream));

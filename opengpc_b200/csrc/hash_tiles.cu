@@ -229,8 +229,8 @@ cudaError_t configure_hash_tiles() {   // per device: opt in to > 48 KB dynamic 
   return e;
 }
 
-// Tensor map over the biased smoothed images [n_img][H][W] u8; box = one operand tile.
-int make_smooth_tensor_map(void* out_map, const uint8_t* base, int W, int H, int n_img) {
+// Tensor map over u8 images [n_img][H][W] with a box of box_w x box_h x 1 (zero fill outside the tensor).
+int make_u8_tensor_map(void* out_map, const uint8_t* base, int W, int H, int n_img, int box_w, int box_h) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -243,12 +243,17 @@ int make_smooth_tensor_map(void* out_map, const uint8_t* base, int W, int H, int
   }
   const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
   const cuuint64_t strides[2] = {(cuuint64_t)W, (cuuint64_t)W * (cuuint64_t)H};      // bytes, dims 1 and 2
-  const cuuint32_t box[3] = {(cuuint32_t)kPitch, (cuuint32_t)kSmRows, 1u};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims,
                             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+// Tensor map over the biased smoothed images; box = one operand tile of kernel A2.
+int make_smooth_tensor_map(void* out_map, const uint8_t* base, int W, int H, int n_img) {
+  return make_u8_tensor_map(out_map, base, W, H, n_img, kPitch, kSmRows);
 }
 
 cudaError_t launch_hash_tiles(const void* tensor_map, const HashArgs& args, const ForestDev& forest, int n_img, cudaStream_t stream) {

@@ -10,6 +10,8 @@
 // outputs is written exactly once, borders included, so kernel A2 can fetch arbitrary tiles of
 // the smoothed image with TMA.  Nothing here is a translation of the SSE code: the horizontal
 // floor-thirds are dp4a row sums, the vertical pass slides a 3-row register window.
+#include <cuda.h>
+
 #include "gpc_device.cuh"
 
 namespace gpc {
@@ -22,6 +24,14 @@ constexpr int kPrePitch = kPreW + 32;              // image cols x0-16 .. x0+kPr
 constexpr int kPrePitchW = kPrePitch / 4;
 constexpr int kPreRows = kPreH + 2;                // image rows y0-1 .. y0+kPreH
 constexpr int kPreThreads = 256;
+// TMA staging (kTma): the tile is fetched as two half tiles of 128 output columns, each with its own 16-byte aligned
+// halo -- image columns x0 + 128 k - 16 .. x0 + 128 k + 143 -- because a TMA box is at most 256 elements wide.  A
+// thread only ever reads the half tile its own output columns belong to.
+constexpr int kPreHalfPitch = 128 + 32;            // bytes per row of a half tile
+constexpr int kPreHalfPitchW = kPreHalfPitch / 4;
+constexpr int kPreHalfBytes = (kPreRows * kPreHalfPitch + 127) / 128 * 128;   // TMA destinations are 128-byte aligned
+constexpr int kPreHalfWords = kPreHalfBytes / 4;
+constexpr int kPreSmemWords = (2 * kPreHalfWords > kPreRows * kPrePitchW) ? 2 * kPreHalfWords : kPreRows * kPrePitchW;
 constexpr int kPreSegRows = kPreH / (kPreThreads / (kPreW / 4));   // rows per thread in the vertical pass
 
 // Horizontal floor-thirds of 4 consecutive pixels: h[k] = (p[x+k-1] + p[x+k] + p[x+k+1]) / 3.
@@ -77,11 +87,19 @@ __device__ __forceinline__ uint32_t border_mask(uint32_t m, int gy, int gxs, int
   return m;
 }
 
-// kDebugOut: also writes the unbiased smooth image and the 0/255 grad image (gpc_preprocess seam)
-template <bool kDebugOut>
-__global__ void __launch_bounds__(kPreThreads)
-smooth_sobel_kernel(const PreprocessArgs args) {
-  __shared__ __align__(16) uint32_t raw32[kPreRows * kPrePitchW];
+// Word that holds image column x0 + 4 * qw of tile row r (qw = 0 .. kPreW/4 - 1); [-1] and [+1 .. +4] are valid too.
+template <bool kTma>
+__device__ __forceinline__ const uint32_t* pre_word(const uint32_t* raw32, int r, int qw) {
+  if (kTma) return raw32 + (qw >> 5) * kPreHalfWords + r * kPreHalfPitchW + 4 + (qw & 31);
+  return raw32 + r * kPrePitchW + 4 + qw;
+}
+
+// kDebugOut: also writes the unbiased smooth image and the 0/255 grad image (gpc_preprocess seam).
+// kTma: the raw tile arrives as two TMA tensor copies (zero fill outside the image) instead of a staging loop.
+template <bool kDebugOut, bool kTma>
+__device__ __forceinline__ void smooth_sobel_body(const PreprocessArgs& args, const CUtensorMap* tmap) {
+  __shared__ __align__(128) uint32_t raw32[kPreSmemWords];
+  __shared__ __align__(8) unsigned long long mbar;
   __shared__ int cta_last;                                   // largest row of this tile with a candidate
   const int W = args.W, H = args.H;
   const int img = blockIdx.z;
@@ -92,7 +110,25 @@ smooth_sobel_kernel(const PreprocessArgs args) {
 
   if (threadIdx.x == 0) cta_last = -1;
   // ---- stage the raw tile (zero outside the image) ---------------------------------------------
-  {
+  if (kTma) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * kPreRows * kPreHalfPitch) : "memory");
+#pragma unroll
+      for (int k = 0; k < 2; k++)
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"((uint32_t)__cvta_generic_to_shared(raw32 + k * kPreHalfWords)), "l"(tmap), "r"(x0 + 128 * k - 16), "r"(y0 - 1), "r"(img), "r"(bar)
+            : "memory");
+    }
+    __syncthreads();                                         // the initialised barrier is visible to all waiters
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(bar) : "memory");
+  } else {
     constexpr int kChunks = kPrePitch / 16;
     uint4* dst = reinterpret_cast<uint4*>(raw32);
     for (int c = tid; c < kPreRows * kChunks; c += kPreThreads) {
@@ -103,8 +139,8 @@ smooth_sobel_kernel(const PreprocessArgs args) {
         v = __ldg(reinterpret_cast<const uint4*>(raw + (size_t)gy * W + gx));
       dst[c] = v;
     }
+    __syncthreads();
   }
-  __syncthreads();
 
   // ---- smoothed pixels: thread = (quad column, band of kPreSegRows rows), 3-row register window ---
   {
@@ -117,7 +153,7 @@ smooth_sobel_kernel(const PreprocessArgs args) {
       if (gxq == W - 4) colmask &= 0x00ffffffu;
       uint32_t ha[4], hb[4], hc[4];
       auto load_h = [&](int r, uint32_t h[4]) {            // raw-tile row r = image row y0 - 1 + r
-        const uint32_t* row = raw32 + r * kPrePitchW + 4 + q;
+        const uint32_t* row = pre_word<kTma>(raw32, r, q);
         hthirds(row[-1], row[0], row[1], h);
       };
       const int j0 = band * kPreSegRows;
@@ -155,7 +191,7 @@ smooth_sobel_kernel(const PreprocessArgs args) {
         uint32_t wm[3], q0[3], q1[3], q2[3], q3[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-          const uint32_t* row = raw32 + (ry + k) * kPrePitchW + 4 + 4 * sg;
+          const uint32_t* row = pre_word<kTma>(raw32, ry + k, 4 * sg);
           const uint4 v = *reinterpret_cast<const uint4*>(row);
           wm[k] = row[-1]; q0[k] = v.x; q1[k] = v.y; q2[k] = v.z; q3[k] = v.w;
         }
@@ -194,6 +230,18 @@ smooth_sobel_kernel(const PreprocessArgs args) {
   __syncthreads();
   if (tid == 0 && cta_last >= 0 && cta_last > *reinterpret_cast<volatile int32_t*>(args.lastrow + img))
     atomicMax(args.lastrow + img, cta_last);              // a stale read only costs a redundant atomic
+}
+
+template <bool kDebugOut>
+__global__ void __launch_bounds__(kPreThreads)
+smooth_sobel_kernel(const PreprocessArgs args) {
+  smooth_sobel_body<kDebugOut, false>(args, nullptr);
+}
+
+template <bool kDebugOut>
+__global__ void __launch_bounds__(kPreThreads)
+smooth_sobel_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PreprocessArgs args) {
+  smooth_sobel_body<kDebugOut, true>(args, &tmap);
 }
 
 // ---- the reference's SSE=OFF build: boxNaive + clearBoundary, sobelNaive (filter.hpp:157-231) --------------------
@@ -326,11 +374,22 @@ smooth_sobel_naive_kernel(const PreprocessArgs args) {
     atomicMax(args.lastrow + img, cta_last);
 }
 
-cudaError_t launch_smooth_sobel(const PreprocessArgs& args, int n_img, bool debug_out, cudaStream_t stream) {
+// box of one half tile of kernel A1 (see kPreHalfPitch): what the raw-image tensor map is encoded with
+void smooth_sobel_tma_box(int* box_w, int* box_h) { *box_w = kPreHalfPitch; *box_h = kPreRows; }
+
+// raw_tmap: tensor map over args.raw ([n_img][H][W] u8, box = smooth_sobel_tma_box) or nullptr (staging loop: the
+// raw pointer is not 16-byte aligned, or the naive result mode, whose tile is staged by linear address).
+cudaError_t launch_smooth_sobel(const PreprocessArgs& args, int n_img, bool debug_out, const void* raw_tmap, cudaStream_t stream) {
   dim3 grid((args.W + kPreW - 1) / kPreW, (args.H + kPreH - 1) / kPreH, n_img);
   if (args.naive) {
     if (debug_out) smooth_sobel_naive_kernel<true><<<grid, kPreThreads, 0, stream>>>(args);
     else smooth_sobel_naive_kernel<false><<<grid, kPreThreads, 0, stream>>>(args);
+    return cudaGetLastError();
+  }
+  if (raw_tmap) {
+    const CUtensorMap& tmap = *reinterpret_cast<const CUtensorMap*>(raw_tmap);
+    if (debug_out) smooth_sobel_tma_kernel<true><<<grid, kPreThreads, 0, stream>>>(tmap, args);
+    else smooth_sobel_tma_kernel<false><<<grid, kPreThreads, 0, stream>>>(tmap, args);
     return cudaGetLastError();
   }
   if (debug_out) smooth_sobel_kernel<true><<<grid, kPreThreads, 0, stream>>>(args);
