@@ -125,14 +125,14 @@ def golden_records(args, w, h):
     return {r["seed"]: r for r in recs} if recs else None
 
 
-def verify_batch(args, w, h, B, rank, d_out, d_n, d_nc, torch):
+def verify_batch(args, w, h, B, pair_ids, d_out, d_n, d_nc, torch):
     """Checks the batch the timed region just produced: every pair's counts against its seed's golden record, the
     ordered support list of the first distinct pairs by digest, and every tiled copy bit-identical to its original."""
     gold = golden_records(args, w, h)
     distinct = min(args.distinct, B)
     n = d_n.cpu().numpy().astype(np.int64)
     nc = d_nc.cpu().numpy().astype(np.int64)
-    seed_of = lambda j: 1234 + ((j - rank) % B) % distinct        # images were rolled by `rank` along the batch axis
+    seed_of = lambda j: 1234 + int(pair_ids[j]) % distinct        # pair g of the job is the synthetic pair of seed 1234 + g mod distinct
     checked = 0
     first = {}
     for j in range(B):
@@ -523,9 +523,11 @@ def main():
 
     B = args.batch
     P = w * h
-    images = make_images(w, h, B, args.distinct, args.sparse)     # [B, 2, h, w] uint8
-    if world > 1:   # each rank gets its own pairs (seeds shifted) -- independent units, no collective
-        images = np.roll(images, rank, axis=0)
+    # the job is world x B pairs; rank r owns pairs r, r + world, ... (opengpc_b200/shard.py) -- independent units, no collective
+    from opengpc_b200.shard import gather_support_counts, shard_pairs
+    mine = shard_pairs(world * B, rank, world)
+    base = make_images(w, h, min(args.distinct, B), args.distinct, args.sparse)
+    images = np.ascontiguousarray(base[mine % len(base)])          # [B, 2, h, w] uint8
     settings = g.sparsematch_settings()
     ctx = g.Context(device=local_rank, max_w=w, max_h=h, max_batch=B)
     ctx.set_forest(FORESTS[args.forest])
@@ -582,7 +584,10 @@ def main():
     if os.environ.get("GPC_BENCH_NO_VERIFY"):                      # kernel experiments that deliberately break the result
         verified = {"skipped": "GPC_BENCH_NO_VERIFY set: this line is NOT a valid measurement"}
     else:
-        verified = verify_batch(args, w, h, B, rank if world > 1 else 0, d_out, d_n, d_nc, torch)   # the batch the timed steps produced
+        verified = verify_batch(args, w, h, B, mine, d_out, d_n, d_nc, torch)   # the batch the timed steps produced
+        job_counts = gather_support_counts(n_sup, mine, world * B, dist, "cuda")          # results gathered per pair of the job
+        verified["job_pairs"] = int(world * B)
+        verified["job_supports"] = int(job_counts.sum())
 
     # ---- end to end through the C ABI with host buffers -----------------------------------------
     e2e = None
