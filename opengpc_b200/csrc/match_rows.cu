@@ -729,7 +729,9 @@ match_rows_tail_kernel(const MatchArgs args, int n_pairs) {
   }
 }
 
-// Block-wide ordering of the rows the tail kernel listed (more than kTailCap matches, or skewed states).
+// Block-wide ordering of the rows the tail kernel listed (more than kTailCap matches, or skewed states): 256 threads
+// whatever the row width -- a row has at most a few hundred matches, wider CTAs only add idle warps to every barrier.
+constexpr int kOrderThreads = 256;
 template <int kThreadsB>
 __global__ void __launch_bounds__(kThreadsB)
 order_rows_kernel(const MatchArgs args, uint32_t* hdr, const uint32_t* ent) {
@@ -766,7 +768,7 @@ template <int KQ, int T>
 static cudaError_t configure_one(int max_smem) {
   cudaError_t e = cudaFuncSetAttribute(match_rows_general_kernel<KQ, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(match_rows_fast_kernel<KQ, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-  if (e == cudaSuccess && KQ == 1) e = cudaFuncSetAttribute(order_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  if (e == cudaSuccess && KQ == 1 && T == kOrderThreads) e = cudaFuncSetAttribute(order_rows_kernel<kOrderThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   return e;
 }
 
@@ -798,13 +800,14 @@ cudaError_t launch_match_rows(const MatchArgs& args, int n_pairs, int general, i
   const long long all_rows = (long long)rows * n_pairs;
   const int list_grid = (int)(all_rows < 4ll * sm_count ? all_rows : 4ll * sm_count);
   const int tail_grid = (int)((all_rows + kTailWarps - 1) / kTailWarps);
+  const int order_grid = (int)(all_rows < 6ll * sm_count ? all_rows : 6ll * sm_count);
 #define GPC_LAUNCH_ROWS(KQ, T)                                                                                  \
   do {                                                                                                          \
     if (general) match_rows_general_kernel<KQ, T><<<grid, T, smem_g, stream>>>(args, nullptr, nullptr);                  \
     else {                                                                                                      \
       match_rows_fast_kernel<KQ, T><<<grid, T, smem_f, stream>>>(args);                                         \
       match_rows_tail_kernel<<<tail_grid, 32 * kTailWarps, tail_smem_bytes(), stream>>>(args, n_pairs);         \
-      order_rows_kernel<T><<<list_grid, T, smem_o, stream>>>(args, args.big_hdr, args.big_ent);                         \
+      order_rows_kernel<kOrderThreads><<<order_grid, kOrderThreads, smem_o, stream>>>(args, args.big_hdr, args.big_ent);                         \
       match_rows_general_kernel<KQ, T><<<list_grid, T, smem_g, stream>>>(args, args.fb_hdr, args.fb_ent);                 \
     }                                                                                                           \
   } while (0)
