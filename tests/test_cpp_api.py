@@ -165,6 +165,26 @@ def test_sparsematch_cli(oracle):
 
 
 @pytest.mark.gpu
+def test_pool_from_plain_c(oracle):
+    """samples/pool_example.c: gpc_pool_match_batch from C99 with gpc_host_alloc'ed buffers (two contexts on device 0),
+    23 copies of one pair; the count equals the oracle's for that pair."""
+    _build()
+    w, h = 512, 120
+    s = np.uint32(12345)
+    vals = np.empty(w * h, np.uint8)
+    x = 12345
+    for i in range(w * h):
+        x = (x * 1664525 + 1013904223) & 0xFFFFFFFF
+        vals[i] = x >> 24
+    L = vals.reshape(h, w)
+    R = np.roll(L, -7, axis=1)
+    ref, _, _ = oracle.pair(L, R, oracle.read_forest(FORESTS["tau"]), osettings())
+    r = subprocess.run([os.path.join(ROOT, "samples", "pool_example"), FORESTS["tau"], str(w), str(h), "23"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"ok {len(ref)}" in r.stdout, (r.stdout, len(ref))
+
+
+@pytest.mark.gpu
 def test_c_api_from_plain_c(oracle):
     """samples/c_api_example.c (C99, no C++ on the caller's side): the SURVEY 8c golden values of the Sintel-sized
     synthetic pair, and the SSE=OFF result mode against the oracle."""
