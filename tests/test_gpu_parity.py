@@ -222,3 +222,22 @@ def test_repeatability_stress(g, ctx_small, oracle):
         supp, offsets, _ = ctx_small.match_batch(imgs, s)
         for p in range(4):
             assert np.array_equal(supp[offsets[p]:offsets[p + 1]], refs[p]), (rep, p)
+
+
+def test_gpu_vs_compiled_reference(g, reference):
+    """The CUDA path against the UNMODIFIED reference itself (oracle/_ref/libgpc_ref.so travels to the GPU box prebuilt),
+    not only against the restatement: supports, candidate counts, order -- both shipped forests, both matching modes."""
+    from opengpc_b200.synth import sparsify, synth_pair
+    cases = [(640, 200, 31, False), (512, 131, 32, False), (1024, 436, 1234, True)]
+    with g.Context(device=0, max_w=1024, max_h=436, max_batch=1) as ctx:
+        for w, h, seed, sparse in cases:
+            L, R = synth_pair(w, h, seed)
+            if sparse:
+                L, R = sparsify(L), sparsify(R)
+            for forest in ("tau", "zero"):
+                ctx.set_forest(FORESTS[forest])
+                for epi, vt, thr in ((True, 0, 5), (False, 1, 10)):
+                    want, rcl, rcr, _ = reference.pair(L, R, FORESTS[forest], thr=thr, disp_high=128, vt=vt, epipolar=epi)
+                    got, ncl, ncr = ctx.match_pair(L, R, g.make_settings(thr=thr, disp_high=128, vt=vt, epipolar=epi))
+                    assert (ncl, ncr) == (rcl, rcr), (w, h, forest, epi)
+                    assert np.array_equal(got, want), (w, h, forest, epi, len(got), len(want))
