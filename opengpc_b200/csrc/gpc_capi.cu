@@ -102,7 +102,7 @@ struct gpc_ctx {
   // chunk works on its own slice of the resident buffers
   static constexpr int kLanes = 3;
   cudaStream_t lane_stream[kLanes] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<cudaEvent_t> ev_chunk;
   int chunk_pairs = 16;
   int32_t* d_rowmatch = nullptr;   // [B][H]
@@ -586,6 +586,7 @@ void gpc_destroy(gpc_ctx* c) {
   cudaFree(c->d_raw); cudaFree(c->d_smooth); cudaFree(c->d_cand); cudaFree(c->d_hash); cudaFree(c->d_stage); cudaFree(c->d_rows); cudaFree(c->d_lastrow); cudaFree(c->d_rowmatch); cudaFree(c->d_fb); cudaFree(c->d_big); cudaFree(c->d_mrec); cudaFree(c->d_ovbuf); cudaFree(c->d_rowhdr);
   for (int l = 0; l < gpc_ctx::kLanes; l++) if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   for (cudaEvent_t e : c->ev_chunk) cudaEventDestroy(e);
   cudaFree(c->d_rowoff); cudaFree(c->d_totals); cudaFree(c->d_ncand); cudaFree(c->d_pair_base); cudaFree(c->d_out);
   gpc::jit_destroy(c->jit);
@@ -736,6 +737,28 @@ int gpc_match_batch_device(gpc_ctx* c, const uint8_t* d_images, int n_pairs, int
   rc = check_settings(c, s); if (rc) return rc;
   if (!c->has_forest) return fail(c, GPC_E_FOREST, "no forest set");
   GPC_CUDA(c, cudaSetDevice(c->device));
+  // Large batches run as two halves on two streams: the second half's stencil / hashing kernels (ALU bound) overlap
+  // the first half's matcher tail, scans and emission (latency bound, few resident warps).  GPC_DEVICE_SPLIT=1: off.
+  static const int split_env = std::getenv("GPC_DEVICE_SPLIT") ? std::atoi(std::getenv("GPC_DEVICE_SPLIT")) : 2;
+  const size_t P = (size_t)w * h;
+  if (split_env >= 2 && n_pairs >= 32 * split_env && !c->timing && !use_sort_matcher(c, s)) {
+    cudaStream_t st[2] = {c->stream, c->lane_stream[0]};
+    GPC_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+    GPC_CUDA(c, cudaStreamWaitEvent(st[1], c->ev_fork, 0));
+    for (int k = 0; k < split_env; k++) {                          // part k on stream k % 2, each on its own slice
+      const int p0 = (int)((long long)n_pairs * k / split_env), p1 = (int)((long long)n_pairs * (k + 1) / split_env);
+      const Slot sl{p0, st[k & 1]};
+      rc = run_preprocess(c, sl, d_images + (size_t)(2 * p0) * P, 2 * (p1 - p0), w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
+      if (rc) return rc;
+      rc = run_match(c, sl, p1 - p0, w, h, s, d_out + (size_t)p0 * cap_per_pair, cap_per_pair, false, d_n_out + p0,
+                     d_n_cand ? d_n_cand + 2 * p0 : nullptr);
+      if (rc) return rc;
+    }
+    if (!c->ev_join) GPC_CUDA(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    GPC_CUDA(c, cudaEventRecord(c->ev_join, st[1]));
+    GPC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    return GPC_OK;
+  }
   rc = run_preprocess(c, Slot{0, c->stream}, d_images, 2 * n_pairs, w, h, s->gradient_threshold, c->forest_dev, nullptr, nullptr);
   if (rc) return rc;
   return run_match(c, Slot{0, c->stream}, n_pairs, w, h, s, d_out, cap_per_pair, false, d_n_out, d_n_cand);
