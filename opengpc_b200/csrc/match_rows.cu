@@ -13,6 +13,8 @@
 // atomic per candidate, one scan, one scatter), lets every left candidate scan its own bucket
 // for equal states (a handful of entries, early exit on the second duplicate), and sorts only
 // the surviving matches (about a tenth of the candidates) before writing them out.
+#include <cstdlib>
+
 #include "gpc_device.cuh"
 
 namespace gpc {
@@ -582,21 +584,33 @@ constexpr int kTailWarps = 8;                 // rows per CTA
 constexpr int kTailCap = 256;                 // matches a warp orders in its slice of shared memory
 
 
-// per-warp shared memory: 256 group counters + 256 cursors (the ordering uses 32 of each), keys and payloads of up to
-// 2 * kOvCap overflow entries / kTailCap match records
-constexpr int kTailSlots = (2 * kOvCap > kTailCap) ? 2 * kOvCap : kTailCap;
-constexpr int kTailWords = 2 * kBuckets + 2 * kTailSlots;          // per warp
-size_t tail_smem_bytes() { return (size_t)kTailWarps * kTailWords * 4; }
+// per-warp shared memory: kGroups group counters + kGroups cursors (the ordering uses 32 of each), keys and payloads of
+// up to kSlots overflow entries / kTailCap match records.  Two sizes: rows up to 1024 pixels rarely list more than a few
+// dozen overflow entries, so the small slice (3 KB per warp, 8 CTAs = 64 warps per SM) serves them; wide rows get the full one.
+#ifndef GPC_TAIL_MINB_SMALL
+#define GPC_TAIL_MINB_SMALL 8
+#endif
+#ifndef GPC_TAIL_GROUPS_SMALL
+#define GPC_TAIL_GROUPS_SMALL 128
+#endif
+constexpr int kTailSlotsBig = (2 * kOvCap > kTailCap) ? 2 * kOvCap : kTailCap, kTailGroupsBig = 256;
+constexpr int kTailSlotsSmall = kTailCap, kTailGroupsSmall = GPC_TAIL_GROUPS_SMALL;
+constexpr size_t tail_smem_bytes(int slots, int groups) { return (size_t)kTailWarps * (2 * groups + 2 * slots) * 4; }
 
-__global__ void __launch_bounds__(32 * kTailWarps, 4)
+template <int kSlots, int kGroups>
+__global__ void __launch_bounds__(32 * kTailWarps, kSlots <= kTailSlotsSmall ? GPC_TAIL_MINB_SMALL : 4)
 match_rows_tail_kernel(const MatchArgs args, int n_pairs) {
+  static_assert(kSlots >= kTailCap && kGroups >= 32 && kGroups % 128 == 0 && (kGroups & (kGroups - 1)) == 0, "slice layout");
+  constexpr int kTailWords = 2 * kGroups + 2 * kSlots;
+  constexpr int kGroupShift = 32 - (kGroups == 128 ? 7 : kGroups == 256 ? 8 : 9);
+  static_assert(kGroups == 128 || kGroups == 256 || kGroups == 512, "group bits");
   extern __shared__ __align__(16) uint32_t tail_smem[];
   __shared__ uint32_t sm_m[kTailWarps];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint32_t* cnt = tail_smem + (size_t)wid * kTailWords;             // [kBuckets]
-  uint32_t* cur = cnt + kBuckets;                                    // [kBuckets]
-  uint32_t* bk = cur + kBuckets;                                     // [kTailSlots] keys
-  uint32_t* bv = bk + kTailSlots;                                    // [kTailSlots] payloads
+  uint32_t* cnt = tail_smem + (size_t)wid * kTailWords;             // [kGroups]
+  uint32_t* cur = cnt + kGroups;                                     // [kGroups]
+  uint32_t* bk = cur + kGroups;                                      // [kSlots] keys
+  uint32_t* bv = bk + kSlots;                                        // [kSlots] payloads
   const int rows = args.H - 2 * kRadius;
   const long long r = (long long)blockIdx.x * kTailWarps + wid;
   if (r >= (long long)rows * n_pairs) return;
@@ -610,6 +624,10 @@ match_rows_tail_kernel(const MatchArgs args, int n_pairs) {
   // ---- overflow entries: a hash-partitioned join (linear in their number) ------------------------------------
   // group = 8 bits of a multiplicative hash of the state; both lists are counted, scanned and scattered into group
   // segments (left entries carry bit 31 clear, right entries set), then every left entry walks its own group
+  if (nl + nr > (uint32_t)kSlots) {                         // more overflow entries than a warp's slice holds: general kernel
+    if (lane == 0) push_row(args.fb_hdr, args.fb_ent, pair, y);
+    return;
+  }
   if (nl > 0u && nr > 0u) {
     const uint32_t* ovl_s = args.ovbuf + grow * (4 * kOvCap);
     const uint32_t* ovl_x = ovl_s + kOvCap;
@@ -617,33 +635,40 @@ match_rows_tail_kernel(const MatchArgs args, int n_pairs) {
     const uint32_t* ovr_x = ovr_s + kOvCap;
     const uint32_t n = nl + nr;
 #pragma unroll
-    for (int k = 0; k < kBuckets / 32 / 4; k++) reinterpret_cast<uint4*>(cnt)[lane + 32 * k] = make_uint4(0, 0, 0, 0);
+    for (int k = 0; k < kGroups / 32 / 4; k++) reinterpret_cast<uint4*>(cnt)[lane + 32 * k] = make_uint4(0, 0, 0, 0);
     if (lane == 0) sm_m[wid] = m;
     __syncwarp();
     for (uint32_t i = lane; i < n; i += 32) {
       const uint32_t v = (i < nl) ? ovl_s[i] : ovr_s[i - nl];
-      atomicAdd(&cnt[((v & 0x7fffffffu) * kHashMul) >> 24], 1u);
+      atomicAdd(&cnt[((v & 0x7fffffffu) * kHashMul) >> kGroupShift], 1u);
     }
     __syncwarp();
-    {                                                       // exclusive scan of the 256 counters, 8 per lane
-      const uint4 a = reinterpret_cast<const uint4*>(cnt)[2 * lane], b = reinterpret_cast<const uint4*>(cnt)[2 * lane + 1];
-      const uint32_t sum = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    {                                                       // exclusive scan of the group counters, kGroups / 32 per lane
+      constexpr int kPer4 = kGroups / 128;                  // uint4s per lane
+      uint4 c4[kPer4];
+      uint32_t sum = 0;
+#pragma unroll
+      for (int k = 0; k < kPer4; k++) {
+        c4[k] = reinterpret_cast<const uint4*>(cnt)[kPer4 * lane + k];
+        sum += c4[k].x + c4[k].y + c4[k].z + c4[k].w;
+      }
       uint32_t incl = sum;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
       uint32_t run = incl - sum;
-      uint4 o0, o1;
-      o0.x = run; run += a.x; o0.y = run; run += a.y; o0.z = run; run += a.z; o0.w = run; run += a.w;
-      o1.x = run; run += b.x; o1.y = run; run += b.y; o1.z = run; run += b.z; o1.w = run;
-      reinterpret_cast<uint4*>(cur)[2 * lane] = o0;
-      reinterpret_cast<uint4*>(cur)[2 * lane + 1] = o1;
+#pragma unroll
+      for (int k = 0; k < kPer4; k++) {
+        uint4 o;
+        o.x = run; run += c4[k].x; o.y = run; run += c4[k].y; o.z = run; run += c4[k].z; o.w = run; run += c4[k].w;
+        reinterpret_cast<uint4*>(cur)[kPer4 * lane + k] = o;
+      }
     }
     __syncwarp();
     for (uint32_t i = lane; i < n; i += 32) {               // scatter; cur[g] ends at the group's end
       const bool left = i < nl;
       const uint32_t v = (left ? ovl_s[i] : ovr_s[i - nl]) & 0x7fffffffu;
       const uint32_t x = left ? ovl_x[i] : ovr_x[i - nl];
-      const uint32_t p = atomicAdd(&cur[(v * kHashMul) >> 24], 1u);
+      const uint32_t p = atomicAdd(&cur[(v * kHashMul) >> kGroupShift], 1u);
       bk[p] = left ? v : (v | 0x80000000u);
       bv[p] = x;
     }
@@ -651,7 +676,7 @@ match_rows_tail_kernel(const MatchArgs args, int n_pairs) {
     for (uint32_t i = lane; i < n; i += 32) {               // every left entry: equal states in its group, per side
       const uint32_t key = bk[i];
       if (key >> 31) continue;
-      const uint32_t g = (key * kHashMul) >> 24;
+      const uint32_t g = (key * kHashMul) >> kGroupShift;
       const uint32_t gn = cnt[g], g0 = cur[g] - gn;
       uint32_t cl = 0, cr = 0, x2 = 0;
       for (uint32_t j = 0; j < gn; j++) {
@@ -773,7 +798,10 @@ static cudaError_t configure_one(int max_smem) {
 }
 
 cudaError_t configure_match_rows(int max_smem) {
-  cudaError_t e = cudaFuncSetAttribute(match_rows_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem_bytes());
+  cudaError_t e = cudaFuncSetAttribute(match_rows_tail_kernel<kTailSlotsBig, kTailGroupsBig>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tail_smem_bytes(kTailSlotsBig, kTailGroupsBig));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(match_rows_tail_kernel<kTailSlotsSmall, kTailGroupsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)tail_smem_bytes(kTailSlotsSmall, kTailGroupsSmall));
   if (e == cudaSuccess) e = configure_one<1, 256>(max_smem);
   if (e == cudaSuccess) e = configure_one<1, 512>(max_smem);
   if (e == cudaSuccess) e = configure_one<1, 1024>(max_smem);
@@ -801,12 +829,15 @@ cudaError_t launch_match_rows(const MatchArgs& args, int n_pairs, int general, i
   const int list_grid = (int)(all_rows < 4ll * sm_count ? all_rows : 4ll * sm_count);
   const int tail_grid = (int)((all_rows + kTailWarps - 1) / kTailWarps);
   const int order_grid = (int)(all_rows < 6ll * sm_count ? all_rows : 6ll * sm_count);
+  static const int tail_env = std::getenv("GPC_B_TAIL") ? std::atoi(std::getenv("GPC_B_TAIL")) : 0;   // 1 small, 2 big slice
+  const bool small_tail = tail_env ? tail_env == 1 : quads <= 256;
 #define GPC_LAUNCH_ROWS(KQ, T)                                                                                  \
   do {                                                                                                          \
     if (general) match_rows_general_kernel<KQ, T><<<grid, T, smem_g, stream>>>(args, nullptr, nullptr);                  \
     else {                                                                                                      \
       match_rows_fast_kernel<KQ, T><<<grid, T, smem_f, stream>>>(args);                                         \
-      match_rows_tail_kernel<<<tail_grid, 32 * kTailWarps, tail_smem_bytes(), stream>>>(args, n_pairs);         \
+      if (small_tail) match_rows_tail_kernel<kTailSlotsSmall, kTailGroupsSmall><<<tail_grid, 32 * kTailWarps, tail_smem_bytes(kTailSlotsSmall, kTailGroupsSmall), stream>>>(args, n_pairs); \
+      else match_rows_tail_kernel<kTailSlotsBig, kTailGroupsBig><<<tail_grid, 32 * kTailWarps, tail_smem_bytes(kTailSlotsBig, kTailGroupsBig), stream>>>(args, n_pairs); \
       order_rows_kernel<kOrderThreads><<<order_grid, kOrderThreads, smem_o, stream>>>(args, args.big_hdr, args.big_ent);                         \
       match_rows_general_kernel<KQ, T><<<list_grid, T, smem_g, stream>>>(args, args.fb_hdr, args.fb_ent);                 \
     }                                                                                                           \
