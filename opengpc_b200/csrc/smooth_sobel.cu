@@ -159,17 +159,22 @@ __device__ __forceinline__ void smooth_sobel_body(const PreprocessArgs& args, co
       const int j0 = band * kPreSegRows;
       load_h(j0, ha);
       load_h(j0 + 1, hb);
-#pragma unroll 4
-      for (int j = j0; j < j0 + kPreSegRows; j++) {
-        load_h(j + 2, hc);
+      // one 64-bit address per thread; the rows of its band are 32-bit word offsets from it
+      uint32_t* const dst = reinterpret_cast<uint32_t*>(args.smooth_x + img_off + (size_t)(y0 + j0) * W + gxq);
+      uint32_t* const dbg = (kDebugOut && args.smooth_out)
+                                ? reinterpret_cast<uint32_t*>(args.smooth_out + img_off + (size_t)(y0 + j0) * W + gxq) : nullptr;
+      const uint32_t roww = (uint32_t)W / 4u;
+      const int rows_here = H - (y0 + j0);                 // rows of the band inside the image
+#pragma unroll
+      for (int jj = 0; jj < kPreSegRows; jj++) {
+        load_h(j0 + jj + 2, hc);
         uint32_t v = third(ha[0] + hb[0] + hc[0]) | (third(ha[1] + hb[1] + hc[1]) << 8) |
                      (third(ha[2] + hb[2] + hc[2]) << 16) | (third(ha[3] + hb[3] + hc[3]) << 24);
-        const int gy = y0 + j;
-        if (gy < 1 || gy > last_written) v = 0u; else v &= colmask;
-        if (gy < H) {
-          *reinterpret_cast<uint32_t*>(args.smooth_x + img_off + (size_t)gy * W + gxq) = v ^ 0x80808080u;
-          if (kDebugOut && args.smooth_out)
-            *reinterpret_cast<uint32_t*>(args.smooth_out + img_off + (size_t)gy * W + gxq) = v;
+        const int gy = y0 + j0 + jj;
+        v = (gy < 1 || gy > last_written) ? 0u : (v & colmask);
+        if (jj < rows_here) {
+          dst[(uint32_t)jj * roww] = v ^ 0x80808080u;
+          if (kDebugOut && dbg) dbg[(uint32_t)jj * roww] = v;
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) { ha[k] = hb[k]; hb[k] = hc[k]; }
@@ -178,20 +183,32 @@ __device__ __forceinline__ void smooth_sobel_body(const PreprocessArgs& args, co
   }
 
   // ---- Sobel predicate per 16-pixel segment -> candidate bit masks, per-row candidate counts ----------
+  // thread = (segment sg of the tile row, tile rows tid / 16 + 16 * it): everything that does not depend on the row is
+  // computed once, the rows are compile-time offsets from one shared-memory and one global address
   {
     static_assert((kPreH * (kPreW / 16)) % kPreThreads == 0 && kPreW / 16 == 16, "uniform trip count, 16 segments per tile row");
+    constexpr int kSobelIters = kPreH * (kPreW / 16) / kPreThreads, kSobelRowStep = kPreThreads / 16;
     const int segs_per_row = W / 16;
-    for (int sr = tid; sr < kPreH * (kPreW / 16); sr += kPreThreads) {
-      const int ry = sr / (kPreW / 16), sg = sr - ry * (kPreW / 16);
-      const int gy = y0 + ry, gxs = x0 + 16 * sg;
-      const bool valid = gy < H && gxs < W;
+    const int sg = tid & 15, ry0 = tid >> 4;
+    const int gxs = x0 + 16 * sg;
+    const bool col_ok = gxs < W;
+    const uint32_t colkeep = border_mask(0xffffu, kRadius, gxs, W, 2 * kRadius + 1);   // columns 13 .. W-14 of this segment
+    const uint32_t* const seg0 = pre_word<kTma>(raw32, ry0, 4 * sg);
+    constexpr int kRowPitchW = kTma ? kPreHalfPitchW : kPrePitchW;
+    uint16_t* const cand0 = args.cand + ((size_t)img * H + y0 + ry0) * segs_per_row + (gxs >> 4);
+    int32_t* const rowcnt0 = args.rowcnt + (size_t)img * H + y0 + ry0;
+    int my_last = -1;
+#pragma unroll
+    for (int it = 0; it < kSobelIters; it++) {
+      const int gy = y0 + ry0 + kSobelRowStep * it;
+      const bool valid = col_ok && gy < H;
       uint32_t m = 0;
       if (valid && gy >= 1 && gy < H - 3) {                // rows the reference writes (filter.hpp:517)
         // words wi0-1 .. wi0+3 of tile rows ry, ry+1, ry+2 (image rows gy-1, gy, gy+1); wi0 = image column gxs
         uint32_t wm[3], q0[3], q1[3], q2[3], q3[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-          const uint32_t* row = pre_word<kTma>(raw32, ry + k, 4 * sg);
+          const uint32_t* row = seg0 + (kSobelRowStep * it + k) * kRowPitchW;
           const uint4 v = *reinterpret_cast<const uint4*>(row);
           wm[k] = row[-1]; q0[k] = v.x; q1[k] = v.y; q2[k] = v.z; q3[k] = v.w;
         }
@@ -213,19 +230,20 @@ __device__ __forceinline__ void smooth_sobel_body(const PreprocessArgs& args, co
         }
         *reinterpret_cast<uint4*>(args.grad_out + img_off + (size_t)gy * W + gxs) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
       }
-      const uint32_t bm = valid ? border_mask(m, gy, gxs, W, H) : 0u;
-      if (valid) args.cand[((size_t)img * H + gy) * segs_per_row + (gxs >> 4)] = (uint16_t)bm;
+      const uint32_t bm = (valid && gy >= kRadius && gy < H - kRadius) ? (m & colkeep) : 0u;   // candidate border (inference.hpp:322)
+      if (valid) cand0[(uint32_t)(kSobelRowStep * it) * (uint32_t)segs_per_row] = (uint16_t)bm;
       // the 16 segments of one tile row sit in 16 consecutive lanes: one global atomic per tile row
       int cnt = __popc(bm);
       cnt += __shfl_xor_sync(0xffffffffu, cnt, 8);
       cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
       cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
       cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
-      if ((tid & 15) == 0 && cnt > 0) {
-        atomicAdd(args.rowcnt + (size_t)img * H + gy, cnt);
-        atomicMax(&cta_last, gy);
+      if (sg == 0 && cnt > 0) {
+        atomicAdd(rowcnt0 + kSobelRowStep * it, cnt);
+        my_last = gy;                                      // rows ascend with it
       }
     }
+    if (my_last >= 0) atomicMax(&cta_last, my_last);
   }
   __syncthreads();
   if (tid == 0 && cta_last >= 0 && cta_last > *reinterpret_cast<volatile int32_t*>(args.lastrow + img))
