@@ -63,14 +63,16 @@ __device__ __forceinline__ uint32_t sobel_quad(const uint32_t wl[3], const uint3
   const uint32_t colO = __byte_perm(w[0], 0u, 0x4341) + __byte_perm(w[2], 0u, 0x4341) + 2u * __byte_perm(w[1], 0u, 0x4341);
   const uint32_t colL = (wl[0] >> 24) + (wl[2] >> 24) + 2u * (wl[1] >> 24);                  // col(x0-1)
   const uint32_t colR = (wr[0] & 0xffu) + (wr[2] & 0xffu) + 2u * (wr[1] & 0xffu);            // col(x0+4)
-  const int nL = (int)ninth(colL), n0 = (int)ninth(colE & 0xffffu), n1 = (int)ninth(colO & 0xffffu);
-  const int n2 = (int)ninth(colE >> 16), n3 = (int)ninth(colO >> 16), nR = (int)ninth(colR);
-  const int ab[4] = {nL - n1, n0 - n2, n1 - n3, n2 - nR};
+  const uint32_t nL = ninth(colL), n0 = ninth(colE & 0xffffu), n1 = ninth(colO & 0xffffu);
+  const uint32_t n2 = ninth(colE >> 16), n3 = ninth(colO >> 16), nR = ninth(colR);
+  // only the squares of the differences are used: |a - b| as one VABSDIFF (a plain subtraction gets fused into the
+  // multiply-high of ninth() as a 64-bit addend, which costs three extra moves per difference)
+  const uint32_t ab[4] = {__usad(nL, n1, 0u), __usad(n0, n2, 0u), __usad(n1, n3, 0u), __usad(n2, nR, 0u)};
   uint32_t m = 0;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    const int cd = (int)c[j] - (int)d[j];
-    if (ab[j] * ab[j] + cd * cd > thr2) m |= 1u << j;        // <= 25538, no int16 wrap / saturation
+    const uint32_t cd = __usad(c[j], d[j], 0u);
+    if ((int)(ab[j] * ab[j] + cd * cd) > thr2) m |= 1u << j;  // <= 25538, no int16 wrap / saturation
   }
   return m;
 }

@@ -423,6 +423,46 @@ def test_degenerate_states(g, oracle):
                     assert np.array_equal(supp, ref), (len(tests), epi, len(supp), len(ref))
 
 
+def test_overflow_lists_beyond_the_tail_slice(g, ctx, oracle):
+    """Crafted state rows (gpc_match_hash_images): n states twice on the left and once on the right put 2n + n entries
+    on the row's overflow lists.  Up to 256 entries the warp-per-row tail kernel joins them in its 3 KB slice; beyond
+    that (each list still within its own 256-entry capacity) the row goes to the general kernel's list; beyond 256
+    per list the fast kernel hands it over itself.  All three must agree with the general matcher, the sort matcher
+    and, through them, the oracle's semantics: duplicated states never match, the unique ones around them do."""
+    w, h = 1024, 40
+    rng = np.random.default_rng(41)
+    s = g.sparsematch_settings()
+    for n_dup in (40, 90, 120, 200):
+        hl = np.zeros((h, w), np.uint32)
+        hr = np.zeros((h, w), np.uint32)
+        for y in range(13, h - 13):
+            states = rng.choice(1 << 30, size=n_dup + 300, replace=False).astype(np.uint32)
+            dup, uniq = states[:n_dup], states[n_dup:]
+            xs = rng.permutation(np.arange(13, w - 13))
+            xl_dup, xl_uniq = xs[:2 * n_dup], xs[2 * n_dup:2 * n_dup + 300]
+            hl[y, xl_dup] = np.repeat(dup, 2) | 0x80000000
+            hl[y, xl_uniq] = uniq | 0x80000000
+            xr = rng.permutation(np.arange(13, w - 13))
+            hr[y, xr[:n_dup]] = dup | 0x80000000
+            # the unique states sit within the disparity range of their partners
+            xr_uniq = np.clip(xl_uniq - rng.integers(0, 60, 300), 13, w - 14)
+            free = hr[y, xr_uniq] == 0
+            _, first = np.unique(xr_uniq, return_index=True)
+            keep = np.zeros(300, bool); keep[first] = True
+            keep &= free
+            hr[y, xr_uniq[keep]] = uniq[keep] | 0x80000000
+        results = {}
+        for matcher in (g.MATCHER_AUTO, g.MATCHER_ROWS_GENERAL, g.MATCHER_SORT):
+            ctx.set_matcher(matcher)
+            try:
+                results[matcher] = ctx.match_hash_images(hl, hr, s)
+            finally:
+                ctx.set_matcher(g.MATCHER_AUTO)
+        assert len(results[g.MATCHER_SORT]) > 100 * (h - 26) // 2, n_dup
+        assert np.array_equal(results[g.MATCHER_AUTO], results[g.MATCHER_SORT]), n_dup
+        assert np.array_equal(results[g.MATCHER_ROWS_GENERAL], results[g.MATCHER_SORT]), n_dup
+
+
 def test_very_wide_rows(g, oracle):
     """Rows wider than 4096 pixels take the 2-quads-per-thread / 1024-thread shape of the row matcher; 8192 is
     the widest supported row (13-bit column fields)."""
