@@ -153,14 +153,22 @@ __device__ __forceinline__ void smooth_sobel_body(const PreprocessArgs& args, co
       uint32_t colmask = 0xffffffffu;                      // clearBoundary: columns 0,1 and W-1
       if (gxq == 0) colmask = 0xffff0000u;
       if (gxq == W - 4) colmask &= 0x00ffffffu;
-      uint32_t ha[4], hb[4], hc[4];
-      auto load_h = [&](int r, uint32_t h[4]) {            // raw-tile row r = image row y0 - 1 + r
+      // 3-row window per pixel column, PACKED: byte 0..2 of win[k] = horizontal thirds of rows j-1, j, j+1.  One PRMT
+      // shifts the window and inserts the new row, one dp4a sums it.  (Keeping the three thirds in separate registers
+      // and adding them looks cheaper but is not: ptxas fuses a multiply-high whose result feeds an addition into
+      // IMAD.HI with a 64-bit addend and then RE-COMPUTES it for each of the three sums it appears in, plus a move to
+      // clear the addend's low word each time -- 364 instead of 248 IMAD.HI per thread.)
+      uint32_t win[4] = {0u, 0u, 0u, 0u};
+      auto push_row = [&](int r) {                         // raw-tile row r = image row y0 - 1 + r
         const uint32_t* row = pre_word<kTma>(raw32, r, q);
+        uint32_t h[4];
         hthirds(row[-1], row[0], row[1], h);
+#pragma unroll
+        for (int k = 0; k < 4; k++) win[k] = __byte_perm(win[k], h[k], 0x7421);   // (b1, b2, h, 0)
       };
       const int j0 = band * kPreSegRows;
-      load_h(j0, ha);
-      load_h(j0 + 1, hb);
+      push_row(j0);
+      push_row(j0 + 1);
       // one 64-bit address per thread; the rows of its band are 32-bit word offsets from it
       uint32_t* const dst = reinterpret_cast<uint32_t*>(args.smooth_x + img_off + (size_t)(y0 + j0) * W + gxq);
       uint32_t* const dbg = (kDebugOut && args.smooth_out)
@@ -169,17 +177,17 @@ __device__ __forceinline__ void smooth_sobel_body(const PreprocessArgs& args, co
       const int rows_here = H - (y0 + j0);                 // rows of the band inside the image
 #pragma unroll
       for (int jj = 0; jj < kPreSegRows; jj++) {
-        load_h(j0 + jj + 2, hc);
-        uint32_t v = third(ha[0] + hb[0] + hc[0]) | (third(ha[1] + hb[1] + hc[1]) << 8) |
-                     (third(ha[2] + hb[2] + hc[2]) << 16) | (third(ha[3] + hb[3] + hc[3]) << 24);
+        push_row(j0 + jj + 2);
+        uint32_t t[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) t[k] = third(__dp4a(win[k], 0x00010101u, 0u));
+        uint32_t v = __byte_perm(__byte_perm(t[0], t[1], 0x0040), __byte_perm(t[2], t[3], 0x0040), 0x5410);
         const int gy = y0 + j0 + jj;
         v = (gy < 1 || gy > last_written) ? 0u : (v & colmask);
         if (jj < rows_here) {
           dst[(uint32_t)jj * roww] = v ^ 0x80808080u;
           if (kDebugOut && dbg) dbg[(uint32_t)jj * roww] = v;
         }
-#pragma unroll
-        for (int k = 0; k < 4; k++) { ha[k] = hb[k]; hb[k] = hc[k]; }
       }
     }
   }
