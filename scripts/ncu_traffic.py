@@ -3,7 +3,7 @@
 dram__bytes_read.sum + dram__bytes_write.sum per launch, divided by the launch's pixel count (kernels A1 / A2: pixels of all
 images of the step, matcher kernels: pixels of one image per pair).  bench.py multiplies back by the pixels of its step.
 The bench's "match_rows" bucket is the sum of the row matcher's kernels (fast + tail); "emit_supports" is kernel C.
-usage: python scripts/ncu_traffic.py <round tag> <pairs per step> report.ncu-rep [more reports]"""
+usage: python scripts/ncu_traffic.py <round tag> <pairs per captured launch> report.ncu-rep [more reports]"""
 import csv
 import io
 import json
@@ -17,7 +17,8 @@ PIX = 1024 * 436
 B = int(sys.argv[2])
 BUCKET = {"smooth_sobel": ("smooth_sobel", 2 * B * PIX), "hash_tiles": ("hash_tiles", 2 * B * PIX), "match_rows_fast": ("match_rows", B * PIX),
           "match_rows_tail": ("match_rows", B * PIX), "emit_supports": ("emit_supports", B * PIX)}
-out = {"source": f"ncu --set full, {sys.argv[1]} (profiles/), bench step of {B} pairs (the benchmarked batch)", "dram_bytes_per_pixel": {},
+out = {"source": f"ncu --set full, {sys.argv[1]} (profiles/), launches of {B} pairs (the benchmarked step of {2 * B} pairs runs as two such launches on two streams)",
+       "dram_bytes_per_pixel": {},
        "per_kernel_dram_bytes_per_launch": {}}
 for rep in sys.argv[3:]:
     rows = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)))
