@@ -36,8 +36,9 @@ constexpr uint32_t kLow7 = 0x7f7f7f7fu;
 //   tau forest  (filter.hpp:647-652):  a > (uint8)sat_int8((int8)b - tau)  unsigned
 //                                      ==  xa > clamp(xb - tau, 0, 255)    signed
 // Signed byte compare: msb = (~a7 & c7) | (~(a7 ^ c7) & carry7), carry from the low 7 bits.
-// The returned word is masked to the msbs.  A tau forest sends every test through the clamp
-// (tau == 0 leaves x unchanged).
+// The returned word is masked with `msk`: the msbs of the quad's CANDIDATE pixels only, so that a pixel that is no
+// candidate accumulates nothing (its state word stays 0 without any per-pixel select afterwards).  A tau forest sends
+// every test through the clamp (tau == 0 leaves x unchanged).
 #ifdef GPC_JIT_HEADER
 #include GPC_JIT_HEADER      // forest baked into the code: jit_imm_a(t), jit_imm_b(t), jit_mtau2(t), kJitTests
 #endif
@@ -47,7 +48,7 @@ constexpr uint32_t kLow7 = 0x7f7f7f7fu;
 constexpr int kModeZero = 0, kModeTau = 1, kModeNaiveZero = 2, kModeNaiveTau = 3;
 
 template <int kMode>
-__device__ __forceinline__ uint32_t eval_test(const uint8_t* base, const ForestDev& forest, const int t) {
+__device__ __forceinline__ uint32_t eval_test(const uint8_t* base, const ForestDev& forest, const int t, const uint32_t msk) {
 #ifdef GPC_JIT_HEADER
   if (t >= kJitTests) return 0u;                                             // compile time after unrolling
   const uint32_t a = *reinterpret_cast<const uint32_t*>(base + jit_imm_a(t));
@@ -63,11 +64,11 @@ __device__ __forceinline__ uint32_t eval_test(const uint8_t* base, const ForestD
     const uint32_t k2 = forest.mtau2[t];
     const uint32_t lo = __byte_perm(c, 0u, 0x4140) + k2 - __byte_perm(a, 0u, 0x4140);
     const uint32_t hi = __byte_perm(c, 0u, 0x4342) + k2 - __byte_perm(a, 0u, 0x4342);
-    return ~__byte_perm(lo, hi, 0x7531) & kMsb;
+    return ~__byte_perm(lo, hi, 0x7531) & msk;
   }
   if (kMode == kModeNaiveZero) {                                             // unsigned a > c on unbiased bytes
     const uint32_t s = (a & kLow7) + (~c & kLow7);
-    return ((a & ~c) | (~(a ^ c) & s)) & kMsb;
+    return ((a & ~c) | (~(a ^ c) & s)) & msk;
   }
   if (kMode == kModeTau) {
     const uint32_t mt = forest.mtau2[t];
@@ -77,23 +78,23 @@ __device__ __forceinline__ uint32_t eval_test(const uint8_t* base, const ForestD
     c = __byte_perm(lo, hi, 0x6420);                                         // clamp(x - tau, 0, 255)
   }
   const uint32_t s = (a & kLow7) + (~c & kLow7);                             // bit 7: low7(a) > low7(c)
-  return ((~a & c) | (~(a ^ c) & s)) & kMsb;
+  return ((~a & c) | (~(a ^ c) & s)) & msk;
 }
 
 // All tests of state byte G (filter.hpp:574-584: tests 0..8 -> byte 0 with test 8 OR-ed into bit 0
 // under m8, 9..16 -> byte 1, 17..24 -> byte 2, 25..31 -> byte 3).
 template <int kMode, int G>
-__device__ __forceinline__ unsigned long long eval_group(const uint8_t* base, const ForestDev& forest, uint32_t m8) {
+__device__ __forceinline__ unsigned long long eval_group(const uint8_t* base, const ForestDev& forest, uint32_t m8, uint32_t msk,
+                                                         unsigned long long acc) {
   constexpr int t0 = (G == 0) ? 1 : 8 * G + 1;
   constexpr int t1 = (G == 0) ? 8 : (G == 3) ? kMaxTests : 8 * G + 9;       // exclusive
-  unsigned long long acc = 0ull;
   if (G == 0) {
-    const uint32_t r0 = eval_test<kMode>(base, forest, 0), r8 = eval_test<kMode>(base, forest, 8);
-    acc = (unsigned long long)(r0 | (r8 & m8));
+    const uint32_t r0 = eval_test<kMode>(base, forest, 0, msk), r8 = eval_test<kMode>(base, forest, 8, msk);
+    acc += (unsigned long long)(r0 | (r8 & m8));
   }
 #pragma unroll
   for (int t = t0; t < t1; t++)
-    acc += (unsigned long long)eval_test<kMode>(base, forest, t) * (unsigned long long)forest.pmul[t];
+    acc += (unsigned long long)eval_test<kMode>(base, forest, t, msk) * (unsigned long long)forest.pmul[t];
   return acc;
 }
 
@@ -176,14 +177,17 @@ __device__ __forceinline__ void hash_tiles_body(const CUtensorMap& tmap, const H
     const int ry = tid / kQuadsX + i * kRowStep;
     const int gy = y0 + ry;
     const uint32_t cm = (cms >> (4 * i)) & 15u;
-    uint32_t st[4] = {0u, 0u, 0u, 0u};
+    // msb of byte j set iff pixel j is a candidate (the 16 partial products of the multiplication hit 16 distinct bits)
+    const uint32_t msk = (cm * 0x10204080u) & kMsb;
+    uint32_t st[4];
     if (cm != 0u && gy >= kRadius && gy < args.hash_y_end) {       // hashed rows (filter.hpp:601-604)
       const uint8_t* base = smem + (ry + kRadius) * kPitch + 16 + 4 * qx;
-      unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
-      acc[0] = eval_group<kMode, 0>(base, forest, m8);
-      if (n_groups > 1) acc[1] = eval_group<kMode, 1>(base, forest, m8);      // uniform branches
-      if (n_groups > 2) acc[2] = eval_group<kMode, 2>(base, forest, m8);
-      if (n_groups > 3) acc[3] = eval_group<kMode, 3>(base, forest, m8);
+      // group 3 starts from the candidate flag: bit 7 of its byte = bit 31 of the state word
+      unsigned long long acc[4] = {0ull, 0ull, 0ull, (unsigned long long)msk << 7};
+      acc[0] = eval_group<kMode, 0>(base, forest, m8, msk, acc[0]);
+      if (n_groups > 1) acc[1] = eval_group<kMode, 1>(base, forest, m8, msk, acc[1]);      // uniform branches
+      if (n_groups > 2) acc[2] = eval_group<kMode, 2>(base, forest, m8, msk, acc[2]);
+      if (n_groups > 3) acc[3] = eval_group<kMode, 3>(base, forest, m8, msk, acc[3]);
       // byte j of (acc[g] >> 7) = state byte g of pixel j; 4x4 byte transpose -> one state per pixel
       uint32_t w[4];
 #pragma unroll
@@ -194,12 +198,11 @@ __device__ __forceinline__ void hash_tiles_body(const CUtensorMap& tmap, const H
       st[1] = __byte_perm(lo01, lo23, 0x7632);
       st[2] = __byte_perm(hi01, hi23, 0x5410);
       st[3] = __byte_perm(hi01, hi23, 0x7632);
+    } else {                                                       // candidates of rows that are not hashed: state 0
+#pragma unroll
+      for (int j = 0; j < 4; j++) st[j] = ((cm >> j) & 1u) ? kCandFlag : 0u;
     }
-    uint4 o;
-    o.x = (cm & 1u) ? (st[0] | kCandFlag) : 0u;
-    o.y = (cm & 2u) ? (st[1] | kCandFlag) : 0u;
-    o.z = (cm & 4u) ? (st[2] | kCandFlag) : 0u;
-    o.w = (cm & 8u) ? (st[3] | kCandFlag) : 0u;
+    const uint4 o = make_uint4(st[0], st[1], st[2], st[3]);
     if (gx < W && gy < H) *reinterpret_cast<uint4*>(hash + (size_t)gy * W + gx) = o;
   }
 }
