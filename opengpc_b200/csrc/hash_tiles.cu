@@ -170,7 +170,11 @@ __device__ __forceinline__ void hash_tiles_body(const CUtensorMap& tmap, const H
   // ---- fern tests, 4 pixels per step ---------------------------------------------------------------------
   uint32_t* __restrict__ hash = args.hash + img_off;
   const uint32_t m8 = (gx & 4) ? kMsb : 0x80808000u;              // test #8: byte lanes x%8==0 dropped (filter.hpp:582); naive mode: slot 8 is a dummy
+#ifdef GPC_JIT_HEADER
+  constexpr int T = kJitTests;                                    // all groups in ONE basic block: their chains interleave
+#else
   const int T = forest.n_tests;
+#endif
   const int n_groups = (T <= 9) ? 1 : (T <= 17) ? 2 : (T <= 25) ? 3 : 4;
 #pragma unroll 1
   for (int i = 0; i < kIters; i++) {
