@@ -1,6 +1,6 @@
 // gpc_capi.cu -- the C ABI of include/gpc_b200.h: resident per-GPU context, forest upload,
 // batched launch sequence, host<->device staging.  No CPU fallback: every compute entry point
-// runs the CUDA kernels of preprocess_hash.cu / match_rows.cu or fails with GPC_E_CUDA.
+// runs the CUDA kernels of smooth_sobel.cu / hash_tiles.cu / match_rows.cu / match_global.cu or fails with GPC_E_CUDA.
 #include "../../include/gpc_b200.h"
 #include "gpc_device.cuh"
 
@@ -546,6 +546,7 @@ int gpc_create(gpc_ctx** out, int device, int max_w, int max_h, int max_batch) {
   TRY(cudaMalloc(&c->d_cand, 2 * B * (size_t)max_h * (max_w / 16) * sizeof(uint16_t)));
   TRY(cudaMalloc(&c->d_hash, 2 * B * P * sizeof(uint32_t)));
   TRY(cudaMalloc(&c->d_stage, B * P * sizeof(uint32_t)));
+  TRY(cudaMemsetAsync(c->d_stage, 0, B * P * sizeof(uint32_t), c->stream));   // kernel C reads a row's words ahead of its length
   TRY(cudaMalloc(&c->d_rows, 2 * B * max_h * sizeof(int32_t)));
   TRY(cudaMalloc(&c->d_lastrow, 2 * B * sizeof(int32_t)));
   for (int l = 0; l < gpc_ctx::kLanes; l++) TRY(cudaStreamCreateWithFlags(&c->lane_stream[l], cudaStreamNonBlocking));

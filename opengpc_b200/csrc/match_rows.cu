@@ -961,27 +961,52 @@ struct EmitArgs {
 
 constexpr int kEmitRows = 8;       // rows per CTA, one warp each
 
+// One warp per row.  The row's length, its two offsets and its first 128 staged matches are requested TOGETHER (the
+// kernel is a chain of dependent global loads per warp otherwise -- ncu: 39 warps stalled on long_scoreboard per issue
+// cycle at 26 % issue slots); the stage words are the row's own (zero-filled at context creation, whatever lies beyond
+// the row's length is ignored), so reading them before the length is known is harmless.
+__device__ __forceinline__ uint32_t ld_nc_u32(const void* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));      // volatile: stays where it is written
+  return v;
+}
+__device__ __forceinline__ long long ld_nc_s64(const void* p) {
+  long long v;
+  asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
 __global__ void __launch_bounds__(32 * kEmitRows)
 emit_supports_kernel(const EmitArgs a) {
   const int y = kRadius + blockIdx.x * kEmitRows + (threadIdx.x >> 5), pair = blockIdx.y, lane = threadIdx.x & 31;
   if (y >= a.H - kRadius) return;
-  const int m = a.rowmatch[(size_t)pair * a.H + y];
-  if (m == 0) return;
-  const long long off = a.rowoff[(size_t)pair * a.H + y];
+  const size_t grow = (size_t)pair * a.H + y;
+  const uint32_t* stage = a.stage + grow * a.W;
+  constexpr int kAhead = 4;                               // 128 matches: more than a Sintel row holds on average
+  const int m = (int)ld_nc_u32(a.rowmatch + grow);
+  const long long off = (long long)(int)ld_nc_u32(a.rowoff + grow);
   long long base, limit;
-  if (a.pair_base) { base = a.pair_base[pair]; limit = a.cap; }
+  if (a.pair_base) { base = ld_nc_s64(a.pair_base + pair); limit = a.cap; }
   else { base = (long long)pair * a.cap; limit = base + a.cap; }
-  const uint32_t* stage = a.stage + ((size_t)pair * a.H + y) * a.W;
-  for (int k = lane; k < m; k += 32) {
-    const long long idx = base + off + k;
-    if (idx >= limit) break;
-    const uint32_t u = stage[k];
+  uint32_t ahead[kAhead];
+#pragma unroll
+  for (int j = 0; j < kAhead; j++) ahead[j] = (lane + 32 * j < a.W) ? ld_nc_u32(stage + lane + 32 * j) : 0u;
+  // no early exit for empty rows: ptxas would sink the loads it does not need for the decision below the branch
+  float* const out = a.out + 3 * (base + off);
+  const long long room = limit - (base + off);            // records of this row that fit the output
+  auto put = [&](int k, uint32_t u) {
     const int xl = (int)(u >> 16), xr = (int)(u & 0xffffu);
-    float* o = a.out + 3 * idx;
+    float* o = out + 3 * (long long)k;
     o[0] = __int_as_float(xl);
     o[1] = __int_as_float(y);
     o[2] = (float)(xl - xr);                 // Support::d = float(xL - xR), exact (inference.hpp:389-390)
+  };
+#pragma unroll
+  for (int j = 0; j < kAhead; j++) {
+    const int k = lane + 32 * j;
+    if (k < m && k < room) put(k, ahead[j]);
   }
+  for (int k = lane + 32 * kAhead; k < m && k < room; k += 32) put(k, stage[k]);
 }
 
 cudaError_t launch_emit_supports(const uint32_t* stage, const int32_t* rowmatch, const int32_t* rowoff,

@@ -9,14 +9,28 @@
 // compares want) and (b) one 16-bit candidate mask per 16-pixel segment.  Every pixel of both
 // outputs is written exactly once, borders included, so kernel A2 can fetch arbitrary tiles of
 // the smoothed image with TMA.  Nothing here is a translation of the SSE code: the horizontal
-// floor-thirds are dp4a row sums, the vertical pass slides a 3-row register window.
+// floor-thirds are dp4a row sums, the vertical pass and the Sobel pass slide 3-row register windows, and every
+// floor-third / floor-ninth is the byte 2 of a plain 32-bit product (no multiply-high: IMAD.HI issues at less than
+// half the rate of IMAD on this machine, scripts/micro/int_pipe_bench.cu).
 #include <cuda.h>
 
 #include "gpc_device.cuh"
 
 namespace gpc {
 
-__device__ __forceinline__ uint32_t third(uint32_t s) { return __umulhi(s, 21846u << 16); }   // (s*21846)>>16
+// IMAD.HI is a slow instruction on this machine (measured: replacing 136 of them per thread by plain IMADs took 13.5 %
+// off the kernel), so a floor-third that a PRMT picks up anyway is left in BYTE 2 of a plain product:
+// s <= 765 -> s * 21846 < 2^24, byte 2 = (s * 21846) >> 16 = the reference's mulhi third, byte 3 = 0.
+__device__ __forceinline__ uint32_t third_b2(uint32_t s) { return s * 21846u; }
+constexpr uint32_t kThirdByte = 2;
+// The same for the ninths of the Sobel sums: s <= 1020 -> s * 7282 < 2^24, byte 2 = (s * 7282) >> 16 <= 113.
+__device__ __forceinline__ uint32_t ninth_b2(uint32_t s) { return s * 7282u; }
+// |a - b|^2 + |c - d|^2 for four ninths left in byte 2 of pa, pb, pc, pd: two PRMTs pack (a, c, 0, 0) and (b, d, 0, 0),
+// VABSDIFF4 takes both differences at once and the dot product of the word with itself sums their squares.
+__device__ __forceinline__ uint32_t sq_diff2_b2(uint32_t pa, uint32_t pb, uint32_t pc, uint32_t pd) {
+  const uint32_t z = __vabsdiffu4(__byte_perm(pa, pc, 0x7362), __byte_perm(pb, pd, 0x7362));
+  return __dp4a(z, z, 0u);
+}
 __device__ __forceinline__ uint32_t ninth(uint32_t s) { return __umulhi(s, 7282u << 16); }    // (s*7282)>>16
 
 constexpr int kPreW = 256, kPreH = 64;             // output tile
@@ -36,43 +50,44 @@ constexpr int kPreSegRows = kPreH / (kPreThreads / (kPreW / 4));   // rows per t
 
 // Horizontal floor-thirds of 4 consecutive pixels: h[k] = (p[x+k-1] + p[x+k] + p[x+k+1]) / 3.
 __device__ __forceinline__ void hthirds(uint32_t wm1, uint32_t w, uint32_t wp1, uint32_t h[4]) {
-  h[0] = third(__dp4a(__funnelshift_r(wm1, w, 24), 0x00010101u, 0u));
-  h[1] = third(__dp4a(w, 0x00010101u, 0u));
-  h[2] = third(__dp4a(w, 0x01010100u, 0u));
-  h[3] = third(__dp4a(__funnelshift_r(w, wp1, 16), 0x00010101u, 0u));
+  h[0] = third_b2(__dp4a(__funnelshift_r(wm1, w, 24), 0x00010101u, 0u));      // the third sits in byte kThirdByte
+  h[1] = third_b2(__dp4a(w, 0x00010101u, 0u));
+  h[2] = third_b2(__dp4a(w, 0x01010100u, 0u));
+  h[3] = third_b2(__dp4a(__funnelshift_r(w, wp1, 16), 0x00010101u, 0u));
 }
 
-// Sobel predicate (filter.hpp:466-503) for the 4 pixels of word `w` (image columns x0..x0+3); wl / wr are the
-// words left and right of it; index 0..2 = image rows y-1, y, y+1.  With P = raw pixel,
+// Sobel predicate (filter.hpp:466-503) for the 4 pixels of one word (image columns x0..x0+3).  With P = raw pixel,
 //   A = ninth(col(x-1)), B = ninth(col(x+1)), col(x) = P[y-1][x] + 2 P[y][x] + P[y+1][x]
 //   C = ninth(row(y-1)), D = ninth(row(y+1)), row(y) = P[y][x-1] + 2 P[y][x] + P[y][x+1]
 // and bit j of the result = ((A-B)^2 + (C-D)^2 > thr2) for pixel x0+j.  Row sums are dp4a on (funnel-shifted)
-// words, column sums are formed for two pixels at a time in 16-bit lanes.
-__device__ __forceinline__ uint32_t sobel_quad(const uint32_t wl[3], const uint32_t w[3], const uint32_t wr[3], int thr2) {
-  uint32_t c[4], d[4];
-  {
-    const uint32_t t0 = __funnelshift_r(wl[0], w[0], 24), t3 = __funnelshift_r(w[0], wr[0], 16);
-    c[0] = ninth(__dp4a(t0, 0x00010201u, 0u)); c[1] = ninth(__dp4a(w[0], 0x00010201u, 0u));
-    c[2] = ninth(__dp4a(w[0], 0x01020100u, 0u)); c[3] = ninth(__dp4a(t3, 0x00010201u, 0u));
-    const uint32_t b0 = __funnelshift_r(wl[2], w[2], 24), b3 = __funnelshift_r(w[2], wr[2], 16);
-    d[0] = ninth(__dp4a(b0, 0x00010201u, 0u)); d[1] = ninth(__dp4a(w[2], 0x00010201u, 0u));
-    d[2] = ninth(__dp4a(w[2], 0x01020100u, 0u)); d[3] = ninth(__dp4a(b3, 0x00010201u, 0u));
-  }
-  // column sums: lanes of colE = (col(x0), col(x0+2)), of colO = (col(x0+1), col(x0+3)); each <= 1020
-  const uint32_t colE = (w[0] & 0x00ff00ffu) + (w[2] & 0x00ff00ffu) + 2u * (w[1] & 0x00ff00ffu);
-  const uint32_t colO = __byte_perm(w[0], 0u, 0x4341) + __byte_perm(w[2], 0u, 0x4341) + 2u * __byte_perm(w[1], 0u, 0x4341);
-  const uint32_t colL = (wl[0] >> 24) + (wl[2] >> 24) + 2u * (wl[1] >> 24);                  // col(x0-1)
-  const uint32_t colR = (wr[0] & 0xffu) + (wr[2] & 0xffu) + 2u * (wr[1] & 0xffu);            // col(x0+4)
-  const uint32_t nL = ninth(colL), n0 = ninth(colE & 0xffffu), n1 = ninth(colO & 0xffffu);
-  const uint32_t n2 = ninth(colE >> 16), n3 = ninth(colO >> 16), nR = ninth(colR);
-  // only the squares of the differences are used: |a - b| as one VABSDIFF (a plain subtraction gets fused into the
-  // multiply-high of ninth() as a 64-bit addend, which costs three extra moves per difference)
-  const uint32_t ab[4] = {__usad(nL, n1, 0u), __usad(n0, n2, 0u), __usad(n1, n3, 0u), __usad(n2, nR, 0u)};
+// words, column sums are formed for two pixels at a time in 16-bit lanes.  A thread walks CONSECUTIVE rows with a
+// sliding 3-row window:
+// per raw row and quad everything that depends on that row alone is computed once (SobelRow) and used by the three
+// pixel rows it touches: the ninths of its horizontal [1 2 1] sums (C of the row below, D of the row above) and its
+// pixels split into 16-bit lanes for the vertical [1 2 1] column sums.
+struct SobelRow {
+  uint32_t rn[4];        // ninth(row(y)) for the quad's four columns
+  uint32_t E, O, LR;     // lanes (P[x0], P[x0+2]), (P[x0+1], P[x0+3]), (P[x0-1], P[x0+4])
+};
+__device__ __forceinline__ SobelRow sobel_row(uint32_t wl, uint32_t w, uint32_t wr) {
+  SobelRow r;
+  const uint32_t t0 = __funnelshift_r(wl, w, 24), t3 = __funnelshift_r(w, wr, 16);
+  r.rn[0] = ninth_b2(__dp4a(t0, 0x00010201u, 0u)); r.rn[1] = ninth_b2(__dp4a(w, 0x00010201u, 0u));
+  r.rn[2] = ninth_b2(__dp4a(w, 0x01020100u, 0u)); r.rn[3] = ninth_b2(__dp4a(t3, 0x00010201u, 0u));
+  r.E = w & 0x00ff00ffu;
+  r.O = __byte_perm(w, 0u, 0x4341);
+  r.LR = __byte_perm(__funnelshift_l(wl, wr, 8), 0u, 0x4140);     // (wl byte 3, wr byte 0)
+  return r;
+}
+// rows y-1, y, y+1 of one quad -> bit j = predicate of pixel x0 + j
+__device__ __forceinline__ uint32_t sobel_window(const SobelRow& a, const SobelRow& b, const SobelRow& c, int thr2) {
+  const uint32_t colE = a.E + c.E + 2u * b.E, colO = a.O + c.O + 2u * b.O, colLR = a.LR + c.LR + 2u * b.LR;   // lanes <= 1020
+  const uint32_t n[6] = {ninth_b2(colLR & 0xffffu), ninth_b2(colE & 0xffffu), ninth_b2(colO & 0xffffu),
+                         ninth_b2(colE >> 16), ninth_b2(colO >> 16), ninth_b2(colLR >> 16)};
   uint32_t m = 0;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    const uint32_t cd = __usad(c[j], d[j], 0u);
-    if ((int)(ab[j] * ab[j] + cd * cd) > thr2) m |= 1u << j;  // <= 25538, no int16 wrap / saturation
+    if ((int)sq_diff2_b2(n[j], n[j + 2], a.rn[j], c.rn[j]) > thr2) m |= 1u << j;     // <= 25538, no int16 wrap / saturation
   }
   return m;
 }
@@ -164,7 +179,7 @@ __device__ __forceinline__ void smooth_sobel_body(const PreprocessArgs& args, co
         uint32_t h[4];
         hthirds(row[-1], row[0], row[1], h);
 #pragma unroll
-        for (int k = 0; k < 4; k++) win[k] = __byte_perm(win[k], h[k], 0x7421);   // (b1, b2, h, 0)
+        for (int k = 0; k < 4; k++) win[k] = __byte_perm(win[k], h[k], 0x7421u + (kThirdByte << 8));   // (b1, b2, h, 0)
       };
       const int j0 = band * kPreSegRows;
       push_row(j0);
@@ -180,8 +195,9 @@ __device__ __forceinline__ void smooth_sobel_body(const PreprocessArgs& args, co
         push_row(j0 + jj + 2);
         uint32_t t[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) t[k] = third(__dp4a(win[k], 0x00010101u, 0u));
-        uint32_t v = __byte_perm(__byte_perm(t[0], t[1], 0x0040), __byte_perm(t[2], t[3], 0x0040), 0x5410);
+        for (int k = 0; k < 4; k++) t[k] = third_b2(__dp4a(win[k], 0x00010101u, 0u));
+        constexpr uint32_t kPick = 0x0040u + kThirdByte * 0x11u;       // byte kThirdByte of both operands
+        uint32_t v = __byte_perm(__byte_perm(t[0], t[1], kPick), __byte_perm(t[2], t[3], kPick), 0x5410);
         const int gy = y0 + j0 + jj;
         v = (gy < 1 || gy > last_written) ? 0u : (v & colmask);
         if (jj < rows_here) {
@@ -193,13 +209,13 @@ __device__ __forceinline__ void smooth_sobel_body(const PreprocessArgs& args, co
   }
 
   // ---- Sobel predicate per 16-pixel segment -> candidate bit masks, per-row candidate counts ----------
-  // thread = (segment sg of the tile row, tile rows tid / 16 + 16 * it): everything that does not depend on the row is
+  // thread = (segment sg of the tile row, tile rows 4 * (tid / 16) + it): everything that does not depend on the row is
   // computed once, the rows are compile-time offsets from one shared-memory and one global address
   {
     static_assert((kPreH * (kPreW / 16)) % kPreThreads == 0 && kPreW / 16 == 16, "uniform trip count, 16 segments per tile row");
-    constexpr int kSobelIters = kPreH * (kPreW / 16) / kPreThreads, kSobelRowStep = kPreThreads / 16;
+    constexpr int kSobelIters = kPreH * (kPreW / 16) / kPreThreads;
     const int segs_per_row = W / 16;
-    const int sg = tid & 15, ry0 = tid >> 4;
+    const int sg = tid & 15, ry0 = (tid >> 4) * kSobelIters;
     const int gxs = x0 + 16 * sg;
     const bool col_ok = gxs < W;
     const uint32_t colkeep = border_mask(0xffffu, kRadius, gxs, W, 2 * kRadius + 1);   // columns 13 .. W-14 of this segment
@@ -208,28 +224,32 @@ __device__ __forceinline__ void smooth_sobel_body(const PreprocessArgs& args, co
     uint16_t* const cand0 = args.cand + ((size_t)img * H + y0 + ry0) * segs_per_row + (gxs >> 4);
     int32_t* const rowcnt0 = args.rowcnt + (size_t)img * H + y0 + ry0;
     int my_last = -1;
+    SobelRow wa[3], wb[3];                                 // window of quad a (columns s..s+3) and quad b (s+8..s+11)
+    auto load_row = [&](int k, int slot) {                 // tile row ry0 + k = image row y0 + ry0 + k - 1
+      const uint32_t* row = seg0 + k * kRowPitchW;
+      const uint4 v = *reinterpret_cast<const uint4*>(row);
+      wa[slot] = sobel_row(row[-1], v.x, v.y);
+      wb[slot] = sobel_row(v.y, v.z, v.w);
+    };
+    load_row(0, 0);
+    load_row(1, 1);
 #pragma unroll
     for (int it = 0; it < kSobelIters; it++) {
-      const int gy = y0 + ry0 + kSobelRowStep * it;
+      const int gy = y0 + ry0 + it;
       const bool valid = col_ok && gy < H;
       uint32_t m = 0;
-      if (valid && gy >= 1 && gy < H - 3) {                // rows the reference writes (filter.hpp:517)
-        // words wi0-1 .. wi0+3 of tile rows ry, ry+1, ry+2 (image rows gy-1, gy, gy+1); wi0 = image column gxs
-        uint32_t wm[3], q0[3], q1[3], q2[3], q3[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          const uint32_t* row = seg0 + (kSobelRowStep * it + k) * kRowPitchW;
-          const uint4 v = *reinterpret_cast<const uint4*>(row);
-          wm[k] = row[-1]; q0[k] = v.x; q1[k] = v.y; q2[k] = v.z; q3[k] = v.w;
-        }
-        // true columns s..s+3 and s+8..s+11 survive the lane duplication (filter.hpp:504-507): output bits 2g, 2g+1
-        const uint32_t ma = sobel_quad(wm, q0, q1, args.thr2), mb = sobel_quad(q1, q2, q3, args.thr2);
+      // rows the reference writes (filter.hpp:517); without the gradient image only the candidate rows are ever looked at
+      const bool row_needed = kDebugOut ? (gy >= 1 && gy < H - 3) : (gy >= kRadius && gy < H - kRadius);
+      load_row(it + 2, 2);
+      if (valid && row_needed) {
+        const uint32_t ma = sobel_window(wa[0], wa[1], wa[2], args.thr2), mb = sobel_window(wb[0], wb[1], wb[2], args.thr2);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           if ((ma >> j) & 1u) m |= 3u << (2 * j);
           if ((mb >> j) & 1u) m |= 3u << (2 * (4 + j));
         }
       }
+      wa[0] = wa[1]; wa[1] = wa[2]; wb[0] = wb[1]; wb[1] = wb[2];
       if (kDebugOut && args.grad_out && valid) {
         uint32_t wv[4];
 #pragma unroll
@@ -241,7 +261,7 @@ __device__ __forceinline__ void smooth_sobel_body(const PreprocessArgs& args, co
         *reinterpret_cast<uint4*>(args.grad_out + img_off + (size_t)gy * W + gxs) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
       }
       const uint32_t bm = (valid && gy >= kRadius && gy < H - kRadius) ? (m & colkeep) : 0u;   // candidate border (inference.hpp:322)
-      if (valid) cand0[(uint32_t)(kSobelRowStep * it) * (uint32_t)segs_per_row] = (uint16_t)bm;
+      if (valid) cand0[(uint32_t)(it) * (uint32_t)segs_per_row] = (uint16_t)bm;
       // the 16 segments of one tile row sit in 16 consecutive lanes: one global atomic per tile row
       int cnt = __popc(bm);
       cnt += __shfl_xor_sync(0xffffffffu, cnt, 8);
@@ -249,7 +269,7 @@ __device__ __forceinline__ void smooth_sobel_body(const PreprocessArgs& args, co
       cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
       cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
       if (sg == 0 && cnt > 0) {
-        atomicAdd(rowcnt0 + kSobelRowStep * it, cnt);
+        atomicAdd(rowcnt0 + it, cnt);
         my_last = gy;                                      // rows ascend with it
       }
     }
@@ -260,14 +280,17 @@ __device__ __forceinline__ void smooth_sobel_body(const PreprocessArgs& args, co
     atomicMax(args.lastrow + img, cta_last);              // a stale read only costs a redundant atomic
 }
 
+#ifndef GPC_A1_MINB
+#define GPC_A1_MINB 4       // 64 registers: the sliding Sobel window wants them (measured: 1 -> 0.181, 4 -> 0.171, 5 -> 0.184, 6 -> 0.188 ms)
+#endif
 template <bool kDebugOut>
-__global__ void __launch_bounds__(kPreThreads)
+__global__ void __launch_bounds__(kPreThreads, GPC_A1_MINB)
 smooth_sobel_kernel(const PreprocessArgs args) {
   smooth_sobel_body<kDebugOut, false>(args, nullptr);
 }
 
 template <bool kDebugOut>
-__global__ void __launch_bounds__(kPreThreads)
+__global__ void __launch_bounds__(kPreThreads, GPC_A1_MINB)
 smooth_sobel_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PreprocessArgs args) {
   smooth_sobel_body<kDebugOut, true>(args, &tmap);
 }
