@@ -212,7 +212,7 @@ void bake_forest(const gpc_forest& f, gpc::ForestDev* d, int result_mode) {
   // whole groups of tests without per-test guards); imm 0 = the quad's own word in copy 0
   for (int t = 0; t < gpc::kMaxTests; t++) {                 // filter.hpp:574-584: t < 8 -> bit t, t >= 9 -> bit t - 1
     const int p = (t < 8) ? t : t - 1;
-    d->pmul[t] = (t == 8) ? 1u : (1u << (p & 7));
+    d->pmul[t] = (t == 8 || (p & 7) == 7) ? (1u << 25) : (1u << (25 + (p & 7)));   // multiply-high by this = >> (7 - bit); bit 7 adds directly
     if (d->naive) d->mtau2[t] = 0x80008000u;                 // 32768 - 0 in both lanes: "a + 0 > a" is false
   }
   if (d->naive) {

@@ -12,8 +12,8 @@
 //   * in the biased domain the reference's "signed-saturating b - tau, then unsigned compare"
 //     (filter.hpp:647-652) is clamp(x - tau, 0, 255) -- two DPX VIADDMNMX on 16-bit lanes --
 //     followed by a SIGNED byte compare, which costs the same carry trick as the unsigned one;
-//   * result bits are accumulated with IMAD.WIDE on the otherwise idle FMA pipe:
-//     acc64 += (r & 0x80808080) * 2^p puts test p of pixel j at bit 8j+7+p without carries;
+//   * result bits are accumulated with IMAD.HI on the otherwise idle FMA pipe:
+//     acc += ((r & 0x80808080) * 2^(25+p)) >> 32 puts test p of pixel j at bit 8j+p without carries;
 //   * the tests of one state byte form a single basic block (no per-test guards: the forest is
 //     padded with never-true tests), so the compiler interleaves their dependency chains.
 // Each pixel's state is written once to the hash image (bit 31 = candidate).
@@ -82,19 +82,26 @@ __device__ __forceinline__ uint32_t eval_test(const uint8_t* base, const ForestD
 }
 
 // All tests of state byte G (filter.hpp:574-584: tests 0..8 -> byte 0 with test 8 OR-ed into bit 0
-// under m8, 9..16 -> byte 1, 17..24 -> byte 2, 25..31 -> byte 3).
+// under m8, 9..16 -> byte 1, 17..24 -> byte 2, 25..31 -> byte 3).  A test's result word carries its four flags in
+// bit 7 of the bytes; bit p of the state byte is reached by a multiply-high with 2^(25 + p) (= a right shift by 7 - p
+// on the FMA pipe, accumulated in the same instruction; p = 7 is a plain addition).  The multiplier comes from the
+// constant bank: an immediate power of two would be strength-reduced to ALU-pipe shifts.  (IMAD.HI issues at 0.70
+// SM-cycles per warp instruction against 1.11 for the IMAD.WIDE of a left-shifting 64-bit accumulator,
+// scripts/micro/int_pipe_bench.cu.)
 template <int kMode, int G>
-__device__ __forceinline__ unsigned long long eval_group(const uint8_t* base, const ForestDev& forest, uint32_t m8, uint32_t msk,
-                                                         unsigned long long acc) {
+__device__ __forceinline__ uint32_t eval_group(const uint8_t* base, const ForestDev& forest, uint32_t m8, uint32_t msk, uint32_t acc) {
   constexpr int t0 = (G == 0) ? 1 : 8 * G + 1;
   constexpr int t1 = (G == 0) ? 8 : (G == 3) ? kMaxTests : 8 * G + 9;       // exclusive
   if (G == 0) {
     const uint32_t r0 = eval_test<kMode>(base, forest, 0, msk), r8 = eval_test<kMode>(base, forest, 8, msk);
-    acc += (unsigned long long)(r0 | (r8 & m8));
+    acc += __umulhi(r0 | (r8 & m8), forest.pmul[0]);
   }
 #pragma unroll
-  for (int t = t0; t < t1; t++)
-    acc += (unsigned long long)eval_test<kMode>(base, forest, t, msk) * (unsigned long long)forest.pmul[t];
+  for (int t = t0; t < t1; t++) {
+    const uint32_t r = eval_test<kMode>(base, forest, t, msk);
+    if ((((t < 8) ? t : t - 1) & 7) == 7) acc += r;                         // compile time after unrolling
+    else acc += __umulhi(r, forest.pmul[t]);
+  }
   return acc;
 }
 
@@ -121,11 +128,16 @@ __device__ __forceinline__ void hash_tiles_body(const CUtensorMap& tmap, const H
   constexpr int kIters = kTileH / kRowStep;
   static_assert(kIters <= 8, "candidate nibbles of a thread are packed into one word");
   uint32_t craw[kIters];
+  {
+    // one 64-bit address per thread, the rows of its iterations are 32-bit offsets from it (no 64-bit multiply per row)
+    const uint16_t* const cand0 = args.cand + ((size_t)img * H + (y0 + tid / kQuadsX)) * (size_t)(W / 16) + (gx >> 4);
+    const uint32_t row_stride = (uint32_t)kRowStep * (uint32_t)(W / 16);
 #pragma unroll
-  for (int i = 0; i < kIters; i++) {
-    const int gy = y0 + tid / kQuadsX + i * kRowStep;
-    craw[i] = 0;
-    if (gy < H && gx < W) craw[i] = __ldg(args.cand + ((size_t)img * H + gy) * (W / 16) + (gx >> 4));
+    for (int i = 0; i < kIters; i++) {
+      const int gy = y0 + tid / kQuadsX + i * kRowStep;
+      craw[i] = 0;
+      if (gy < H && gx < W) craw[i] = __ldg(cand0 + (uint32_t)i * row_stride);
+    }
   }
 
   // ---- TMA: copy 0 = image columns x0 - 16 .., rows y0 - 13 ..; zero fill outside the image ---------
@@ -152,14 +164,18 @@ __device__ __forceinline__ void hash_tiles_body(const CUtensorMap& tmap, const H
   for (int i = 0; i < kIters; i++) cms |= ((craw[i] >> ((qx & 3) * 4)) & 15u) << (4 * i);
 
   // ---- copies 1..3 = copy 0 shifted left by 1..3 bytes (two words per step) ----------------------------
+  // The rows of a copy lie back to back, so the tile is shifted as ONE linear array: the last word of a row then takes
+  // its top bytes from the next row instead of zeros, which no test can see -- an operand's four bytes end at column
+  // 16 + 127 + 13 + 3 = kPitch - 1 of its own row at the latest.
   {
     static_assert(kPitchW % 2 == 0 && kCopyBytes % 8 == 0, "64-bit accesses");
+    static_assert(16 + (kTileW - 1) + kRadius + 3 < kPitch, "operands never reach past their row");
     const uint32_t* x32 = reinterpret_cast<const uint32_t*>(smem);
-    for (int i = tid; i < kSmRows * (kPitchW / 2); i += kThreadsA) {
-      const int r = i / (kPitchW / 2), q = 2 * (i - r * (kPitchW / 2));
-      const uint2 w = *reinterpret_cast<const uint2*>(x32 + r * kPitchW + q);
-      const uint32_t nx = (q + 2 < kPitchW) ? x32[r * kPitchW + q + 2] : 0u;
-      uint8_t* dst = smem + (r * kPitchW + q) * 4;
+    constexpr int kPairs = kSmRows * (kPitchW / 2);
+    for (int i = tid; i < kPairs; i += kThreadsA) {
+      const uint2 w = *reinterpret_cast<const uint2*>(x32 + 2 * i);
+      const uint32_t nx = (i + 1 < kPairs) ? x32[2 * i + 2] : 0u;
+      uint8_t* dst = smem + 8 * i;
       *reinterpret_cast<uint2*>(dst + 1 * kCopyBytes) = make_uint2(__funnelshift_r(w.x, w.y, 8), __funnelshift_r(w.y, nx, 8));
       *reinterpret_cast<uint2*>(dst + 2 * kCopyBytes) = make_uint2(__funnelshift_r(w.x, w.y, 16), __funnelshift_r(w.y, nx, 16));
       *reinterpret_cast<uint2*>(dst + 3 * kCopyBytes) = make_uint2(__funnelshift_r(w.x, w.y, 24), __funnelshift_r(w.y, nx, 24));
@@ -168,7 +184,7 @@ __device__ __forceinline__ void hash_tiles_body(const CUtensorMap& tmap, const H
   __syncthreads();
 
   // ---- fern tests, 4 pixels per step ---------------------------------------------------------------------
-  uint32_t* __restrict__ hash = args.hash + img_off;
+  uint32_t* __restrict__ hash_out = args.hash + img_off + (size_t)(y0 + tid / kQuadsX) * W + gx;   // this thread's quad, iteration 0
   const uint32_t m8 = (gx & 4) ? kMsb : 0x80808000u;              // test #8: byte lanes x%8==0 dropped (filter.hpp:582); naive mode: slot 8 is a dummy
 #ifdef GPC_JIT_HEADER
   constexpr int T = kJitTests;                                    // all groups in ONE basic block: their chains interleave
@@ -187,15 +203,12 @@ __device__ __forceinline__ void hash_tiles_body(const CUtensorMap& tmap, const H
     if (cm != 0u && gy >= kRadius && gy < args.hash_y_end) {       // hashed rows (filter.hpp:601-604)
       const uint8_t* base = smem + (ry + kRadius) * kPitch + 16 + 4 * qx;
       // group 3 starts from the candidate flag: bit 7 of its byte = bit 31 of the state word
-      unsigned long long acc[4] = {0ull, 0ull, 0ull, (unsigned long long)msk << 7};
-      acc[0] = eval_group<kMode, 0>(base, forest, m8, msk, acc[0]);
-      if (n_groups > 1) acc[1] = eval_group<kMode, 1>(base, forest, m8, msk, acc[1]);      // uniform branches
-      if (n_groups > 2) acc[2] = eval_group<kMode, 2>(base, forest, m8, msk, acc[2]);
-      if (n_groups > 3) acc[3] = eval_group<kMode, 3>(base, forest, m8, msk, acc[3]);
-      // byte j of (acc[g] >> 7) = state byte g of pixel j; 4x4 byte transpose -> one state per pixel
-      uint32_t w[4];
-#pragma unroll
-      for (int g = 0; g < 4; g++) w[g] = (uint32_t)(acc[g] >> 7);
+      uint32_t w[4] = {0u, 0u, 0u, msk};
+      w[0] = eval_group<kMode, 0>(base, forest, m8, msk, w[0]);
+      if (n_groups > 1) w[1] = eval_group<kMode, 1>(base, forest, m8, msk, w[1]);      // uniform branches
+      if (n_groups > 2) w[2] = eval_group<kMode, 2>(base, forest, m8, msk, w[2]);
+      if (n_groups > 3) w[3] = eval_group<kMode, 3>(base, forest, m8, msk, w[3]);
+      // byte j of w[g] = state byte g of pixel j; 4x4 byte transpose -> one state per pixel
       uint32_t lo01 = __byte_perm(w[0], w[1], 0x5140), hi01 = __byte_perm(w[0], w[1], 0x7362);
       uint32_t lo23 = __byte_perm(w[2], w[3], 0x5140), hi23 = __byte_perm(w[2], w[3], 0x7362);
       st[0] = __byte_perm(lo01, lo23, 0x5410);
@@ -207,7 +220,8 @@ __device__ __forceinline__ void hash_tiles_body(const CUtensorMap& tmap, const H
       for (int j = 0; j < 4; j++) st[j] = ((cm >> j) & 1u) ? kCandFlag : 0u;
     }
     const uint4 o = make_uint4(st[0], st[1], st[2], st[3]);
-    if (gx < W && gy < H) *reinterpret_cast<uint4*>(hash + (size_t)gy * W + gx) = o;
+    if (gx < W && gy < H) *reinterpret_cast<uint4*>(hash_out) = o;
+    hash_out += (uint32_t)kRowStep * (uint32_t)W;
   }
 }
 
