@@ -79,7 +79,9 @@ __device__ __forceinline__ SobelRow sobel_row(uint32_t wl, uint32_t w, uint32_t 
   r.LR = __byte_perm(__funnelshift_l(wl, wr, 8), 0u, 0x4140);     // (wl byte 3, wr byte 0)
   return r;
 }
-// rows y-1, y, y+1 of one quad -> bit j = predicate of pixel x0 + j
+// rows y-1, y, y+1 of one quad -> bits kBit + 2 j and kBit + 2 j + 1 = predicate of pixel x0 + j (the segment mask
+// carries every surviving column twice, filter.hpp:504-507)
+template <int kBit>
 __device__ __forceinline__ uint32_t sobel_window(const SobelRow& a, const SobelRow& b, const SobelRow& c, int thr2) {
   const uint32_t colE = a.E + c.E + 2u * b.E, colO = a.O + c.O + 2u * b.O, colLR = a.LR + c.LR + 2u * b.LR;   // lanes <= 1020
   const uint32_t n[6] = {ninth_b2(colLR & 0xffffu), ninth_b2(colE & 0xffffu), ninth_b2(colO & 0xffffu),
@@ -87,7 +89,7 @@ __device__ __forceinline__ uint32_t sobel_window(const SobelRow& a, const SobelR
   uint32_t m = 0;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    if ((int)sq_diff2_b2(n[j], n[j + 2], a.rn[j], c.rn[j]) > thr2) m |= 1u << j;     // <= 25538, no int16 wrap / saturation
+    if ((int)sq_diff2_b2(n[j], n[j + 2], a.rn[j], c.rn[j]) > thr2) m |= 3u << (kBit + 2 * j);     // <= 25538, no int16 wrap / saturation
   }
   return m;
 }
@@ -242,12 +244,8 @@ __device__ __forceinline__ void smooth_sobel_body(const PreprocessArgs& args, co
       const bool row_needed = kDebugOut ? (gy >= 1 && gy < H - 3) : (gy >= kRadius && gy < H - kRadius);
       load_row(it + 2, 2);
       if (valid && row_needed) {
-        const uint32_t ma = sobel_window(wa[0], wa[1], wa[2], args.thr2), mb = sobel_window(wb[0], wb[1], wb[2], args.thr2);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          if ((ma >> j) & 1u) m |= 3u << (2 * j);
-          if ((mb >> j) & 1u) m |= 3u << (2 * (4 + j));
-        }
+        // true columns s..s+3 and s+8..s+11 survive the lane duplication (filter.hpp:504-507): output bits 2g, 2g+1
+        m = sobel_window<0>(wa[0], wa[1], wa[2], args.thr2) | sobel_window<8>(wb[0], wb[1], wb[2], args.thr2);
       }
       wa[0] = wa[1]; wa[1] = wa[2]; wb[0] = wb[1]; wb[1] = wb[2];
       if (kDebugOut && args.grad_out && valid) {
