@@ -407,7 +407,7 @@ int run_match(gpc_ctx* c, const Slot& sl, int n_pairs, int w, int h, const gpc_s
   int32_t* rowoff = c->d_rowoff + (size_t)sl.p0 * h;
   uint32_t* stage = c->d_stage + (size_t)sl.p0 * P;
   gpc::MatchArgs m{};
-  m.hash = hash; m.lastrow = c->d_lastrow + 2 * sl.p0; m.stage = stage; m.rowmatch = rowmatch;
+  m.hash = hash; m.lastrow = c->d_lastrow + 2 * sl.p0; m.rowcnt = rowcnt; m.stage = stage; m.rowmatch = rowmatch;
   m.W = w; m.H = h; m.disp_high = s->disp_high; m.vertical_tolerance = s->vertical_tolerance;
   m.wcap = std::max(w - 2 * gpc::kRadius, 16);
   m.table_log2 = table_log2_for(w, m.wcap);

@@ -100,6 +100,7 @@ struct HashArgs {           // kernel A2; pointers are buffer BASES, img0 = firs
 struct MatchArgs {
   const uint32_t* hash;    // [2*n_pair][H][W]
   const int32_t* lastrow;  // [2*n_pair]
+  const int32_t* rowcnt;   // [2*n_pair][H] candidates per image row (kernel A1)
   uint32_t* stage;         // [n_pair][H][W]
   int32_t* rowmatch;       // [n_pair][H]
   int32_t W, H;

@@ -162,6 +162,7 @@ __device__ __forceinline__ void general_row(const MatchArgs& args, uint8_t* smem
   const uint4* row_l = reinterpret_cast<const uint4*>(args.hash + ((size_t)(2 * pair) * H + y) * W);
   const uint4* row_r = reinterpret_cast<const uint4*>(args.hash + ((size_t)(2 * pair + 1) * H + y) * W);
   const int nquads = W / 4;
+  const int rowcnt_l = __ldg(args.rowcnt + (size_t)(2 * pair) * H + y), rowcnt_r = __ldg(args.rowcnt + (size_t)(2 * pair + 1) * H + y);
   uint32_t v[2][4 * KQ];                       // [side][element]
   uint32_t any_l = 0, any_r = 0;
 #pragma unroll
@@ -413,6 +414,7 @@ match_rows_fast_kernel(const MatchArgs args) {
   const uint4* row_l = reinterpret_cast<const uint4*>(args.hash + row0);
   const uint4* row_r = reinterpret_cast<const uint4*>(args.hash + row0 + (size_t)H * W);
   const int nquads = W / 4;
+  const int rowcnt_l = __ldg(args.rowcnt + (size_t)(2 * pair) * H + y), rowcnt_r = __ldg(args.rowcnt + (size_t)(2 * pair + 1) * H + y);
   uint32_t v[2][4 * KQ];                       // [side][element]
 #pragma unroll
   for (int k = 0; k < KQ; k++) {
@@ -434,11 +436,10 @@ match_rows_fast_kernel(const MatchArgs args) {
       for (int i = 0; i < rounds; i++, z += kThreadsB) *z = zero;
     }
   }
-  uint32_t any_l = 0, any_r = 0;
-#pragma unroll
-  for (int e = 0; e < 4 * KQ; e++) { any_l |= v[0][e]; any_r |= v[1][e]; }
-  const int have_l = __syncthreads_or((int)(any_l >> 31));       // also orders the zero fill before the atomics
-  const int have_r = __syncthreads_or((int)(any_r >> 31));
+  // a side without candidates: kernel A1's per-row counts say so (one uniform load each instead of two block-wide
+  // reductions over the candidate flags; the rows are issued with the hash loads above)
+  const int have_l = rowcnt_l, have_r = rowcnt_r;
+  __syncthreads();                                               // orders the zero fill before the atomics
   if (!(have_l && have_r)) {
     if (tid == 0) { args.rowmatch[grow] = 0; hdr[0] = 0; hdr[1] = 0; hdr[2] = 0; hdr[3] = 1; }
     return;
