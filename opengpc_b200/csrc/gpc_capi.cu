@@ -210,11 +210,10 @@ void bake_forest(const gpc_forest& f, gpc::ForestDev* d, int result_mode) {
   };
   // test slots the forest does not fill compare a pixel with itself: never true, state bit 0 (kernel A evaluates
   // whole groups of tests without per-test guards); imm 0 = the quad's own word in copy 0
-  for (int t = 0; t < gpc::kMaxTests; t++) {                 // filter.hpp:574-584: t < 8 -> bit t, t >= 9 -> bit t - 1
-    const int p = (t < 8) ? t : t - 1;
-    d->pmul[t] = (t == 8 || (p & 7) == 7) ? (1u << 25) : (1u << (25 + (p & 7)));   // multiply-high by this = >> (7 - bit); bit 7 adds directly
-    if (d->naive) d->mtau2[t] = 0x80008000u;                 // 32768 - 0 in both lanes: "a + 0 > a" is false
-  }
+  // (bit placement of filter.hpp:574-584 -- test t < 8 -> bit t, test 8 OR-ed into bit 0, t >= 9 -> bit t - 1 -- is
+  // compiled into the kernel's unrolled test loop)
+  if (d->naive)
+    for (int t = 0; t < gpc::kMaxTests; t++) d->mtau2[t] = 0x80008000u;      // 32768 - 0 in both lanes: "a + 0 > a" is false
   if (d->naive) {
     // gpcFilterNaive / gpcFilterTauNaive (filter.hpp:245-293): test t of T lands in bit T-1-t.  The kernel's slot s
     // feeds state bit s (s < 8) or s - 1 (s > 8); slot 8 (the SSE build's ninth test, OR-ed into bit 0) stays empty.
@@ -515,6 +514,8 @@ int gpc_create(gpc_ctx** out, int device, int max_w, int max_h, int max_batch) {
   *out = nullptr;
   if (max_w <= 0 || max_h <= 0 || max_batch <= 0) return fail(nullptr, GPC_E_ARG, "non-positive capacity");
   if (max_w % 16 != 0) return fail(nullptr, GPC_E_WIDTH16, "max_w must be a multiple of 16");
+  // the kernels index image rows of a batch in 32 bits (2 * max_batch * max_h rows); far beyond any buffer that fits HBM
+  if ((long long)max_batch * max_h > (1ll << 29)) return fail(nullptr, GPC_E_DIMS, "max_batch * max_h exceeds 2^29 rows");
   int n_dev = 0;
   cudaError_t e = cudaGetDeviceCount(&n_dev);
   if (e != cudaSuccess || n_dev == 0)

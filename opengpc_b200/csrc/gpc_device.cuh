@@ -70,10 +70,6 @@ struct ForestDev {
   int32_t imm_b[kMaxTests];
   uint32_t mtau2[kMaxTests];     // -tau (int8 tau) as int16 replicated into both 16-bit lanes; 0 = no tau
                                  // (naive mode: 32768 - tau in both lanes, tau clamped to +-256)
-  uint32_t pmul[kMaxTests];      // 1 << (25 + bit position of the test inside its state byte): the multiply-high by it moves a
-                                 // flag from bit 7 of its byte to that bit.  Kept in the constant bank so that the
-                                 // accumulate stays one IMAD.HI (an immediate power of two is strength-reduced to
-                                 // ALU-pipe shifts)
 };
 
 struct PreprocessArgs {     // kernel A1; all pointers already offset to the first image of the launch

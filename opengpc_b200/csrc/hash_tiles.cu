@@ -12,8 +12,8 @@
 //   * in the biased domain the reference's "signed-saturating b - tau, then unsigned compare"
 //     (filter.hpp:647-652) is clamp(x - tau, 0, 255) -- two DPX VIADDMNMX on 16-bit lanes --
 //     followed by a SIGNED byte compare, which costs the same carry trick as the unsigned one;
-//   * result bits are accumulated with IMAD.HI on the otherwise idle FMA pipe:
-//     acc += ((r & 0x80808080) * 2^(25+p)) >> 32 puts test p of pixel j at bit 8j+p without carries;
+//   * result bits are accumulated with one LEA.HI each: acc += (r & 0x80808080) >> (7 - p) puts test p of pixel j
+//     at bit 8j+p without carries (no wide multiply in the loop: IMAD.WIDE / IMAD.HI hold the dispatch port);
 //   * the tests of one state byte form a single basic block (no per-test guards: the forest is
 //     padded with never-true tests), so the compiler interleaves their dependency chains.
 // Each pixel's state is written once to the hash image (bit 31 = candidate).
@@ -83,24 +83,23 @@ __device__ __forceinline__ uint32_t eval_test(const uint8_t* base, const ForestD
 
 // All tests of state byte G (filter.hpp:574-584: tests 0..8 -> byte 0 with test 8 OR-ed into bit 0
 // under m8, 9..16 -> byte 1, 17..24 -> byte 2, 25..31 -> byte 3).  A test's result word carries its four flags in
-// bit 7 of the bytes; bit p of the state byte is reached by a multiply-high with 2^(25 + p) (= a right shift by 7 - p
-// on the FMA pipe, accumulated in the same instruction; p = 7 is a plain addition).  The multiplier comes from the
-// constant bank: an immediate power of two would be strength-reduced to ALU-pipe shifts.  (IMAD.HI issues at 0.70
-// SM-cycles per warp instruction against 1.11 for the IMAD.WIDE of a left-shifting 64-bit accumulator,
-// scripts/micro/int_pipe_bench.cu.)
+// bit 7 of the bytes; bit p of the state byte is reached by a right shift by 7 - p, and "acc + (r >> k)" is ONE
+// ALU-pipe instruction (LEA.HI: funnel shift + add).  Measured against the alternatives on the FMA pipe -- IMAD.WIDE
+// (left shifts into a 64-bit accumulator) and IMAD.HI (multiply-high by 2^(25+p)) -- it wins although the ALU pipe is
+// the busiest one: both wide multiplies hold the dispatch port for several cycles (0.68 / 0.63 / 0.59 ms, zero forest).
 template <int kMode, int G>
 __device__ __forceinline__ uint32_t eval_group(const uint8_t* base, const ForestDev& forest, uint32_t m8, uint32_t msk, uint32_t acc) {
   constexpr int t0 = (G == 0) ? 1 : 8 * G + 1;
   constexpr int t1 = (G == 0) ? 8 : (G == 3) ? kMaxTests : 8 * G + 9;       // exclusive
   if (G == 0) {
     const uint32_t r0 = eval_test<kMode>(base, forest, 0, msk), r8 = eval_test<kMode>(base, forest, 8, msk);
-    acc += __umulhi(r0 | (r8 & m8), forest.pmul[0]);
+    acc += (r0 | (r8 & m8)) >> 7;
   }
 #pragma unroll
   for (int t = t0; t < t1; t++) {
     const uint32_t r = eval_test<kMode>(base, forest, t, msk);
-    if ((((t < 8) ? t : t - 1) & 7) == 7) acc += r;                         // compile time after unrolling
-    else acc += __umulhi(r, forest.pmul[t]);
+    const int p = ((t < 8) ? t : t - 1) & 7;                                // compile time after unrolling
+    acc += r >> (7 - p);
   }
   return acc;
 }

@@ -401,20 +401,22 @@ match_rows_fast_kernel(const MatchArgs args) {
   uint32_t* live_v = slot + ((size_t)1 << nsl);                                     // [pow2cap] live left candidates: v
   uint32_t* live_x = live_v + args.pow2cap;                                         // [pow2cap] x
   __shared__ uint32_t n_live, n_ovl, n_ovr, n_out;
-  const size_t grow = (size_t)pair * H + y;                                         // this row's records in global memory:
-  unsigned long long* mrec = args.mrec + grow * W;                                  //   matches, unordered (key << 32 | xl << 16 | xr)
-  uint32_t* ovl_s = args.ovbuf + grow * (4 * kOvCap);                               //   overflow lists: left v, x
+  // row indices in 32 bits (gpc_create bounds max_batch * max_h): ONE widening multiply per base address instead of
+  // 64-bit products assembled from several IMAD.WIDE / IMAD (a wide multiply holds the dispatch port for 3 - 4 cycles)
+  const uint32_t grow = (uint32_t)pair * (uint32_t)H + (uint32_t)y;                 // this row's records in global memory:
+  unsigned long long* mrec = args.mrec + (size_t)grow * (uint32_t)W;                //   matches, unordered (key << 32 | xl << 16 | xr)
+  uint32_t* ovl_s = args.ovbuf + (size_t)grow * (uint32_t)(4 * kOvCap);             //   overflow lists: left v, x
   uint32_t* ovl_x = ovl_s + kOvCap;
   uint32_t* ovr_s = ovl_x + kOvCap;                                                 //   right v, x
   uint32_t* ovr_x = ovr_s + kOvCap;
-  int32_t* hdr = args.rowhdr + grow * 4;                                            //   {matches, left overflow, right overflow, done}
+  int32_t* hdr = args.rowhdr + (size_t)grow * 4u;                                   //   {matches, left overflow, right overflow, done}
 
   // ---- this thread's pixels of the left and right hash rows (issued first: the zero fill hides their latency)
-  const size_t row0 = ((size_t)(2 * pair) * H + y) * W;
-  const uint4* row_l = reinterpret_cast<const uint4*>(args.hash + row0);
-  const uint4* row_r = reinterpret_cast<const uint4*>(args.hash + row0 + (size_t)H * W);
+  const uint32_t irow_l = grow + (uint32_t)pair * (uint32_t)H;                      // row y of image 2 * pair
+  const uint4* row_l = reinterpret_cast<const uint4*>(args.hash + (size_t)irow_l * (uint32_t)W);
+  const uint4* row_r = row_l + (uint32_t)H * (uint32_t)(W / 4);                     // image 2 * pair + 1
   const int nquads = W / 4;
-  const int rowcnt_l = __ldg(args.rowcnt + (size_t)(2 * pair) * H + y), rowcnt_r = __ldg(args.rowcnt + (size_t)(2 * pair + 1) * H + y);
+  const int rowcnt_l = __ldg(args.rowcnt + irow_l), rowcnt_r = __ldg(args.rowcnt + irow_l + (uint32_t)H);
   uint32_t v[2][4 * KQ];                       // [side][element]
 #pragma unroll
   for (int k = 0; k < KQ; k++) {
@@ -600,7 +602,7 @@ constexpr size_t tail_smem_bytes(int slots, int groups) { return (size_t)kTailWa
 
 template <int kSlots, int kGroups>
 __global__ void __launch_bounds__(32 * kTailWarps, kSlots <= kTailSlotsSmall ? GPC_TAIL_MINB_SMALL : 4)
-match_rows_tail_kernel(const MatchArgs args, int n_pairs) {
+match_rows_tail_kernel(const MatchArgs args) {
   static_assert(kSlots >= kTailCap && kGroups >= 32 && kGroups % 128 == 0 && (kGroups & (kGroups - 1)) == 0, "slice layout");
   constexpr int kTailWords = 2 * kGroups + 2 * kSlots;
   constexpr int kGroupShift = 32 - (kGroups == 128 ? 7 : kGroups == 256 ? 8 : 9);
@@ -612,14 +614,13 @@ match_rows_tail_kernel(const MatchArgs args, int n_pairs) {
   uint32_t* cur = cnt + kGroups;                                     // [kGroups]
   uint32_t* bk = cur + kGroups;                                      // [kSlots] keys
   uint32_t* bv = bk + kSlots;                                        // [kSlots] payloads
-  const int rows = args.H - 2 * kRadius;
-  const long long r = (long long)blockIdx.x * kTailWarps + wid;
-  if (r >= (long long)rows * n_pairs) return;
-  const int pair = (int)(r / rows), y = kRadius + (int)(r % rows);
-  const size_t grow = (size_t)pair * args.H + y;
-  const int4 hdr = *reinterpret_cast<const int4*>(args.rowhdr + grow * 4);
+  // grid (row groups, pairs): no division, row indices in 32 bits
+  const int pair = blockIdx.y, y = kRadius + (int)blockIdx.x * kTailWarps + wid;
+  if (y >= args.H - kRadius) return;
+  const uint32_t grow = (uint32_t)pair * (uint32_t)args.H + (uint32_t)y;
+  const int4 hdr = *reinterpret_cast<const int4*>(args.rowhdr + (size_t)grow * 4u);
   if (hdr.w != 0) return;                                   // empty row, or one the general kernel owns
-  unsigned long long* mrec = args.mrec + grow * args.W;
+  unsigned long long* mrec = args.mrec + (size_t)grow * (uint32_t)args.W;
   uint32_t m = (uint32_t)hdr.x;
   const uint32_t nl = (uint32_t)hdr.y, nr = (uint32_t)hdr.z;
   // ---- overflow entries: a hash-partitioned join (linear in their number) ------------------------------------
@@ -630,7 +631,7 @@ match_rows_tail_kernel(const MatchArgs args, int n_pairs) {
     return;
   }
   if (nl > 0u && nr > 0u) {
-    const uint32_t* ovl_s = args.ovbuf + grow * (4 * kOvCap);
+    const uint32_t* ovl_s = args.ovbuf + (size_t)grow * (uint32_t)(4 * kOvCap);
     const uint32_t* ovl_x = ovl_s + kOvCap;
     const uint32_t* ovr_s = ovl_x + kOvCap;
     const uint32_t* ovr_x = ovr_s + kOvCap;
@@ -702,7 +703,7 @@ match_rows_tail_kernel(const MatchArgs args, int n_pairs) {
   if (lane == 0) args.rowmatch[grow] = (int32_t)m;
   if (m == 0u) return;
   // ---- order by state and stage -------------------------------------------------------------------------
-  uint32_t* stage = args.stage + grow * args.W;
+  uint32_t* stage = args.stage + (size_t)grow * (uint32_t)args.W;
   if (m > (uint32_t)kTailCap) {                           // a crowd: the block-wide ordering kernel
     if (lane == 0) push_row(args.big_hdr, args.big_ent, pair, y);
     return;
@@ -828,7 +829,7 @@ cudaError_t launch_match_rows(const MatchArgs& args, int n_pairs, int general, i
   const size_t smem_o = order_rows_smem_bytes(args.pow2cap);
   const long long all_rows = (long long)rows * n_pairs;
   const int list_grid = (int)(all_rows < 4ll * sm_count ? all_rows : 4ll * sm_count);
-  const int tail_grid = (int)((all_rows + kTailWarps - 1) / kTailWarps);
+  const dim3 tail_grid((rows + kTailWarps - 1) / kTailWarps, n_pairs);
   const int order_grid = (int)(all_rows < 6ll * sm_count ? all_rows : 6ll * sm_count);
   static const int tail_env = std::getenv("GPC_B_TAIL") ? std::atoi(std::getenv("GPC_B_TAIL")) : 0;   // 1 small, 2 big slice
   const bool small_tail = tail_env ? tail_env == 1 : quads <= 256;
@@ -837,8 +838,8 @@ cudaError_t launch_match_rows(const MatchArgs& args, int n_pairs, int general, i
     if (general) match_rows_general_kernel<KQ, T><<<grid, T, smem_g, stream>>>(args, nullptr, nullptr);                  \
     else {                                                                                                      \
       match_rows_fast_kernel<KQ, T><<<grid, T, smem_f, stream>>>(args);                                         \
-      if (small_tail) match_rows_tail_kernel<kTailSlotsSmall, kTailGroupsSmall><<<tail_grid, 32 * kTailWarps, tail_smem_bytes(kTailSlotsSmall, kTailGroupsSmall), stream>>>(args, n_pairs); \
-      else match_rows_tail_kernel<kTailSlotsBig, kTailGroupsBig><<<tail_grid, 32 * kTailWarps, tail_smem_bytes(kTailSlotsBig, kTailGroupsBig), stream>>>(args, n_pairs); \
+      if (small_tail) match_rows_tail_kernel<kTailSlotsSmall, kTailGroupsSmall><<<tail_grid, 32 * kTailWarps, tail_smem_bytes(kTailSlotsSmall, kTailGroupsSmall), stream>>>(args); \
+      else match_rows_tail_kernel<kTailSlotsBig, kTailGroupsBig><<<tail_grid, 32 * kTailWarps, tail_smem_bytes(kTailSlotsBig, kTailGroupsBig), stream>>>(args); \
       order_rows_kernel<kOrderThreads><<<order_grid, kOrderThreads, smem_o, stream>>>(args, args.big_hdr, args.big_ent);                         \
       match_rows_general_kernel<KQ, T><<<list_grid, T, smem_g, stream>>>(args, args.fb_hdr, args.fb_ent);                 \
     }                                                                                                           \
