@@ -1008,7 +1008,17 @@ emit_supports_kernel(const EmitArgs a) {
     const int k = lane + 32 * j;
     if (k < m && k < room) put(k, ahead[j]);
   }
-  for (int k = lane + 32 * kAhead; k < m && k < room; k += 32) put(k, stage[k]);
+  // longer rows (dense images): four more loads in flight per round instead of a load -> store chain per match
+  for (int k0 = lane + 32 * kAhead; k0 < m && k0 < room; k0 += 32 * kAhead) {
+    uint32_t more[kAhead];
+#pragma unroll
+    for (int j = 0; j < kAhead; j++) more[j] = (k0 + 32 * j < m) ? ld_nc_u32(stage + k0 + 32 * j) : 0u;
+#pragma unroll
+    for (int j = 0; j < kAhead; j++) {
+      const int k = k0 + 32 * j;
+      if (k < m && k < room) put(k, more[j]);
+    }
+  }
 }
 
 cudaError_t launch_emit_supports(const uint32_t* stage, const int32_t* rowmatch, const int32_t* rowoff,
