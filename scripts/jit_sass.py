@@ -65,6 +65,7 @@ def main():
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.exit(r.stderr)
+        prev = ""
         for line in r.stderr.splitlines():
             if "gpc_hash_tiles_jit" in line or ("registers" in line and "jit" in prev):
                 print(line.strip())
