@@ -171,10 +171,10 @@ __device__ __forceinline__ void smooth_sobel_body(const PreprocessArgs& args, co
       if (gxq == 0) colmask = 0xffff0000u;
       if (gxq == W - 4) colmask &= 0x00ffffffu;
       // 3-row window per pixel column, PACKED: byte 0..2 of win[k] = horizontal thirds of rows j-1, j, j+1.  One PRMT
-      // shifts the window and inserts the new row, one dp4a sums it.  (Keeping the three thirds in separate registers
-      // and adding them looks cheaper but is not: ptxas fuses a multiply-high whose result feeds an addition into
-      // IMAD.HI with a 64-bit addend and then RE-COMPUTES it for each of the three sums it appears in, plus a move to
-      // clear the addend's low word each time -- 364 instead of 248 IMAD.HI per thread.)
+      // shifts the window and inserts the new row (picking the third out of byte 2 of its product, see third_b2), one
+      // dp4a sums it.  (History: with the thirds as multiply-highs in separate registers ptxas fused each one into an
+      // IMAD.HI with a 64-bit addend and re-computed it for each of the three sums it appears in -- 364 instead of 248
+      // IMAD.HI per thread; the packed window fixed that, the plain products then removed the IMAD.HI altogether.)
       uint32_t win[4] = {0u, 0u, 0u, 0u};
       auto push_row = [&](int r) {                         // raw-tile row r = image row y0 - 1 + r
         const uint32_t* row = pre_word<kTma>(raw32, r, q);
